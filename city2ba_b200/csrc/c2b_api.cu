@@ -1,0 +1,847 @@
+// c2b_api.cu — the extern "C" boundary of libcity2ba_cuda.so (include/city2ba_cuda.h) and the
+// host-side orchestration of the kernels: upload -> (grid build) -> cull -> radix sort ->
+// warp-cooperative BVH traversal -> compaction -> download.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <new>
+#include <vector>
+
+#include "c2b_bvh.cuh"
+#include "c2b_common.cuh"
+#include "c2b_compact.cuh"
+#include "c2b_cull.cuh"
+#include "c2b_math.cuh"
+#include "c2b_noise.cuh"
+#include "c2b_sort.cuh"
+#include "c2b_traverse.cuh"
+
+using namespace c2b;
+
+namespace {
+
+inline int bit_length(uint64_t v) {
+  int b = 0;
+  while (v) {
+    ++b;
+    v >>= 1;
+  }
+  return b;
+}
+
+// smallest double T with sqrt_rn(T) >= max_dist, so that  m2 < T  <=>  sqrt_rn(m2) < max_dist
+// (sqrt_rn is monotone non-decreasing).  NaN / non-positive max_dist admit nothing.
+double exact_sq_threshold(double max_dist) {
+  if (!(max_dist > 0.0)) return 0.0;  // m2 < 0 is never true (and NaN compares false)
+  if (std::isinf(max_dist)) return INFINITY;
+  double x = max_dist * max_dist;
+  if (std::isinf(x)) x = 1.7976931348623157e308;
+  while (x > 0.0 && std::sqrt(x) >= max_dist) x = std::nextafter(x, 0.0);
+  while (std::sqrt(x) < max_dist) {
+    double nx = std::nextafter(x, INFINITY);
+    if (std::isinf(nx)) return nx;
+    x = nx;
+  }
+  return x;
+}
+
+__global__ void k_iota_u32(uint32_t *v, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+struct GridCache {
+  bool valid = false;
+  double max_dist = 0;
+  uint64_t points_version = 0;
+  GridDesc desc;
+  uint64_t n_cells = 0;
+};
+
+struct CtxExtra {
+  GridCache grid;
+  uint64_t points_version = 0;
+  double pts_bounds[6] = {0, 0, 0, 0, 0, 0};
+  bool have_points = false, have_cameras = false, have_result = false;
+  uint64_t res_candidates = 0;
+};
+
+}  // namespace
+
+// c2b_ctx carries its non-POD extras behind one pointer so the struct in c2b_common.cuh stays plain
+static std::vector<std::pair<c2b_ctx *, CtxExtra *>> &extras() {
+  static std::vector<std::pair<c2b_ctx *, CtxExtra *>> v;
+  return v;
+}
+static CtxExtra *extra_of(c2b_ctx *ctx) {
+  for (auto &e : extras())
+    if (e.first == ctx) return e.second;
+  return nullptr;
+}
+
+extern "C" {
+
+const char *c2b_last_error(void) { return last_error_ref().c_str(); }
+int c2b_abi_version(void) { return C2B_ABI_VERSION; }
+
+int c2b_init(int device, c2b_ctx **out) {
+  if (!out) return set_error(C2B_ERR_INVALID, "c2b_init: out is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return set_error(C2B_ERR_NO_DEVICE, "no CUDA device visible (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return set_error(C2B_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  C2B_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  C2B_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_error(C2B_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                     device, prop.major, prop.minor);
+  c2b_ctx *ctx = new (std::nothrow) c2b_ctx();
+  if (!ctx) return set_error(C2B_ERR_OOM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  C2B_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < EV_COUNT; ++i) C2B_CUDA(cudaEventCreate(&ctx->ev[i]));
+  extras().push_back({ctx, new CtxExtra()});
+  *out = ctx;
+  return C2B_OK;
+}
+
+void c2b_shutdown(c2b_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf *bufs[] = {&ctx->cams, &ctx->cam_center, &ctx->pts, &ctx->stage, &ctx->cell_of_pt,
+                    &ctx->cell_start, &ctx->cell_cursor, &ctx->grid_x, &ctx->grid_y, &ctx->grid_z,
+                    &ctx->grid_idx, &ctx->pool_key, &ctx->pool_uv, &ctx->cam_count, &ctx->counters,
+                    &ctx->sort_keys[0], &ctx->sort_keys[1], &ctx->sort_vals[0], &ctx->sort_vals[1],
+                    &ctx->sort_hist, &ctx->scan_tmp[0], &ctx->scan_tmp[1], &ctx->scan_tmp[2],
+                    &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets, &ctx->out_idx,
+                    &ctx->out_uv, &ctx->misc};
+  for (auto *b : bufs) b->release();
+  PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
+  for (auto *p : pins) p->release();
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  auto &v = extras();
+  for (size_t i = 0; i < v.size(); ++i)
+    if (v[i].first == ctx) {
+      delete v[i].second;
+      v.erase(v.begin() + i);
+      break;
+    }
+  delete ctx;
+}
+
+// ---- scene -------------------------------------------------------------------------------------
+int c2b_scene_create(c2b_ctx *ctx, const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt,
+                     c2b_scene **out) {
+  if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_scene_create: null ctx/out");
+  *out = nullptr;
+  if ((nv && !xyz) || (nt && !tri)) return set_error(C2B_ERR_INVALID, "c2b_scene_create: null mesh arrays");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  std::vector<uint32_t> keep;
+  keep.reserve(3 * nt);
+  for (uint64_t i = 0; i < nt; ++i) {
+    uint32_t a = tri[3 * i], b = tri[3 * i + 1], c = tri[3 * i + 2];
+    if (a >= nv || b >= nv || c >= nv)
+      return set_error(C2B_ERR_INVALID, "triangle %llu references vertex >= %llu",
+                       (unsigned long long)i, (unsigned long long)nv);
+    if (a == b || b == c || a == c) continue;  // zero-area (tobj `l` records): can never be hit
+    keep.push_back(a);
+    keep.push_back(b);
+    keep.push_back(c);
+  }
+  c2b_scene *sc = new (std::nothrow) c2b_scene();
+  if (!sc) return set_error(C2B_ERR_OOM, "out of host memory");
+  sc->ctx = ctx;
+  int rc = bvh_build(ctx, sc, xyz, nv, keep.data(), keep.size() / 3);
+  if (rc != C2B_OK) {
+    sc->nodes.release();
+    sc->tris.release();
+    delete sc;
+    return rc;
+  }
+  *out = sc;
+  return C2B_OK;
+}
+
+int c2b_scene_bounds(const c2b_scene *scene, float lower[3], float upper[3]) {
+  if (!scene || !lower || !upper) return set_error(C2B_ERR_INVALID, "c2b_scene_bounds: null argument");
+  for (int k = 0; k < 3; ++k) {
+    lower[k] = scene->lo[k];
+    upper[k] = scene->hi[k];
+  }
+  return C2B_OK;
+}
+uint64_t c2b_scene_num_triangles(const c2b_scene *scene) { return scene ? scene->n_tris : 0; }
+uint64_t c2b_scene_num_nodes(const c2b_scene *scene) { return scene ? scene->n_nodes : 0; }
+void c2b_scene_destroy(c2b_scene *scene) {
+  if (!scene) return;
+  if (scene->ctx) cudaSetDevice(scene->ctx->device);
+  scene->nodes.release();
+  scene->tris.release();
+  delete scene;
+}
+
+// ---- ray-level entries ------------------------------------------------------------------------------
+int c2b_occluded(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t n) {
+  if (!ctx || !scene || (n && !rays)) return set_error(C2B_ERR_INVALID, "c2b_occluded: null argument");
+  if (n == 0 || scene->n_nodes == 0) return C2B_OK;
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  C2B_TRY(ctx->stage.ensure(n * sizeof(c2b_ray48)));
+  C2B_TRY(ctx->counters.ensure(32));
+  C2B_CUDA(cudaMemcpyAsync(ctx->stage.p, rays, n * sizeof(c2b_ray48), cudaMemcpyHostToDevice, ctx->stream));
+  k_occluded_rays<false><<<blocks_for(n, 256), 256, 0, ctx->stream>>>(
+      scene->nodes.as<float4>(), scene->tris.as<float4>(), (int)scene->n_nodes,
+      ctx->stage.as<c2b_ray48>(), n, ctx->counters.as<unsigned long long>());
+  C2B_KERNEL_CHECK();
+  C2B_CUDA(cudaMemcpyAsync(rays, ctx->stage.p, n * sizeof(c2b_ray48), cudaMemcpyDeviceToHost, ctx->stream));
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
+  return C2B_OK;
+}
+
+int c2b_intersect1(c2b_ctx *ctx, const c2b_scene *scene, const float org[3], const float dir[3],
+                   int *hit, float *tfar) {
+  if (!ctx || !scene || !org || !dir || !hit || !tfar)
+    return set_error(C2B_ERR_INVALID, "c2b_intersect1: null argument");
+  *hit = 0;
+  *tfar = INFINITY;
+  if (scene->n_tris == 0) return C2B_OK;
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  C2B_TRY(ctx->misc.ensure(64));
+  Ray r;
+  r.ox = org[0];
+  r.oy = org[1];
+  r.oz = org[2];
+  r.dx = dir[0];
+  r.dy = dir[1];
+  r.dz = dir[2];
+  r.tfar = INFINITY;
+  k_intersect1<<<1, 32, 0, ctx->stream>>>(scene->tris.as<float4>(), scene->n_tris, r, ctx->misc.as<float>());
+  C2B_KERNEL_CHECK();
+  float h[2];
+  C2B_CUDA(cudaMemcpyAsync(h, ctx->misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
+  *hit = h[0] != 0.0f;
+  *tfar = h[1];
+  return C2B_OK;
+}
+
+// ---- uploads ------------------------------------------------------------------------------------------
+void c2b_vis_options_default(c2b_vis_options *opt) {
+  if (!opt) return;
+  opt->cull_mode = C2B_CULL_GRID;
+  opt->occlusion = C2B_OCC_MESH;
+  opt->endpoint_guard_rel = 0;
+  opt->count_traversal = 0;
+  opt->block_length = 20.0;
+  opt->block_inset = 1.0;
+}
+
+int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
+  if (!ctx || (P && !pts)) return set_error(C2B_ERR_INVALID, "c2b_upload_points: null argument");
+  if (P >= 0xffffffffull) return set_error(C2B_ERR_INVALID, "too many points (%llu)", (unsigned long long)P);
+  CtxExtra *x = extra_of(ctx);
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  ctx->P = P;
+  x->points_version++;
+  x->grid.valid = false;
+  x->have_points = true;
+  x->have_result = false;
+  if (P == 0) return C2B_OK;
+  C2B_TRY(ctx->stage.ensure(P * 24));
+  C2B_TRY(ctx->pts.ensure(P * 24));
+  C2B_CUDA(cudaMemcpyAsync(ctx->stage.p, pts, P * 24, cudaMemcpyHostToDevice, ctx->stream));
+  double *px = ctx->pts.as<double>(), *py = px + P, *pz = py + P;
+  k_aos_to_soa3<<<blocks_for(P, 256), 256, 0, ctx->stream>>>(ctx->stage.as<double>(), P, px, py, pz);
+  C2B_KERNEL_CHECK();
+  // coordinate bounds (grid extent); tiny D2H happens lazily when a grid is built
+  int nb = (int)std::min<uint64_t>(blocks_for(P, 256), (uint64_t)4 * ctx->sm_count);
+  C2B_TRY(ctx->misc.ensure((size_t)nb * 48 + 64));
+  double *partial = ctx->misc.as<double>() + 8;
+  k_pts_bounds_partial<<<nb, 256, 0, ctx->stream>>>(px, py, pz, P, partial);
+  C2B_KERNEL_CHECK();
+  k_pts_bounds_final<<<1, 32, 0, ctx->stream>>>(partial, nb, ctx->misc.as<double>());
+  C2B_KERNEL_CHECK();
+  C2B_CUDA(cudaMemcpyAsync(x->pts_bounds, ctx->misc.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+  return C2B_OK;
+}
+
+int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C) {
+  if (!ctx || (C && !cams)) return set_error(C2B_ERR_INVALID, "c2b_upload_cameras: null argument");
+  if (C >= 0xffffffffull) return set_error(C2B_ERR_INVALID, "too many cameras (%llu)", (unsigned long long)C);
+  CtxExtra *x = extra_of(ctx);
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  ctx->C = C;
+  x->have_cameras = true;
+  x->have_result = false;
+  if (C == 0) return C2B_OK;
+  C2B_TRY(ctx->cams.ensure(C * 120));
+  C2B_TRY(ctx->cam_center.ensure(C * 24));
+  C2B_CUDA(cudaMemcpyAsync(ctx->cams.p, cams, C * 120, cudaMemcpyHostToDevice, ctx->stream));
+  double *cx = ctx->cam_center.as<double>();
+  k_cam_prep<<<blocks_for(C, 128), 128, 0, ctx->stream>>>(ctx->cams.as<double>(), C, cx, cx + C, cx + 2 * C);
+  C2B_KERNEL_CHECK();
+  return C2B_OK;
+}
+
+// ---- the pipeline ---------------------------------------------------------------------------------------
+static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t P = ctx->P;
+  C2B_CUDA(cudaStreamSynchronize(st));  // pts_bounds has landed
+  GridDesc g;
+  double h = max_dist * 0.5;
+  if (const char *e = getenv("C2B_GRID_CELL_FACTOR")) {
+    double f = atof(e);
+    if (f > 0.0) h = max_dist * f;
+  }
+  double ext[3];
+  for (int k = 0; k < 3; ++k) {
+    g.min_c[k] = x->pts_bounds[k];
+    g.max_c[k] = x->pts_bounds[3 + k];
+    ext[k] = g.max_c[k] - g.min_c[k];
+    if (!(ext[k] >= 0.0) || std::isinf(ext[k])) ext[k] = 0.0;  // NaN / inf coordinates: one cell
+    g.lo[k] = std::isfinite(g.min_c[k]) ? g.min_c[k] : 0.0;
+  }
+  if (!(h > 0.0) || !std::isfinite(h)) h = 1.0;
+  const double max_cells = 4194304.0;  // 2^22
+  for (;;) {
+    double total = 1.0;
+    for (int k = 0; k < 3; ++k) {
+      double nk = std::floor(ext[k] / h) + 1.0;
+      if (nk > 1e9) nk = 1e9;
+      g.n[k] = (int)nk;
+      total *= nk;
+    }
+    if (total <= max_cells) break;
+    h *= 1.5;
+  }
+  g.inv_h = 1.0 / h;
+  uint64_t n_cells = (uint64_t)g.n[0] * g.n[1] * g.n[2];
+  C2B_TRY(ctx->cell_of_pt.ensure(P * 4));
+  C2B_TRY(ctx->cell_start.ensure((n_cells + 1) * 4));
+  C2B_TRY(ctx->cell_cursor.ensure((n_cells + 1) * 4));
+  C2B_TRY(ctx->grid_x.ensure(P * 8));
+  C2B_TRY(ctx->grid_y.ensure(P * 8));
+  C2B_TRY(ctx->grid_z.ensure(P * 8));
+  C2B_TRY(ctx->grid_idx.ensure(P * 4));
+  C2B_CUDA(cudaMemsetAsync(ctx->cell_start.p, 0, (n_cells + 1) * 4, st));
+  C2B_CUDA(cudaMemsetAsync(ctx->cell_cursor.p, 0, (n_cells + 1) * 4, st));
+  const double *px = ctx->pts.as<double>(), *py = px + P, *pz = py + P;
+  k_grid_count<<<blocks_for(P, 256), 256, 0, st>>>(px, py, pz, P, g, ctx->cell_of_pt.as<uint32_t>(),
+                                                   ctx->cell_start.as<uint32_t>());
+  C2B_KERNEL_CHECK();
+  C2B_TRY(exclusive_scan_u32(st, ctx->cell_start.as<uint32_t>(), ctx->cell_start.as<uint32_t>(),
+                             n_cells + 1, nullptr, ctx->scan_tmp));
+  k_grid_fill<<<blocks_for(P, 256), 256, 0, st>>>(
+      px, py, pz, P, ctx->cell_of_pt.as<uint32_t>(), ctx->cell_start.as<uint32_t>(),
+      ctx->cell_cursor.as<uint32_t>(), ctx->grid_x.as<double>(), ctx->grid_y.as<double>(),
+      ctx->grid_z.as<double>(), ctx->grid_idx.as<uint32_t>());
+  C2B_KERNEL_CHECK();
+  x->grid.valid = true;
+  x->grid.max_dist = max_dist;
+  x->grid.points_version = x->points_version;
+  x->grid.desc = g;
+  x->grid.n_cells = n_cells;
+  return C2B_OK;
+}
+
+int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
+                                  const c2b_vis_options *opt_in, c2b_obs *stats) {
+  if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph_resident: null ctx");
+  CtxExtra *x = extra_of(ctx);
+  if (!x->have_points || !x->have_cameras)
+    return set_error(C2B_ERR_INVALID, "upload cameras and points first");
+  c2b_vis_options opt;
+  if (opt_in)
+    opt = *opt_in;
+  else
+    c2b_vis_options_default(&opt);
+  if (opt.occlusion == C2B_OCC_MESH && !scene)
+    return set_error(C2B_ERR_INVALID, "C2B_OCC_MESH needs a scene");
+  if (opt.cull_mode != C2B_CULL_GRID && opt.cull_mode != C2B_CULL_EXHAUSTIVE)
+    return set_error(C2B_ERR_INVALID, "unknown cull_mode %d", opt.cull_mode);
+  if (opt.occlusion < C2B_OCC_MESH || opt.occlusion > C2B_OCC_ANALYTIC)
+    return set_error(C2B_ERR_INVALID, "unknown occlusion %d", opt.occlusion);
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint64_t C = ctx->C, P = ctx->P;
+  x->have_result = false;
+
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_START], st));
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_H2D], st));
+
+  const int pbits = std::max(1, bit_length(P ? P - 1 : 0));
+  const int cbits = std::max(1, bit_length(C ? C - 1 : 0));
+  if (pbits + cbits > 64) return set_error(C2B_ERR_INVALID, "camera x point index space exceeds 64 bits");
+
+  C2B_TRY(ctx->counters.ensure(64));
+  C2B_TRY(ctx->cam_count.ensure((C + 1) * 4));
+  C2B_TRY(ctx->out_offsets.ensure((C + 1) * 8));
+
+  uint64_t n_cand = 0, pairs_eval = 0;
+  const bool use_grid = opt.cull_mode == C2B_CULL_GRID;
+  if (C && P) {
+    if (use_grid && !(x->grid.valid && x->grid.max_dist == max_dist &&
+                      x->grid.points_version == x->points_version))
+      C2B_TRY(build_grid(ctx, x, max_dist));
+  }
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
+
+  if (C && P) {
+    CullArgs a;
+    a.cams = ctx->cams.as<double>();
+    a.cen_x = ctx->cam_center.as<double>();
+    a.cen_y = a.cen_x + C;
+    a.cen_z = a.cen_y + C;
+    a.C = C;
+    a.P = P;
+    a.t_star = exact_sq_threshold(max_dist);
+    a.t_cons = a.t_star * (1.0 + 4e-15);
+    if (a.t_star > 0.0 && a.t_cons == a.t_star) a.t_cons = std::nextafter(a.t_star, INFINITY);
+    a.pbits = pbits;
+    a.cam_count = ctx->cam_count.as<uint32_t>();
+    a.counters = ctx->counters.as<unsigned long long>();
+    if (use_grid) {
+      a.px = ctx->grid_x.as<double>();
+      a.py = ctx->grid_y.as<double>();
+      a.pz = ctx->grid_z.as<double>();
+    } else {
+      a.px = ctx->pts.as<double>();
+      a.py = a.px + P;
+      a.pz = a.py + P;
+    }
+    if (ctx->pool_capacity == 0) {
+      long double pairs = (long double)C * (long double)P;
+      uint64_t guess = std::max<uint64_t>(1u << 20, 96 * C);
+      if ((long double)guess > pairs) guess = (uint64_t)pairs;
+      ctx->pool_capacity = std::max<uint64_t>(guess, 1024);
+    }
+    for (int attempt = 0;; ++attempt) {
+      // the sorted copy of the keys lives in sort_keys[], the pool itself is sort_keys[0]
+      C2B_TRY(ctx->sort_keys[0].ensure(ctx->pool_capacity * 8));
+      C2B_TRY(ctx->pool_uv.ensure(ctx->pool_capacity * 16));
+      a.pool_key = ctx->sort_keys[0].as<uint64_t>();
+      a.pool_uv = ctx->pool_uv.as<double2>();
+      a.pool_capacity = ctx->pool_capacity;
+      C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+      C2B_CUDA(cudaMemsetAsync(ctx->cam_count.p, 0, (C + 1) * 4, st));
+      if (use_grid) {
+        k_cull_grid<<<blocks_for(C, 8), 256, 0, st>>>(a, x->grid.desc, max_dist,
+                                                      ctx->cell_start.as<uint32_t>(),
+                                                      ctx->grid_idx.as<uint32_t>());
+      } else {
+        dim3 grid(blocks_for(P, CB_THREADS * CB_PPT), blocks_for(C, CB_TC));
+        if (grid.y > 65535u) return set_error(C2B_ERR_INVALID, "too many cameras for one exhaustive launch");
+        k_cull_exhaustive<<<grid, CB_THREADS, 0, st>>>(a);
+      }
+      C2B_KERNEL_CHECK();
+      unsigned long long h_cnt[4];
+      C2B_CUDA(cudaMemcpyAsync(h_cnt, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
+      C2B_CUDA(cudaStreamSynchronize(st));
+      n_cand = h_cnt[0];
+      pairs_eval = use_grid ? h_cnt[1] : C * P;
+      if (n_cand <= ctx->pool_capacity) break;
+      if (attempt >= 2) return set_error(C2B_ERR_CUDA, "candidate pool overflow persisted");
+      ctx->pool_capacity = n_cand + n_cand / 16 + 1024;  // exact count is known now: re-run once
+    }
+    if (n_cand >= 0xffffffffull)
+      return set_error(C2B_ERR_INVALID, "more than 2^32 candidates in one call; shard the cameras");
+  } else {
+    C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    C2B_CUDA(cudaMemsetAsync(ctx->cam_count.p, 0, (C + 1) * 4, st));
+  }
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_CULL], st));
+
+  // candidate start per camera
+  C2B_TRY(exclusive_scan_u32(st, ctx->cam_count.as<uint32_t>(), ctx->cam_count.as<uint32_t>(), C + 1,
+                             nullptr, ctx->scan_tmp));
+
+  // order candidates: camera-major, ascending point index
+  int res = 0;
+  uint64_t *keys[2] = {nullptr, nullptr};
+  uint32_t *vals[2] = {nullptr, nullptr};
+  if (n_cand) {
+    C2B_TRY(ctx->sort_keys[1].ensure(n_cand * 8));
+    C2B_TRY(ctx->sort_vals[0].ensure(n_cand * 4));
+    C2B_TRY(ctx->sort_vals[1].ensure(n_cand * 4));
+    keys[0] = ctx->sort_keys[0].as<uint64_t>();
+    keys[1] = ctx->sort_keys[1].as<uint64_t>();
+    vals[0] = ctx->sort_vals[0].as<uint32_t>();
+    vals[1] = ctx->sort_vals[1].as<uint32_t>();
+    k_iota_u32<<<blocks_for(n_cand, 256), 256, 0, st>>>(vals[0], n_cand);
+    C2B_KERNEL_CHECK();
+    C2B_TRY(radix_sort_pairs(st, keys, vals, n_cand, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
+  }
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
+
+  // occlusion
+  const uint64_t n_words = (n_cand + 31) / 32;
+  C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
+  C2B_TRY(ctx->word_prefix.ensure((n_words + 1) * 4));
+  if (n_cand) {
+    const double *cx = ctx->cam_center.as<double>();
+    const double *px = ctx->pts.as<double>();
+    if (opt.occlusion == C2B_OCC_MESH && scene->n_nodes > 0) {
+      TraverseArgs t;
+      t.nodes = scene->nodes.as<float4>();
+      t.tris = scene->tris.as<float4>();
+      t.n_nodes = (int)scene->n_nodes;
+      t.keys = keys[res];
+      t.n_cand = n_cand;
+      t.pbits = pbits;
+      t.cen_x = cx;
+      t.cen_y = cx + C;
+      t.cen_z = cx + 2 * C;
+      t.px = px;
+      t.py = px + P;
+      t.pz = px + 2 * P;
+      t.endpoint_guard_rel = opt.endpoint_guard_rel;
+      t.vis_words = ctx->vis_words.as<uint32_t>();
+      t.counters = ctx->counters.as<unsigned long long>();
+      if (opt.count_traversal)
+        k_traverse<true><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
+      else
+        k_traverse<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
+    } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
+      k_analytic_occlusion<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
+          keys[res], n_cand, pbits, cx, cx + C, cx + 2 * C, px, px + P, px + 2 * P, opt.block_length,
+          opt.block_inset, ctx->vis_words.as<uint32_t>());
+    } else {
+      k_words_all_visible<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_cand);
+    }
+    C2B_KERNEL_CHECK();
+  }
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
+
+  // compaction
+  uint32_t *d_total = ctx->counters.as<uint32_t>() + 12;  // bytes 48..51 of the counter block
+  C2B_CUDA(cudaMemsetAsync(d_total, 0, 4, st));
+  if (n_cand) {
+    C2B_TRY(ctx->out_idx.ensure(n_cand * 8));
+    C2B_TRY(ctx->out_uv.ensure(n_cand * 16));
+    k_word_popc<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
+                                                          ctx->word_prefix.as<uint32_t>());
+    C2B_KERNEL_CHECK();
+    C2B_TRY(exclusive_scan_u32(st, ctx->word_prefix.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
+                               n_words, d_total, ctx->scan_tmp));
+    k_compact_write<<<blocks_for(n_cand, 256), 256, 0, st>>>(
+        ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(), keys[res], vals[res],
+        ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx.as<uint64_t>(),
+        ctx->out_uv.as<double2>());
+    C2B_KERNEL_CHECK();
+  }
+  k_csr_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(
+      ctx->cam_count.as<uint32_t>(), C, ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
+      n_cand, d_total, ctx->out_offsets.as<uint64_t>());
+  C2B_KERNEL_CHECK();
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
+
+  unsigned long long h_cnt[8];
+  C2B_CUDA(cudaMemcpyAsync(h_cnt, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  uint32_t total32;
+  memcpy(&total32, reinterpret_cast<const char *>(h_cnt) + 48, 4);
+  ctx->out_C = C;
+  ctx->out_O = total32;
+  x->have_result = true;
+  x->res_candidates = n_cand;
+
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->n_cameras = C;
+    stats->n_obs = ctx->out_O;
+    stats->n_candidates = n_cand;
+    stats->pairs_evaluated = pairs_eval;
+    stats->nodes_visited = h_cnt[2];
+    stats->tris_tested = h_cnt[3];
+    auto ms = [&](int a, int b) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+      return t;
+    };
+    stats->ms_prep = ms(EV_H2D, EV_PREP);
+    stats->ms_cull = ms(EV_PREP, EV_CULL);
+    stats->ms_sort = ms(EV_CULL, EV_SORT);
+    stats->ms_traverse = ms(EV_SORT, EV_TRAVERSE);
+    stats->ms_compact = ms(EV_TRAVERSE, EV_COMPACT);
+    stats->ms_total = ms(EV_START, EV_D2H);
+  }
+  return C2B_OK;
+}
+
+int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out) {
+  if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_download_obs: null argument");
+  CtxExtra *x = extra_of(ctx);
+  if (!x->have_result) return set_error(C2B_ERR_INVALID, "no resident result to download");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint64_t C = ctx->out_C, O = ctx->out_O;
+  C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
+  C2B_TRY(ctx->h_idx.ensure(std::max<uint64_t>(O, 1) * 8));
+  C2B_TRY(ctx->h_uv.ensure(std::max<uint64_t>(O, 1) * 16));
+  cudaEvent_t e0 = ctx->ev[EV_COMPACT], e1 = ctx->ev[EV_D2H];
+  C2B_CUDA(cudaEventRecord(e0, st));
+  C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.p, ctx->out_offsets.p, (C + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (O) {
+    C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.p, ctx->out_idx.p, O * 8, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.p, ctx->out_uv.p, O * 16, cudaMemcpyDeviceToHost, st));
+  }
+  C2B_CUDA(cudaEventRecord(e1, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  out->n_cameras = C;
+  out->n_obs = O;
+  out->offsets = ctx->h_offsets.as<uint64_t>();
+  out->point_idx = ctx->h_idx.as<uint64_t>();
+  out->uv = ctx->h_uv.as<double>();
+  out->d2h_bytes = (C + 1) * 8 + O * 24;
+  float t = 0;
+  cudaEventElapsedTime(&t, e0, e1);
+  out->ms_d2h = t;
+  return C2B_OK;
+}
+
+int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cams, uint64_t C,
+                         const double *pts, uint64_t P, double max_dist, const c2b_vis_options *opt,
+                         c2b_obs *out) {
+  if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null argument");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaEvent_t e0 = ctx->ev[EV_START], e1 = ctx->ev[EV_H2D];
+  // the two events are re-recorded by the resident call; time the uploads with a local pair
+  cudaEvent_t u0, u1;
+  C2B_CUDA(cudaEventCreate(&u0));
+  C2B_CUDA(cudaEventCreate(&u1));
+  (void)e0;
+  (void)e1;
+  C2B_CUDA(cudaEventRecord(u0, ctx->stream));
+  int rc = c2b_upload_points(ctx, pts, P);
+  if (rc == C2B_OK) rc = c2b_upload_cameras(ctx, cams, C);
+  cudaEventRecord(u1, ctx->stream);
+  c2b_obs st;
+  if (rc == C2B_OK) rc = c2b_visibility_graph_resident(ctx, scene, max_dist, opt, &st);
+  if (rc == C2B_OK) rc = c2b_download_obs(ctx, &st);
+  float t = 0;
+  if (rc == C2B_OK) cudaEventElapsedTime(&t, u0, u1);
+  cudaEventDestroy(u0);
+  cudaEventDestroy(u1);
+  if (rc != C2B_OK) return rc;
+  st.ms_h2d = t;
+  st.h2d_bytes = P * 24 + C * 120;
+  st.ms_total += st.ms_h2d + st.ms_d2h;
+  *out = st;
+  return C2B_OK;
+}
+
+void c2b_obs_free(c2b_ctx *ctx, c2b_obs *obs) {
+  (void)ctx;  // the pinned buffers are pooled in the ctx and reused by the next call
+  if (!obs) return;
+  obs->offsets = nullptr;
+  obs->point_idx = nullptr;
+  obs->uv = nullptr;
+  obs->n_obs = 0;
+}
+
+int c2b_reprojection_error_resident(c2b_ctx *ctx, double norm, double *out) {
+  if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_reprojection_error_resident: null argument");
+  CtxExtra *x = extra_of(ctx);
+  if (!x->have_result) return set_error(C2B_ERR_INVALID, "no resident result");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint64_t C = ctx->out_C, O = ctx->out_O, P = ctx->P;
+  *out = 0.0;
+  if (O == 0) return C2B_OK;
+  int nb = (int)std::min<uint64_t>(blocks_for(O, ST_THREADS), ST_BLOCKS);
+  C2B_TRY(ctx->misc.ensure((size_t)nb * 8 + 64));
+  const double *px = ctx->pts.as<double>();
+  k_reproj_partial<<<nb, ST_THREADS, 0, st>>>(ctx->cams.as<double>(), px, px + P, px + 2 * P,
+                                              ctx->out_offsets.as<uint64_t>(), C,
+                                              ctx->out_idx.as<uint64_t>(), ctx->out_uv.as<double2>(), O,
+                                              norm, ctx->misc.as<double>());
+  C2B_KERNEL_CHECK();
+  std::vector<double> h(nb);
+  C2B_CUDA(cudaMemcpyAsync(h.data(), ctx->misc.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  double s = 0;
+  for (double v : h) s += v;
+  *out = std::pow(s, 1.0 / norm);
+  return C2B_OK;
+}
+
+// ---- noise ----------------------------------------------------------------------------------------------
+namespace {
+struct NoiseBufs {
+  DevBuf cams, centers, pts, uv, scratch;
+  ~NoiseBufs() {
+    cams.release();
+    centers.release();
+    pts.release();
+    uv.release();
+    scratch.release();
+  }
+};
+
+// mean / std / nearest-origin of the chained sequence on the device.  scratch layout (doubles):
+// [0..2] mean, [3..5] sumsq, [6..8] origin, then partials.
+int device_stats(c2b_ctx *ctx, NoiseBufs &nb, uint64_t C, uint64_t P, double mean[3], double sd[3],
+                 bool want_origin) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t n = C + P;
+  const double num = (double)n;
+  int blocks = (int)std::min<uint64_t>(std::max<uint64_t>(blocks_for(n, ST_THREADS), 1), ST_BLOCKS);
+  C2B_TRY(nb.scratch.ensure((size_t)(16 + 8 * blocks) * 8));
+  double *s = nb.scratch.as<double>();
+  double *partial = s + 16;
+  const double *cx = nb.centers.as<double>();
+  const double *pts = nb.pts.as<double>();
+  k_stats_partial<0><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num, V3{0, 0, 0}, partial);
+  C2B_KERNEL_CHECK();
+  k_stats_final<<<1, 32, 0, st>>>(partial, blocks, s);
+  C2B_KERNEL_CHECK();
+  C2B_CUDA(cudaMemcpyAsync(mean, s, 24, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  k_stats_partial<1><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num,
+                                                   V3{mean[0], mean[1], mean[2]}, partial);
+  C2B_KERNEL_CHECK();
+  k_stats_final<<<1, 32, 0, st>>>(partial, blocks, s + 3);
+  C2B_KERNEL_CHECK();
+  double ss[3];
+  C2B_CUDA(cudaMemcpyAsync(ss, s + 3, 24, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < 3; ++k) sd[k] = std::sqrt(ss[k] / num);
+  if (want_origin) {
+    double *pd = partial;
+    unsigned long long *pi = reinterpret_cast<unsigned long long *>(partial + blocks);
+    k_nearest_partial<<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, pd, pi);
+    C2B_KERNEL_CHECK();
+    k_nearest_final<<<1, 32, 0, st>>>(pd, pi, blocks, cx, cx + C, cx + 2 * C, C, pts, s + 6);
+    C2B_KERNEL_CHECK();
+  }
+  return C2B_OK;
+}
+
+int noise_upload(c2b_ctx *ctx, NoiseBufs &nb, const double *cams, uint64_t C, const double *pts,
+                 uint64_t P, const double *uv, uint64_t O) {
+  cudaStream_t st = ctx->stream;
+  C2B_TRY(nb.cams.ensure(std::max<uint64_t>(C, 1) * 120));
+  C2B_TRY(nb.centers.ensure(std::max<uint64_t>(C, 1) * 24));
+  C2B_TRY(nb.pts.ensure(std::max<uint64_t>(P, 1) * 24));
+  if (C) {
+    C2B_CUDA(cudaMemcpyAsync(nb.cams.p, cams, C * 120, cudaMemcpyHostToDevice, st));
+    double *cx = nb.centers.as<double>();
+    k_cam_prep<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, cx, cx + C, cx + 2 * C);
+    C2B_KERNEL_CHECK();
+  }
+  if (P) C2B_CUDA(cudaMemcpyAsync(nb.pts.p, pts, P * 24, cudaMemcpyHostToDevice, st));
+  if (O) {
+    C2B_TRY(nb.uv.ensure(O * 16));
+    C2B_CUDA(cudaMemcpyAsync(nb.uv.p, uv, O * 16, cudaMemcpyHostToDevice, st));
+  }
+  return C2B_OK;
+}
+
+int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double strength,
+               double angle_strength, double std_, const double *dir_in, bool normalized,
+               uint64_t seed) {
+  if (!ctx || (C && !cams) || (P && !pts)) return set_error(C2B_ERR_INVALID, "add_drift: null argument");
+  if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_drift: problem has no cameras and no points");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  NoiseBufs nb;
+  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
+  double mean[3], sd[3];
+  C2B_TRY(device_stats(ctx, nb, C, P, mean, sd, true));
+  V3 dir;
+  if (normalized) {
+    // add_drift_normalized, src/noise.rs:53-55
+    V3 s{sd[0], sd[1], sd[2]};
+    double m = std::sqrt((s.x * s.x + s.y * s.y) + s.z * s.z);
+    double inv = 1.0 / m;
+    dir = V3{s.x * inv, s.y * inv, s.z * inv};
+    strength = strength * m;
+  } else {
+    dir = V3{dir_in[0], dir_in[1], dir_in[2]};
+  }
+  const double *origin = nb.scratch.as<double>() + 6;
+  if (C) {
+    k_drift_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, origin, dir, strength,
+                                                     angle_strength, std_, seed);
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
+  }
+  if (P) {
+    k_drift_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, origin, dir, strength, std_, seed);
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  }
+  C2B_CUDA(cudaStreamSynchronize(st));
+  return C2B_OK;
+}
+}  // namespace
+
+int c2b_add_drift(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double strength,
+                  double angle_strength, double std_, const double dir[3], uint64_t seed) {
+  if (!dir) return set_error(C2B_ERR_INVALID, "c2b_add_drift: dir is null");
+  return drift_impl(ctx, cams, C, pts, P, strength, angle_strength, std_, dir, false, seed);
+}
+
+int c2b_add_drift_normalized(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P,
+                             double strength, double angle_strength, double std_, uint64_t seed) {
+  return drift_impl(ctx, cams, C, pts, P, strength, angle_strength, std_, nullptr, true, seed);
+}
+
+int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double *uv,
+                  uint64_t O, double translation_std, double rotation_std, double point_std,
+                  double observations_std, uint64_t seed) {
+  if (!ctx || (C && !cams) || (P && !pts) || (O && !uv))
+    return set_error(C2B_ERR_INVALID, "c2b_add_noise: null argument");
+  if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_noise: problem has no cameras and no points");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  NoiseBufs nb;
+  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, uv, O));
+  double mean[3], sd[3];
+  C2B_TRY(device_stats(ctx, nb, C, P, mean, sd, false));
+  double bal_std = std::sqrt((sd[0] * sd[0] + sd[1] * sd[1]) + sd[2] * sd[2]);
+  if (C) {
+    k_noise_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, bal_std, translation_std,
+                                                     rotation_std, seed);
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
+  }
+  if (P) {
+    k_noise_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, point_std, seed);
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  }
+  if (O) {
+    k_noise_obs<<<blocks_for(O, 256), 256, 0, st>>>(nb.uv.as<double2>(), O, observations_std, seed);
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaMemcpyAsync(uv, nb.uv.p, O * 16, cudaMemcpyDeviceToHost, st));
+  }
+  C2B_CUDA(cudaStreamSynchronize(st));
+  return C2B_OK;
+}
+
+int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts, uint64_t P,
+                 double mean[3], double sd[3]) {
+  if (!ctx || (C && !cams) || (P && !pts) || !mean || !sd)
+    return set_error(C2B_ERR_INVALID, "c2b_mean_std: null argument");
+  if (C + P == 0) return set_error(C2B_ERR_EMPTY, "mean/std of an empty problem");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  NoiseBufs nb;
+  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
+  return device_stats(ctx, nb, C, P, mean, sd, false);
+}
+
+}  // extern "C"

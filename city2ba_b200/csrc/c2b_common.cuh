@@ -1,0 +1,173 @@
+// c2b_common.cuh — context, error plumbing, grow-only device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/city2ba_cuda.h"
+
+namespace c2b {
+
+// thread-local last error (c2b_last_error)
+inline std::string &last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline int set_error(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+#define C2B_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      return c2b::set_error(_e == cudaErrorMemoryAllocation ? C2B_ERR_OOM : C2B_ERR_CUDA,     \
+                            "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    }                                                                                         \
+  } while (0)
+
+#define C2B_TRY(call)        \
+  do {                       \
+    int _s = (call);         \
+    if (_s != C2B_OK) return _s; \
+  } while (0)
+
+#define C2B_KERNEL_CHECK() C2B_CUDA(cudaGetLastError())
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return C2B_OK;
+    if (p) {
+      cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+      return set_error(C2B_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes,
+                       cudaGetErrorString(e));
+    }
+    cap = want;
+    return C2B_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+// grow-only pinned host buffer
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return C2B_OK;
+    if (p) {
+      cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+      return set_error(C2B_ERR_OOM, "cudaMallocHost(%zu bytes) failed: %s", want,
+                       cudaGetErrorString(e));
+    }
+    cap = want;
+    return C2B_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+enum StageEvent {
+  EV_START = 0,
+  EV_H2D,
+  EV_PREP,
+  EV_CULL,
+  EV_SORT,
+  EV_TRAVERSE,
+  EV_COMPACT,
+  EV_D2H,
+  EV_COUNT
+};
+
+}  // namespace c2b
+
+struct c2b_scene {
+  c2b_ctx *ctx = nullptr;
+  uint64_t n_tris = 0;   // after dropping degenerate index triples
+  uint64_t n_nodes = 0;  // 2*n_tris - 1 (0 when empty)
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  c2b::DevBuf nodes;  // float4[2*n_nodes]: {lo.xyz, escape}, {hi.xyz, leaf tri slot or -1}
+  c2b::DevBuf tris;   // float4[3*n_tris]: v0, v1, v2 in leaf (Morton) order
+};
+
+struct c2b_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[c2b::EV_COUNT] = {};
+
+  // resident problem
+  uint64_t C = 0, P = 0;
+  c2b::DevBuf cams;          // double[15*C] as given
+  c2b::DevBuf cam_center;    // double[3*C]  SoA: x[C], y[C], z[C]
+  c2b::DevBuf pts;           // double[3*P]  SoA: x[P], y[P], z[P]
+  c2b::DevBuf stage;         // staging for H2D of AoS inputs
+  c2b::PinBuf pin_in;        // pinned staging for pageable callers
+
+  // grid over points
+  c2b::DevBuf cell_of_pt, cell_start, cell_cursor, grid_x, grid_y, grid_z, grid_idx;
+
+  // candidate pool + sort
+  c2b::DevBuf pool_key, pool_uv, cam_count, counters;
+  c2b::DevBuf sort_keys[2], sort_vals[2], sort_hist;
+  c2b::DevBuf scan_tmp[3];
+  uint64_t pool_capacity = 0;
+
+  // traversal + compaction
+  c2b::DevBuf vis_words, word_prefix;
+  c2b::DevBuf out_offsets, out_idx, out_uv;  // device CSR
+  uint64_t out_C = 0, out_O = 0;
+  c2b::DevBuf misc;  // small scratch (reductions)
+
+  // host results
+  c2b::PinBuf h_offsets, h_idx, h_uv, h_small;
+};

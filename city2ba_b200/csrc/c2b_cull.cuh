@@ -1,0 +1,306 @@
+// c2b_cull.cuh — kernel (1): camera x point distance / front / frustum culling with the f64
+// SnavelyCamera projection (src/generate.rs:446-454, src/baproblem.rs:141-151).
+//
+// Two schedules produce the SAME candidate set (the exact f64 predicate always decides):
+//   exhaustive : every pair, like the reference loop.  Camera tile in shared memory, 4 points
+//                per thread in registers, a conservative 7-op FMA distance reject in the hot
+//                loop; survivors are queued per warp and re-tested densely with the exact
+//                predicate (so the rare expensive path does not diverge the hot loop).
+//   grid       : points binned into a uniform grid (cell = max_dist/2); one warp per camera
+//                scans the x-contiguous cell rows its max_dist ball touches.
+// Candidates go to an unordered pool as (key = camera << pbits | point, u, v); the pool is then
+// radix-sorted by key, which yields camera-major, ascending-point order (src/generate.rs:446).
+#pragma once
+#include "c2b_common.cuh"
+#include "c2b_math.cuh"
+
+namespace c2b {
+
+struct CullArgs {
+  const double *cams;              // [15*C]
+  const double *cen_x, *cen_y, *cen_z;  // [C]
+  const double *px, *py, *pz;      // [P] (exhaustive) or grid-sorted copies (grid)
+  uint64_t C, P;
+  double t_star;   // m2 < t_star  <=>  sqrt_rn(m2) < max_dist   (exact)
+  double t_cons;   // conservative bound for the FMA pre-test
+  int pbits;
+  uint64_t *pool_key;
+  double2 *pool_uv;
+  uint32_t *cam_count;
+  unsigned long long *counters;  // [0] pool count, [1] pairs evaluated, [2] nodes, [3] tris
+  uint64_t pool_capacity;
+};
+
+// SnavelyCamera::center once per camera (the reference recomputes it per pair: same value)
+__global__ void k_cam_prep(const double *__restrict__ cams, uint64_t C, double *__restrict__ cx,
+                           double *__restrict__ cy, double *__restrict__ cz) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  double cam[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) cam[k] = cams[15 * i + k];
+  V3 c = camera_center(cam);
+  cx[i] = c.x;
+  cy[i] = c.y;
+  cz[i] = c.z;
+}
+
+// AoS xyz -> SoA
+__global__ void k_aos_to_soa3(const double *__restrict__ in, uint64_t n, double *__restrict__ x,
+                              double *__restrict__ y, double *__restrict__ z) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = in[3 * i];
+  y[i] = in[3 * i + 1];
+  z[i] = in[3 * i + 2];
+}
+
+// exact predicate with the sqrt folded into an exact threshold on the squared distance
+__device__ __forceinline__ bool cull_project_thr(const double *cam, V3 center, V3 p, double t_star,
+                                                 double &u, double &v) {
+  V3 d{dsub(center.x, p.x), dsub(center.y, p.y), dsub(center.z, p.z)};
+  double m2 = mag2(d);
+  if (!(m2 < t_star)) return false;
+  V3 pc = project_world(cam, p);
+  if (!(pc.z <= 0.0)) return false;
+  project(cam[12], cam[13], cam[14], pc, u, v);
+  return u >= -1.0 && u <= 1.0 && v >= -1.0 && v <= 1.0;
+}
+
+// warp-converged emission of candidates into the pool (every lane of the warp must call)
+__device__ __forceinline__ void emit_candidates(const CullArgs &a, bool pass, uint32_t cam,
+                                                uint32_t pt, double u, double v) {
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned m = __ballot_sync(0xffffffffu, pass);
+  if (m == 0u) return;
+  unsigned long long base = 0;
+  if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&a.counters[0], (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (pass) {
+    unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+    if (slot < a.pool_capacity) {
+      a.pool_key[slot] = ((uint64_t)cam << a.pbits) | (uint64_t)pt;
+      a.pool_uv[slot] = make_double2(u, v);
+      atomicAdd(&a.cam_count[cam], 1u);
+    }
+  }
+}
+
+// ---- exhaustive schedule --------------------------------------------------------------------------
+constexpr int CB_THREADS = 256;
+constexpr int CB_PPT = 4;    // points per thread
+constexpr int CB_TC = 64;    // cameras per tile
+constexpr int CB_QCAP = 64;  // per-warp queue entries
+
+__device__ __forceinline__ void brute_drain(const CullArgs &a, const uint2 *q, int first, int count) {
+  const int lane = threadIdx.x & 31;
+  bool have = lane < count;
+  bool pass = false;
+  uint32_t cam = 0, pt = 0;
+  double u = 0, v = 0;
+  if (have) {
+    uint2 e = q[first + lane];
+    cam = e.x;
+    pt = e.y;
+    double c[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) c[k] = __ldg(&a.cams[15 * (uint64_t)cam + k]);
+    V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
+    V3 p{a.px[pt], a.py[pt], a.pz[pt]};
+    pass = cull_project_thr(c, cen, p, a.t_star, u, v);
+  }
+  emit_candidates(a, pass, cam, pt, u, v);
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_cull_exhaustive(CullArgs a) {
+  __shared__ double s_cx[CB_TC], s_cy[CB_TC], s_cz[CB_TC];
+  __shared__ uint2 s_q[CB_THREADS / 32][CB_QCAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t cam0 = (uint64_t)blockIdx.y * CB_TC;
+  const int ncam = (int)((a.C - cam0) < (uint64_t)CB_TC ? (a.C - cam0) : (uint64_t)CB_TC);
+  if (threadIdx.x < ncam) {
+    s_cx[threadIdx.x] = a.cen_x[cam0 + threadIdx.x];
+    s_cy[threadIdx.x] = a.cen_y[cam0 + threadIdx.x];
+    s_cz[threadIdx.x] = a.cen_z[cam0 + threadIdx.x];
+  }
+  double px[CB_PPT], py[CB_PPT], pz[CB_PPT];
+  uint64_t pi[CB_PPT];
+#pragma unroll
+  for (int k = 0; k < CB_PPT; ++k) {
+    pi[k] = (uint64_t)blockIdx.x * (CB_THREADS * CB_PPT) + (uint64_t)k * CB_THREADS + threadIdx.x;
+    bool ok = pi[k] < a.P;
+    px[k] = ok ? a.px[pi[k]] : 1e300;  // (1e300)^2 = inf: never passes
+    py[k] = ok ? a.py[pi[k]] : 1e300;
+    pz[k] = ok ? a.pz[pi[k]] : 1e300;
+  }
+  __syncthreads();
+  uint2 *q = s_q[warp];
+  int qn = 0;  // warp-uniform
+  const double tc = a.t_cons;
+  for (int j = 0; j < ncam; ++j) {
+    const double cx = s_cx[j], cy = s_cy[j], cz = s_cz[j];
+    bool pass[CB_PPT];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < CB_PPT; ++k) {
+      double dx = px[k] - cx, dy = py[k] - cy, dz = pz[k] - cz;
+      double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      pass[k] = d2 < tc;
+      any |= pass[k];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int k = 0; k < CB_PPT; ++k) {
+        unsigned m = __ballot_sync(0xffffffffu, pass[k]);
+        if (m) {
+          if (pass[k]) q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)(cam0 + j), (uint32_t)pi[k]);
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32) {
+            brute_drain(a, q, qn - 32, 32);
+            qn -= 32;
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  if (qn > 0) brute_drain(a, q, 0, qn);
+}
+
+// ---- grid schedule -----------------------------------------------------------------------------------
+struct GridDesc {
+  double lo[3];
+  double inv_h;
+  int n[3];
+  double max_c[3];  // point bounds (for the ball / grid early-out)
+  double min_c[3];
+};
+
+__device__ __forceinline__ int grid_coord(const GridDesc &g, int k, double x) {
+  double t = floor((x - g.lo[k]) * g.inv_h);
+  int c = t < 0.0 ? 0 : (t >= (double)g.n[k] ? g.n[k] - 1 : (int)t);  // NaN -> comparisons false
+  if (!(t == t)) c = 0;
+  return c;
+}
+
+__global__ void k_grid_count(const double *__restrict__ px, const double *__restrict__ py,
+                             const double *__restrict__ pz, uint64_t P, GridDesc g,
+                             uint32_t *__restrict__ cell_of_pt, uint32_t *__restrict__ cell_count) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  int cx = grid_coord(g, 0, px[i]), cy = grid_coord(g, 1, py[i]), cz = grid_coord(g, 2, pz[i]);
+  uint32_t cell = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
+  cell_of_pt[i] = cell;
+  atomicAdd(&cell_count[cell], 1u);
+}
+
+__global__ void k_grid_fill(const double *__restrict__ px, const double *__restrict__ py,
+                            const double *__restrict__ pz, uint64_t P,
+                            const uint32_t *__restrict__ cell_of_pt,
+                            const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ cursor,
+                            double *__restrict__ gx, double *__restrict__ gy, double *__restrict__ gz,
+                            uint32_t *__restrict__ gidx) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  uint32_t cell = cell_of_pt[i];
+  uint32_t pos = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
+  gx[pos] = px[i];
+  gy[pos] = py[i];
+  gz[pos] = pz[i];
+  gidx[pos] = (uint32_t)i;
+}
+
+// one warp per camera
+__global__ void __launch_bounds__(256) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
+                                                   const uint32_t *__restrict__ cell_start,
+                                                   const uint32_t *__restrict__ gidx) {
+  const int lane = threadIdx.x & 31;
+  uint64_t cam = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (cam >= a.C) return;
+  double c[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) c[k] = __ldg(&a.cams[15 * cam + k]);
+  V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
+  const double cc[3] = {cen.x, cen.y, cen.z};
+  int lo[3], hi[3];
+  bool empty = !(max_dist > 0.0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double a0 = cc[k] - max_dist, a1 = cc[k] + max_dist;
+    // ball entirely outside the populated slab (with slack for the rounding of a0/a1)
+    double slack = 1e-9 * (fabs(cc[k]) + fabs(max_dist)) + 1e-300;
+    if (a0 - slack > g.max_c[k] || a1 + slack < g.min_c[k]) empty = true;
+    int l = grid_coord(g, k, a0) - 1, h = grid_coord(g, k, a1) + 1;
+    lo[k] = l < 0 ? 0 : l;
+    hi[k] = h >= g.n[k] ? g.n[k] - 1 : h;
+  }
+  if (!(cen.x == cen.x && cen.y == cen.y && cen.z == cen.z)) empty = true;  // NaN centre sees nothing
+  if (empty) return;
+  unsigned long long evaluated = 0;
+  for (int z = lo[2]; z <= hi[2]; ++z)
+    for (int y = lo[1]; y <= hi[1]; ++y) {
+      uint32_t row = ((uint32_t)z * g.n[1] + y) * g.n[0];
+      uint32_t start = cell_start[row + lo[0]], end = cell_start[row + hi[0] + 1];
+      evaluated += end - start;
+      for (uint32_t base = start; base < end; base += 32) {
+        uint32_t i = base + lane;
+        bool pass = false;
+        uint32_t pt = 0;
+        double u = 0, v = 0;
+        if (i < end) {
+          V3 p{a.px[i], a.py[i], a.pz[i]};
+          pass = cull_project_thr(c, cen, p, a.t_star, u, v);
+          if (pass) pt = gidx[i];
+        }
+        emit_candidates(a, pass, (uint32_t)cam, pt, u, v);
+      }
+    }
+  if (lane == 0) atomicAdd(&a.counters[1], evaluated);
+}
+
+// min / max of point coordinates (two-stage, deterministic): out[0..2] = min, out[3..5] = max
+__global__ void k_pts_bounds_partial(const double *__restrict__ px, const double *__restrict__ py,
+                                     const double *__restrict__ pz, uint64_t P,
+                                     double *__restrict__ partial /* 6*gridDim.x */) {
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    double v[3] = {px[i], py[i], pz[i]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fmin(lo[k], v[k]);
+      hi[k] = fmax(hi[k], v[k]);
+    }
+  }
+  __shared__ double s[6][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s[k][threadIdx.x >> 5] = lo[k];
+      s[3 + k][threadIdx.x >> 5] = hi[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double r = s[threadIdx.x][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      r = threadIdx.x < 3 ? fmin(r, s[threadIdx.x][w]) : fmax(r, s[threadIdx.x][w]);
+    partial[6 * (uint64_t)blockIdx.x + threadIdx.x] = r;
+  }
+}
+__global__ void k_pts_bounds_final(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+  if (threadIdx.x < 6) {
+    double r = partial[threadIdx.x];
+    for (int b = 1; b < nb; ++b)
+      r = threadIdx.x < 3 ? fmin(r, partial[6 * b + threadIdx.x]) : fmax(r, partial[6 * b + threadIdx.x]);
+    out[threadIdx.x] = r;
+  }
+}
+
+}  // namespace c2b

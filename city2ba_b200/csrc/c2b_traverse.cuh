@@ -1,0 +1,193 @@
+// c2b_traverse.cuh — kernel (2): occlusion rays against the LBVH (replaces Embree's
+// rtcOccluded1M, src/generate.rs:472).
+//
+// Warp-cooperative, stackless: a warp owns 32 consecutive candidates (rays that share or nearly
+// share a camera origin) and walks the threaded pre-order tree ONCE for all of them.  The node
+// index is warp-uniform, so every node / triangle fetch is a single broadcast load and there is
+// no divergence in the walk: a node is entered if ANY live lane's ray overlaps its box
+// (__ballot_sync), otherwise the warp jumps to the node's escape index.  Lanes whose ray has been
+// occluded drop out of the vote; the walk ends when none is left or the escape index runs off
+// the tree.  Any-hit is an OR over triangles, and the box test is conservative with respect to
+// the watertight triangle test, so the result is independent of the tree's shape.
+#pragma once
+#include "c2b_common.cuh"
+#include "c2b_math.cuh"
+
+namespace c2b {
+
+struct BoxRay {
+  float ox, oy, oz, ix, iy, iz, tfar;
+};
+
+__device__ __forceinline__ BoxRay make_box_ray(const Ray &r) {
+  BoxRay b;
+  b.ox = r.ox;
+  b.oy = r.oy;
+  b.oz = r.oz;
+  b.ix = 1.0f / r.dx;
+  b.iy = 1.0f / r.dy;
+  b.iz = 1.0f / r.dz;
+  b.tfar = r.tfar;
+  return b;
+}
+
+// conservative slab test: the box is inflated by 4e-6 of its distance from the origin per axis
+// and the interval compare carries 1e-5 relative slack; the triangle test's own rounding error is
+// a few f32 ulps (~1e-7) of the same magnitudes.
+__device__ __forceinline__ bool box_overlap(const BoxRay &r, float4 lo, float4 hi) {
+  float tmin = 0.0f, tmax = r.tfar;
+  {
+    float a = lo.x - r.ox, b = hi.x - r.ox;
+    float e = 4e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
+    float t0 = (a - e) * r.ix, t1 = (b + e) * r.ix;
+    tmin = fmaxf(tmin, fminf(t0, t1));
+    tmax = fminf(tmax, fmaxf(t0, t1));
+  }
+  {
+    float a = lo.y - r.oy, b = hi.y - r.oy;
+    float e = 4e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
+    float t0 = (a - e) * r.iy, t1 = (b + e) * r.iy;
+    tmin = fmaxf(tmin, fminf(t0, t1));
+    tmax = fminf(tmax, fmaxf(t0, t1));
+  }
+  {
+    float a = lo.z - r.oz, b = hi.z - r.oz;
+    float e = 4e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
+    float t0 = (a - e) * r.iz, t1 = (b + e) * r.iz;
+    tmin = fmaxf(tmin, fminf(t0, t1));
+    tmax = fminf(tmax, fmaxf(t0, t1));
+  }
+  return tmin <= tmax * 1.00001f + 1e-30f;
+}
+
+// warp-cooperative any-hit.  `alive` = this lane has a ray that is not yet occluded.
+// Returns true if this lane's ray is occluded.
+template <bool COUNT>
+__device__ __forceinline__ bool warp_any_hit(const float4 *__restrict__ nodes,
+                                             const float4 *__restrict__ tris, int n_nodes,
+                                             const Ray &ray, bool alive,
+                                             unsigned long long *counters) {
+  const Shear sh = ray_shear(ray);
+  const BoxRay br = make_box_ray(ray);
+  alive = alive && (ray.tfar >= 0.0f);  // NaN / negative tfar can never satisfy 0 < t <= tfar
+  bool occluded = false;
+  int node = 0;
+  unsigned n_vis = 0, n_tri = 0;
+  while (node < n_nodes) {
+    if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+    const float4 lo = __ldg(&nodes[2 * node]);
+    const float4 hi = __ldg(&nodes[2 * node + 1]);
+    if (COUNT) ++n_vis;
+    const bool hit = alive && box_overlap(br, lo, hi);
+    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+    const int esc = __float_as_int(lo.w);
+    if (hm == 0u) {
+      node = esc;
+      continue;
+    }
+    const int leaf = __float_as_int(hi.w);
+    if (leaf >= 0) {
+      const float4 v0 = __ldg(&tris[3 * leaf]);
+      const float4 v1 = __ldg(&tris[3 * leaf + 1]);
+      const float4 v2 = __ldg(&tris[3 * leaf + 2]);
+      if (COUNT) ++n_tri;
+      if (hit && ray_triangle(ray, sh, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)) {
+        occluded = true;
+        alive = false;
+      }
+      node = esc;  // == node + 1 for a leaf
+    } else {
+      node = node + 1;
+    }
+  }
+  if (COUNT && (threadIdx.x & 31) == 0) {
+    atomicAdd(&counters[2], (unsigned long long)n_vis);
+    atomicAdd(&counters[3], (unsigned long long)n_tri);
+  }
+  return occluded;
+}
+
+struct TraverseArgs {
+  const float4 *nodes;
+  const float4 *tris;
+  int n_nodes;
+  const uint64_t *keys;  // sorted candidate keys
+  uint64_t n_cand;
+  int pbits;
+  const double *cen_x, *cen_y, *cen_z;
+  const double *px, *py, *pz;  // original point order
+  int endpoint_guard_rel;
+  uint32_t *vis_words;  // bit i of word w set  <=>  candidate 32*w+i is VISIBLE
+  unsigned long long *counters;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t i = w * 32 + lane;
+  if (w * 32 >= a.n_cand) return;
+  const bool have = i < a.n_cand;
+  Ray ray;
+  ray.ox = ray.oy = ray.oz = 0.0f;
+  ray.dx = ray.dy = ray.dz = 1.0f;
+  ray.tfar = -1.0f;
+  if (have) {
+    const uint64_t key = a.keys[i];
+    const uint64_t cam = key >> a.pbits, pt = key & ((1ull << a.pbits) - 1ull);
+    V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
+    V3 p{a.px[pt], a.py[pt], a.pz[pt]};
+    ray = make_ray(c, p, a.endpoint_guard_rel != 0);
+  }
+  const bool occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.counters);
+  const unsigned vm = __ballot_sync(0xffffffffu, have && !occ);
+  if (lane == 0) a.vis_words[w] = vm;
+}
+
+// ---- Embree-shaped ray batch (parity tooling): AoS 48-byte rays, tfar = -inf on hit ---------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict__ nodes,
+                                                       const float4 *__restrict__ tris, int n_nodes,
+                                                       c2b_ray48 *rays, uint64_t n,
+                                                       unsigned long long *counters) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((i & ~31ull) >= n) return;
+  const bool have = i < n;
+  Ray ray;
+  ray.ox = ray.oy = ray.oz = 0.0f;
+  ray.dx = ray.dy = ray.dz = 1.0f;
+  ray.tfar = -1.0f;
+  if (have) {
+    ray.ox = rays[i].org_x;
+    ray.oy = rays[i].org_y;
+    ray.oz = rays[i].org_z;
+    ray.dx = rays[i].dir_x;
+    ray.dy = rays[i].dir_y;
+    ray.dz = rays[i].dir_z;
+    ray.tfar = rays[i].tfar;
+  }
+  const bool occ = warp_any_hit<COUNT>(nodes, tris, n_nodes, ray, have, counters);
+  if (have && occ) rays[i].tfar = -INFINITY;
+}
+
+// closest hit for ONE ray (camera placement, src/generate.rs:253-262): a single warp strides the
+// triangle list; the watertight test reports t = T/det.
+__global__ void k_intersect1(const float4 *__restrict__ tris, uint64_t n_tris, Ray ray,
+                             float *__restrict__ out /* [0]=hit flag, [1]=t */) {
+  const Shear sh = ray_shear(ray);
+  float best = INFINITY;
+  for (uint64_t t = threadIdx.x; t < n_tris; t += 32) {
+    const float4 v0 = tris[3 * t], v1 = tris[3 * t + 1], v2 = tris[3 * t + 2];
+    float tt;
+    if (ray_triangle(ray, sh, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, &tt))
+      best = fminf(best, tt);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (threadIdx.x == 0) {
+    out[0] = best < INFINITY ? 1.0f : 0.0f;
+    out[1] = best;
+  }
+}
+
+}  // namespace c2b

@@ -1,0 +1,191 @@
+/* city2ba_cuda.h — C ABI of libcity2ba_cuda.so: the B200 (sm_100a) replacement for city2ba's
+ * visibility / observation-generation hot path and its elementwise noise pass.
+ *
+ * This is what a `build.rs` + `ffi.rs` on the Rust side would bind.
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * tkonolige/city2ba source tree).  Plain pointers and sizes only; no exceptions cross this
+ * boundary; every function returns C2B_OK (0) or a negative c2b_status and leaves a message
+ * retrievable with c2b_last_error() (thread local).  Calls are blocking.  One c2b_ctx drives
+ * one GPU; issue calls from one host thread at a time per ctx (one process per GPU under
+ * torchrun / MPI is the intended multi-GPU layout: each rank passes its own contiguous camera
+ * range, see c2b_visibility_graph).
+ *
+ * There is NO CPU fallback: c2b_init fails with C2B_ERR_NO_DEVICE when no sm_100 GPU is
+ * visible, and nothing else works without a ctx.
+ */
+#ifndef CITY2BA_CUDA_H
+#define CITY2BA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2B_ABI_VERSION 1
+
+typedef enum {
+  C2B_OK = 0,
+  C2B_ERR_INVALID = -1,   /* bad argument (null pointer, index out of range, ...)        */
+  C2B_ERR_NO_DEVICE = -2, /* no usable CUDA device                                        */
+  C2B_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed; message has the detail */
+  C2B_ERR_OOM = -4,       /* device or pinned-host allocation failed                      */
+  C2B_ERR_EMPTY = -5      /* empty problem (reference: Error::EmptyProblem, src/baproblem.rs:36) */
+} c2b_status;
+
+typedef struct c2b_ctx c2b_ctx;
+typedef struct c2b_scene c2b_scene;
+
+/* camera record = 15 doubles: R column-major [9] (cgmath Matrix3 {x,y,z} columns of
+ * SnavelyCamera::dir), t [3] (SnavelyCamera::loc), f,k1,k2 (SnavelyCamera::intrin)
+ * — src/baproblem.rs:131-138 */
+#define C2B_CAM_STRIDE 15
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* replaces embree_rs::Device::new(), src/bin/city2ba.rs:515.  device = CUDA ordinal. */
+int c2b_init(int device, c2b_ctx **out);
+void c2b_shutdown(c2b_ctx *ctx);
+const char *c2b_last_error(void);
+int c2b_abi_version(void);
+
+/* ---- scene (triangle mesh -> GPU LBVH) ----------------------------------------------------------
+ * replaces Scene::new + model_to_geometry + attach_geometry + commit
+ * (src/generate.rs:74-105, src/bin/city2ba.rs:515-521).  xyz = 3*nv tightly packed f32 (tobj
+ * positions), tri = 3*nt u32 (all OBJ objects concatenated, indices already offset).  Triples
+ * with a repeated index (tobj's 2-index `l` records padded into triples) can never be hit and
+ * are dropped; a triple touching a vertex >= nv is C2B_ERR_INVALID.  nt may be 0. */
+int c2b_scene_create(c2b_ctx *ctx, const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt,
+                     c2b_scene **out);
+/* replaces CommittedScene::bounds(), src/generate.rs:237 */
+int c2b_scene_bounds(const c2b_scene *scene, float lower[3], float upper[3]);
+uint64_t c2b_scene_num_triangles(const c2b_scene *scene);
+uint64_t c2b_scene_num_nodes(const c2b_scene *scene);
+void c2b_scene_destroy(c2b_scene *scene);
+
+/* ---- ray-level entries (parity tooling + camera placement) -------------------------------------
+ * Embree-compatible 48-byte AoS ray (RTCRay): replaces CommittedScene::occluded_stream_aos
+ * (src/generate.rs:472): on a hit tfar is set to -inf, otherwise the ray is left untouched.
+ * tnear is honoured as 0 (the reference never sets it). */
+typedef struct {
+  float org_x, org_y, org_z, tnear;
+  float dir_x, dir_y, dir_z, time;
+  float tfar;
+  uint32_t mask, id, flags;
+} c2b_ray48;
+int c2b_occluded(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t n_rays);
+/* replaces CommittedScene::intersect on a single ray (src/generate.rs:253-262): closest hit;
+ * *hit = 1 and *tfar = distance when something is hit, else *hit = 0. */
+int c2b_intersect1(c2b_ctx *ctx, const c2b_scene *scene, const float org[3], const float dir[3],
+                   int *hit, float *tfar);
+
+/* ---- the hot path: visibility graph ------------------------------------------------------------
+ * replaces city2ba::generate::visibility_graph (src/generate.rs:424-481) for one contiguous
+ * camera range. */
+typedef enum {
+  C2B_CULL_GRID = 0,      /* default: points binned in a uniform grid, each camera scans only the
+                             cells its max_dist ball touches, then the exact f64 predicates */
+  C2B_CULL_EXHAUSTIVE = 1 /* every camera x point pair is tested, like the reference's loop at
+                             src/generate.rs:446 */
+} c2b_cull_mode;
+
+typedef enum {
+  C2B_OCC_MESH = 0,    /* rays against the scene's BVH (generate path) */
+  C2B_OCC_NONE = 1,    /* no occlusion (synthetic_line, src/synthetic.rs:353-379) */
+  C2B_OCC_ANALYTIC = 2 /* 2-D wall test of `synthetic` (src/synthetic.rs:52-124) */
+} c2b_occlusion;
+
+typedef struct {
+  int cull_mode;          /* c2b_cull_mode */
+  int occlusion;          /* c2b_occlusion; MESH needs a scene */
+  int endpoint_guard_rel; /* 0 = reference: tfar = f32(|d|) - 1e-6f (src/generate.rs:464);
+                             1 = additionally tfar *= (1 - 2^-18) (documented, non-default) */
+  int count_traversal;    /* 1 = count BVH nodes visited / triangles tested (slower) */
+  double block_length;    /* C2B_OCC_ANALYTIC only */
+  double block_inset;     /* C2B_OCC_ANALYTIC only */
+} c2b_vis_options;
+void c2b_vis_options_default(c2b_vis_options *opt);
+
+typedef struct {
+  /* CSR of visible observations, camera-major, ascending point index inside each camera
+   * (the order src/generate.rs:446,473-478 produces).  Pinned host memory owned by the ctx:
+   * valid until the next c2b_visibility_graph* call on the same ctx or c2b_obs_free. */
+  uint64_t n_cameras;
+  uint64_t n_obs;
+  uint64_t *offsets;   /* [n_cameras+1] */
+  uint64_t *point_idx; /* [n_obs]       */
+  double *uv;          /* [2*n_obs] u,v interleaved (normalised image coordinates) */
+  /* statistics of this call */
+  uint64_t n_candidates;    /* pairs that passed distance/front/frustum (= rays cast)      */
+  uint64_t pairs_evaluated; /* camera x point pairs the cull kernel actually tested          */
+  uint64_t nodes_visited;   /* warp-level BVH node visits (count_traversal only)            */
+  uint64_t tris_tested;     /* warp-level triangle tests  (count_traversal only)            */
+  uint64_t h2d_bytes, d2h_bytes;
+  /* device time of each stage, CUDA events on the ctx stream, milliseconds */
+  float ms_h2d, ms_prep, ms_cull, ms_sort, ms_traverse, ms_compact, ms_d2h, ms_total;
+} c2b_obs;
+
+/* one call, host buffers in, host CSR out (what the Rust visibility_graph body would call).
+ * cams: C x 15 doubles; pts: P x 3 doubles (cgmath Point3<f64> is repr(C)). */
+int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cams, uint64_t C,
+                         const double *pts, uint64_t P, double max_dist,
+                         const c2b_vis_options *opt, c2b_obs *out);
+void c2b_obs_free(c2b_ctx *ctx, c2b_obs *obs);
+
+/* the same path split in three so a caller can keep inputs/outputs resident in HBM
+ * (bench `value`, multi-pass pipelines).  upload -> run (device CSR stays in the ctx) -> download. */
+int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P);
+int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C);
+int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
+                                  const c2b_vis_options *opt, c2b_obs *stats_out);
+int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out);
+
+/* total_reprojection_error (src/baproblem.rs:265-279) of the resident problem, norm 1 or 2 fast
+ * paths, anything else through pow(). */
+int c2b_reprojection_error_resident(c2b_ctx *ctx, double norm, double *out);
+
+/* ---- noise pass (src/noise.rs:35-177) ------------------------------------------------------------
+ * In place on host arrays: cams C x 15, pts P x 3, uv O x 2.  Randomness is Philox4x32-10 keyed
+ * by `seed` with counter (element index, stream, slot) — the reference uses thread_rng(), which
+ * cannot be seeded, so parity is exact against the oracle's identical stream and distributional
+ * against the reference. */
+/* replaces noise::add_drift (src/noise.rs:68-116) */
+int c2b_add_drift(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double strength,
+                  double angle_strength, double std, const double dir[3], uint64_t seed);
+/* replaces noise::add_drift_normalized (src/noise.rs:47-56) */
+int c2b_add_drift_normalized(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P,
+                             double strength, double angle_strength, double std, uint64_t seed);
+/* replaces noise::add_noise (src/noise.rs:119-177) */
+int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double *uv,
+                  uint64_t O, double translation_std, double rotation_std, double point_std,
+                  double observations_std, uint64_t seed);
+/* BAProblem::mean / std (src/baproblem.rs:282-304) */
+int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts, uint64_t P,
+                 double mean[3], double std[3]);
+
+/* ---- host-side input generators (no GPU work) ----------------------------------------------------
+ * camera/point lattices of synthetic_grid / synthetic_line (src/synthetic.rs:178-258, 323-344)
+ * and the city-block box mesh used as the synthetic triangle scene. */
+uint64_t c2b_grid_num_cameras(uint64_t cameras_per_block, uint64_t num_blocks);
+uint64_t c2b_grid_num_points(uint64_t points_per_block, uint64_t num_blocks);
+int c2b_grid_cameras(uint64_t cameras_per_block, uint64_t num_blocks, double block_length,
+                     double camera_height, double *cams_out);
+int c2b_grid_points(uint64_t points_per_block, uint64_t num_blocks, double block_length,
+                    double block_inset, double point_height, double *pts_out);
+int c2b_line_cameras(uint64_t num_cameras, double length, double camera_height, double *cams_out);
+int c2b_line_points(uint64_t num_points, double length, double point_offset, double point_height,
+                    double *pts_out);
+int c2b_city_mesh(uint64_t num_blocks, double block_length, double block_inset, double height,
+                  float *xyz_out /* 3*8*n^2 */, uint32_t *tri_out /* 3*12*n^2 */);
+
+/* SnavelyCamera helpers on the host (src/baproblem.rs:141-176) — used by the host mirror */
+void c2b_camera_center(const double *cam, double out[3]);
+void c2b_camera_project_world(const double *cam, const double p[3], double out[3]);
+void c2b_camera_project(const double *cam, const double pc[3], double out[2]);
+void c2b_camera_from_position_direction(const double pos[3], const double R[9], double *cam_out);
+void c2b_camera_transform(const double *cam, const double dR[9], const double dloc[3],
+                          double *cam_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITY2BA_CUDA_H */

@@ -1,0 +1,82 @@
+"""Noise pass on the GPU against the oracle's identical Philox stream (tolerance 1e-9 relative:
+log/sin/cos/pow differ by a few ulp between glibc and CUDA's libm; everything else is exact)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-9, 1e-12
+
+
+@pytest.fixture(scope="module")
+def problem(c2b, orc):
+    cams, pts = orc.grid_cameras(10, 4), orc.grid_points(10, 4)
+    gold = np.load(os.path.join(GOLDEN, "cfg2_blocks4.npz"))
+    g = c2b.VisGraph(gold["mesh_offsets"], gold["mesh_idx"].astype(np.uint64), gold["mesh_uv"])
+    return c2b.BAProblem.from_visibility(cams, pts, g)
+
+
+def test_mean_std(problem, orc, ctx):
+    m, s = problem.mean_std(ctx)
+    assert np.allclose(m, orc.mean(problem.cameras, problem.points), rtol=1e-12)
+    assert np.allclose(s, orc.std(problem.cameras, problem.points), rtol=1e-12)
+
+
+def test_drift_deterministic_case_matches_oracle_and_golden(c2b, problem, orc, ctx):
+    # cfg2: --drift-strength 0.001, drift std 0 => Normal(1,0) == 1: fully deterministic
+    out = c2b.noise.add_drift_normalized(problem, 0.001, 0.0, 0.0, seed=1, ctx=ctx)
+    oc, op = orc.add_drift_normalized(problem.cameras, problem.points, 0.001, 0.0, 0.0, 1)
+    assert np.allclose(out.cameras, oc, rtol=RTOL, atol=ATOL) and np.allclose(out.points, op, rtol=RTOL, atol=ATOL)
+    gold = np.load(os.path.join(GOLDEN, "cfg2_noise.npz"))
+    assert np.allclose(out.cameras, gold["drift_cams"], rtol=RTOL, atol=ATOL)
+    assert np.allclose(out.points, gold["drift_pts"], rtol=RTOL, atol=ATOL)
+
+
+def test_drift_random_case(c2b, problem, orc, ctx):
+    out = c2b.noise.add_drift(problem, 0.002, 0.0005, 0.3, [0.0, 1.0, 0.5], seed=99, ctx=ctx)
+    oc, op = orc.add_drift(problem.cameras, problem.points, 0.002, 0.0005, 0.3, [0.0, 1.0, 0.5], 99)
+    assert np.allclose(out.cameras, oc, rtol=RTOL, atol=ATOL) and np.allclose(out.points, op, rtol=RTOL, atol=ATOL)
+    assert not np.allclose(out.points, problem.points)
+
+
+def test_add_noise_matches_oracle_and_golden(c2b, problem, orc, ctx):
+    out = c2b.noise.add_noise(problem, 0.01, 0.0001, 0.01, 0.001, seed=42, ctx=ctx)
+    oc, op, ouv = orc.add_noise(problem.cameras, problem.points, problem.vis_graph.uv, 0.01, 0.0001, 0.01, 0.001, 42)
+    assert np.allclose(out.cameras, oc, rtol=RTOL, atol=ATOL)
+    assert np.allclose(out.points, op, rtol=RTOL, atol=ATOL)
+    assert np.allclose(out.vis_graph.uv, ouv, rtol=RTOL, atol=ATOL)
+    gold = np.load(os.path.join(GOLDEN, "cfg2_noise.npz"))
+    assert np.allclose(out.cameras, gold["noise_cams"], rtol=RTOL, atol=ATOL)
+    assert np.allclose(out.vis_graph.uv, gold["noise_uv"], rtol=RTOL, atol=ATOL)
+
+
+def test_noise_is_distributionally_gaussian(c2b, ctx):
+    # 2e5 points, sigma 0.5: displacement magnitude |N(0, sigma)|, direction uniform on the sphere
+    n = 200_000
+    cams = np.zeros((1, 15))
+    cams[0, [0, 4, 8, 12]] = 1.0
+    g = c2b.VisGraph(np.array([0, n], np.uint64), np.arange(n, dtype=np.uint64), np.zeros((n, 2)))
+    ba = c2b.BAProblem(cams, np.zeros((n, 3)), g)
+    out = c2b.noise.add_noise(ba, 0.0, 0.0, 0.5, 0.25, seed=5, ctx=ctx)
+    d = out.points
+    r = np.linalg.norm(d, axis=1)
+    assert abs(r.mean() - 0.5 * np.sqrt(2 / np.pi)) < 5e-3 and abs(np.sqrt((r ** 2).mean()) - 0.5) < 5e-3
+    assert np.all(np.abs((d / r[:, None]).mean(axis=0)) < 1e-2)
+    ro = np.linalg.norm(out.vis_graph.uv, axis=1)
+    assert abs(np.sqrt((ro ** 2).mean()) - 0.25) < 3e-3
+    # different seeds differ, same seed repeats
+    again = c2b.noise.add_noise(ba, 0.0, 0.0, 0.5, 0.25, seed=5, ctx=ctx)
+    other = c2b.noise.add_noise(ba, 0.0, 0.0, 0.5, 0.25, seed=6, ctx=ctx)
+    assert np.array_equal(again.points, out.points) and not np.array_equal(other.points, out.points)
+
+
+def test_reference_library_properties(c2b, ctx):
+    """tests/main.rs:130-150: drift and noise must increase the total reprojection error"""
+    from city2ba_b200 import synthetic
+    ba = synthetic.synthetic_grid(10, 20, 3, 5.0, 1.0, 1.0, 1.0, 10.0, False, ctx=ctx)
+    e0 = ba.total_reprojection_error(2.0)
+    assert c2b.noise.add_drift_normalized(ba, 0.1, 0.1, 0.1, seed=3, ctx=ctx).total_reprojection_error(2.0) > e0
+    assert c2b.noise.add_noise(ba, 0.1, 0.1, 0.1, 0.1, seed=3, ctx=ctx).total_reprojection_error(2.0) > e0
