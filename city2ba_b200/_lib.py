@@ -69,7 +69,7 @@ OCC_MESH, OCC_NONE, OCC_ANALYTIC = 0, 1, 2
 
 # every symbol include/city2ba_cuda.h declares
 EXPORTS = [
-    "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version",
+    "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version", "c2b_kernel_launches",
     "c2b_scene_create", "c2b_scene_bounds", "c2b_scene_num_triangles", "c2b_scene_num_nodes",
     "c2b_scene_destroy", "c2b_occluded", "c2b_intersect1", "c2b_vis_options_default",
     "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_cameras",
@@ -97,6 +97,7 @@ def lib():
     vp, u64, dbl, i32 = C.c_void_p, C.c_uint64, C.c_double, C.c_int
     pd, pf, pu32 = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
     L.c2b_last_error.restype = C.c_char_p
+    L.c2b_kernel_launches.restype = u64
     L.c2b_init.argtypes = [i32, C.POINTER(vp)]
     L.c2b_shutdown.argtypes = [vp]
     L.c2b_shutdown.restype = None

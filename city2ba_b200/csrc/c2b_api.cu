@@ -85,6 +85,7 @@ extern "C" {
 
 const char *c2b_last_error(void) { return last_error_ref().c_str(); }
 int c2b_abi_version(void) { return C2B_ABI_VERSION; }
+uint64_t c2b_kernel_launches(void) { return launch_counter(); }
 
 int c2b_init(int device, c2b_ctx **out) {
   if (!out) return set_error(C2B_ERR_INVALID, "c2b_init: out is null");
@@ -617,13 +618,10 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
                          c2b_obs *out) {
   if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null argument");
   C2B_CUDA(cudaSetDevice(ctx->device));
-  cudaEvent_t e0 = ctx->ev[EV_START], e1 = ctx->ev[EV_H2D];
-  // the two events are re-recorded by the resident call; time the uploads with a local pair
+  // the ctx events are re-recorded by the resident call; time the uploads with a local pair
   cudaEvent_t u0, u1;
   C2B_CUDA(cudaEventCreate(&u0));
   C2B_CUDA(cudaEventCreate(&u1));
-  (void)e0;
-  (void)e1;
   C2B_CUDA(cudaEventRecord(u0, ctx->stream));
   int rc = c2b_upload_points(ctx, pts, P);
   if (rc == C2B_OK) rc = c2b_upload_cameras(ctx, cams, C);

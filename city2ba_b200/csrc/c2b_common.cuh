@@ -43,7 +43,17 @@ inline int set_error(int code, const char *fmt, ...) {
     if (_s != C2B_OK) return _s; \
   } while (0)
 
-#define C2B_KERNEL_CHECK() C2B_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by this macro: it also counts launches
+// (c2b_kernel_launches, used by bench.py's gpu_launches)
+inline uint64_t &launch_counter() {
+  static uint64_t n = 0;
+  return n;
+}
+#define C2B_KERNEL_CHECK()           \
+  do {                               \
+    ++c2b::launch_counter();         \
+    C2B_CUDA(cudaGetLastError());    \
+  } while (0)
 
 // grow-only device buffer
 struct DevBuf {

@@ -47,6 +47,8 @@ int c2b_init(int device, c2b_ctx **out);
 void c2b_shutdown(c2b_ctx *ctx);
 const char *c2b_last_error(void);
 int c2b_abi_version(void);
+/* number of CUDA kernels this library has launched in this process so far */
+uint64_t c2b_kernel_launches(void);
 
 /* ---- scene (triangle mesh -> GPU LBVH) ----------------------------------------------------------
  * replaces Scene::new + model_to_geometry + attach_geometry + commit
