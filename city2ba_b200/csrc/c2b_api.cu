@@ -163,7 +163,7 @@ int c2b_scene_create(c2b_ctx *ctx, const float *xyz, uint64_t nv, const uint32_t
   }
   c2b_scene *sc = new (std::nothrow) c2b_scene();
   if (!sc) return set_error(C2B_ERR_OOM, "out of host memory");
-  sc->ctx = ctx;
+  sc->device = ctx->device;
   int rc = bvh_build(ctx, sc, xyz, nv, keep.data(), keep.size() / 3);
   if (rc != C2B_OK) {
     sc->nodes.release();
@@ -187,7 +187,7 @@ uint64_t c2b_scene_num_triangles(const c2b_scene *scene) { return scene ? scene-
 uint64_t c2b_scene_num_nodes(const c2b_scene *scene) { return scene ? scene->n_nodes : 0; }
 void c2b_scene_destroy(c2b_scene *scene) {
   if (!scene) return;
-  if (scene->ctx) cudaSetDevice(scene->ctx->device);
+  cudaSetDevice(scene->device);
   scene->nodes.release();
   scene->tris.release();
   delete scene;

@@ -141,7 +141,7 @@ enum StageEvent {
 }  // namespace c2b
 
 struct c2b_scene {
-  c2b_ctx *ctx = nullptr;
+  int device = 0;  // the scene may outlive the ctx that built it; keep the ordinal, not the ctx
   uint64_t n_tris = 0;   // after dropping degenerate index triples
   uint64_t n_nodes = 0;  // 2*n_tris - 1 (0 when empty)
   float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
