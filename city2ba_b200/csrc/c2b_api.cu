@@ -200,10 +200,12 @@ int c2b_occluded(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t
   C2B_CUDA(cudaSetDevice(ctx->device));
   C2B_TRY(ctx->stage.ensure(n * sizeof(c2b_ray48)));
   C2B_TRY(ctx->counters.ensure(32));
+  float absmax = 0.0f;
+  for (int k = 0; k < 3; ++k) absmax = std::max(absmax, std::max(std::fabs(scene->lo[k]), std::fabs(scene->hi[k])));
   C2B_CUDA(cudaMemcpyAsync(ctx->stage.p, rays, n * sizeof(c2b_ray48), cudaMemcpyHostToDevice, ctx->stream));
   k_occluded_rays<false><<<blocks_for(n, 256), 256, 0, ctx->stream>>>(
       scene->nodes.as<float4>(), scene->tris.as<float4>(), (int)scene->n_nodes,
-      ctx->stage.as<c2b_ray48>(), n, ctx->counters.as<unsigned long long>());
+      ctx->stage.as<c2b_ray48>(), n, absmax, ctx->counters.as<unsigned long long>());
   C2B_KERNEL_CHECK();
   C2B_CUDA(cudaMemcpyAsync(rays, ctx->stage.p, n * sizeof(c2b_ray48), cudaMemcpyDeviceToHost, ctx->stream));
   C2B_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -384,13 +386,13 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
 
   const int pbits = std::max(1, bit_length(P ? P - 1 : 0));
   const int cbits = std::max(1, bit_length(C ? C - 1 : 0));
-  if (pbits + cbits > 64) return set_error(C2B_ERR_INVALID, "camera x point index space exceeds 64 bits");
+  if (pbits + cbits > 63) return set_error(C2B_ERR_INVALID, "camera x point index space exceeds 63 bits");
 
   C2B_TRY(ctx->counters.ensure(64));
   C2B_TRY(ctx->cam_count.ensure((C + 1) * 4));
   C2B_TRY(ctx->out_offsets.ensure((C + 1) * 8));
 
-  uint64_t n_cand = 0, pairs_eval = 0;
+  uint64_t n_cand = 0, pairs_eval = 0, pool_n = 0;
   const bool use_grid = opt.cull_mode == C2B_CULL_GRID;
   if (C && P) {
     if (use_grid && !(x->grid.valid && x->grid.max_dist == max_dist &&
@@ -429,7 +431,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       ctx->pool_capacity = std::max<uint64_t>(guess, 1024);
     }
     for (int attempt = 0;; ++attempt) {
-      // the sorted copy of the keys lives in sort_keys[], the pool itself is sort_keys[0]
+      // the pool's key array doubles as buffer 0 of the radix sort
       C2B_TRY(ctx->sort_keys[0].ensure(ctx->pool_capacity * 8));
       C2B_TRY(ctx->pool_uv.ensure(ctx->pool_capacity * 16));
       a.pool_key = ctx->sort_keys[0].as<uint64_t>();
@@ -438,25 +440,25 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
       C2B_CUDA(cudaMemsetAsync(ctx->cam_count.p, 0, (C + 1) * 4, st));
       if (use_grid) {
-        k_cull_grid<<<blocks_for(C, 8), 256, 0, st>>>(a, x->grid.desc, max_dist,
-                                                      ctx->cell_start.as<uint32_t>(),
-                                                      ctx->grid_idx.as<uint32_t>());
+        k_cull_grid<<<blocks_for(C, CG_WARPS), CG_WARPS * 32, 0, st>>>(
+            a, x->grid.desc, max_dist, ctx->cell_start.as<uint32_t>(), ctx->grid_idx.as<uint32_t>());
       } else {
         dim3 grid(blocks_for(P, CB_THREADS * CB_PPT), blocks_for(C, CB_TC));
         if (grid.y > 65535u) return set_error(C2B_ERR_INVALID, "too many cameras for one exhaustive launch");
         k_cull_exhaustive<<<grid, CB_THREADS, 0, st>>>(a);
       }
       C2B_KERNEL_CHECK();
-      unsigned long long h_cnt[4];
-      C2B_CUDA(cudaMemcpyAsync(h_cnt, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
+      unsigned long long h_cnt[8];
+      C2B_CUDA(cudaMemcpyAsync(h_cnt, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
       C2B_CUDA(cudaStreamSynchronize(st));
-      n_cand = h_cnt[0];
+      pool_n = h_cnt[0];
+      n_cand = use_grid ? h_cnt[4] : h_cnt[0];
       pairs_eval = use_grid ? h_cnt[1] : C * P;
-      if (n_cand <= ctx->pool_capacity) break;
+      if (pool_n <= ctx->pool_capacity) break;
       if (attempt >= 2) return set_error(C2B_ERR_CUDA, "candidate pool overflow persisted");
-      ctx->pool_capacity = n_cand + n_cand / 16 + 1024;  // exact count is known now: re-run once
+      ctx->pool_capacity = pool_n + pool_n / 16 + 1024;  // exact count is known now: re-run once
     }
-    if (n_cand >= 0xffffffffull)
+    if (pool_n >= 0xffffffffull)
       return set_error(C2B_ERR_INVALID, "more than 2^32 candidates in one call; shard the cameras");
   } else {
     C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
@@ -464,49 +466,32 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
   }
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_CULL], st));
 
-  // candidate start per camera
-  C2B_TRY(exclusive_scan_u32(st, ctx->cam_count.as<uint32_t>(), ctx->cam_count.as<uint32_t>(), C + 1,
-                             nullptr, ctx->scan_tmp));
+  const double *cxp = ctx->cam_center.as<double>();
+  const double *pxp = ctx->pts.as<double>();
+  float scene_absmax = 0.0f;
+  if (scene)
+    for (int k = 0; k < 3; ++k)
+      scene_absmax = std::max(scene_absmax, std::max(std::fabs(scene->lo[k]), std::fabs(scene->hi[k])));
+  if (!std::isfinite(scene_absmax)) scene_absmax = 3.0e38f;
 
-  // order candidates: camera-major, ascending point index
-  int res = 0;
-  uint64_t *keys[2] = {nullptr, nullptr};
-  uint32_t *vals[2] = {nullptr, nullptr};
-  if (n_cand) {
-    C2B_TRY(ctx->sort_keys[1].ensure(n_cand * 8));
-    C2B_TRY(ctx->sort_vals[0].ensure(n_cand * 4));
-    C2B_TRY(ctx->sort_vals[1].ensure(n_cand * 4));
-    keys[0] = ctx->sort_keys[0].as<uint64_t>();
-    keys[1] = ctx->sort_keys[1].as<uint64_t>();
-    vals[0] = ctx->sort_vals[0].as<uint32_t>();
-    vals[1] = ctx->sort_vals[1].as<uint32_t>();
-    k_iota_u32<<<blocks_for(n_cand, 256), 256, 0, st>>>(vals[0], n_cand);
-    C2B_KERNEL_CHECK();
-    C2B_TRY(radix_sort_pairs(st, keys, vals, n_cand, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
-  }
-  C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
-
-  // occlusion
-  const uint64_t n_words = (n_cand + 31) / 32;
-  C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
-  C2B_TRY(ctx->word_prefix.ensure((n_words + 1) * 4));
-  if (n_cand) {
-    const double *cx = ctx->cam_center.as<double>();
-    const double *px = ctx->pts.as<double>();
+  // occlusion of `n` keys (sorted candidates, or the chunked pool) -> one ballot word per 32 keys
+  auto run_occlusion = [&](const uint64_t *keys_in, uint64_t n, uint64_t n_words) -> int {
+    if (!n) return C2B_OK;
     if (opt.occlusion == C2B_OCC_MESH && scene->n_nodes > 0) {
       TraverseArgs t;
       t.nodes = scene->nodes.as<float4>();
       t.tris = scene->tris.as<float4>();
       t.n_nodes = (int)scene->n_nodes;
-      t.keys = keys[res];
-      t.n_cand = n_cand;
+      t.keys = keys_in;
+      t.n_cand = n;
+      t.scene_absmax = scene_absmax;
       t.pbits = pbits;
-      t.cen_x = cx;
-      t.cen_y = cx + C;
-      t.cen_z = cx + 2 * C;
-      t.px = px;
-      t.py = px + P;
-      t.pz = px + 2 * P;
+      t.cen_x = cxp;
+      t.cen_y = cxp + C;
+      t.cen_z = cxp + 2 * C;
+      t.px = pxp;
+      t.py = pxp + P;
+      t.pz = pxp + 2 * P;
       t.endpoint_guard_rel = opt.endpoint_guard_rel;
       t.vis_words = ctx->vis_words.as<uint32_t>();
       t.counters = ctx->counters.as<unsigned long long>();
@@ -516,46 +501,146 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
         k_traverse<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
     } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
       k_analytic_occlusion<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
-          keys[res], n_cand, pbits, cx, cx + C, cx + 2 * C, px, px + P, px + 2 * P, opt.block_length,
+          keys_in, n, pbits, cxp, cxp + C, cxp + 2 * C, pxp, pxp + P, pxp + 2 * P, opt.block_length,
           opt.block_inset, ctx->vis_words.as<uint32_t>());
     } else {
-      k_words_all_visible<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_cand);
+      k_words_all_visible<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(keys_in, ctx->vis_words.as<uint32_t>(), n);
     }
     C2B_KERNEL_CHECK();
-  }
-  C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
+    return C2B_OK;
+  };
 
-  // compaction
   uint32_t *d_total = ctx->counters.as<uint32_t>() + 12;  // bytes 48..51 of the counter block
-  C2B_CUDA(cudaMemsetAsync(d_total, 0, 4, st));
-  if (n_cand) {
-    C2B_TRY(ctx->out_idx.ensure(n_cand * 8));
-    C2B_TRY(ctx->out_uv.ensure(n_cand * 16));
-    k_word_popc<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
-                                                          ctx->word_prefix.as<uint32_t>());
-    C2B_KERNEL_CHECK();
-    C2B_TRY(exclusive_scan_u32(st, ctx->word_prefix.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
-                               n_words, d_total, ctx->scan_tmp));
-    k_compact_write<<<blocks_for(n_cand, 256), 256, 0, st>>>(
-        ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(), keys[res], vals[res],
-        ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx.as<uint64_t>(),
-        ctx->out_uv.as<double2>());
-    C2B_KERNEL_CHECK();
-  }
-  k_csr_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(
-      ctx->cam_count.as<uint32_t>(), C, ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
-      n_cand, d_total, ctx->out_offsets.as<uint64_t>());
-  C2B_KERNEL_CHECK();
-  C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
-  C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
+  uint32_t *d_max = ctx->counters.as<uint32_t>() + 13;    // bytes 52..55
+  uint64_t total_obs = 0;
+  unsigned long long h_fin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-  unsigned long long h_cnt[8];
-  C2B_CUDA(cudaMemcpyAsync(h_cnt, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
-  C2B_CUDA(cudaStreamSynchronize(st));
-  uint32_t total32;
-  memcpy(&total32, reinterpret_cast<const char *>(h_cnt) + 48, 4);
+  if (use_grid) {
+    // ---- segmented path: traverse the chunked pool in place, then group + sort per camera -----------
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
+    const uint64_t n_words = pool_n / 32;
+    C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
+    const uint64_t *pool_key = ctx->sort_keys[0].as<uint64_t>();
+    C2B_TRY(run_occlusion(pool_key, pool_n, n_words));
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
+
+    C2B_TRY(ctx->word_prefix.ensure((C + 1) * 4));  // per-camera segment offsets (u32)
+    uint32_t *vis_count = ctx->cam_count.as<uint32_t>();  // zeroed before the cull
+    uint32_t *seg_off = ctx->word_prefix.as<uint32_t>();
+    C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
+    if (n_words) {
+      k_count_visible<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
+                                                              pool_key, pbits, vis_count);
+      C2B_KERNEL_CHECK();
+      k_max_u32<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(vis_count, C, d_max);
+      C2B_KERNEL_CHECK();
+    }
+    C2B_TRY(exclusive_scan_u32(st, vis_count, seg_off, C + 1, d_total, ctx->scan_tmp));
+    C2B_CUDA(cudaMemcpyAsync(h_fin, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaStreamSynchronize(st));
+    uint32_t total32, max32;
+    memcpy(&total32, reinterpret_cast<const char *>(h_fin) + 48, 4);
+    memcpy(&max32, reinterpret_cast<const char *>(h_fin) + 52, 4);
+    total_obs = total32;
+    if (total_obs) {
+      C2B_TRY(ctx->sort_keys[1].ensure(total_obs * 8));  // seg_key
+      C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));  // seg_src
+      C2B_TRY(ctx->out_idx.ensure(total_obs * 8));
+      C2B_TRY(ctx->out_uv.ensure(total_obs * 16));
+      uint64_t *seg_key = ctx->sort_keys[1].as<uint64_t>();
+      uint32_t *seg_src = ctx->sort_vals[0].as<uint32_t>();
+      C2B_CUDA(cudaMemsetAsync(vis_count, 0, (C + 1) * 4, st));  // reused as the per-camera cursor
+      k_scatter_visible<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
+          ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, seg_key, seg_src);
+      C2B_KERNEL_CHECK();
+      const uint32_t seg_max = 4096;
+      if (max32 <= seg_max) {
+        uint32_t n2 = 2;
+        while (n2 < max32) n2 <<= 1;
+        k_seg_sort_write<<<(unsigned)C, 256, n2 * 8, st>>>(seg_off, C, seg_key, seg_src,
+                                                          ctx->pool_uv.as<double2>(), pbits,
+                                                          ctx->out_offsets.as<uint64_t>(),
+                                                          ctx->out_idx.as<uint64_t>(),
+                                                          ctx->out_uv.as<double2>());
+        C2B_KERNEL_CHECK();
+      } else {
+        // a camera sees more points than the shared-memory sort holds: radix-sort all visible pairs
+        C2B_TRY(ctx->sort_vals[1].ensure(total_obs * 4));
+        uint64_t *keys[2] = {seg_key, ctx->out_idx.as<uint64_t>()};
+        uint32_t *vals[2] = {seg_src, ctx->sort_vals[1].as<uint32_t>()};
+        int res = 0;
+        C2B_TRY(radix_sort_pairs(st, keys, vals, total_obs, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
+        k_write_sorted<<<blocks_for(total_obs, 256), 256, 0, st>>>(
+            keys[res], vals[res], ctx->pool_uv.as<double2>(), total_obs, pbits,
+            ctx->out_idx.as<uint64_t>(), ctx->out_uv.as<double2>());
+        C2B_KERNEL_CHECK();
+        k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(seg_off, C + 1, ctx->out_offsets.as<uint64_t>());
+        C2B_KERNEL_CHECK();
+      }
+    } else {
+      C2B_CUDA(cudaMemsetAsync(ctx->out_offsets.p, 0, (C + 1) * 8, st));
+    }
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
+    if (opt.count_traversal) C2B_CUDA(cudaMemcpyAsync(h_fin, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaStreamSynchronize(st));
+  } else {
+    // ---- ordered path: radix sort all candidates, traverse in order, stream-compact ------------------
+    C2B_TRY(exclusive_scan_u32(st, ctx->cam_count.as<uint32_t>(), ctx->cam_count.as<uint32_t>(), C + 1,
+                               nullptr, ctx->scan_tmp));
+    int res = 0;
+    uint64_t *keys[2] = {nullptr, nullptr};
+    uint32_t *vals[2] = {nullptr, nullptr};
+    if (n_cand) {
+      C2B_TRY(ctx->sort_keys[1].ensure(n_cand * 8));
+      C2B_TRY(ctx->sort_vals[0].ensure(n_cand * 4));
+      C2B_TRY(ctx->sort_vals[1].ensure(n_cand * 4));
+      keys[0] = ctx->sort_keys[0].as<uint64_t>();
+      keys[1] = ctx->sort_keys[1].as<uint64_t>();
+      vals[0] = ctx->sort_vals[0].as<uint32_t>();
+      vals[1] = ctx->sort_vals[1].as<uint32_t>();
+      k_iota_u32<<<blocks_for(n_cand, 256), 256, 0, st>>>(vals[0], n_cand);
+      C2B_KERNEL_CHECK();
+      C2B_TRY(radix_sort_pairs(st, keys, vals, n_cand, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
+    }
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
+
+    const uint64_t n_words = (n_cand + 31) / 32;
+    C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
+    C2B_TRY(ctx->word_prefix.ensure((n_words + 1) * 4));
+    C2B_TRY(run_occlusion(keys[res], n_cand, n_words));
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
+
+    C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
+    if (n_cand) {
+      C2B_TRY(ctx->out_idx.ensure(n_cand * 8));
+      C2B_TRY(ctx->out_uv.ensure(n_cand * 16));
+      k_word_popc<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
+                                                            ctx->word_prefix.as<uint32_t>());
+      C2B_KERNEL_CHECK();
+      C2B_TRY(exclusive_scan_u32(st, ctx->word_prefix.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
+                                 n_words, d_total, ctx->scan_tmp));
+      k_compact_write<<<blocks_for(n_cand, 256), 256, 0, st>>>(
+          ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(), keys[res], vals[res],
+          ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx.as<uint64_t>(),
+          ctx->out_uv.as<double2>());
+      C2B_KERNEL_CHECK();
+    }
+    k_csr_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(
+        ctx->cam_count.as<uint32_t>(), C, ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
+        n_cand, d_total, ctx->out_offsets.as<uint64_t>());
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
+    C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
+    C2B_CUDA(cudaMemcpyAsync(h_fin, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaStreamSynchronize(st));
+    uint32_t total32;
+    memcpy(&total32, reinterpret_cast<const char *>(h_fin) + 48, 4);
+    total_obs = total32;
+  }
+  const unsigned long long *h_cnt = h_fin;
   ctx->out_C = C;
-  ctx->out_O = total32;
+  ctx->out_O = total_obs;
   x->have_result = true;
   x->res_candidates = n_cand;
 

@@ -52,13 +52,137 @@ __global__ void k_csr_offsets(const uint32_t *__restrict__ cand_start /*C+1*/, u
   offsets[c] = (uint64_t)word_prefix[s >> 5] + __popc(word & ((1u << bit) - 1u));
 }
 
-// all candidates visible (C2B_OCC_NONE, and scenes without triangles)
-__global__ void k_words_all_visible(uint32_t *__restrict__ words, uint64_t n_cand) {
+// all candidates visible (C2B_OCC_NONE, and scenes without triangles); padding slots stay clear
+__global__ void k_words_all_visible(const uint64_t *__restrict__ keys, uint32_t *__restrict__ words,
+                                    uint64_t n_cand) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((i & ~31ull) >= n_cand) return;
+  const bool vis = i < n_cand && keys[i] != ~0ull;
+  const unsigned m = __ballot_sync(0xffffffffu, vis);
+  if ((threadIdx.x & 31) == 0) words[i >> 5] = m;
+}
+
+// ---- segmented path (grid schedule) ---------------------------------------------------------------
+// The pool is a sequence of 32-slot chunks, each owned by one camera (k_cull_grid), traversed in
+// place.  Visible candidates are counted per camera, scanned into CSR offsets, scattered into their
+// camera's segment (arbitrary order inside the segment), and each segment is then sorted by point
+// index in shared memory (bitonic network) while the final (index, u, v) records are written.
+
+// one thread per visibility word: vis_count[camera of the chunk] += popc(word)
+__global__ void k_count_visible(const uint32_t *__restrict__ words, uint64_t n_words,
+                                const uint64_t *__restrict__ pool_key, int pbits,
+                                uint32_t *__restrict__ vis_count) {
   uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t n_words = (n_cand + 31) >> 5;
   if (w >= n_words) return;
-  uint64_t rem = n_cand - w * 32;
-  words[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+  uint32_t word = words[w];
+  if (!word) return;
+  uint64_t key = pool_key[32 * w + (__ffs(word) - 1)];
+  atomicAdd(&vis_count[key >> pbits], (uint32_t)__popc(word));
+}
+
+__global__ void k_max_u32(const uint32_t *__restrict__ v, uint64_t n, uint32_t *__restrict__ out) {
+  uint32_t m = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    m = max(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// one warp per chunk: reserve popc(word) slots in the camera's segment, write (key, pool slot)
+__global__ void __launch_bounds__(256)
+    k_scatter_visible(const uint32_t *__restrict__ words, uint64_t n_words,
+                      const uint64_t *__restrict__ pool_key, int pbits,
+                      const uint32_t *__restrict__ seg_off, uint32_t *__restrict__ cursor,
+                      uint64_t *__restrict__ seg_key, uint32_t *__restrict__ seg_src) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t w = i >> 5;
+  if (w >= n_words) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t word = words[w];
+  if (!word) return;
+  const bool vis = (word >> lane) & 1u;
+  const uint64_t key = vis ? pool_key[i] : 0ull;
+  const uint64_t key0 = __shfl_sync(0xffffffffu, key, __ffs(word) - 1);
+  uint32_t base = 0;
+  if (lane == 0) {
+    const uint64_t cam = key0 >> pbits;
+    base = seg_off[cam] + atomicAdd(&cursor[cam], (uint32_t)__popc(word));
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (vis) {
+    const uint32_t pos = base + __popc(word & ((1u << lane) - 1u));
+    seg_key[pos] = key;
+    seg_src[pos] = (uint32_t)i;
+  }
+}
+
+// one block per camera: bitonic sort of (point << 32 | position in segment) in shared memory, then
+// the final records.  n2 (power of two >= the longest segment) sizes the dynamic shared memory.
+__global__ void __launch_bounds__(256)
+    k_seg_sort_write(const uint32_t *__restrict__ seg_off, uint64_t C, const uint64_t *__restrict__ seg_key,
+                     const uint32_t *__restrict__ seg_src, const double2 *__restrict__ pool_uv, int pbits,
+                     uint64_t *__restrict__ out_offsets, uint64_t *__restrict__ out_idx,
+                     double2 *__restrict__ out_uv) {
+  extern __shared__ uint64_t s_sort[];
+  const uint64_t c = blockIdx.x;
+  const uint32_t base = seg_off[c], n = seg_off[c + 1] - base;
+  if (threadIdx.x == 0) {
+    out_offsets[c] = base;
+    if (c == C - 1) out_offsets[C] = seg_off[C];
+  }
+  if (n == 0) return;
+  const uint64_t pmask = (1ull << pbits) - 1ull;
+  if (n == 1) {
+    if (threadIdx.x == 0) {
+      out_idx[base] = seg_key[base] & pmask;
+      out_uv[base] = pool_uv[seg_src[base]];
+    }
+    return;
+  }
+  uint32_t n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x)
+    s_sort[t] = t < n ? (((seg_key[base + t] & pmask) << 32) | (uint64_t)t) : ~0ull;
+  __syncthreads();
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) {
+        const uint32_t p = t ^ j;
+        if (p > t) {
+          const uint64_t a = s_sort[t], b = s_sort[p];
+          const bool up = (t & k) == 0;
+          if ((a > b) == up) {
+            s_sort[t] = b;
+            s_sort[p] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+    const uint64_t e = s_sort[t];
+    out_idx[base + t] = e >> 32;
+    out_uv[base + t] = pool_uv[seg_src[base + (uint32_t)e]];
+  }
+}
+
+// fallback for segments longer than the shared-memory sort: the scattered (key, slot) pairs were
+// radix-sorted globally; write the records and widen the offsets
+__global__ void k_write_sorted(const uint64_t *keys, const uint32_t *__restrict__ src,
+                               const double2 *__restrict__ pool_uv, uint64_t n, int pbits,
+                               uint64_t *out_idx, double2 *__restrict__ out_uv) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];  // may alias out_idx: read before write, same slot
+  out_uv[i] = pool_uv[src[i]];
+  out_idx[i] = key & ((1ull << pbits) - 1ull);
+}
+__global__ void k_widen_offsets(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
 }
 
 // ---- analytic occlusion of `city2ba synthetic` ------------------------------------------------------
@@ -121,8 +245,8 @@ __global__ void __launch_bounds__(256)
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if ((i & ~31ull) >= n_cand) return;
   bool vis = false;
-  if (i < n_cand) {
-    const uint64_t key = keys[i];
+  const uint64_t key = i < n_cand ? keys[i] : ~0ull;
+  if (key != ~0ull) {
     const uint64_t cam = key >> pbits, pt = key & ((1ull << pbits) - 1ull);
     V3 c{cen_x[cam], cen_y[cam], cen_z[cam]};
     V3 p{px[pt], py[pt], pz[pt]};

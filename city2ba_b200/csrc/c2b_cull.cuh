@@ -27,9 +27,12 @@ struct CullArgs {
   uint64_t *pool_key;
   double2 *pool_uv;
   uint32_t *cam_count;
-  unsigned long long *counters;  // [0] pool count, [1] pairs evaluated, [2] nodes, [3] tris
+  unsigned long long *counters;  // [0] pool slots used, [1] pairs evaluated, [2] nodes, [3] tris,
+                                 // [4] candidates (grid schedule: slots include chunk padding)
   uint64_t pool_capacity;
 };
+
+constexpr uint64_t POOL_SENTINEL = ~0ull;  // padding slot of a 32-aligned chunk
 
 // SnavelyCamera::center once per camera (the reference recomputes it per pair: same value)
 __global__ void k_cam_prep(const double *__restrict__ cams, uint64_t C, double *__restrict__ cx,
@@ -211,13 +214,35 @@ __global__ void k_grid_fill(const double *__restrict__ px, const double *__restr
   gidx[pos] = (uint32_t)i;
 }
 
-// one warp per camera
-__global__ void __launch_bounds__(256) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
-                                                   const uint32_t *__restrict__ cell_start,
-                                                   const uint32_t *__restrict__ gidx) {
-  const int lane = threadIdx.x & 31;
-  uint64_t cam = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// One warp per camera.  Survivors are staged per warp in shared memory and written to the pool
+// in 32-ALIGNED chunks that belong to one camera each (the tail chunk of a camera is padded with
+// POOL_SENTINEL), so that a traversal warp reading 32 consecutive pool slots gets rays that share
+// one origin and are neighbours in the grid scan order (coherent packets), and the stores are
+// full 256 B / 512 B lines.
+constexpr int CG_WARPS = 8;
+constexpr int CG_STAGE = 64;
+
+__device__ __forceinline__ void grid_flush32(const CullArgs &a, uint64_t *sk, double2 *su, int count,
+                                             int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(&a.counters[0], 32ull);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base + 32 <= a.pool_capacity) {
+    a.pool_key[base + lane] = lane < count ? sk[lane] : POOL_SENTINEL;
+    a.pool_uv[base + lane] = lane < count ? su[lane] : make_double2(0.0, 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(CG_WARPS * 32) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
+                                                             const uint32_t *__restrict__ cell_start,
+                                                             const uint32_t *__restrict__ gidx) {
+  __shared__ uint64_t s_key[CG_WARPS][CG_STAGE];
+  __shared__ double2 s_uv[CG_WARPS][CG_STAGE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t cam = (uint64_t)blockIdx.x * CG_WARPS + warp;
   if (cam >= a.C) return;
+  uint64_t *sk = s_key[warp];
+  double2 *su = s_uv[warp];
   double c[15];
 #pragma unroll
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&a.cams[15 * cam + k]);
@@ -237,7 +262,8 @@ __global__ void __launch_bounds__(256) k_cull_grid(CullArgs a, GridDesc g, doubl
   }
   if (!(cen.x == cen.x && cen.y == cen.y && cen.z == cen.z)) empty = true;  // NaN centre sees nothing
   if (empty) return;
-  unsigned long long evaluated = 0;
+  unsigned long long evaluated = 0, found = 0;
+  int qn = 0;  // warp-uniform number of staged candidates
   for (int z = lo[2]; z <= hi[2]; ++z)
     for (int y = lo[1]; y <= hi[1]; ++y) {
       uint32_t row = ((uint32_t)z * g.n[1] + y) * g.n[0];
@@ -246,17 +272,45 @@ __global__ void __launch_bounds__(256) k_cull_grid(CullArgs a, GridDesc g, doubl
       for (uint32_t base = start; base < end; base += 32) {
         uint32_t i = base + lane;
         bool pass = false;
-        uint32_t pt = 0;
         double u = 0, v = 0;
         if (i < end) {
           V3 p{a.px[i], a.py[i], a.pz[i]};
           pass = cull_project_thr(c, cen, p, a.t_star, u, v);
-          if (pass) pt = gidx[i];
         }
-        emit_candidates(a, pass, (uint32_t)cam, pt, u, v);
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0u) continue;
+        if (pass) {
+          int pos = qn + __popc(m & ((1u << lane) - 1u));
+          sk[pos] = (cam << a.pbits) | (uint64_t)gidx[i];
+          su[pos] = make_double2(u, v);
+        }
+        qn += __popc(m);
+        found += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          grid_flush32(a, sk, su, 32, lane);
+          const int rem = qn - 32;
+          uint64_t tk = 0;
+          double2 tu = make_double2(0.0, 0.0);
+          if (lane < rem) {
+            tk = sk[32 + lane];
+            tu = su[32 + lane];
+          }
+          __syncwarp();
+          if (lane < rem) {
+            sk[lane] = tk;
+            su[lane] = tu;
+          }
+          __syncwarp();
+          qn = rem;
+        }
       }
     }
-  if (lane == 0) atomicAdd(&a.counters[1], evaluated);
+  if (qn > 0) grid_flush32(a, sk, su, qn, lane);
+  if (lane == 0) {
+    atomicAdd(&a.counters[1], evaluated);
+    atomicAdd(&a.counters[4], found);
+  }
 }
 
 // min / max of point coordinates (two-stage, deterministic): out[0..2] = min, out[3..5] = max

@@ -16,46 +16,54 @@
 namespace c2b {
 
 struct BoxRay {
-  float ox, oy, oz, ix, iy, iz, tfar;
+  float ix, iy, iz;     // 1/dir, magnitude clamped to 1e30 so that o*i stays finite
+  float cx, cy, cz;     // -org * inv
+  float px, py, pz;     // slab padding in t units: pad * |inv|
+  float tfar;
 };
 
-__device__ __forceinline__ BoxRay make_box_ray(const Ray &r) {
+// Per-ray set-up of the conservative slab test.  `scene_absmax` = largest |coordinate| of the
+// scene bounds.  Every box is (implicitly) inflated by pad = 4e-6 * (|org|_inf + scene_absmax)
+// on each side, which covers (a) the rounding of fma(lo, inv, -org*inv) — at most
+// 6e-8 * |org*inv| in t — and (b) the few-ulp geometric slop of the watertight triangle test,
+// which works on vertices translated by org (magnitudes <= |org| + scene_absmax).  The residual
+// relative error of t (one rounding) is absorbed by the 1e-5 slack of the final compare.
+__device__ __forceinline__ BoxRay make_box_ray(const Ray &r, float scene_absmax) {
   BoxRay b;
-  b.ox = r.ox;
-  b.oy = r.oy;
-  b.oz = r.oz;
-  b.ix = 1.0f / r.dx;
-  b.iy = 1.0f / r.dy;
-  b.iz = 1.0f / r.dz;
+  const float big = 1e30f;
+  float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
+  b.ix = fabsf(ix) > big ? copysignf(big, r.dx) : ix;
+  b.iy = fabsf(iy) > big ? copysignf(big, r.dy) : iy;
+  b.iz = fabsf(iz) > big ? copysignf(big, r.dz) : iz;
+  b.cx = -r.ox * b.ix;
+  b.cy = -r.oy * b.iy;
+  b.cz = -r.oz * b.iz;
+  const float pad = 4e-6f * (fmaxf(fabsf(r.ox), fmaxf(fabsf(r.oy), fabsf(r.oz))) + scene_absmax) + 1e-30f;
+  b.px = pad * fabsf(b.ix);
+  b.py = pad * fabsf(b.iy);
+  b.pz = pad * fabsf(b.iz);
   b.tfar = r.tfar;
   return b;
 }
 
-// conservative slab test: the box is inflated by 4e-6 of its distance from the origin per axis
-// and the interval compare carries 1e-5 relative slack; the triangle test's own rounding error is
-// a few f32 ulps (~1e-7) of the same magnitudes.
+// 2 FMA + 4 FMNMX + 2 FADD per axis.  fminf/fmaxf return the non-NaN operand, so an axis whose
+// products overflow to inf - inf is simply ignored (conservative).
 __device__ __forceinline__ bool box_overlap(const BoxRay &r, float4 lo, float4 hi) {
   float tmin = 0.0f, tmax = r.tfar;
   {
-    float a = lo.x - r.ox, b = hi.x - r.ox;
-    float e = 4e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
-    float t0 = (a - e) * r.ix, t1 = (b + e) * r.ix;
-    tmin = fmaxf(tmin, fminf(t0, t1));
-    tmax = fminf(tmax, fmaxf(t0, t1));
+    float t0 = fmaf(lo.x, r.ix, r.cx), t1 = fmaf(hi.x, r.ix, r.cx);
+    tmin = fmaxf(tmin, fminf(t0, t1) - r.px);
+    tmax = fminf(tmax, fmaxf(t0, t1) + r.px);
   }
   {
-    float a = lo.y - r.oy, b = hi.y - r.oy;
-    float e = 4e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
-    float t0 = (a - e) * r.iy, t1 = (b + e) * r.iy;
-    tmin = fmaxf(tmin, fminf(t0, t1));
-    tmax = fminf(tmax, fmaxf(t0, t1));
+    float t0 = fmaf(lo.y, r.iy, r.cy), t1 = fmaf(hi.y, r.iy, r.cy);
+    tmin = fmaxf(tmin, fminf(t0, t1) - r.py);
+    tmax = fminf(tmax, fmaxf(t0, t1) + r.py);
   }
   {
-    float a = lo.z - r.oz, b = hi.z - r.oz;
-    float e = 4e-6f * fmaxf(fabsf(a), fabsf(b)) + 1e-30f;
-    float t0 = (a - e) * r.iz, t1 = (b + e) * r.iz;
-    tmin = fmaxf(tmin, fminf(t0, t1));
-    tmax = fminf(tmax, fmaxf(t0, t1));
+    float t0 = fmaf(lo.z, r.iz, r.cz), t1 = fmaf(hi.z, r.iz, r.cz);
+    tmin = fmaxf(tmin, fminf(t0, t1) - r.pz);
+    tmax = fminf(tmax, fmaxf(t0, t1) + r.pz);
   }
   return tmin <= tmax * 1.00001f + 1e-30f;
 }
@@ -65,11 +73,12 @@ __device__ __forceinline__ bool box_overlap(const BoxRay &r, float4 lo, float4 h
 template <bool COUNT>
 __device__ __forceinline__ bool warp_any_hit(const float4 *__restrict__ nodes,
                                              const float4 *__restrict__ tris, int n_nodes,
-                                             const Ray &ray, bool alive,
+                                             const Ray &ray, bool alive, float scene_absmax,
                                              unsigned long long *counters) {
   const Shear sh = ray_shear(ray);
-  const BoxRay br = make_box_ray(ray);
-  alive = alive && (ray.tfar >= 0.0f);  // NaN / negative tfar can never satisfy 0 < t <= tfar
+  const BoxRay br = make_box_ray(ray, scene_absmax);
+  // NaN / negative tfar can never satisfy 0 < t <= tfar; a NaN direction can never hit either
+  alive = alive && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
   bool occluded = false;
   int node = 0;
   unsigned n_vis = 0, n_tri = 0;
@@ -111,8 +120,9 @@ struct TraverseArgs {
   const float4 *nodes;
   const float4 *tris;
   int n_nodes;
-  const uint64_t *keys;  // sorted candidate keys
+  const uint64_t *keys;  // candidate keys (sorted, or the pool with POOL_SENTINEL padding)
   uint64_t n_cand;
+  float scene_absmax;
   int pbits;
   const double *cen_x, *cen_y, *cen_z;
   const double *px, *py, *pz;  // original point order
@@ -127,19 +137,20 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
   const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const uint64_t i = w * 32 + lane;
   if (w * 32 >= a.n_cand) return;
-  const bool have = i < a.n_cand;
+  bool have = i < a.n_cand;
   Ray ray;
   ray.ox = ray.oy = ray.oz = 0.0f;
   ray.dx = ray.dy = ray.dz = 1.0f;
   ray.tfar = -1.0f;
+  const uint64_t key = have ? a.keys[i] : ~0ull;
+  have = have && key != ~0ull;  // padding slot of an aligned chunk
   if (have) {
-    const uint64_t key = a.keys[i];
     const uint64_t cam = key >> a.pbits, pt = key & ((1ull << a.pbits) - 1ull);
     V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
     V3 p{a.px[pt], a.py[pt], a.pz[pt]};
     ray = make_ray(c, p, a.endpoint_guard_rel != 0);
   }
-  const bool occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.counters);
+  const bool occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
   const unsigned vm = __ballot_sync(0xffffffffu, have && !occ);
   if (lane == 0) a.vis_words[w] = vm;
 }
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict__ nodes,
                                                        const float4 *__restrict__ tris, int n_nodes,
-                                                       c2b_ray48 *rays, uint64_t n,
+                                                       c2b_ray48 *rays, uint64_t n, float scene_absmax,
                                                        unsigned long long *counters) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if ((i & ~31ull) >= n) return;
@@ -166,7 +177,7 @@ __global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict_
     ray.dz = rays[i].dir_z;
     ray.tfar = rays[i].tfar;
   }
-  const bool occ = warp_any_hit<COUNT>(nodes, tris, n_nodes, ray, have, counters);
+  const bool occ = warp_any_hit<COUNT>(nodes, tris, n_nodes, ray, have, scene_absmax, counters);
   if (have && occ) rays[i].tfar = -INFINITY;
 }
 
