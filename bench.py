@@ -116,7 +116,9 @@ def cpu_arm(cams, pts, xyz, tri, budget_s, threads=0):
     Returns (tests_per_s, cores, sample description, obs_per_s)."""
     from oracle import oracle as orc
     C, P = len(cams), len(pts)
-    ncores = os.cpu_count() or 1
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if threads <= 0:
+        threads = ncores  # explicit: torchrun exports OMP_NUM_THREADS=1, which would serialise the arm
     n = min(C, max(ncores, 8))
     for _ in range(4):  # grow the sample until it fills about the budget
         idx = np.linspace(0, C - 1, n).astype(np.int64)

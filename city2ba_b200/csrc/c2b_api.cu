@@ -125,7 +125,7 @@ void c2b_shutdown(c2b_ctx *ctx) {
                     &ctx->sort_keys[0], &ctx->sort_keys[1], &ctx->sort_vals[0], &ctx->sort_vals[1],
                     &ctx->sort_hist, &ctx->scan_tmp[0], &ctx->scan_tmp[1], &ctx->scan_tmp[2],
                     &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets, &ctx->out_idx,
-                    &ctx->out_uv, &ctx->misc};
+                    &ctx->out_uv, &ctx->misc, &ctx->tri_list, &ctx->tri_count};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
@@ -303,7 +303,7 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   const uint64_t P = ctx->P;
   C2B_CUDA(cudaStreamSynchronize(st));  // pts_bounds has landed
   GridDesc g;
-  double h = max_dist * 0.5;
+  double h = max_dist * 0.25;
   if (const char *e = getenv("C2B_GRID_CELL_FACTOR")) {
     double f = atof(e);
     if (f > 0.0) h = max_dist * f;
@@ -475,7 +475,9 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
   if (!std::isfinite(scene_absmax)) scene_absmax = 3.0e38f;
 
   // occlusion of `n` keys (sorted candidates, or the chunked pool) -> one ballot word per 32 keys
-  auto run_occlusion = [&](const uint64_t *keys_in, uint64_t n, uint64_t n_words) -> int {
+  uint32_t trilist_cap = 128;
+  if (const char *e = getenv("C2B_TRILIST_CAP")) trilist_cap = (uint32_t)std::max(0, atoi(e));
+  auto run_occlusion = [&](const uint64_t *keys_in, uint64_t n, uint64_t n_words, bool chunked) -> int {
     if (!n) return C2B_OK;
     if (opt.occlusion == C2B_OCC_MESH && scene->n_nodes > 0) {
       TraverseArgs t;
@@ -495,10 +497,28 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       t.endpoint_guard_rel = opt.endpoint_guard_rel;
       t.vis_words = ctx->vis_words.as<uint32_t>();
       t.counters = ctx->counters.as<unsigned long long>();
-      if (opt.count_traversal)
+      if (chunked && trilist_cap > 0) {
+        // per-camera triangle lists (one stackless walk per camera), then list-driven packets
+        C2B_TRY(ctx->tri_list.ensure((size_t)C * trilist_cap * 4));
+        C2B_TRY(ctx->tri_count.ensure(C * 4));
+        float rmax = (float)max_dist;
+        if ((double)rmax < max_dist) rmax = std::nextafter(rmax, INFINITY);
+        rmax = rmax * (1.0f + 4e-6f);
+        k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(t.nodes, t.n_nodes, t.cen_x, t.cen_y, t.cen_z, C,
+                                                         rmax, scene_absmax, trilist_cap,
+                                                         ctx->tri_list.as<uint32_t>(),
+                                                         ctx->tri_count.as<uint32_t>());
+        C2B_KERNEL_CHECK();
+        TriListArgs tl{ctx->tri_list.as<uint32_t>(), ctx->tri_count.as<uint32_t>(), trilist_cap};
+        if (opt.count_traversal)
+          k_traverse_lists<true><<<blocks_for(n_words, 8), 256, 0, st>>>(t, tl);
+        else
+          k_traverse_lists<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t, tl);
+      } else if (opt.count_traversal) {
         k_traverse<true><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
-      else
+      } else {
         k_traverse<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
+      }
     } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
       k_analytic_occlusion<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
           keys_in, n, pbits, cxp, cxp + C, cxp + 2 * C, pxp, pxp + P, pxp + 2 * P, opt.block_length,
@@ -521,7 +541,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     const uint64_t n_words = pool_n / 32;
     C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
     const uint64_t *pool_key = ctx->sort_keys[0].as<uint64_t>();
-    C2B_TRY(run_occlusion(pool_key, pool_n, n_words));
+    C2B_TRY(run_occlusion(pool_key, pool_n, n_words, true));
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
 
     C2B_TRY(ctx->word_prefix.ensure((C + 1) * 4));  // per-camera segment offsets (u32)
@@ -608,7 +628,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     const uint64_t n_words = (n_cand + 31) / 32;
     C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
     C2B_TRY(ctx->word_prefix.ensure((n_words + 1) * 4));
-    C2B_TRY(run_occlusion(keys[res], n_cand, n_words));
+    C2B_TRY(run_occlusion(keys[res], n_cand, n_words, false));
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
 
     C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));

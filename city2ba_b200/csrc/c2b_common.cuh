@@ -177,6 +177,7 @@ struct c2b_ctx {
   c2b::DevBuf out_offsets, out_idx, out_uv;  // device CSR
   uint64_t out_C = 0, out_O = 0;
   c2b::DevBuf misc;  // small scratch (reductions)
+  c2b::DevBuf tri_list, tri_count;  // per-camera leaf lists for list-driven traversal
 
   // host results
   c2b::PinBuf h_offsets, h_idx, h_uv, h_small;

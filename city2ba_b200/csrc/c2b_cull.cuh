@@ -6,7 +6,7 @@
 //                per thread in registers, a conservative 7-op FMA distance reject in the hot
 //                loop; survivors are queued per warp and re-tested densely with the exact
 //                predicate (so the rare expensive path does not diverge the hot loop).
-//   grid       : points binned into a uniform grid (cell = max_dist/2); one warp per camera
+//   grid       : points binned into a uniform grid (cell = max_dist/4); one warp per camera
 //                scans the x-contiguous cell rows its max_dist ball touches.
 // Candidates go to an unordered pool as (key = camera << pbits | point, u, v); the pool is then
 // radix-sorted by key, which yields camera-major, ascending-point order (src/generate.rs:446).
@@ -238,36 +238,77 @@ __global__ void __launch_bounds__(CG_WARPS * 32) k_cull_grid(CullArgs a, GridDes
                                                              const uint32_t *__restrict__ gidx) {
   __shared__ uint64_t s_key[CG_WARPS][CG_STAGE];
   __shared__ double2 s_uv[CG_WARPS][CG_STAGE];
+  __shared__ double s_cam[CG_WARPS][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t cam = (uint64_t)blockIdx.x * CG_WARPS + warp;
   if (cam >= a.C) return;
   uint64_t *sk = s_key[warp];
   double2 *su = s_uv[warp];
-  double c[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) c[k] = __ldg(&a.cams[15 * cam + k]);
+  // the camera record lives in shared memory (broadcast reads) to keep registers for occupancy
+  double *c = s_cam[warp];
+  if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
+  __syncwarp();
   V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
   const double cc[3] = {cen.x, cen.y, cen.z};
   int lo[3], hi[3];
   bool empty = !(max_dist > 0.0);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    double a0 = cc[k] - max_dist, a1 = cc[k] + max_dist;
-    // ball entirely outside the populated slab (with slack for the rounding of a0/a1)
-    double slack = 1e-9 * (fabs(cc[k]) + fabs(max_dist)) + 1e-300;
-    if (a0 - slack > g.max_c[k] || a1 + slack < g.min_c[k]) empty = true;
-    int l = grid_coord(g, k, a0) - 1, h = grid_coord(g, k, a1) + 1;
-    lo[k] = l < 0 ? 0 : l;
-    hi[k] = h >= g.n[k] ? g.n[k] - 1 : h;
+    // every point with |p - c| < max_dist has c_k - r - eps < p_k < c_k + r + eps, and grid_coord is
+    // monotone, so [coord(a0), coord(a1)] holds its cell; eps covers the rounding of a0 / a1
+    const double eps = 1e-9 * (fabs(cc[k]) + fabs(max_dist)) + 1e-300;
+    const double a0 = cc[k] - max_dist - eps, a1 = cc[k] + max_dist + eps;
+    if (a0 > g.max_c[k] || a1 < g.min_c[k]) empty = true;  // ball misses the populated slab
+    lo[k] = grid_coord(g, k, a0);
+    hi[k] = grid_coord(g, k, a1);
   }
   if (!(cen.x == cen.x && cen.y == cen.y && cen.z == cen.z)) empty = true;  // NaN centre sees nothing
   if (empty) return;
+  // "in front of the camera" is pc.z = r2x*x + r2y*y + r2z*z + tz <= 0 (src/generate.rs:450): linear
+  // in x along a row of cells, so each row is trimmed to the x-range that can hold such a point
+  const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
+  const double cell_h = 1.0 / g.inv_h;
   unsigned long long evaluated = 0, found = 0;
   int qn = 0;  // warp-uniform number of staged candidates
   for (int z = lo[2]; z <= hi[2]; ++z)
     for (int y = lo[1]; y <= hi[1]; ++y) {
+      int x0 = lo[0], x1 = hi[0];
+      {
+        // bounds of the row's cells in y and z; edge cells also hold the clamped coordinates, so
+        // they extend to the data bounds
+        const double sl = 1e-6 * cell_h;
+        const double y0 = y == 0 ? g.min_c[1] : g.lo[1] + y * cell_h - sl;
+        const double y1 = y == g.n[1] - 1 ? g.max_c[1] : g.lo[1] + (y + 1) * cell_h + sl;
+        const double z0 = z == 0 ? g.min_c[2] : g.lo[2] + z * cell_h - sl;
+        const double z1 = z == g.n[2] - 1 ? g.max_c[2] : g.lo[2] + (z + 1) * cell_h + sl;
+        // smallest value r2y*y + r2z*z + tz can take on the row (0 * inf is avoided explicitly)
+        const double my = r2y == 0.0 ? 0.0 : r2y * (r2y > 0.0 ? y0 : y1);
+        const double mz = r2z == 0.0 ? 0.0 : r2z * (r2z > 0.0 ? z0 : z1);
+        const double bmin = my + mz + tz;
+        const double mag = fabs(my) + fabs(mz) + fabs(tz) + fabs(r2x) * (fabs(cc[0]) + fabs(max_dist));
+        if (bmin == bmin && fabs(bmin) < INFINITY) {
+          const double slack = 1e-9 * mag + 1e-300;
+          if (fabs(r2x) * (fabs(cc[0]) + fabs(max_dist)) <= slack) {
+            if (bmin > 2.0 * slack) continue;  // the whole row is behind the camera
+          } else {
+            const double xlim = (-(bmin - slack)) / r2x;  // r2x*x <= -(bmin - slack)
+            if (xlim == xlim) {
+              if (r2x > 0.0) {
+                const int xc = grid_coord(g, 0, xlim + 1e-9 * (fabs(xlim) + cell_h)) ;
+                if (xlim + 1e-9 * (fabs(xlim) + cell_h) < g.lo[0]) continue;  // nothing in front on this row
+                x1 = xc < x1 ? xc : x1;
+              } else {
+                const int xc = grid_coord(g, 0, xlim - 1e-9 * (fabs(xlim) + cell_h));
+                if (xlim - 1e-9 * (fabs(xlim) + cell_h) > g.max_c[0]) continue;
+                x0 = xc > x0 ? xc : x0;
+              }
+              if (x0 > x1) continue;
+            }
+          }
+        }
+      }
       uint32_t row = ((uint32_t)z * g.n[1] + y) * g.n[0];
-      uint32_t start = cell_start[row + lo[0]], end = cell_start[row + hi[0] + 1];
+      uint32_t start = cell_start[row + x0], end = cell_start[row + x1 + 1];
       evaluated += end - start;
       for (uint32_t base = start; base < end; base += 32) {
         uint32_t i = base + lane;

@@ -155,6 +155,155 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
   if (lane == 0) a.vis_words[w] = vm;
 }
 
+// ---- per-camera triangle lists ------------------------------------------------------------------------
+// All rays of a camera start at its centre and are shorter than max_dist, so every triangle any of
+// them can hit lies in the cube [c - R, c + R]^3.  k_cam_trilist walks the tree once per camera
+// (one thread each, stackless) and records the leaves whose box overlaps that cube, up to `cap`
+// per camera (more => TRILIST_OVERFLOW, the camera's packets use the generic walk).  A packet then
+// needs no tree walk at all: lanes test 32 list entries at a time against the packet's bounding
+// box (lane = triangle), and only the surviving triangles are run through the watertight test
+// (lane = ray).  The result is identical: a triangle that a ray hits overlaps both the cube and the
+// packet box (both inflated by the same conservative pad as the slab test).
+constexpr uint32_t TRILIST_OVERFLOW = 0xffffffffu;
+
+__device__ __forceinline__ float conservative_pad(float ox, float oy, float oz, float scene_absmax) {
+  return 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + scene_absmax) + 1e-30f;
+}
+
+__global__ void __launch_bounds__(128)
+    k_cam_trilist(const float4 *__restrict__ nodes, int n_nodes, const double *__restrict__ cen_x,
+                  const double *__restrict__ cen_y, const double *__restrict__ cen_z, uint64_t C,
+                  float rmax, float scene_absmax, uint32_t cap, uint32_t *__restrict__ list,
+                  uint32_t *__restrict__ count) {
+  const uint64_t cam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cam >= C) return;
+  const float ox = __double2float_rn(cen_x[cam]), oy = __double2float_rn(cen_y[cam]),
+              oz = __double2float_rn(cen_z[cam]);
+  const float r = rmax + conservative_pad(ox, oy, oz, scene_absmax);
+  const float lx = ox - r, ly = oy - r, lz = oz - r, hx = ox + r, hy = oy + r, hz = oz + r;
+  uint32_t n = 0;
+  int node = 0;
+  while (node < n_nodes) {
+    const float4 lo = __ldg(&nodes[2 * node]);
+    const float4 hi = __ldg(&nodes[2 * node + 1]);
+    // written so that NaN compares keep the node (conservative)
+    const bool outside = lo.x > hx || hi.x < lx || lo.y > hy || hi.y < ly || lo.z > hz || hi.z < lz;
+    if (outside) {
+      node = __float_as_int(lo.w);
+    } else if (__float_as_int(hi.w) >= 0) {
+      if (n < cap) list[cam * cap + n] = (uint32_t)node;
+      ++n;
+      if (n > cap) break;
+      node = __float_as_int(lo.w);
+    } else {
+      node = node + 1;
+    }
+  }
+  count[cam] = n <= cap ? n : TRILIST_OVERFLOW;
+}
+
+struct TriListArgs {
+  const uint32_t *list;   // [C * cap] leaf node indices
+  const uint32_t *count;  // [C]
+  uint32_t cap;
+};
+
+// chunked pool only: the 32 slots of a warp belong to ONE camera (k_cull_grid)
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_traverse_lists(TraverseArgs a, TriListArgs tl) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t i = w * 32 + lane;
+  if (w * 32 >= a.n_cand) return;
+  bool have = i < a.n_cand;
+  Ray ray;
+  ray.ox = ray.oy = ray.oz = 0.0f;
+  ray.dx = ray.dy = ray.dz = 1.0f;
+  ray.tfar = -1.0f;
+  const uint64_t key = have ? a.keys[i] : ~0ull;
+  have = have && key != ~0ull;
+  const unsigned hv = __ballot_sync(0xffffffffu, have);
+  if (hv == 0u) {
+    if (lane == 0) a.vis_words[w] = 0u;
+    return;
+  }
+  const uint64_t cam = __shfl_sync(0xffffffffu, key, __ffs(hv) - 1) >> a.pbits;
+  if (have) {
+    const uint64_t pt = key & ((1ull << a.pbits) - 1ull);
+    V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
+    V3 p{a.px[pt], a.py[pt], a.pz[pt]};
+    ray = make_ray(c, p, a.endpoint_guard_rel != 0);
+  }
+  const uint32_t n_list = tl.count[cam];
+  bool occ;
+  if (n_list == TRILIST_OVERFLOW) {
+    occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
+  } else {
+    bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
+    occ = false;
+    unsigned n_vis = 0, n_tri = 0;
+    // bounding box of the packet's ray segments (origin + end points), conservatively padded
+    float blx = INFINITY, bly = INFINITY, blz = INFINITY, bhx = -INFINITY, bhy = -INFINITY, bhz = -INFINITY;
+    if (alive) {
+      const float pad = conservative_pad(ray.ox, ray.oy, ray.oz, a.scene_absmax) + 4e-6f * ray.tfar;
+      const float ex = fmaf(ray.dx, ray.tfar, ray.ox), ey = fmaf(ray.dy, ray.tfar, ray.oy),
+                  ez = fmaf(ray.dz, ray.tfar, ray.oz);
+      blx = fminf(ray.ox, ex) - pad;
+      bly = fminf(ray.oy, ey) - pad;
+      blz = fminf(ray.oz, ez) - pad;
+      bhx = fmaxf(ray.ox, ex) + pad;
+      bhy = fmaxf(ray.oy, ey) + pad;
+      bhz = fmaxf(ray.oz, ez) + pad;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      blx = fminf(blx, __shfl_xor_sync(0xffffffffu, blx, o));
+      bly = fminf(bly, __shfl_xor_sync(0xffffffffu, bly, o));
+      blz = fminf(blz, __shfl_xor_sync(0xffffffffu, blz, o));
+      bhx = fmaxf(bhx, __shfl_xor_sync(0xffffffffu, bhx, o));
+      bhy = fmaxf(bhy, __shfl_xor_sync(0xffffffffu, bhy, o));
+      bhz = fmaxf(bhz, __shfl_xor_sync(0xffffffffu, bhz, o));
+    }
+    const Shear sh = ray_shear(ray);
+    const uint32_t *mylist = tl.list + cam * tl.cap;
+    for (uint32_t base = 0; base < n_list; base += 32) {
+      if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+      const uint32_t j = base + lane;
+      int slot = -1;
+      bool overlap = false;
+      if (j < n_list) {
+        const uint32_t node = mylist[j];
+        const float4 lo = __ldg(&a.nodes[2 * node]);
+        const float4 hi = __ldg(&a.nodes[2 * node + 1]);
+        slot = __float_as_int(hi.w);
+        overlap = !(lo.x > bhx || hi.x < blx || lo.y > bhy || hi.y < bly || lo.z > bhz || hi.z < blz);
+      }
+      if (COUNT) n_vis += min(32u, n_list - base);
+      unsigned m = __ballot_sync(0xffffffffu, overlap);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int s = __shfl_sync(0xffffffffu, slot, b);
+        const float4 v0 = __ldg(&a.tris[3 * s]);
+        const float4 v1 = __ldg(&a.tris[3 * s + 1]);
+        const float4 v2 = __ldg(&a.tris[3 * s + 2]);
+        if (COUNT) ++n_tri;
+        if (alive && ray_triangle(ray, sh, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)) {
+          occ = true;
+          alive = false;
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+      }
+    }
+    if (COUNT && lane == 0) {
+      atomicAdd(&a.counters[2], (unsigned long long)n_vis);
+      atomicAdd(&a.counters[3], (unsigned long long)n_tri);
+    }
+  }
+  const unsigned vm = __ballot_sync(0xffffffffu, have && !occ);
+  if (lane == 0) a.vis_words[w] = vm;
+}
+
 // ---- Embree-shaped ray batch (parity tooling): AoS 48-byte rays, tfar = -inf on hit ---------------
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict__ nodes,

@@ -218,3 +218,58 @@ def test_full_size_properties_cfg3(c2b, ctx):
     # translation symmetry of the lattice: interior cameras one block apart see the same count
     counts = a.counts()
     assert counts.max() > 0 and counts.min() >= 0
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_arbitrary_orientations_and_cell_trimming(c2b, ctx, orc, seed):
+    """fully random camera rotations (pitch/roll), anisotropic point clouds, several max_dist:
+    the grid schedule's cell-range and front-plane row trimming must never lose a candidate"""
+    rng = np.random.default_rng(500 + seed)
+    n_c, n_p = 96, 6000
+    cams = np.empty((n_c, 15))
+    for i in range(n_c):
+        v9 = np.concatenate([rng.normal(size=3) * 1.5, [0, 0, 0], [rng.uniform(0.6, 1.6), 0.02, -0.001]])
+        cam = orc.from_vec(v9)
+        cams[i] = orc.from_position_direction(rng.uniform(-30, 30, 3) * np.array([1, 0.3, 1]), cam[:9])
+        cams[i, 12:15] = v9[6:9]
+    pts = rng.uniform(-35, 35, (n_p, 3)) * np.array([1, [0.02, 0.5][seed], 1])
+    pts[::7, 1] = pts[0, 1]                      # many points on one exact plane
+    empty = c2b.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), ctx=ctx)
+    for md in (3.0, 11.0, 47.0):
+        ref = orc.visibility_graph(np.zeros((0, 3)), np.zeros((0, 3)), cams, pts, md)
+        assert ref.n_obs > 0
+        for mode in MODES:
+            assert_same_graph(c2b.visibility_graph(empty, cams, pts, md, cull_mode=mode, ctx=ctx), ref,
+                              f"orient{seed}/{mode}/{md}")
+
+
+def test_long_segments_use_the_radix_fallback(c2b, ctx, orc):
+    """a camera that sees more than 4096 points exceeds the shared-memory segment sort"""
+    rng = np.random.default_rng(77)
+    cams = random_cameras(rng, 12, spread=1.0)
+    pts = rng.uniform(-40, 40, (60000, 3)) * np.array([1, 0.2, 1])
+    empty = c2b.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), ctx=ctx)
+    g = c2b.visibility_graph(empty, cams, pts, 100.0, cull_mode="grid", ctx=ctx)
+    ref = orc.visibility_graph(np.zeros((0, 3)), np.zeros((0, 3)), cams, pts, 100.0)
+    assert g.counts().max() > 4096
+    assert_same_graph(g, ref, "long segments")
+
+
+def test_dense_mesh_overflows_triangle_lists(c2b, ctx, orc):
+    """more than 128 triangles near a camera: the per-camera lists overflow and the generic
+    stackless walk takes over for those cameras"""
+    rng = np.random.default_rng(31)
+    n = 24
+    gx, gz = np.meshgrid(np.linspace(-6, 6, n), np.linspace(-6, 6, n), indexing="ij")
+    y = 0.3 * np.sin(gx) * np.cos(gz) + rng.normal(0, 0.02, gx.shape)
+    xyz = np.stack([gx, y, gz], axis=-1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(n * n).reshape(n, n)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()
+    tri = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
+    cams = random_cameras(rng, 40, center=(0, 1.0, 0), spread=5.0)
+    pts = points_on_mesh(rng, xyz, tri, 1500) + np.array([0, 0.05, 0])
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    ref = orc.visibility_graph(xyz, tri, cams, pts, 12.0)
+    assert 0 < ref.n_obs < ref.n_candidates
+    for mode in MODES:
+        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 12.0, cull_mode=mode, ctx=ctx), ref, f"dense/{mode}")
