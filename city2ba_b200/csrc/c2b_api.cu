@@ -433,9 +433,9 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     for (int attempt = 0;; ++attempt) {
       // the pool's key array doubles as buffer 0 of the radix sort
       C2B_TRY(ctx->sort_keys[0].ensure(ctx->pool_capacity * 8));
-      C2B_TRY(ctx->pool_uv.ensure(ctx->pool_capacity * 16));
+      if (!use_grid) C2B_TRY(ctx->pool_uv.ensure(ctx->pool_capacity * 16));
       a.pool_key = ctx->sort_keys[0].as<uint64_t>();
-      a.pool_uv = ctx->pool_uv.as<double2>();
+      a.pool_uv = use_grid ? nullptr : ctx->pool_uv.as<double2>();
       a.pool_capacity = ctx->pool_capacity;
       C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
       C2B_CUDA(cudaMemsetAsync(ctx->cam_count.p, 0, (C + 1) * 4, st));
@@ -563,35 +563,39 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     memcpy(&max32, reinterpret_cast<const char *>(h_fin) + 52, 4);
     total_obs = total32;
     if (total_obs) {
-      C2B_TRY(ctx->sort_keys[1].ensure(total_obs * 8));  // seg_key
-      C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));  // seg_src
       C2B_TRY(ctx->out_idx.ensure(total_obs * 8));
       C2B_TRY(ctx->out_uv.ensure(total_obs * 16));
-      uint64_t *seg_key = ctx->sort_keys[1].as<uint64_t>();
-      uint32_t *seg_src = ctx->sort_vals[0].as<uint32_t>();
       C2B_CUDA(cudaMemsetAsync(vis_count, 0, (C + 1) * 4, st));  // reused as the per-camera cursor
-      k_scatter_visible<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
-          ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, seg_key, seg_src);
-      C2B_KERNEL_CHECK();
-      const uint32_t seg_max = 4096;
-      if (max32 <= seg_max) {
-        uint32_t n2 = 2;
-        while (n2 < max32) n2 <<= 1;
-        k_seg_sort_write<<<(unsigned)C, 256, n2 * 8, st>>>(seg_off, C, seg_key, seg_src,
-                                                          ctx->pool_uv.as<double2>(), pbits,
-                                                          ctx->out_offsets.as<uint64_t>(),
-                                                          ctx->out_idx.as<uint64_t>(),
-                                                          ctx->out_uv.as<double2>());
+      if (max32 <= SEG_BLOCK_MAX) {
+        C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));  // seg_pt
+        uint32_t *seg_pt = ctx->sort_vals[0].as<uint32_t>();
+        k_scatter_visible<false><<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
+            ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, seg_pt, nullptr);
         C2B_KERNEL_CHECK();
+        SegWriteArgs sw{seg_off, C, seg_pt, ctx->cams.as<double>(), pxp, pxp + P, pxp + 2 * P,
+                        ctx->out_offsets.as<uint64_t>(), ctx->out_idx.as<uint64_t>(),
+                        ctx->out_uv.as<double2>()};
+        k_seg_sort_write_warp<<<blocks_for(C, 4), 128, 0, st>>>(sw);
+        C2B_KERNEL_CHECK();
+        if (max32 > SEG_WARP_MAX) {
+          k_seg_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);
+          C2B_KERNEL_CHECK();
+        }
       } else {
-        // a camera sees more points than the shared-memory sort holds: radix-sort all visible pairs
+        // a camera sees more points than the shared-memory sort holds: radix-sort all visible keys
+        C2B_TRY(ctx->sort_keys[1].ensure(total_obs * 8));
+        C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));
         C2B_TRY(ctx->sort_vals[1].ensure(total_obs * 4));
+        uint64_t *seg_key = ctx->sort_keys[1].as<uint64_t>();
+        k_scatter_visible<true><<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
+            ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, nullptr, seg_key);
+        C2B_KERNEL_CHECK();
         uint64_t *keys[2] = {seg_key, ctx->out_idx.as<uint64_t>()};
-        uint32_t *vals[2] = {seg_src, ctx->sort_vals[1].as<uint32_t>()};
+        uint32_t *vals[2] = {ctx->sort_vals[0].as<uint32_t>(), ctx->sort_vals[1].as<uint32_t>()};
         int res = 0;
         C2B_TRY(radix_sort_pairs(st, keys, vals, total_obs, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
         k_write_sorted<<<blocks_for(total_obs, 256), 256, 0, st>>>(
-            keys[res], vals[res], ctx->pool_uv.as<double2>(), total_obs, pbits,
+            keys[res], total_obs, pbits, ctx->cams.as<double>(), pxp, pxp + P, pxp + 2 * P,
             ctx->out_idx.as<uint64_t>(), ctx->out_uv.as<double2>());
         C2B_KERNEL_CHECK();
         k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(seg_off, C + 1, ctx->out_offsets.as<uint64_t>());

@@ -222,28 +222,24 @@ __global__ void k_grid_fill(const double *__restrict__ px, const double *__restr
 constexpr int CG_WARPS = 8;
 constexpr int CG_STAGE = 64;
 
-__device__ __forceinline__ void grid_flush32(const CullArgs &a, uint64_t *sk, double2 *su, int count,
-                                             int lane) {
+// (u, v) are not stored on this path: the final write recomputes them from (camera, point) with
+// the same device function, which is bit-identical and saves 16 of 24 bytes per candidate.
+__device__ __forceinline__ void grid_flush32(const CullArgs &a, const uint64_t *sk, int count, int lane) {
   unsigned long long base = 0;
   if (lane == 0) base = atomicAdd(&a.counters[0], 32ull);
   base = __shfl_sync(0xffffffffu, base, 0);
-  if (base + 32 <= a.pool_capacity) {
-    a.pool_key[base + lane] = lane < count ? sk[lane] : POOL_SENTINEL;
-    a.pool_uv[base + lane] = lane < count ? su[lane] : make_double2(0.0, 0.0);
-  }
+  if (base + 32 <= a.pool_capacity) a.pool_key[base + lane] = lane < count ? sk[lane] : POOL_SENTINEL;
 }
 
 __global__ void __launch_bounds__(CG_WARPS * 32) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
                                                              const uint32_t *__restrict__ cell_start,
                                                              const uint32_t *__restrict__ gidx) {
   __shared__ uint64_t s_key[CG_WARPS][CG_STAGE];
-  __shared__ double2 s_uv[CG_WARPS][CG_STAGE];
   __shared__ double s_cam[CG_WARPS][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t cam = (uint64_t)blockIdx.x * CG_WARPS + warp;
   if (cam >= a.C) return;
   uint64_t *sk = s_key[warp];
-  double2 *su = s_uv[warp];
   // the camera record lives in shared memory (broadcast reads) to keep registers for occupancy
   double *c = s_cam[warp];
   if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
@@ -320,34 +316,23 @@ __global__ void __launch_bounds__(CG_WARPS * 32) k_cull_grid(CullArgs a, GridDes
         }
         unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m == 0u) continue;
-        if (pass) {
-          int pos = qn + __popc(m & ((1u << lane) - 1u));
-          sk[pos] = (cam << a.pbits) | (uint64_t)gidx[i];
-          su[pos] = make_double2(u, v);
-        }
+        if (pass) sk[qn + __popc(m & ((1u << lane) - 1u))] = (cam << a.pbits) | (uint64_t)gidx[i];
         qn += __popc(m);
         found += __popc(m);
         __syncwarp();
         if (qn >= 32) {
-          grid_flush32(a, sk, su, 32, lane);
+          grid_flush32(a, sk, 32, lane);
           const int rem = qn - 32;
           uint64_t tk = 0;
-          double2 tu = make_double2(0.0, 0.0);
-          if (lane < rem) {
-            tk = sk[32 + lane];
-            tu = su[32 + lane];
-          }
+          if (lane < rem) tk = sk[32 + lane];
           __syncwarp();
-          if (lane < rem) {
-            sk[lane] = tk;
-            su[lane] = tu;
-          }
+          if (lane < rem) sk[lane] = tk;
           __syncwarp();
           qn = rem;
         }
       }
     }
-  if (qn > 0) grid_flush32(a, sk, su, qn, lane);
+  if (qn > 0) grid_flush32(a, sk, qn, lane);
   if (lane == 0) {
     atomicAdd(&a.counters[1], evaluated);
     atomicAdd(&a.counters[4], found);
