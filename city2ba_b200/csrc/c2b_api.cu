@@ -45,6 +45,13 @@ double exact_sq_threshold(double max_dist) {
   return x;
 }
 
+// Small read-backs (counters) go through a kernel that stores into mapped pinned host memory, not
+// through cudaMemcpy: a memcpy would queue behind the bulk result transfer on the D2H copy engine
+// and stall the next camera batch.
+__global__ void k_copy_words(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
 __global__ void k_iota_u32(uint32_t *v, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = (uint32_t)i;
@@ -110,6 +117,11 @@ int c2b_init(int device, c2b_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   C2B_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int i = 0; i < EV_COUNT; ++i) C2B_CUDA(cudaEventCreate(&ctx->ev[i]));
+  C2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+    C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+  }
   extras().push_back({ctx, new CtxExtra()});
   *out = ctx;
   return C2B_OK;
@@ -119,18 +131,25 @@ void c2b_shutdown(c2b_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   DevBuf *bufs[] = {&ctx->cams, &ctx->cam_center, &ctx->pts, &ctx->stage, &ctx->cell_of_pt,
                     &ctx->cell_start, &ctx->cell_cursor, &ctx->grid_x, &ctx->grid_y, &ctx->grid_z,
                     &ctx->grid_idx, &ctx->pool_key, &ctx->pool_uv, &ctx->cam_count, &ctx->counters,
                     &ctx->sort_keys[0], &ctx->sort_keys[1], &ctx->sort_vals[0], &ctx->sort_vals[1],
                     &ctx->sort_hist, &ctx->scan_tmp[0], &ctx->scan_tmp[1], &ctx->scan_tmp[2],
-                    &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets, &ctx->out_idx,
-                    &ctx->out_uv, &ctx->misc, &ctx->tri_list, &ctx->tri_count};
+                    &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets[0], &ctx->out_idx[0],
+                    &ctx->out_uv[0], &ctx->out_offsets[1], &ctx->out_idx[1], &ctx->out_uv[1],
+                    &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
   for (int i = 0; i < EV_COUNT; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   auto &v = extras();
   for (size_t i = 0; i < v.size(); ++i)
@@ -261,11 +280,11 @@ int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
   x->have_points = true;
   x->have_result = false;
   if (P == 0) return C2B_OK;
-  C2B_TRY(ctx->stage.ensure(P * 24));
+  C2B_TRY(ctx->pts_aos.ensure(P * 24));
   C2B_TRY(ctx->pts.ensure(P * 24));
-  C2B_CUDA(cudaMemcpyAsync(ctx->stage.p, pts, P * 24, cudaMemcpyHostToDevice, ctx->stream));
+  C2B_CUDA(cudaMemcpyAsync(ctx->pts_aos.p, pts, P * 24, cudaMemcpyHostToDevice, ctx->stream));
   double *px = ctx->pts.as<double>(), *py = px + P, *pz = py + P;
-  k_aos_to_soa3<<<blocks_for(P, 256), 256, 0, ctx->stream>>>(ctx->stage.as<double>(), P, px, py, pz);
+  k_aos_to_soa3<<<blocks_for(P, 256), 256, 0, ctx->stream>>>(ctx->pts_aos.as<double>(), P, px, py, pz);
   C2B_KERNEL_CHECK();
   // coordinate bounds (grid extent); tiny D2H happens lazily when a grid is built
   int nb = (int)std::min<uint64_t>(blocks_for(P, 256), (uint64_t)4 * ctx->sm_count);
@@ -298,6 +317,16 @@ int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C) {
 }
 
 // ---- the pipeline ---------------------------------------------------------------------------------------
+// the 64-byte counter block -> host, synchronising the compute stream
+static int read_counters(c2b_ctx *ctx, unsigned long long *h_cnt) {
+  C2B_TRY(ctx->h_small.ensure(256));
+  k_copy_words<<<1, 32, 0, ctx->stream>>>(ctx->counters.as<uint32_t>(), ctx->h_small.as<uint32_t>(), 16);
+  C2B_KERNEL_CHECK();
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(h_cnt, ctx->h_small.p, 64);
+  return C2B_OK;
+}
+
 static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   cudaStream_t st = ctx->stream;
   const uint64_t P = ctx->P;
@@ -390,7 +419,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
 
   C2B_TRY(ctx->counters.ensure(64));
   C2B_TRY(ctx->cam_count.ensure((C + 1) * 4));
-  C2B_TRY(ctx->out_offsets.ensure((C + 1) * 8));
+  C2B_TRY(ctx->out_offsets[ctx->out_sel].ensure((C + 1) * 8));
 
   uint64_t n_cand = 0, pairs_eval = 0, pool_n = 0;
   const bool use_grid = opt.cull_mode == C2B_CULL_GRID;
@@ -449,8 +478,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       }
       C2B_KERNEL_CHECK();
       unsigned long long h_cnt[8];
-      C2B_CUDA(cudaMemcpyAsync(h_cnt, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
-      C2B_CUDA(cudaStreamSynchronize(st));
+      C2B_TRY(read_counters(ctx, h_cnt));
       pool_n = h_cnt[0];
       n_cand = use_grid ? h_cnt[4] : h_cnt[0];
       pairs_eval = use_grid ? h_cnt[1] : C * P;
@@ -491,9 +519,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       t.cen_x = cxp;
       t.cen_y = cxp + C;
       t.cen_z = cxp + 2 * C;
-      t.px = pxp;
-      t.py = pxp + P;
-      t.pz = pxp + 2 * P;
+      t.p_aos = ctx->pts_aos.as<double>();
       t.endpoint_guard_rel = opt.endpoint_guard_rel;
       t.vis_words = ctx->vis_words.as<uint32_t>();
       t.counters = ctx->counters.as<unsigned long long>();
@@ -556,15 +582,14 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       C2B_KERNEL_CHECK();
     }
     C2B_TRY(exclusive_scan_u32(st, vis_count, seg_off, C + 1, d_total, ctx->scan_tmp));
-    C2B_CUDA(cudaMemcpyAsync(h_fin, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
-    C2B_CUDA(cudaStreamSynchronize(st));
+    C2B_TRY(read_counters(ctx, h_fin));
     uint32_t total32, max32;
     memcpy(&total32, reinterpret_cast<const char *>(h_fin) + 48, 4);
     memcpy(&max32, reinterpret_cast<const char *>(h_fin) + 52, 4);
     total_obs = total32;
     if (total_obs) {
-      C2B_TRY(ctx->out_idx.ensure(total_obs * 8));
-      C2B_TRY(ctx->out_uv.ensure(total_obs * 16));
+      C2B_TRY(ctx->out_idx[ctx->out_sel].ensure(total_obs * 8));
+      C2B_TRY(ctx->out_uv[ctx->out_sel].ensure(total_obs * 16));
       C2B_CUDA(cudaMemsetAsync(vis_count, 0, (C + 1) * 4, st));  // reused as the per-camera cursor
       if (max32 <= SEG_BLOCK_MAX) {
         C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));  // seg_pt
@@ -572,9 +597,9 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
         k_scatter_visible<false><<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
             ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, seg_pt, nullptr);
         C2B_KERNEL_CHECK();
-        SegWriteArgs sw{seg_off, C, seg_pt, ctx->cams.as<double>(), pxp, pxp + P, pxp + 2 * P,
-                        ctx->out_offsets.as<uint64_t>(), ctx->out_idx.as<uint64_t>(),
-                        ctx->out_uv.as<double2>()};
+        SegWriteArgs sw{seg_off, C, seg_pt, ctx->cams.as<double>(), ctx->pts_aos.as<double>(),
+                        ctx->out_offsets[ctx->out_sel].as<uint64_t>(), ctx->out_idx[ctx->out_sel].as<uint64_t>(),
+                        ctx->out_uv[ctx->out_sel].as<double2>()};
         k_seg_sort_write_warp<<<blocks_for(C, 4), 128, 0, st>>>(sw);
         C2B_KERNEL_CHECK();
         if (max32 > SEG_WARP_MAX) {
@@ -590,23 +615,22 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
         k_scatter_visible<true><<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
             ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, nullptr, seg_key);
         C2B_KERNEL_CHECK();
-        uint64_t *keys[2] = {seg_key, ctx->out_idx.as<uint64_t>()};
+        uint64_t *keys[2] = {seg_key, ctx->out_idx[ctx->out_sel].as<uint64_t>()};
         uint32_t *vals[2] = {ctx->sort_vals[0].as<uint32_t>(), ctx->sort_vals[1].as<uint32_t>()};
         int res = 0;
         C2B_TRY(radix_sort_pairs(st, keys, vals, total_obs, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
         k_write_sorted<<<blocks_for(total_obs, 256), 256, 0, st>>>(
-            keys[res], total_obs, pbits, ctx->cams.as<double>(), pxp, pxp + P, pxp + 2 * P,
-            ctx->out_idx.as<uint64_t>(), ctx->out_uv.as<double2>());
+            keys[res], total_obs, pbits, ctx->cams.as<double>(), ctx->pts_aos.as<double>(),
+            ctx->out_idx[ctx->out_sel].as<uint64_t>(), ctx->out_uv[ctx->out_sel].as<double2>());
         C2B_KERNEL_CHECK();
-        k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(seg_off, C + 1, ctx->out_offsets.as<uint64_t>());
+        k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(seg_off, C + 1, ctx->out_offsets[ctx->out_sel].as<uint64_t>());
         C2B_KERNEL_CHECK();
       }
     } else {
-      C2B_CUDA(cudaMemsetAsync(ctx->out_offsets.p, 0, (C + 1) * 8, st));
+      C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[ctx->out_sel].p, 0, (C + 1) * 8, st));
     }
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
-    if (opt.count_traversal) C2B_CUDA(cudaMemcpyAsync(h_fin, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
     C2B_CUDA(cudaStreamSynchronize(st));
   } else {
     // ---- ordered path: radix sort all candidates, traverse in order, stream-compact ------------------
@@ -637,8 +661,8 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
 
     C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
     if (n_cand) {
-      C2B_TRY(ctx->out_idx.ensure(n_cand * 8));
-      C2B_TRY(ctx->out_uv.ensure(n_cand * 16));
+      C2B_TRY(ctx->out_idx[ctx->out_sel].ensure(n_cand * 8));
+      C2B_TRY(ctx->out_uv[ctx->out_sel].ensure(n_cand * 16));
       k_word_popc<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
                                                             ctx->word_prefix.as<uint32_t>());
       C2B_KERNEL_CHECK();
@@ -646,18 +670,17 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
                                  n_words, d_total, ctx->scan_tmp));
       k_compact_write<<<blocks_for(n_cand, 256), 256, 0, st>>>(
           ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(), keys[res], vals[res],
-          ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx.as<uint64_t>(),
-          ctx->out_uv.as<double2>());
+          ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx[ctx->out_sel].as<uint64_t>(),
+          ctx->out_uv[ctx->out_sel].as<double2>());
       C2B_KERNEL_CHECK();
     }
     k_csr_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(
         ctx->cam_count.as<uint32_t>(), C, ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(),
-        n_cand, d_total, ctx->out_offsets.as<uint64_t>());
+        n_cand, d_total, ctx->out_offsets[ctx->out_sel].as<uint64_t>());
     C2B_KERNEL_CHECK();
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
-    C2B_CUDA(cudaMemcpyAsync(h_fin, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
-    C2B_CUDA(cudaStreamSynchronize(st));
+    C2B_TRY(read_counters(ctx, h_fin));
     uint32_t total32;
     memcpy(&total32, reinterpret_cast<const char *>(h_fin) + 48, 4);
     total_obs = total32;
@@ -703,10 +726,10 @@ int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out) {
   C2B_TRY(ctx->h_uv.ensure(std::max<uint64_t>(O, 1) * 16));
   cudaEvent_t e0 = ctx->ev[EV_COMPACT], e1 = ctx->ev[EV_D2H];
   C2B_CUDA(cudaEventRecord(e0, st));
-  C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.p, ctx->out_offsets.p, (C + 1) * 8, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.p, ctx->out_offsets[ctx->out_sel].p, (C + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (O) {
-    C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.p, ctx->out_idx.p, O * 8, cudaMemcpyDeviceToHost, st));
-    C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.p, ctx->out_uv.p, O * 16, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.p, ctx->out_idx[ctx->out_sel].p, O * 8, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.p, ctx->out_uv[ctx->out_sel].p, O * 16, cudaMemcpyDeviceToHost, st));
   }
   C2B_CUDA(cudaEventRecord(e1, st));
   C2B_CUDA(cudaStreamSynchronize(st));
@@ -722,31 +745,116 @@ int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out) {
   return C2B_OK;
 }
 
+namespace {
+__global__ void k_add_u64(uint64_t *v, uint64_t n, uint64_t add) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += add;
+}
+
+// grow a pinned result buffer while copies into it may be in flight: drain, allocate, carry over
+int grow_pinned(c2b_ctx *ctx, PinBuf &b, size_t need, size_t used) {
+  if (need <= b.cap) return C2B_OK;
+  C2B_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  PinBuf nb;
+  C2B_TRY(nb.ensure(need + need / 2));
+  if (used) memcpy(nb.p, b.p, used);
+  b.release();
+  b = nb;
+  return C2B_OK;
+}
+}  // namespace
+
 int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cams, uint64_t C,
                          const double *pts, uint64_t P, double max_dist, const c2b_vis_options *opt,
                          c2b_obs *out) {
   if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null argument");
+  if ((C && !cams) || (P && !pts)) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null input array");
   C2B_CUDA(cudaSetDevice(ctx->device));
-  // the ctx events are re-recorded by the resident call; time the uploads with a local pair
+  CtxExtra *x = extra_of(ctx);
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  // camera batches: the CSR slab of batch b travels to the host while batch b+1 is computed
+  uint64_t n_batches = 1;
+  if (C >= 16384) n_batches = std::min<uint64_t>(8, C / 8192);
+  if (const char *e = getenv("C2B_BATCHES")) n_batches = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)atoll(e)));
+
   cudaEvent_t u0, u1;
   C2B_CUDA(cudaEventCreate(&u0));
   C2B_CUDA(cudaEventCreate(&u1));
-  C2B_CUDA(cudaEventRecord(u0, ctx->stream));
-  int rc = c2b_upload_points(ctx, pts, P);
-  if (rc == C2B_OK) rc = c2b_upload_cameras(ctx, cams, C);
-  cudaEventRecord(u1, ctx->stream);
-  c2b_obs st;
-  if (rc == C2B_OK) rc = c2b_visibility_graph_resident(ctx, scene, max_dist, opt, &st);
-  if (rc == C2B_OK) rc = c2b_download_obs(ctx, &st);
-  float t = 0;
-  if (rc == C2B_OK) cudaEventElapsedTime(&t, u0, u1);
+  c2b_obs acc;
+  memset(&acc, 0, sizeof acc);
+  int rc = C2B_OK;
+  uint64_t obs_base = 0;
+  float ms_upload = 0;
+  auto run = [&]() -> int {
+    C2B_CUDA(cudaEventRecord(u0, st));
+    C2B_TRY(c2b_upload_points(ctx, pts, P));
+    C2B_CUDA(cudaEventRecord(u1, st));
+    C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
+    for (uint64_t b = 0; b < n_batches; ++b) {
+      const uint64_t c0 = (b * C) / n_batches, c1 = ((b + 1) * C) / n_batches, nc = c1 - c0;
+      const int sel = (int)(b & 1);
+      ctx->out_sel = sel;
+      if (b >= 2) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[sel], 0));  // set `sel` is free again
+      C2B_TRY(c2b_upload_cameras(ctx, cams ? cams + 15 * c0 : nullptr, nc));
+      c2b_obs s1;
+      C2B_TRY(c2b_visibility_graph_resident(ctx, scene, max_dist, opt, &s1));
+      const uint64_t O = ctx->out_O;
+      if (obs_base)
+        k_add_u64<<<blocks_for(nc + 1, 256), 256, 0, st>>>(ctx->out_offsets[sel].as<uint64_t>(), nc + 1, obs_base);
+      ++launch_counter();
+      C2B_CUDA(cudaEventRecord(ctx->ev_ready[sel], st));
+      // pinned result arrays: sized from the first batch's density, grown if the guess was short
+      size_t need = obs_base + O;
+      if (b + 1 < n_batches) need = std::max<size_t>(need, (size_t)((double)(obs_base + O) * (double)C / (double)c1 * 1.05) + 1024);
+      C2B_TRY(grow_pinned(ctx, ctx->h_idx, std::max<size_t>(need, 1) * 8, obs_base * 8));
+      C2B_TRY(grow_pinned(ctx, ctx->h_uv, std::max<size_t>(need, 1) * 16, obs_base * 16));
+      C2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sel], 0));
+      C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.as<uint64_t>() + c0, ctx->out_offsets[sel].p, (nc + 1) * 8,
+                               cudaMemcpyDeviceToHost, cs));
+      if (O) {
+        C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.as<uint64_t>() + obs_base, ctx->out_idx[sel].p, O * 8,
+                                 cudaMemcpyDeviceToHost, cs));
+        C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.as<double>() + 2 * obs_base, ctx->out_uv[sel].p, O * 16,
+                                 cudaMemcpyDeviceToHost, cs));
+      }
+      C2B_CUDA(cudaEventRecord(ctx->ev_copied[sel], cs));
+      obs_base += O;
+      acc.n_candidates += s1.n_candidates;
+      acc.pairs_evaluated += s1.pairs_evaluated;
+      acc.nodes_visited += s1.nodes_visited;
+      acc.tris_tested += s1.tris_tested;
+      acc.ms_prep += s1.ms_prep;
+      acc.ms_cull += s1.ms_cull;
+      acc.ms_sort += s1.ms_sort;
+      acc.ms_traverse += s1.ms_traverse;
+      acc.ms_compact += s1.ms_compact;
+      acc.ms_total += s1.ms_total;
+    }
+    C2B_CUDA(cudaStreamSynchronize(cs));
+    C2B_CUDA(cudaStreamSynchronize(st));
+    C2B_CUDA(cudaEventElapsedTime(&ms_upload, u0, u1));
+    return C2B_OK;
+  };
+  rc = run();
   cudaEventDestroy(u0);
   cudaEventDestroy(u1);
-  if (rc != C2B_OK) return rc;
-  st.ms_h2d = t;
-  st.h2d_bytes = P * 24 + C * 120;
-  st.ms_total += st.ms_h2d + st.ms_d2h;
-  *out = st;
+  ctx->out_sel = 0;
+  x->have_result = false;  // the resident state now holds the last batch only
+  if (rc != C2B_OK) {
+    cudaStreamSynchronize(cs);
+    return rc;
+  }
+  acc.n_cameras = C;
+  acc.n_obs = obs_base;
+  acc.offsets = ctx->h_offsets.as<uint64_t>();
+  acc.point_idx = ctx->h_idx.as<uint64_t>();
+  acc.uv = ctx->h_uv.as<double>();
+  acc.ms_h2d = ms_upload;
+  acc.h2d_bytes = P * 24 + C * 120;
+  acc.d2h_bytes = (C + 1) * 8 + obs_base * 24;
+  acc.ms_d2h = 0;  // overlapped with compute on the copy stream
+  acc.ms_total += ms_upload;
+  *out = acc;
   return C2B_OK;
 }
 
@@ -772,8 +880,8 @@ int c2b_reprojection_error_resident(c2b_ctx *ctx, double norm, double *out) {
   C2B_TRY(ctx->misc.ensure((size_t)nb * 8 + 64));
   const double *px = ctx->pts.as<double>();
   k_reproj_partial<<<nb, ST_THREADS, 0, st>>>(ctx->cams.as<double>(), px, px + P, px + 2 * P,
-                                              ctx->out_offsets.as<uint64_t>(), C,
-                                              ctx->out_idx.as<uint64_t>(), ctx->out_uv.as<double2>(), O,
+                                              ctx->out_offsets[ctx->out_sel].as<uint64_t>(), C,
+                                              ctx->out_idx[ctx->out_sel].as<uint64_t>(), ctx->out_uv[ctx->out_sel].as<double2>(), O,
                                               norm, ctx->misc.as<double>());
   C2B_KERNEL_CHECK();
   std::vector<double> h(nb);

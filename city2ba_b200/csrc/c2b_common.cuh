@@ -159,7 +159,8 @@ struct c2b_ctx {
   uint64_t C = 0, P = 0;
   c2b::DevBuf cams;          // double[15*C] as given
   c2b::DevBuf cam_center;    // double[3*C]  SoA: x[C], y[C], z[C]
-  c2b::DevBuf pts;           // double[3*P]  SoA: x[P], y[P], z[P]
+  c2b::DevBuf pts;           // double[3*P]  SoA: x[P], y[P], z[P] (streamed by the cull kernels)
+  c2b::DevBuf pts_aos;       // double[3*P]  as given (24 B records for the per-candidate gathers)
   c2b::DevBuf stage;         // staging for H2D of AoS inputs
   c2b::PinBuf pin_in;        // pinned staging for pageable callers
 
@@ -174,8 +175,12 @@ struct c2b_ctx {
 
   // traversal + compaction
   c2b::DevBuf vis_words, word_prefix;
-  c2b::DevBuf out_offsets, out_idx, out_uv;  // device CSR
+  // device CSR, double-buffered so that the D2H copy of one camera batch overlaps the next batch
+  c2b::DevBuf out_offsets[2], out_idx[2], out_uv[2];
+  int out_sel = 0;
   uint64_t out_C = 0, out_O = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {}, ev_copied[2] = {};
   c2b::DevBuf misc;  // small scratch (reductions)
   c2b::DevBuf tri_list, tri_count;  // per-camera leaf lists for list-driven traversal
 

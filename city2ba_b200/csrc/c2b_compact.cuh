@@ -135,7 +135,7 @@ struct SegWriteArgs {
   uint64_t C;
   const uint32_t *seg_pt;   // scattered point indices, arbitrary order inside a segment
   const double *cams;
-  const double *px, *py, *pz;
+  const double *p_aos;  // xyz records, original point order
   uint64_t *out_offsets;
   uint64_t *out_idx;
   double2 *out_uv;
@@ -195,7 +195,7 @@ __device__ __forceinline__ void seg_sort_write_warp(const SegWriteArgs &s, uint6
     if (i < n) {
       const uint32_t pt = a[r];
       s.out_idx[base + i] = pt;
-      s.out_uv[base + i] = observe(c, s.px[pt], s.py[pt], s.pz[pt]);
+      s.out_uv[base + i] = observe(c, s.p_aos[3 * (uint64_t)pt], s.p_aos[3 * (uint64_t)pt + 1], s.p_aos[3 * (uint64_t)pt + 2]);
     }
   }
 }
@@ -255,15 +255,14 @@ __global__ void __launch_bounds__(256) k_seg_sort_write_block(SegWriteArgs s) {
   for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
     const uint32_t pt = s_sort[t];
     s.out_idx[base + t] = pt;
-    s.out_uv[base + t] = observe(c, s.px[pt], s.py[pt], s.pz[pt]);
+    s.out_uv[base + t] = observe(c, s.p_aos[3 * (uint64_t)pt], s.p_aos[3 * (uint64_t)pt + 1], s.p_aos[3 * (uint64_t)pt + 2]);
   }
 }
 
 // fallback for segments longer than SEG_BLOCK_MAX: the scattered 64-bit keys were radix-sorted
 // globally; split each key and recompute (u, v)
 __global__ void k_write_sorted(const uint64_t *keys, uint64_t n, int pbits, const double *__restrict__ cams,
-                               const double *__restrict__ px, const double *__restrict__ py,
-                               const double *__restrict__ pz, uint64_t *out_idx,
+                               const double *__restrict__ p_aos, uint64_t *out_idx,
                                double2 *__restrict__ out_uv) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -272,7 +271,7 @@ __global__ void k_write_sorted(const uint64_t *keys, uint64_t n, int pbits, cons
   double c[15];
 #pragma unroll
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&cams[15 * cam + k]);
-  out_uv[i] = observe(c, px[pt], py[pt], pz[pt]);
+  out_uv[i] = observe(c, p_aos[3 * pt], p_aos[3 * pt + 1], p_aos[3 * pt + 2]);
   out_idx[i] = pt;
 }
 __global__ void k_widen_offsets(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {

@@ -125,7 +125,7 @@ struct TraverseArgs {
   float scene_absmax;
   int pbits;
   const double *cen_x, *cen_y, *cen_z;
-  const double *px, *py, *pz;  // original point order
+  const double *p_aos;  // xyz records, original point order
   int endpoint_guard_rel;
   uint32_t *vis_words;  // bit i of word w set  <=>  candidate 32*w+i is VISIBLE
   unsigned long long *counters;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
   if (have) {
     const uint64_t cam = key >> a.pbits, pt = key & ((1ull << a.pbits) - 1ull);
     V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
-    V3 p{a.px[pt], a.py[pt], a.pz[pt]};
+    V3 p{a.p_aos[3 * pt], a.p_aos[3 * pt + 1], a.p_aos[3 * pt + 2]};
     ray = make_ray(c, p, a.endpoint_guard_rel != 0);
   }
   const bool occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) k_traverse_lists(TraverseArgs a, TriListA
   if (have) {
     const uint64_t pt = key & ((1ull << a.pbits) - 1ull);
     V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
-    V3 p{a.px[pt], a.py[pt], a.pz[pt]};
+    V3 p{a.p_aos[3 * pt], a.p_aos[3 * pt + 1], a.p_aos[3 * pt + 2]};
     ray = make_ray(c, p, a.endpoint_guard_rel != 0);
   }
   const uint32_t n_list = tl.count[cam];
