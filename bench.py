@@ -326,12 +326,22 @@ def main():
     e2e_value = C * P * K / e2e_max
     # algorithmic bytes per stage (DESIGN.md "roofline bookkeeping"), whole job, per step
     n_words = (n_cand + 31) // 32
-    b_cull = 28.0 * pairs_eval + 144.0 * C + 28.0 * n_cand      # sorted point (24) + its index (4) per
-    #                                                             evaluated pair, camera record + centre,
-    #                                                             pool entry written (key 8 + uv 16 + count 4)
-    b_trav = 56.0 * n_cand + 32.0 * nodes + 48.0 * tris_t + 4.0 * n_words
-    b_sort = 24.0 * n_cand * max(1, -(-(int(np.ceil(np.log2(max(C // world, 2)))) + int(np.ceil(np.log2(P)))) // 8))
-    b_comp = 12.0 * n_cand + 8.0 * n_words + 24.0 * n_obs * 2 + 8.0 * (C + 1)
+    if args.cull_mode == "grid":
+        # segmented pipeline: keys-only pool, list-driven traversal,
+        # per-camera segment sort with (u, v) recomputed at the final write
+        b_cull = 28.0 * pairs_eval + 144.0 * C + 8.0 * n_cand   # grid-ordered point (24) + index (4) per
+        #                                                         evaluated pair, camera + centre, key written
+        b_trav = 56.0 * n_cand + 36.0 * nodes + 48.0 * tris_t + 4.0 * n_words  # key+centre+point per ray,
+        #            list entry (4) + its leaf box (32) per entry examined, 48 B per warp triangle test
+        b_sort = 0.0
+        b_comp = 24.0 * n_words + 16.0 * n_obs + 28.0 * n_obs + 24.0 * n_obs + 128.0 * C
+        #        words+first key (count, scatter), key read + index scattered/re-read, point gather + index,
+        #        CSR record written, camera record + offsets
+    else:
+        b_cull = 28.0 * pairs_eval + 144.0 * C + 28.0 * n_cand
+        b_trav = 56.0 * n_cand + 32.0 * nodes + 48.0 * tris_t + 4.0 * n_words
+        b_sort = 24.0 * n_cand * max(1, -(-(int(np.ceil(np.log2(max(C // world, 2)))) + int(np.ceil(np.log2(P)))) // 8))
+        b_comp = 12.0 * n_cand + 8.0 * n_words + 24.0 * n_obs * 2 + 8.0 * (C + 1)
     stages = {
         "cull": (b_cull, stage_ms["ms_cull"]), "sort": (b_sort, stage_ms["ms_sort"]),
         "traverse": (b_trav, stage_ms["ms_traverse"]), "compact": (b_comp, stage_ms["ms_compact"]),

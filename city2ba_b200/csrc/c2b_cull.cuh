@@ -231,7 +231,7 @@ __device__ __forceinline__ void grid_flush32(const CullArgs &a, const uint64_t *
   if (base + 32 <= a.pool_capacity) a.pool_key[base + lane] = lane < count ? sk[lane] : POOL_SENTINEL;
 }
 
-__global__ void __launch_bounds__(CG_WARPS * 32) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
+__global__ void __launch_bounds__(CG_WARPS * 32, 4) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
                                                              const uint32_t *__restrict__ cell_start,
                                                              const uint32_t *__restrict__ gidx) {
   __shared__ uint64_t s_key[CG_WARPS][CG_STAGE];

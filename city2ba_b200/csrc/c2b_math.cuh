@@ -215,7 +215,8 @@ C2B_HD Ray make_ray(V3 c, V3 p, bool endpoint_guard_rel) {
 
 // ---- watertight ray/triangle test (Woop, Benthin, Wald 2013), hit interval 0 < t <= tfar -------
 struct Shear {
-  int kx, ky, kz;
+  int kz;     // dominant axis of the direction
+  bool swap;  // dir[kz] < 0: kx and ky trade places (keeps the winding)
   float Sx, Sy, Sz;
 };
 
@@ -230,21 +231,31 @@ C2B_HD Shear ray_shear(const Ray &r) {
     m = fabsf(r.dy);
   }
   if (fabsf(r.dz) > m) kz = 2;
-  int kx = kz == 2 ? 0 : kz + 1;
-  int ky = kx == 2 ? 0 : kx + 1;
-  float dz = sel3(kz, r.dx, r.dy, r.dz);
-  if (dz < 0.0f) {
-    int t = kx;
-    kx = ky;
-    ky = t;
-  }
-  s.kx = kx;
-  s.ky = ky;
+  // kx = (kz+1)%3, ky = (kx+1)%3, swapped when the dominant component is negative
+  const float dz = sel3(kz, r.dx, r.dy, r.dz);
+  float dkx = sel3(kz, r.dy, r.dz, r.dx);
+  float dky = sel3(kz, r.dz, r.dx, r.dy);
   s.kz = kz;
-  s.Sx = fdiv(sel3(kx, r.dx, r.dy, r.dz), dz);
-  s.Sy = fdiv(sel3(ky, r.dx, r.dy, r.dz), dz);
+  s.swap = dz < 0.0f;
+  if (s.swap) {
+    const float t = dkx;
+    dkx = dky;
+    dky = t;
+  }
+  s.Sx = fdiv(dkx, dz);
+  s.Sy = fdiv(dky, dz);
   s.Sz = fdiv(1.0f, dz);
   return s;
+}
+
+// components (kx, ky, kz) of a translated vertex, as two rounds of selects (no branches)
+C2B_HD void permute(const Shear &s, float a0, float a1, float a2, float &x, float &y, float &z) {
+  const bool z0 = s.kz == 0, z1 = s.kz == 1;
+  const float rx = z0 ? a1 : (z1 ? a2 : a0);
+  const float ry = z0 ? a2 : (z1 ? a0 : a1);
+  z = z0 ? a0 : (z1 ? a1 : a2);
+  x = s.swap ? ry : rx;
+  y = s.swap ? rx : ry;
 }
 
 // returns true when the triangle occludes the ray.  t_out (optional) receives T/det for the
@@ -252,12 +263,10 @@ C2B_HD Shear ray_shear(const Ray &r) {
 C2B_HD bool ray_triangle(const Ray &r, const Shear &s, float v0x, float v0y, float v0z, float v1x,
                          float v1y, float v1z, float v2x, float v2y, float v2z,
                          float *t_out = nullptr) {
-  float A0 = fsub(v0x, r.ox), A1 = fsub(v0y, r.oy), A2 = fsub(v0z, r.oz);
-  float B0 = fsub(v1x, r.ox), B1 = fsub(v1y, r.oy), B2 = fsub(v1z, r.oz);
-  float C0 = fsub(v2x, r.ox), C1 = fsub(v2y, r.oy), C2 = fsub(v2z, r.oz);
-  float Akx = sel3(s.kx, A0, A1, A2), Aky = sel3(s.ky, A0, A1, A2), Akz = sel3(s.kz, A0, A1, A2);
-  float Bkx = sel3(s.kx, B0, B1, B2), Bky = sel3(s.ky, B0, B1, B2), Bkz = sel3(s.kz, B0, B1, B2);
-  float Ckx = sel3(s.kx, C0, C1, C2), Cky = sel3(s.ky, C0, C1, C2), Ckz = sel3(s.kz, C0, C1, C2);
+  float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
+  permute(s, fsub(v0x, r.ox), fsub(v0y, r.oy), fsub(v0z, r.oz), Akx, Aky, Akz);
+  permute(s, fsub(v1x, r.ox), fsub(v1y, r.oy), fsub(v1z, r.oz), Bkx, Bky, Bkz);
+  permute(s, fsub(v2x, r.ox), fsub(v2y, r.oy), fsub(v2z, r.oz), Ckx, Cky, Ckz);
   float Ax = fsub(Akx, fmul(s.Sx, Akz)), Ay = fsub(Aky, fmul(s.Sy, Akz));
   float Bx = fsub(Bkx, fmul(s.Sx, Bkz)), By = fsub(Bky, fmul(s.Sy, Bkz));
   float Cx = fsub(Ckx, fmul(s.Sx, Ckz)), Cy = fsub(Cky, fmul(s.Sy, Ckz));
