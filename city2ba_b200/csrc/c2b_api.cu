@@ -11,6 +11,7 @@
 #include "c2b_common.cuh"
 #include "c2b_compact.cuh"
 #include "c2b_cull.cuh"
+#include "c2b_fused.cuh"
 #include "c2b_math.cuh"
 #include "c2b_noise.cuh"
 #include "c2b_sort.cuh"
@@ -139,7 +140,8 @@ void c2b_shutdown(c2b_ctx *ctx) {
                     &ctx->sort_hist, &ctx->scan_tmp[0], &ctx->scan_tmp[1], &ctx->scan_tmp[2],
                     &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets[0], &ctx->out_idx[0],
                     &ctx->out_uv[0], &ctx->out_offsets[1], &ctx->out_idx[1], &ctx->out_uv[1],
-                    &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos};
+                    &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos, &ctx->ev_off,
+                    &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
@@ -388,6 +390,211 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   return C2B_OK;
 }
 
+namespace {
+
+float scene_abs_max(const c2b_scene *scene) {
+  float m = 0.0f;
+  if (scene)
+    for (int k = 0; k < 3; ++k) m = std::max(m, std::max(std::fabs(scene->lo[k]), std::fabs(scene->hi[k])));
+  if (!std::isfinite(m)) m = 3.0e38f;
+  return m;
+}
+
+void fill_stats(c2b_ctx *ctx, c2b_obs *stats, uint64_t C, uint64_t n_cand, uint64_t pairs_eval,
+                uint64_t nodes, uint64_t tris) {
+  if (!stats) return;
+  memset(stats, 0, sizeof *stats);
+  stats->n_cameras = C;
+  stats->n_obs = ctx->out_O;
+  stats->n_candidates = n_cand;
+  stats->pairs_evaluated = pairs_eval;
+  stats->nodes_visited = nodes;
+  stats->tris_tested = tris;
+  auto ms = [&](int a, int b) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+    return t;
+  };
+  stats->ms_prep = ms(EV_H2D, EV_PREP);
+  stats->ms_cull = ms(EV_PREP, EV_CULL);
+  stats->ms_sort = ms(EV_CULL, EV_SORT);
+  stats->ms_traverse = ms(EV_SORT, EV_TRAVERSE);
+  stats->ms_compact = ms(EV_TRAVERSE, EV_COMPACT);
+  stats->ms_total = ms(EV_START, EV_D2H);
+}
+
+// ---- grid schedule: plan -> fused cull + occlusion -> per-camera sort + write (c2b_fused.cuh) ------
+// Stage timers: ms_cull = plan + scan (+ per-camera leaf lists), ms_traverse = the fused kernel,
+// ms_compact = visible-count scan + sort/write; ms_sort stays 0 (there is no global sort).
+int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, double max_dist,
+                          const c2b_vis_options &opt, int pbits, int cbits, c2b_obs *stats) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t C = ctx->C, P = ctx->P;
+  const int sel = ctx->out_sel;
+  if (C && P && !(x->grid.valid && x->grid.max_dist == max_dist && x->grid.points_version == x->points_version))
+    C2B_TRY(build_grid(ctx, x, max_dist));
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
+
+  C2B_TRY(ctx->counters.ensure(64));
+  C2B_TRY(ctx->out_offsets[sel].ensure((C + 1) * 8));
+  C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+  uint64_t n_cand = 0, pairs_eval = 0, total_obs = 0, nodes = 0, tris_t = 0;
+  if (!(C && P)) {
+    C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[sel].p, 0, (C + 1) * 8, st));
+    for (int e : {EV_CULL, EV_SORT, EV_TRAVERSE, EV_COMPACT, EV_D2H}) C2B_CUDA(cudaEventRecord(ctx->ev[e], st));
+    C2B_CUDA(cudaStreamSynchronize(st));
+    ctx->out_C = C;
+    ctx->out_O = 0;
+    x->have_result = true;
+    x->res_candidates = 0;
+    fill_stats(ctx, stats, C, 0, 0, 0, 0);
+    return C2B_OK;
+  }
+
+  C2B_TRY(ctx->ev_off.ensure((C + 1) * 4));
+  C2B_TRY(ctx->vis_count.ensure((C + 1) * 4));
+  C2B_TRY(ctx->seg_off.ensure((C + 1) * 4));
+  const double *cxp = ctx->cam_center.as<double>();
+  const bool mesh = opt.occlusion == C2B_OCC_MESH && scene && scene->n_nodes > 0;
+  FusedArgs fa;
+  memset(&fa, 0, sizeof fa);
+  fa.cams = ctx->cams.as<double>();
+  fa.cen_x = cxp;
+  fa.cen_y = cxp + C;
+  fa.cen_z = cxp + 2 * C;
+  fa.C = C;
+  fa.gx = ctx->grid_x.as<double>();
+  fa.gy = ctx->grid_y.as<double>();
+  fa.gz = ctx->grid_z.as<double>();
+  fa.gidx = ctx->grid_idx.as<uint32_t>();
+  fa.cell_start = ctx->cell_start.as<uint32_t>();
+  fa.g = x->grid.desc;
+  fa.max_dist = max_dist;
+  fa.t_star = exact_sq_threshold(max_dist);
+  fa.scene_absmax = scene_abs_max(scene);
+  fa.endpoint_guard_rel = opt.endpoint_guard_rel;
+  fa.block_length = opt.block_length;
+  fa.block_inset = opt.block_inset;
+  fa.ev_count = ctx->ev_off.as<uint32_t>();
+  fa.vis_count = ctx->vis_count.as<uint32_t>();
+  fa.counters = ctx->counters.as<unsigned long long>();
+
+  uint32_t *d_total = ctx->counters.as<uint32_t>() + 12;  // bytes 48..51 of the counter block
+  uint32_t *d_max = ctx->counters.as<uint32_t>() + 13;    // bytes 52..55
+  unsigned long long h_cnt[8];
+
+  // plan: row points per camera -> scratch slices
+  k_cam_plan<<<blocks_for(C + 1, 128), 128, 0, st>>>(fa);
+  C2B_KERNEL_CHECK();
+  C2B_TRY(exclusive_scan_u32(st, fa.ev_count, fa.ev_count, C + 1, nullptr, ctx->scan_tmp));
+  if (mesh) {
+    uint32_t trilist_cap = 128;
+    if (const char *e = getenv("C2B_TRILIST_CAP")) trilist_cap = (uint32_t)std::max(1, atoi(e));
+    C2B_TRY(ctx->tri_list.ensure((size_t)C * trilist_cap * 4));
+    C2B_TRY(ctx->tri_count.ensure(C * 4));
+    float rmax = (float)max_dist;
+    if ((double)rmax < max_dist) rmax = std::nextafter(rmax, INFINITY);
+    rmax = rmax * (1.0f + 4e-6f);
+    fa.nodes = scene->nodes.as<float4>();
+    fa.tris = scene->tris.as<float4>();
+    fa.n_nodes = (int)scene->n_nodes;
+    fa.tri_list = ctx->tri_list.as<uint32_t>();
+    fa.tri_count = ctx->tri_count.as<uint32_t>();
+    fa.tri_cap = trilist_cap;
+    k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
+                                                     fa.scene_absmax, trilist_cap, ctx->tri_list.as<uint32_t>(),
+                                                     ctx->tri_count.as<uint32_t>());
+    C2B_KERNEL_CHECK();
+  }
+  C2B_TRY(read_counters(ctx, h_cnt));
+  pairs_eval = h_cnt[1];
+  if (pairs_eval >= 0xffffffffull)
+    return set_error(C2B_ERR_INVALID, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
+  C2B_TRY(ctx->scratch_idx.ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
+  fa.scratch_idx = ctx->scratch_idx.as<uint32_t>();
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_CULL], st));
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
+
+  // fused cull + occlusion
+  C2B_CUDA(cudaMemsetAsync(ctx->vis_count.p, 0, (C + 1) * 4, st));
+  {
+    const unsigned nb = blocks_for(C, FU_WARPS), nt = FU_WARPS * 32;
+    const bool cnt = opt.count_traversal != 0;
+    if (mesh) {
+      if (cnt)
+        k_visibility_fused<FU_OCC_MESH, true><<<nb, nt, 0, st>>>(fa);
+      else
+        k_visibility_fused<FU_OCC_MESH, false><<<nb, nt, 0, st>>>(fa);
+    } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
+      k_visibility_fused<FU_OCC_ANALYTIC, false><<<nb, nt, 0, st>>>(fa);
+    } else {
+      k_visibility_fused<FU_OCC_NONE, false><<<nb, nt, 0, st>>>(fa);
+    }
+    C2B_KERNEL_CHECK();
+  }
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
+
+  // visible counts -> CSR offsets
+  k_max_u32<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(fa.vis_count, C, d_max);
+  C2B_KERNEL_CHECK();
+  C2B_TRY(exclusive_scan_u32(st, fa.vis_count, ctx->seg_off.as<uint32_t>(), C + 1, d_total, ctx->scan_tmp));
+  C2B_TRY(read_counters(ctx, h_cnt));
+  if (h_cnt[5]) return set_error(C2B_ERR_CUDA, "internal: a camera's scratch slice overflowed");
+  uint32_t total32, max32;
+  memcpy(&total32, reinterpret_cast<const char *>(h_cnt) + 48, 4);
+  memcpy(&max32, reinterpret_cast<const char *>(h_cnt) + 52, 4);
+  total_obs = total32;
+  n_cand = h_cnt[4];
+  nodes = h_cnt[2];
+  tris_t = h_cnt[3];
+  if (total_obs) {
+    C2B_TRY(ctx->out_idx[sel].ensure(total_obs * 8));
+    C2B_TRY(ctx->out_uv[sel].ensure(total_obs * 16));
+    SortWriteArgs sw{fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, fa.cams, ctx->pts_aos.as<double>(),
+                     ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint64_t>(), ctx->out_uv[sel].as<double2>()};
+    if (max32 <= SW_BLOCK_MAX) {
+      k_sort_write<<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+      C2B_KERNEL_CHECK();
+      if (max32 > SW_WARP_MAX) {
+        k_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);
+        C2B_KERNEL_CHECK();
+      }
+    } else {
+      // a camera sees more points than the shared-memory sort holds: radix-sort all visible keys
+      C2B_TRY(ctx->sort_keys[0].ensure(total_obs * 8));
+      C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));
+      C2B_TRY(ctx->sort_vals[1].ensure(total_obs * 4));
+      k_expand_keys<<<blocks_for(C, 8), 256, 0, st>>>(fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, pbits,
+                                                      ctx->sort_keys[0].as<uint64_t>());
+      C2B_KERNEL_CHECK();
+      uint64_t *keys[2] = {ctx->sort_keys[0].as<uint64_t>(), ctx->out_idx[sel].as<uint64_t>()};
+      uint32_t *vals[2] = {ctx->sort_vals[0].as<uint32_t>(), ctx->sort_vals[1].as<uint32_t>()};
+      int res = 0;
+      C2B_TRY(radix_sort_pairs(st, keys, vals, total_obs, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
+      k_write_sorted<<<blocks_for(total_obs, 256), 256, 0, st>>>(keys[res], total_obs, pbits, fa.cams,
+                                                                ctx->pts_aos.as<double>(), ctx->out_idx[sel].as<uint64_t>(),
+                                                                ctx->out_uv[sel].as<double2>());
+      C2B_KERNEL_CHECK();
+      k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C + 1,
+                                                             ctx->out_offsets[sel].as<uint64_t>());
+      C2B_KERNEL_CHECK();
+    }
+  } else {
+    C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[sel].p, 0, (C + 1) * 8, st));
+  }
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
+  C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  ctx->out_C = C;
+  ctx->out_O = total_obs;
+  x->have_result = true;
+  x->res_candidates = n_cand;
+  fill_stats(ctx, stats, C, n_cand, pairs_eval, nodes, tris_t);
+  return C2B_OK;
+}
+
+}  // namespace
+
 int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
                                   const c2b_vis_options *opt_in, c2b_obs *stats) {
   if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph_resident: null ctx");
@@ -416,20 +623,15 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
   const int pbits = std::max(1, bit_length(P ? P - 1 : 0));
   const int cbits = std::max(1, bit_length(C ? C - 1 : 0));
   if (pbits + cbits > 63) return set_error(C2B_ERR_INVALID, "camera x point index space exceeds 63 bits");
+  if (opt.cull_mode == C2B_CULL_GRID) return visibility_grid_fused(ctx, x, scene, max_dist, opt, pbits, cbits, stats);
 
+  // ---- exhaustive schedule: every pair -> pool -> radix sort -> ordered traversal -> stream compaction --
   C2B_TRY(ctx->counters.ensure(64));
   C2B_TRY(ctx->cam_count.ensure((C + 1) * 4));
   C2B_TRY(ctx->out_offsets[ctx->out_sel].ensure((C + 1) * 8));
-
-  uint64_t n_cand = 0, pairs_eval = 0, pool_n = 0;
-  const bool use_grid = opt.cull_mode == C2B_CULL_GRID;
-  if (C && P) {
-    if (use_grid && !(x->grid.valid && x->grid.max_dist == max_dist &&
-                      x->grid.points_version == x->points_version))
-      C2B_TRY(build_grid(ctx, x, max_dist));
-  }
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
 
+  uint64_t n_cand = 0, pairs_eval = 0, pool_n = 0;
   if (C && P) {
     CullArgs a;
     a.cams = ctx->cams.as<double>();
@@ -444,15 +646,9 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     a.pbits = pbits;
     a.cam_count = ctx->cam_count.as<uint32_t>();
     a.counters = ctx->counters.as<unsigned long long>();
-    if (use_grid) {
-      a.px = ctx->grid_x.as<double>();
-      a.py = ctx->grid_y.as<double>();
-      a.pz = ctx->grid_z.as<double>();
-    } else {
-      a.px = ctx->pts.as<double>();
-      a.py = a.px + P;
-      a.pz = a.py + P;
-    }
+    a.px = ctx->pts.as<double>();
+    a.py = a.px + P;
+    a.pz = a.py + P;
     if (ctx->pool_capacity == 0) {
       long double pairs = (long double)C * (long double)P;
       uint64_t guess = std::max<uint64_t>(1u << 20, 96 * C);
@@ -462,26 +658,21 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     for (int attempt = 0;; ++attempt) {
       // the pool's key array doubles as buffer 0 of the radix sort
       C2B_TRY(ctx->sort_keys[0].ensure(ctx->pool_capacity * 8));
-      if (!use_grid) C2B_TRY(ctx->pool_uv.ensure(ctx->pool_capacity * 16));
+      C2B_TRY(ctx->pool_uv.ensure(ctx->pool_capacity * 16));
       a.pool_key = ctx->sort_keys[0].as<uint64_t>();
-      a.pool_uv = use_grid ? nullptr : ctx->pool_uv.as<double2>();
+      a.pool_uv = ctx->pool_uv.as<double2>();
       a.pool_capacity = ctx->pool_capacity;
       C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
       C2B_CUDA(cudaMemsetAsync(ctx->cam_count.p, 0, (C + 1) * 4, st));
-      if (use_grid) {
-        k_cull_grid<<<blocks_for(C, CG_WARPS), CG_WARPS * 32, 0, st>>>(
-            a, x->grid.desc, max_dist, ctx->cell_start.as<uint32_t>(), ctx->grid_idx.as<uint32_t>());
-      } else {
-        dim3 grid(blocks_for(P, CB_THREADS * CB_PPT), blocks_for(C, CB_TC));
-        if (grid.y > 65535u) return set_error(C2B_ERR_INVALID, "too many cameras for one exhaustive launch");
-        k_cull_exhaustive<<<grid, CB_THREADS, 0, st>>>(a);
-      }
+      dim3 grid(blocks_for(P, CB_THREADS * CB_PPT), blocks_for(C, CB_TC));
+      if (grid.y > 65535u) return set_error(C2B_ERR_INVALID, "too many cameras for one exhaustive launch");
+      k_cull_exhaustive<<<grid, CB_THREADS, 0, st>>>(a);
       C2B_KERNEL_CHECK();
       unsigned long long h_cnt[8];
       C2B_TRY(read_counters(ctx, h_cnt));
       pool_n = h_cnt[0];
-      n_cand = use_grid ? h_cnt[4] : h_cnt[0];
-      pairs_eval = use_grid ? h_cnt[1] : C * P;
+      n_cand = h_cnt[0];
+      pairs_eval = C * P;
       if (pool_n <= ctx->pool_capacity) break;
       if (attempt >= 2) return set_error(C2B_ERR_CUDA, "candidate pool overflow persisted");
       ctx->pool_capacity = pool_n + pool_n / 16 + 1024;  // exact count is known now: re-run once
@@ -496,16 +687,10 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
 
   const double *cxp = ctx->cam_center.as<double>();
   const double *pxp = ctx->pts.as<double>();
-  float scene_absmax = 0.0f;
-  if (scene)
-    for (int k = 0; k < 3; ++k)
-      scene_absmax = std::max(scene_absmax, std::max(std::fabs(scene->lo[k]), std::fabs(scene->hi[k])));
-  if (!std::isfinite(scene_absmax)) scene_absmax = 3.0e38f;
+  const float scene_absmax = scene_abs_max(scene);
 
-  // occlusion of `n` keys (sorted candidates, or the chunked pool) -> one ballot word per 32 keys
-  uint32_t trilist_cap = 128;
-  if (const char *e = getenv("C2B_TRILIST_CAP")) trilist_cap = (uint32_t)std::max(0, atoi(e));
-  auto run_occlusion = [&](const uint64_t *keys_in, uint64_t n, uint64_t n_words, bool chunked) -> int {
+  // occlusion of `n` sorted candidate keys -> one ballot word per 32 keys
+  auto run_occlusion = [&](const uint64_t *keys_in, uint64_t n, uint64_t n_words) -> int {
     if (!n) return C2B_OK;
     if (opt.occlusion == C2B_OCC_MESH && scene->n_nodes > 0) {
       TraverseArgs t;
@@ -523,28 +708,10 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       t.endpoint_guard_rel = opt.endpoint_guard_rel;
       t.vis_words = ctx->vis_words.as<uint32_t>();
       t.counters = ctx->counters.as<unsigned long long>();
-      if (chunked && trilist_cap > 0) {
-        // per-camera triangle lists (one stackless walk per camera), then list-driven packets
-        C2B_TRY(ctx->tri_list.ensure((size_t)C * trilist_cap * 4));
-        C2B_TRY(ctx->tri_count.ensure(C * 4));
-        float rmax = (float)max_dist;
-        if ((double)rmax < max_dist) rmax = std::nextafter(rmax, INFINITY);
-        rmax = rmax * (1.0f + 4e-6f);
-        k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(t.nodes, t.n_nodes, t.cen_x, t.cen_y, t.cen_z, C,
-                                                         rmax, scene_absmax, trilist_cap,
-                                                         ctx->tri_list.as<uint32_t>(),
-                                                         ctx->tri_count.as<uint32_t>());
-        C2B_KERNEL_CHECK();
-        TriListArgs tl{ctx->tri_list.as<uint32_t>(), ctx->tri_count.as<uint32_t>(), trilist_cap};
-        if (opt.count_traversal)
-          k_traverse_lists<true><<<blocks_for(n_words, 8), 256, 0, st>>>(t, tl);
-        else
-          k_traverse_lists<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t, tl);
-      } else if (opt.count_traversal) {
+      if (opt.count_traversal)
         k_traverse<true><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
-      } else {
+      else
         k_traverse<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
-      }
     } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
       k_analytic_occlusion<<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
           keys_in, n, pbits, cxp, cxp + C, cxp + 2 * C, pxp, pxp + P, pxp + 2 * P, opt.block_length,
@@ -557,83 +724,9 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
   };
 
   uint32_t *d_total = ctx->counters.as<uint32_t>() + 12;  // bytes 48..51 of the counter block
-  uint32_t *d_max = ctx->counters.as<uint32_t>() + 13;    // bytes 52..55
   uint64_t total_obs = 0;
   unsigned long long h_fin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-  if (use_grid) {
-    // ---- segmented path: traverse the chunked pool in place, then group + sort per camera -----------
-    C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
-    const uint64_t n_words = pool_n / 32;
-    C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
-    const uint64_t *pool_key = ctx->sort_keys[0].as<uint64_t>();
-    C2B_TRY(run_occlusion(pool_key, pool_n, n_words, true));
-    C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
-
-    C2B_TRY(ctx->word_prefix.ensure((C + 1) * 4));  // per-camera segment offsets (u32)
-    uint32_t *vis_count = ctx->cam_count.as<uint32_t>();  // zeroed before the cull
-    uint32_t *seg_off = ctx->word_prefix.as<uint32_t>();
-    C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
-    if (n_words) {
-      k_count_visible<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
-                                                              pool_key, pbits, vis_count);
-      C2B_KERNEL_CHECK();
-      k_max_u32<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(vis_count, C, d_max);
-      C2B_KERNEL_CHECK();
-    }
-    C2B_TRY(exclusive_scan_u32(st, vis_count, seg_off, C + 1, d_total, ctx->scan_tmp));
-    C2B_TRY(read_counters(ctx, h_fin));
-    uint32_t total32, max32;
-    memcpy(&total32, reinterpret_cast<const char *>(h_fin) + 48, 4);
-    memcpy(&max32, reinterpret_cast<const char *>(h_fin) + 52, 4);
-    total_obs = total32;
-    if (total_obs) {
-      C2B_TRY(ctx->out_idx[ctx->out_sel].ensure(total_obs * 8));
-      C2B_TRY(ctx->out_uv[ctx->out_sel].ensure(total_obs * 16));
-      C2B_CUDA(cudaMemsetAsync(vis_count, 0, (C + 1) * 4, st));  // reused as the per-camera cursor
-      if (max32 <= SEG_BLOCK_MAX) {
-        C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));  // seg_pt
-        uint32_t *seg_pt = ctx->sort_vals[0].as<uint32_t>();
-        k_scatter_visible<false><<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
-            ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, seg_pt, nullptr);
-        C2B_KERNEL_CHECK();
-        SegWriteArgs sw{seg_off, C, seg_pt, ctx->cams.as<double>(), ctx->pts_aos.as<double>(),
-                        ctx->out_offsets[ctx->out_sel].as<uint64_t>(), ctx->out_idx[ctx->out_sel].as<uint64_t>(),
-                        ctx->out_uv[ctx->out_sel].as<double2>()};
-        k_seg_sort_write_warp<<<blocks_for(C, 4), 128, 0, st>>>(sw);
-        C2B_KERNEL_CHECK();
-        if (max32 > SEG_WARP_MAX) {
-          k_seg_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);
-          C2B_KERNEL_CHECK();
-        }
-      } else {
-        // a camera sees more points than the shared-memory sort holds: radix-sort all visible keys
-        C2B_TRY(ctx->sort_keys[1].ensure(total_obs * 8));
-        C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));
-        C2B_TRY(ctx->sort_vals[1].ensure(total_obs * 4));
-        uint64_t *seg_key = ctx->sort_keys[1].as<uint64_t>();
-        k_scatter_visible<true><<<blocks_for(n_words * 32, 256), 256, 0, st>>>(
-            ctx->vis_words.as<uint32_t>(), n_words, pool_key, pbits, seg_off, vis_count, nullptr, seg_key);
-        C2B_KERNEL_CHECK();
-        uint64_t *keys[2] = {seg_key, ctx->out_idx[ctx->out_sel].as<uint64_t>()};
-        uint32_t *vals[2] = {ctx->sort_vals[0].as<uint32_t>(), ctx->sort_vals[1].as<uint32_t>()};
-        int res = 0;
-        C2B_TRY(radix_sort_pairs(st, keys, vals, total_obs, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
-        k_write_sorted<<<blocks_for(total_obs, 256), 256, 0, st>>>(
-            keys[res], total_obs, pbits, ctx->cams.as<double>(), ctx->pts_aos.as<double>(),
-            ctx->out_idx[ctx->out_sel].as<uint64_t>(), ctx->out_uv[ctx->out_sel].as<double2>());
-        C2B_KERNEL_CHECK();
-        k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(seg_off, C + 1, ctx->out_offsets[ctx->out_sel].as<uint64_t>());
-        C2B_KERNEL_CHECK();
-      }
-    } else {
-      C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[ctx->out_sel].p, 0, (C + 1) * 8, st));
-    }
-    C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
-    C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
-    C2B_CUDA(cudaStreamSynchronize(st));
-  } else {
-    // ---- ordered path: radix sort all candidates, traverse in order, stream-compact ------------------
+  {
     C2B_TRY(exclusive_scan_u32(st, ctx->cam_count.as<uint32_t>(), ctx->cam_count.as<uint32_t>(), C + 1,
                                nullptr, ctx->scan_tmp));
     int res = 0;
@@ -656,7 +749,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     const uint64_t n_words = (n_cand + 31) / 32;
     C2B_TRY(ctx->vis_words.ensure((n_words + 1) * 4));
     C2B_TRY(ctx->word_prefix.ensure((n_words + 1) * 4));
-    C2B_TRY(run_occlusion(keys[res], n_cand, n_words, false));
+    C2B_TRY(run_occlusion(keys[res], n_cand, n_words));
     C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
 
     C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
@@ -685,32 +778,11 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
     memcpy(&total32, reinterpret_cast<const char *>(h_fin) + 48, 4);
     total_obs = total32;
   }
-  const unsigned long long *h_cnt = h_fin;
   ctx->out_C = C;
   ctx->out_O = total_obs;
   x->have_result = true;
   x->res_candidates = n_cand;
-
-  if (stats) {
-    memset(stats, 0, sizeof *stats);
-    stats->n_cameras = C;
-    stats->n_obs = ctx->out_O;
-    stats->n_candidates = n_cand;
-    stats->pairs_evaluated = pairs_eval;
-    stats->nodes_visited = h_cnt[2];
-    stats->tris_tested = h_cnt[3];
-    auto ms = [&](int a, int b) {
-      float t = 0;
-      cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
-      return t;
-    };
-    stats->ms_prep = ms(EV_H2D, EV_PREP);
-    stats->ms_cull = ms(EV_PREP, EV_CULL);
-    stats->ms_sort = ms(EV_CULL, EV_SORT);
-    stats->ms_traverse = ms(EV_SORT, EV_TRAVERSE);
-    stats->ms_compact = ms(EV_TRAVERSE, EV_COMPACT);
-    stats->ms_total = ms(EV_START, EV_D2H);
-  }
+  fill_stats(ctx, stats, C, n_cand, pairs_eval, h_fin[2], h_fin[3]);
   return C2B_OK;
 }
 

@@ -183,6 +183,8 @@ struct c2b_ctx {
   cudaEvent_t ev_ready[2] = {}, ev_copied[2] = {};
   c2b::DevBuf misc;  // small scratch (reductions)
   c2b::DevBuf tri_list, tri_count;  // per-camera leaf lists for list-driven traversal
+  // fused grid schedule: per-camera plan (row points -> scratch slice), visible counts, CSR offsets
+  c2b::DevBuf ev_off, vis_count, seg_off, scratch_idx;
 
   // host results
   c2b::PinBuf h_offsets, h_idx, h_uv, h_small;

@@ -62,24 +62,7 @@ __global__ void k_words_all_visible(const uint64_t *__restrict__ keys, uint32_t 
   if ((threadIdx.x & 31) == 0) words[i >> 5] = m;
 }
 
-// ---- segmented path (grid schedule) ---------------------------------------------------------------
-// The pool is a sequence of 32-slot chunks, each owned by one camera (k_cull_grid), traversed in
-// place.  Visible candidates are counted per camera, scanned into CSR offsets, scattered into their
-// camera's segment (arbitrary order inside the segment), and each segment is then sorted by point
-// index in shared memory (bitonic network) while the final (index, u, v) records are written.
-
-// one thread per visibility word: vis_count[camera of the chunk] += popc(word)
-__global__ void k_count_visible(const uint32_t *__restrict__ words, uint64_t n_words,
-                                const uint64_t *__restrict__ pool_key, int pbits,
-                                uint32_t *__restrict__ vis_count) {
-  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= n_words) return;
-  uint32_t word = words[w];
-  if (!word) return;
-  uint64_t key = pool_key[32 * w + (__ffs(word) - 1)];
-  atomicAdd(&vis_count[key >> pbits], (uint32_t)__popc(word));
-}
-
+// ---- helpers shared with the grid schedule (c2b_fused.cuh) ----------------------------------------
 __global__ void k_max_u32(const uint32_t *__restrict__ v, uint64_t n, uint32_t *__restrict__ out) {
   uint32_t m = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -90,38 +73,6 @@ __global__ void k_max_u32(const uint32_t *__restrict__ v, uint64_t n, uint32_t *
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-// one warp per chunk: reserve popc(word) slots in the camera's segment and write the point index
-// (WIDE: the whole 64-bit key, for the radix fallback)
-template <bool WIDE>
-__global__ void __launch_bounds__(256)
-    k_scatter_visible(const uint32_t *__restrict__ words, uint64_t n_words,
-                      const uint64_t *__restrict__ pool_key, int pbits,
-                      const uint32_t *__restrict__ seg_off, uint32_t *__restrict__ cursor,
-                      uint32_t *__restrict__ seg_pt, uint64_t *__restrict__ seg_key) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t w = i >> 5;
-  if (w >= n_words) return;
-  const int lane = threadIdx.x & 31;
-  const uint32_t word = words[w];
-  if (!word) return;
-  const bool vis = (word >> lane) & 1u;
-  const uint64_t key = vis ? pool_key[i] : 0ull;
-  const uint64_t key0 = __shfl_sync(0xffffffffu, key, __ffs(word) - 1);
-  uint32_t base = 0;
-  if (lane == 0) {
-    const uint64_t cam = key0 >> pbits;
-    base = seg_off[cam] + atomicAdd(&cursor[cam], (uint32_t)__popc(word));
-  }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (vis) {
-    const uint32_t pos = base + __popc(word & ((1u << lane) - 1u));
-    if (WIDE)
-      seg_key[pos] = key;
-    else
-      seg_pt[pos] = (uint32_t)(key & ((1ull << pbits) - 1ull));
-  }
-}
-
 // (u, v) of an observation, recomputed exactly as the cull kernel computed it
 __device__ __forceinline__ double2 observe(const double *cam, double x, double y, double z) {
   V3 pc = project_world(cam, V3{x, y, z});
@@ -130,136 +81,7 @@ __device__ __forceinline__ double2 observe(const double *cam, double x, double y
   return make_double2(u, v);
 }
 
-struct SegWriteArgs {
-  const uint32_t *seg_off;  // [C+1]
-  uint64_t C;
-  const uint32_t *seg_pt;   // scattered point indices, arbitrary order inside a segment
-  const double *cams;
-  const double *p_aos;  // xyz records, original point order
-  uint64_t *out_offsets;
-  uint64_t *out_idx;
-  double2 *out_uv;
-};
-
-// Bitonic network over E*32 keys held in registers, element index i = lane*E + r: partner distance
-// j < E is a register-to-register compare, j >= E one __shfl_xor per register.  No shared memory,
-// no barriers.
-template <int E>
-__device__ __forceinline__ void warp_bitonic_sort(uint32_t (&a)[E], int lane) {
-#pragma unroll
-  for (int k = 2; k <= E * 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= E) {
-        const int lj = j / E;
-        const bool up = k >= E * 32 ? true : ((lane & (k / E)) == 0);
-        const bool keep_min = ((lane & lj) == 0) == up;
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, a[r], lj);
-          a[r] = keep_min ? min(a[r], other) : max(a[r], other);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const int p = r ^ j;
-          if (p > r) {
-            // (i & k) with i = lane*E + r: a register property when k < E, a lane property otherwise
-            const bool up = k < E ? ((r & k) == 0) : (k >= E * 32 ? true : ((lane & (k / E)) == 0));
-            const uint32_t lo = min(a[r], a[p]), hi = max(a[r], a[p]);
-            a[r] = up ? lo : hi;
-            a[p] = up ? hi : lo;
-          }
-        }
-      }
-    }
-  }
-}
-
-template <int E>
-__device__ __forceinline__ void seg_sort_write_warp(const SegWriteArgs &s, uint64_t cam, uint32_t base,
-                                                    uint32_t n, int lane) {
-  uint32_t a[E];
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    const uint32_t t = r * 32 + lane;  // coalesced load; any starting permutation sorts
-    a[r] = t < n ? s.seg_pt[base + t] : 0xffffffffu;
-  }
-  warp_bitonic_sort<E>(a, lane);
-  double c[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    const uint32_t i = lane * E + r;
-    if (i < n) {
-      const uint32_t pt = a[r];
-      s.out_idx[base + i] = pt;
-      s.out_uv[base + i] = observe(c, s.p_aos[3 * (uint64_t)pt], s.p_aos[3 * (uint64_t)pt + 1], s.p_aos[3 * (uint64_t)pt + 2]);
-    }
-  }
-}
-
-constexpr uint32_t SEG_WARP_MAX = 1024;   // register sort, one warp per camera
-constexpr uint32_t SEG_BLOCK_MAX = 4096;  // shared-memory sort, one block per camera
-
-__global__ void __launch_bounds__(128) k_seg_sort_write_warp(SegWriteArgs s) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t cam = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (cam >= s.C) return;
-  const uint32_t base = s.seg_off[cam], n = s.seg_off[cam + 1] - base;
-  if (lane == 0) {
-    s.out_offsets[cam] = base;
-    if (cam == s.C - 1) s.out_offsets[s.C] = s.seg_off[s.C];
-  }
-  if (n == 0 || n > SEG_WARP_MAX) return;
-  if (n <= 128)
-    seg_sort_write_warp<4>(s, cam, base, n, lane);
-  else if (n <= 256)
-    seg_sort_write_warp<8>(s, cam, base, n, lane);
-  else if (n <= 512)
-    seg_sort_write_warp<16>(s, cam, base, n, lane);
-  else
-    seg_sort_write_warp<32>(s, cam, base, n, lane);
-}
-
-// cameras with SEG_WARP_MAX < n <= SEG_BLOCK_MAX: bitonic network in shared memory, one block each
-__global__ void __launch_bounds__(256) k_seg_sort_write_block(SegWriteArgs s) {
-  __shared__ uint32_t s_sort[SEG_BLOCK_MAX];
-  const uint64_t cam = blockIdx.x;
-  const uint32_t base = s.seg_off[cam], n = s.seg_off[cam + 1] - base;
-  if (n <= SEG_WARP_MAX || n > SEG_BLOCK_MAX) return;
-  uint32_t n2 = 2;
-  while (n2 < n) n2 <<= 1;
-  for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) s_sort[t] = t < n ? s.seg_pt[base + t] : 0xffffffffu;
-  __syncthreads();
-  for (uint32_t k = 2; k <= n2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) {
-        const uint32_t p = t ^ j;
-        if (p > t) {
-          const uint32_t x = s_sort[t], y = s_sort[p];
-          const bool up = (t & k) == 0;
-          if ((x > y) == up) {
-            s_sort[t] = y;
-            s_sort[p] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  double c[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
-  for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
-    const uint32_t pt = s_sort[t];
-    s.out_idx[base + t] = pt;
-    s.out_uv[base + t] = observe(c, s.p_aos[3 * (uint64_t)pt], s.p_aos[3 * (uint64_t)pt + 1], s.p_aos[3 * (uint64_t)pt + 2]);
-  }
-}
-
-// fallback for segments longer than SEG_BLOCK_MAX: the scattered 64-bit keys were radix-sorted
+// fallback for cameras that see more points than the shared-memory sort holds (SW_BLOCK_MAX): the scattered 64-bit keys were radix-sorted
 // globally; split each key and recompute (u, v)
 __global__ void k_write_sorted(const uint64_t *keys, uint64_t n, int pbits, const double *__restrict__ cams,
                                const double *__restrict__ p_aos, uint64_t *out_idx,

@@ -2,14 +2,16 @@
 // SnavelyCamera projection (src/generate.rs:446-454, src/baproblem.rs:141-151).
 //
 // Two schedules produce the SAME candidate set (the exact f64 predicate always decides):
-//   exhaustive : every pair, like the reference loop.  Camera tile in shared memory, 4 points
-//                per thread in registers, a conservative 7-op FMA distance reject in the hot
-//                loop; survivors are queued per warp and re-tested densely with the exact
-//                predicate (so the rare expensive path does not diverge the hot loop).
-//   grid       : points binned into a uniform grid (cell = max_dist/4); one warp per camera
-//                scans the x-contiguous cell rows its max_dist ball touches.
-// Candidates go to an unordered pool as (key = camera << pbits | point, u, v); the pool is then
-// radix-sorted by key, which yields camera-major, ascending-point order (src/generate.rs:446).
+//   exhaustive : every pair, like the reference loop (this file).  Camera tile in shared memory,
+//                4 points per thread in registers, a conservative 7-op FMA distance reject in the
+//                hot loop; survivors are queued per warp and re-tested densely with the exact
+//                predicate (so the rare expensive path does not diverge the hot loop).  Candidates
+//                go to an unordered pool as (key = camera << pbits | point, u, v); the pool is then
+//                radix-sorted by key, which yields camera-major, ascending-point order
+//                (src/generate.rs:446).
+//   grid       : points binned into a uniform grid (cell = max_dist/4, built here); one warp per
+//                camera scans the x-contiguous cell rows its max_dist ball touches and resolves
+//                occlusion in the same pass (c2b_fused.cuh).
 #pragma once
 #include "c2b_common.cuh"
 #include "c2b_math.cuh"
@@ -212,131 +214,6 @@ __global__ void k_grid_fill(const double *__restrict__ px, const double *__restr
   gy[pos] = py[i];
   gz[pos] = pz[i];
   gidx[pos] = (uint32_t)i;
-}
-
-// One warp per camera.  Survivors are staged per warp in shared memory and written to the pool
-// in 32-ALIGNED chunks that belong to one camera each (the tail chunk of a camera is padded with
-// POOL_SENTINEL), so that a traversal warp reading 32 consecutive pool slots gets rays that share
-// one origin and are neighbours in the grid scan order (coherent packets), and the stores are
-// full 256 B / 512 B lines.
-constexpr int CG_WARPS = 8;
-constexpr int CG_STAGE = 64;
-
-// (u, v) are not stored on this path: the final write recomputes them from (camera, point) with
-// the same device function, which is bit-identical and saves 16 of 24 bytes per candidate.
-__device__ __forceinline__ void grid_flush32(const CullArgs &a, const uint64_t *sk, int count, int lane) {
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(&a.counters[0], 32ull);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (base + 32 <= a.pool_capacity) a.pool_key[base + lane] = lane < count ? sk[lane] : POOL_SENTINEL;
-}
-
-__global__ void __launch_bounds__(CG_WARPS * 32, 4) k_cull_grid(CullArgs a, GridDesc g, double max_dist,
-                                                             const uint32_t *__restrict__ cell_start,
-                                                             const uint32_t *__restrict__ gidx) {
-  __shared__ uint64_t s_key[CG_WARPS][CG_STAGE];
-  __shared__ double s_cam[CG_WARPS][16];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint64_t cam = (uint64_t)blockIdx.x * CG_WARPS + warp;
-  if (cam >= a.C) return;
-  uint64_t *sk = s_key[warp];
-  // the camera record lives in shared memory (broadcast reads) to keep registers for occupancy
-  double *c = s_cam[warp];
-  if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
-  __syncwarp();
-  V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
-  const double cc[3] = {cen.x, cen.y, cen.z};
-  int lo[3], hi[3];
-  bool empty = !(max_dist > 0.0);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    // every point with |p - c| < max_dist has c_k - r - eps < p_k < c_k + r + eps, and grid_coord is
-    // monotone, so [coord(a0), coord(a1)] holds its cell; eps covers the rounding of a0 / a1
-    const double eps = 1e-9 * (fabs(cc[k]) + fabs(max_dist)) + 1e-300;
-    const double a0 = cc[k] - max_dist - eps, a1 = cc[k] + max_dist + eps;
-    if (a0 > g.max_c[k] || a1 < g.min_c[k]) empty = true;  // ball misses the populated slab
-    lo[k] = grid_coord(g, k, a0);
-    hi[k] = grid_coord(g, k, a1);
-  }
-  if (!(cen.x == cen.x && cen.y == cen.y && cen.z == cen.z)) empty = true;  // NaN centre sees nothing
-  if (empty) return;
-  // "in front of the camera" is pc.z = r2x*x + r2y*y + r2z*z + tz <= 0 (src/generate.rs:450): linear
-  // in x along a row of cells, so each row is trimmed to the x-range that can hold such a point
-  const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
-  const double cell_h = 1.0 / g.inv_h;
-  unsigned long long evaluated = 0, found = 0;
-  int qn = 0;  // warp-uniform number of staged candidates
-  for (int z = lo[2]; z <= hi[2]; ++z)
-    for (int y = lo[1]; y <= hi[1]; ++y) {
-      int x0 = lo[0], x1 = hi[0];
-      {
-        // bounds of the row's cells in y and z; edge cells also hold the clamped coordinates, so
-        // they extend to the data bounds
-        const double sl = 1e-6 * cell_h;
-        const double y0 = y == 0 ? g.min_c[1] : g.lo[1] + y * cell_h - sl;
-        const double y1 = y == g.n[1] - 1 ? g.max_c[1] : g.lo[1] + (y + 1) * cell_h + sl;
-        const double z0 = z == 0 ? g.min_c[2] : g.lo[2] + z * cell_h - sl;
-        const double z1 = z == g.n[2] - 1 ? g.max_c[2] : g.lo[2] + (z + 1) * cell_h + sl;
-        // smallest value r2y*y + r2z*z + tz can take on the row (0 * inf is avoided explicitly)
-        const double my = r2y == 0.0 ? 0.0 : r2y * (r2y > 0.0 ? y0 : y1);
-        const double mz = r2z == 0.0 ? 0.0 : r2z * (r2z > 0.0 ? z0 : z1);
-        const double bmin = my + mz + tz;
-        const double mag = fabs(my) + fabs(mz) + fabs(tz) + fabs(r2x) * (fabs(cc[0]) + fabs(max_dist));
-        if (bmin == bmin && fabs(bmin) < INFINITY) {
-          const double slack = 1e-9 * mag + 1e-300;
-          if (fabs(r2x) * (fabs(cc[0]) + fabs(max_dist)) <= slack) {
-            if (bmin > 2.0 * slack) continue;  // the whole row is behind the camera
-          } else {
-            const double xlim = (-(bmin - slack)) / r2x;  // r2x*x <= -(bmin - slack)
-            if (xlim == xlim) {
-              if (r2x > 0.0) {
-                const int xc = grid_coord(g, 0, xlim + 1e-9 * (fabs(xlim) + cell_h)) ;
-                if (xlim + 1e-9 * (fabs(xlim) + cell_h) < g.lo[0]) continue;  // nothing in front on this row
-                x1 = xc < x1 ? xc : x1;
-              } else {
-                const int xc = grid_coord(g, 0, xlim - 1e-9 * (fabs(xlim) + cell_h));
-                if (xlim - 1e-9 * (fabs(xlim) + cell_h) > g.max_c[0]) continue;
-                x0 = xc > x0 ? xc : x0;
-              }
-              if (x0 > x1) continue;
-            }
-          }
-        }
-      }
-      uint32_t row = ((uint32_t)z * g.n[1] + y) * g.n[0];
-      uint32_t start = cell_start[row + x0], end = cell_start[row + x1 + 1];
-      evaluated += end - start;
-      for (uint32_t base = start; base < end; base += 32) {
-        uint32_t i = base + lane;
-        bool pass = false;
-        double u = 0, v = 0;
-        if (i < end) {
-          V3 p{a.px[i], a.py[i], a.pz[i]};
-          pass = cull_project_thr(c, cen, p, a.t_star, u, v);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m == 0u) continue;
-        if (pass) sk[qn + __popc(m & ((1u << lane) - 1u))] = (cam << a.pbits) | (uint64_t)gidx[i];
-        qn += __popc(m);
-        found += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-          grid_flush32(a, sk, 32, lane);
-          const int rem = qn - 32;
-          uint64_t tk = 0;
-          if (lane < rem) tk = sk[32 + lane];
-          __syncwarp();
-          if (lane < rem) sk[lane] = tk;
-          __syncwarp();
-          qn = rem;
-        }
-      }
-    }
-  if (qn > 0) grid_flush32(a, sk, qn, lane);
-  if (lane == 0) {
-    atomicAdd(&a.counters[1], evaluated);
-    atomicAdd(&a.counters[4], found);
-  }
 }
 
 // min / max of point coordinates (two-stage, deterministic): out[0..2] = min, out[3..5] = max

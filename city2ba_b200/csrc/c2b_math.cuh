@@ -213,81 +213,86 @@ C2B_HD Ray make_ray(V3 c, V3 p, bool endpoint_guard_rel) {
   return r;
 }
 
-// ---- watertight ray/triangle test (Woop, Benthin, Wald 2013), hit interval 0 < t <= tfar -------
-struct Shear {
-  int kz;     // dominant axis of the direction
-  bool swap;  // dir[kz] < 0: kx and ky trade places (keeps the winding)
-  float Sx, Sy, Sz;
+// ---- watertight ray/triangle test, hit interval 0 < t <= tfar ------------------------------------
+// Edge functions in the form of Embree's robust ("Pluecker") triangle intersector: with the
+// ORIGIN-RELATIVE vertices A = v0 - o, B = v1 - o, C = v2 - o and the edges e0 = C - A,
+// e1 = A - B, e2 = B - C,
+//     U = d . (e0 x (C + A)),  V = d . (e1 x (A + B)),  W = d . (e2 x (B + C)),
+//     det = U + V + W  (= 2 d.N),   T = 2 A.N  with  N = e0 x e1,   t = T / det.
+// e x (sum) equals twice the plain cross product of the two vertices but keeps the error
+// proportional to the EDGE length, so small triangles far from the origin stay accurate.
+// The three edge normals and T depend on (origin, triangle) only: for the rays of one camera they
+// are computed once per triangle (TriRec) and a ray test is 9 FMA and a few compares.
+// Watertight: differences and sums are exactly anti-/symmetric in their operands and the cross
+// products are evaluated unfused (p1 - p2), so the two triangles sharing an edge get edge normals
+// that are exact negatives of each other, hence edge-function values of equal magnitude and
+// opposite sign; a zero counts as inside for both.  No back-face culling.  NaN anywhere => no hit.
+struct TriRec {
+  float ux, uy, uz;  // e0 x (C + A)
+  float vx, vy, vz;  // e1 x (A + B)
+  float wx, wy, wz;  // e2 x (B + C)
+  float T;           // 2 A . (e0 x e1)
 };
 
-C2B_HD float sel3(int k, float a, float b, float c) { return k == 0 ? a : (k == 1 ? b : c); }
+#if defined(__CUDA_ARCH__)
+C2B_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
+C2B_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+#endif
 
-C2B_HD Shear ray_shear(const Ray &r) {
-  Shear s;
-  int kz = 0;
-  float m = fabsf(r.dx);
-  if (fabsf(r.dy) > m) {
-    kz = 1;
-    m = fabsf(r.dy);
-  }
-  if (fabsf(r.dz) > m) kz = 2;
-  // kx = (kz+1)%3, ky = (kx+1)%3, swapped when the dominant component is negative
-  const float dz = sel3(kz, r.dx, r.dy, r.dz);
-  float dkx = sel3(kz, r.dy, r.dz, r.dx);
-  float dky = sel3(kz, r.dz, r.dx, r.dy);
-  s.kz = kz;
-  s.swap = dz < 0.0f;
-  if (s.swap) {
-    const float t = dkx;
-    dkx = dky;
-    dky = t;
-  }
-  s.Sx = fdiv(dkx, dz);
-  s.Sy = fdiv(dky, dz);
-  s.Sz = fdiv(1.0f, dz);
-  return s;
+C2B_HD float dot3f(float ax, float ay, float az, float bx, float by, float bz) {
+  return ffma(az, bz, ffma(ay, by, fmul(ax, bx)));
 }
 
-// components (kx, ky, kz) of a translated vertex, as two rounds of selects (no branches)
-C2B_HD void permute(const Shear &s, float a0, float a1, float a2, float &x, float &y, float &z) {
-  const bool z0 = s.kz == 0, z1 = s.kz == 1;
-  const float rx = z0 ? a1 : (z1 ? a2 : a0);
-  const float ry = z0 ? a2 : (z1 ? a0 : a1);
-  z = z0 ? a0 : (z1 ? a1 : a2);
-  x = s.swap ? ry : rx;
-  y = s.swap ? rx : ry;
+C2B_HD TriRec tri_record(float ox, float oy, float oz, float v0x, float v0y, float v0z, float v1x,
+                         float v1y, float v1z, float v2x, float v2y, float v2z) {
+  const float Ax = fsub(v0x, ox), Ay = fsub(v0y, oy), Az = fsub(v0z, oz);
+  const float Bx = fsub(v1x, ox), By = fsub(v1y, oy), Bz = fsub(v1z, oz);
+  const float Cx = fsub(v2x, ox), Cy = fsub(v2y, oy), Cz = fsub(v2z, oz);
+  const float e0x = fsub(Cx, Ax), e0y = fsub(Cy, Ay), e0z = fsub(Cz, Az);
+  const float e1x = fsub(Ax, Bx), e1y = fsub(Ay, By), e1z = fsub(Az, Bz);
+  const float e2x = fsub(Bx, Cx), e2y = fsub(By, Cy), e2z = fsub(Bz, Cz);
+  const float sux = fadd(Cx, Ax), suy = fadd(Cy, Ay), suz = fadd(Cz, Az);
+  const float svx = fadd(Ax, Bx), svy = fadd(Ay, By), svz = fadd(Az, Bz);
+  const float swx = fadd(Bx, Cx), swy = fadd(By, Cy), swz = fadd(Bz, Cz);
+  TriRec t;
+  t.ux = fsub(fmul(e0y, suz), fmul(e0z, suy));
+  t.uy = fsub(fmul(e0z, sux), fmul(e0x, suz));
+  t.uz = fsub(fmul(e0x, suy), fmul(e0y, sux));
+  t.vx = fsub(fmul(e1y, svz), fmul(e1z, svy));
+  t.vy = fsub(fmul(e1z, svx), fmul(e1x, svz));
+  t.vz = fsub(fmul(e1x, svy), fmul(e1y, svx));
+  t.wx = fsub(fmul(e2y, swz), fmul(e2z, swy));
+  t.wy = fsub(fmul(e2z, swx), fmul(e2x, swz));
+  t.wz = fsub(fmul(e2x, swy), fmul(e2y, swx));
+  const float nx = fsub(fmul(e0y, e1z), fmul(e0z, e1y));
+  const float ny = fsub(fmul(e0z, e1x), fmul(e0x, e1z));
+  const float nz = fsub(fmul(e0x, e1y), fmul(e0y, e1x));
+  t.T = fmul(2.0f, dot3f(Ax, Ay, Az, nx, ny, nz));
+  return t;
 }
 
-// returns true when the triangle occludes the ray.  t_out (optional) receives T/det for the
-// closest-hit entry (c2b_intersect1); it is not part of the occlusion decision.
-C2B_HD bool ray_triangle(const Ray &r, const Shear &s, float v0x, float v0y, float v0z, float v1x,
-                         float v1y, float v1z, float v2x, float v2y, float v2z,
-                         float *t_out = nullptr) {
-  float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
-  permute(s, fsub(v0x, r.ox), fsub(v0y, r.oy), fsub(v0z, r.oz), Akx, Aky, Akz);
-  permute(s, fsub(v1x, r.ox), fsub(v1y, r.oy), fsub(v1z, r.oz), Bkx, Bky, Bkz);
-  permute(s, fsub(v2x, r.ox), fsub(v2y, r.oy), fsub(v2z, r.oz), Ckx, Cky, Ckz);
-  float Ax = fsub(Akx, fmul(s.Sx, Akz)), Ay = fsub(Aky, fmul(s.Sy, Akz));
-  float Bx = fsub(Bkx, fmul(s.Sx, Bkz)), By = fsub(Bky, fmul(s.Sy, Bkz));
-  float Cx = fsub(Ckx, fmul(s.Sx, Ckz)), Cy = fsub(Cky, fmul(s.Sy, Ckz));
-  float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
-  float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
-  float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
-  if (U == 0.0f || V == 0.0f || W == 0.0f) {
-    U = d2f(dsub(dmul((double)Cx, (double)By), dmul((double)Cy, (double)Bx)));
-    V = d2f(dsub(dmul((double)Ax, (double)Cy), dmul((double)Ay, (double)Cx)));
-    W = d2f(dsub(dmul((double)Bx, (double)Ay), dmul((double)By, (double)Ax)));
-  }
+// true when the triangle occludes the ray (dx, dy, dz, tfar) whose origin the record was built
+// for.  t_out (optional) receives t for the closest-hit entry (c2b_intersect1).
+C2B_HD bool ray_tri_record(float dx, float dy, float dz, float tfar, const TriRec &t,
+                           float *t_out = nullptr) {
+  const float U = dot3f(dx, dy, dz, t.ux, t.uy, t.uz);
+  const float V = dot3f(dx, dy, dz, t.vx, t.vy, t.vz);
+  const float W = dot3f(dx, dy, dz, t.wx, t.wy, t.wz);
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-  float det = fadd(fadd(U, V), W);
+  const float det = fadd(fadd(U, V), W);
   if (det == 0.0f) return false;
-  float Az = fmul(s.Sz, Akz), Bz = fmul(s.Sz, Bkz), Cz = fmul(s.Sz, Ckz);
-  float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
-  float ad = fabsf(det);
-  float Ts = det < 0.0f ? -T : T;
-  bool hit = Ts > 0.0f && Ts <= fmul(r.tfar, ad);
+  const float ad = fabsf(det);
+  const float Ts = det < 0.0f ? -t.T : t.T;
+  const bool hit = Ts > 0.0f && Ts <= fmul(tfar, ad);
   if (hit && t_out) *t_out = fdiv(Ts, ad);
   return hit;
+}
+
+C2B_HD bool ray_triangle(const Ray &r, float v0x, float v0y, float v0z, float v1x, float v1y,
+                         float v1z, float v2x, float v2y, float v2z, float *t_out = nullptr) {
+  const TriRec t = tri_record(r.ox, r.oy, r.oz, v0x, v0y, v0z, v1x, v1y, v1z, v2x, v2y, v2z);
+  return ray_tri_record(r.dx, r.dy, r.dz, r.tfar, t, t_out);
 }
 
 }  // namespace c2b

@@ -75,7 +75,6 @@ __device__ __forceinline__ bool warp_any_hit(const float4 *__restrict__ nodes,
                                              const float4 *__restrict__ tris, int n_nodes,
                                              const Ray &ray, bool alive, float scene_absmax,
                                              unsigned long long *counters) {
-  const Shear sh = ray_shear(ray);
   const BoxRay br = make_box_ray(ray, scene_absmax);
   // NaN / negative tfar can never satisfy 0 < t <= tfar; a NaN direction can never hit either
   alive = alive && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
@@ -100,7 +99,7 @@ __device__ __forceinline__ bool warp_any_hit(const float4 *__restrict__ nodes,
       const float4 v1 = __ldg(&tris[3 * leaf + 1]);
       const float4 v2 = __ldg(&tris[3 * leaf + 2]);
       if (COUNT) ++n_tri;
-      if (hit && ray_triangle(ray, sh, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)) {
+      if (hit && ray_triangle(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)) {
         occluded = true;
         alive = false;
       }
@@ -160,10 +159,11 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
 // them can hit lies in the cube [c - R, c + R]^3.  k_cam_trilist walks the tree once per camera
 // (one thread each, stackless) and records the leaves whose box overlaps that cube, up to `cap`
 // per camera (more => TRILIST_OVERFLOW, the camera's packets use the generic walk).  A packet then
-// needs no tree walk at all: lanes test 32 list entries at a time against the packet's bounding
-// box (lane = triangle), and only the surviving triangles are run through the watertight test
-// (lane = ray).  The result is identical: a triangle that a ray hits overlaps both the cube and the
-// packet box (both inflated by the same conservative pad as the slab test).
+// needs no tree walk at all (packet_any_hit, c2b_fused.cuh): lanes test 32 list entries at a time
+// against the packet's bounding box (lane = triangle), and only the surviving triangles are run
+// through the watertight test (lane = ray).  The result is identical: a triangle that a ray hits
+// overlaps both the cube and the packet box (both inflated by the same conservative pad as the
+// slab test).
 constexpr uint32_t TRILIST_OVERFLOW = 0xffffffffu;
 
 __device__ __forceinline__ float conservative_pad(float ox, float oy, float oz, float scene_absmax) {
@@ -202,108 +202,6 @@ __global__ void __launch_bounds__(128)
   count[cam] = n <= cap ? n : TRILIST_OVERFLOW;
 }
 
-struct TriListArgs {
-  const uint32_t *list;   // [C * cap] leaf node indices
-  const uint32_t *count;  // [C]
-  uint32_t cap;
-};
-
-// chunked pool only: the 32 slots of a warp belong to ONE camera (k_cull_grid)
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_traverse_lists(TraverseArgs a, TriListArgs tl) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const uint64_t i = w * 32 + lane;
-  if (w * 32 >= a.n_cand) return;
-  bool have = i < a.n_cand;
-  Ray ray;
-  ray.ox = ray.oy = ray.oz = 0.0f;
-  ray.dx = ray.dy = ray.dz = 1.0f;
-  ray.tfar = -1.0f;
-  const uint64_t key = have ? a.keys[i] : ~0ull;
-  have = have && key != ~0ull;
-  const unsigned hv = __ballot_sync(0xffffffffu, have);
-  if (hv == 0u) {
-    if (lane == 0) a.vis_words[w] = 0u;
-    return;
-  }
-  const uint64_t cam = __shfl_sync(0xffffffffu, key, __ffs(hv) - 1) >> a.pbits;
-  if (have) {
-    const uint64_t pt = key & ((1ull << a.pbits) - 1ull);
-    V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
-    V3 p{a.p_aos[3 * pt], a.p_aos[3 * pt + 1], a.p_aos[3 * pt + 2]};
-    ray = make_ray(c, p, a.endpoint_guard_rel != 0);
-  }
-  const uint32_t n_list = tl.count[cam];
-  bool occ;
-  if (n_list == TRILIST_OVERFLOW) {
-    occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
-  } else {
-    bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
-    occ = false;
-    unsigned n_vis = 0, n_tri = 0;
-    // bounding box of the packet's ray segments (origin + end points), conservatively padded
-    float blx = INFINITY, bly = INFINITY, blz = INFINITY, bhx = -INFINITY, bhy = -INFINITY, bhz = -INFINITY;
-    if (alive) {
-      const float pad = conservative_pad(ray.ox, ray.oy, ray.oz, a.scene_absmax) + 4e-6f * ray.tfar;
-      const float ex = fmaf(ray.dx, ray.tfar, ray.ox), ey = fmaf(ray.dy, ray.tfar, ray.oy),
-                  ez = fmaf(ray.dz, ray.tfar, ray.oz);
-      blx = fminf(ray.ox, ex) - pad;
-      bly = fminf(ray.oy, ey) - pad;
-      blz = fminf(ray.oz, ez) - pad;
-      bhx = fmaxf(ray.ox, ex) + pad;
-      bhy = fmaxf(ray.oy, ey) + pad;
-      bhz = fmaxf(ray.oz, ez) + pad;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      blx = fminf(blx, __shfl_xor_sync(0xffffffffu, blx, o));
-      bly = fminf(bly, __shfl_xor_sync(0xffffffffu, bly, o));
-      blz = fminf(blz, __shfl_xor_sync(0xffffffffu, blz, o));
-      bhx = fmaxf(bhx, __shfl_xor_sync(0xffffffffu, bhx, o));
-      bhy = fmaxf(bhy, __shfl_xor_sync(0xffffffffu, bhy, o));
-      bhz = fmaxf(bhz, __shfl_xor_sync(0xffffffffu, bhz, o));
-    }
-    const Shear sh = ray_shear(ray);
-    const uint32_t *mylist = tl.list + cam * tl.cap;
-    for (uint32_t base = 0; base < n_list; base += 32) {
-      if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-      const uint32_t j = base + lane;
-      int slot = -1;
-      bool overlap = false;
-      if (j < n_list) {
-        const uint32_t node = mylist[j];
-        const float4 lo = __ldg(&a.nodes[2 * node]);
-        const float4 hi = __ldg(&a.nodes[2 * node + 1]);
-        slot = __float_as_int(hi.w);
-        overlap = !(lo.x > bhx || hi.x < blx || lo.y > bhy || hi.y < bly || lo.z > bhz || hi.z < blz);
-      }
-      if (COUNT) n_vis += min(32u, n_list - base);
-      unsigned m = __ballot_sync(0xffffffffu, overlap);
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int s = __shfl_sync(0xffffffffu, slot, b);
-        const float4 v0 = __ldg(&a.tris[3 * s]);
-        const float4 v1 = __ldg(&a.tris[3 * s + 1]);
-        const float4 v2 = __ldg(&a.tris[3 * s + 2]);
-        if (COUNT) ++n_tri;
-        if (alive && ray_triangle(ray, sh, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)) {
-          occ = true;
-          alive = false;
-        }
-        if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-      }
-    }
-    if (COUNT && lane == 0) {
-      atomicAdd(&a.counters[2], (unsigned long long)n_vis);
-      atomicAdd(&a.counters[3], (unsigned long long)n_tri);
-    }
-  }
-  const unsigned vm = __ballot_sync(0xffffffffu, have && !occ);
-  if (lane == 0) a.vis_words[w] = vm;
-}
-
 // ---- Embree-shaped ray batch (parity tooling): AoS 48-byte rays, tfar = -inf on hit ---------------
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict__ nodes,
@@ -334,12 +232,11 @@ __global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict_
 // triangle list; the watertight test reports t = T/det.
 __global__ void k_intersect1(const float4 *__restrict__ tris, uint64_t n_tris, Ray ray,
                              float *__restrict__ out /* [0]=hit flag, [1]=t */) {
-  const Shear sh = ray_shear(ray);
   float best = INFINITY;
   for (uint64_t t = threadIdx.x; t < n_tris; t += 32) {
     const float4 v0 = tris[3 * t], v1 = tris[3 * t + 1], v2 = tris[3 * t + 2];
     float tt;
-    if (ray_triangle(ray, sh, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, &tt))
+    if (ray_triangle(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, &tt))
       best = fminf(best, tt);
   }
 #pragma unroll

@@ -263,7 +263,7 @@ void orc_to_vec(const double *cam, double *x) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * ray construction + watertight ray/triangle predicate (f32, fixed order, no FMA)
+ * ray construction + watertight ray/triangle predicate (f32, fixed order, explicit fmaf only)
  * ---------------------------------------------------------------------------------------- */
 
 /* src/generate.rs:456-464 */
@@ -280,68 +280,72 @@ void orc_make_ray(const double *c, const double *p, orc_ray *ray) {
   ray->tfar = (float)n - 1e-6f;
 }
 
+/* Watertight ray/triangle predicate, hit interval 0 < t <= tfar (Embree: |den|*tnear < T <=
+ * |den|*tfar with tnear = 0), no backface culling.  Edge functions in the form of Embree 3's robust
+ * ("Pluecker") triangle intersector — the reference links Embree 3.8.0 through embree-rs 0.3.6
+ * (Cargo.lock:278-279), whose source is not vendored, so this is a restatement of the published
+ * algorithm, not of the binary (PARITY UNPINNED at this boundary, see the header):
+ *   A = v0-o, B = v1-o, C = v2-o;  e0 = C-A, e1 = A-B, e2 = B-C
+ *   U = d.(e0 x (C+A)),  V = d.(e1 x (A+B)),  W = d.(e2 x (B+C));  det = U+V+W;  T = 2 A.(e0 x e1)
+ * Cross products unfused (exactly antisymmetric), dot products as fmaf chains: the record of a
+ * triangle depends on (origin, triangle) only, which the CUDA path exploits per camera.
+ * Fixed operation order = c2b_math.cuh tri_record / ray_tri_record. */
 typedef struct {
-  int kx, ky, kz;
-  float Sx, Sy, Sz;
-} ray_shear;
+  float u[3], v[3], w[3], T;
+} tri_rec;
 
-static void ray_prepare(const orc_ray *r, ray_shear *s) {
-  int kz = 0;
-  if (fabsf(r->dir[1]) > fabsf(r->dir[kz])) kz = 1;
-  if (fabsf(r->dir[2]) > fabsf(r->dir[kz])) kz = 2;
-  int kx = (kz + 1) % 3, ky = (kx + 1) % 3;
-  if (r->dir[kz] < 0.0f) {
-    int t = kx;
-    kx = ky;
-    ky = t;
-  }
-  s->kx = kx;
-  s->ky = ky;
-  s->kz = kz;
-  s->Sx = r->dir[kx] / r->dir[kz];
-  s->Sy = r->dir[ky] / r->dir[kz];
-  s->Sz = 1.0f / r->dir[kz];
+static float dot3f(const float *a, const float *b) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+
+static void cross3f(const float *a, const float *b, float *o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-/* Woop, Benthin, Wald: "Watertight Ray/Triangle Intersection" (JCGT 2013), no backface
- * culling, hit interval 0 < t <= tfar (Embree: |den|*tnear < T <= |den|*tfar with tnear = 0).
- * Outputs the scaled quantities for the flag pass. */
-static int tri_test(const orc_ray *r, const ray_shear *s, const float *v0, const float *v1,
-                    const float *v2, float *oU, float *oV, float *oW, float *oT) {
-  float A[3] = {v0[0] - r->org[0], v0[1] - r->org[1], v0[2] - r->org[2]};
-  float B[3] = {v1[0] - r->org[0], v1[1] - r->org[1], v1[2] - r->org[2]};
-  float C[3] = {v2[0] - r->org[0], v2[1] - r->org[1], v2[2] - r->org[2]};
-  float Ax = A[s->kx] - s->Sx * A[s->kz], Ay = A[s->ky] - s->Sy * A[s->kz];
-  float Bx = B[s->kx] - s->Sx * B[s->kz], By = B[s->ky] - s->Sy * B[s->kz];
-  float Cx = C[s->kx] - s->Sx * C[s->kz], Cy = C[s->ky] - s->Sy * C[s->kz];
-  float U = Cx * By - Cy * Bx;
-  float V = Ax * Cy - Ay * Cx;
-  float W = Bx * Ay - By * Ax;
-  if (U == 0.0f || V == 0.0f || W == 0.0f) {
-    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+static void tri_record(const float *org, const float *v0, const float *v1, const float *v2, tri_rec *t) {
+  float A[3], B[3], C[3], e0[3], e1[3], e2[3], su[3], sv[3], sw[3], n[3];
+  for (int k = 0; k < 3; ++k) {
+    A[k] = v0[k] - org[k];
+    B[k] = v1[k] - org[k];
+    C[k] = v2[k] - org[k];
   }
-  float det = (U + V) + W;
-  float Az = s->Sz * A[s->kz], Bz = s->Sz * B[s->kz], Cz = s->Sz * C[s->kz];
-  float T = (U * Az + V * Bz) + W * Cz;
+  for (int k = 0; k < 3; ++k) {
+    e0[k] = C[k] - A[k];
+    e1[k] = A[k] - B[k];
+    e2[k] = B[k] - C[k];
+    su[k] = C[k] + A[k];
+    sv[k] = A[k] + B[k];
+    sw[k] = B[k] + C[k];
+  }
+  cross3f(e0, su, t->u);
+  cross3f(e1, sv, t->v);
+  cross3f(e2, sw, t->w);
+  cross3f(e0, e1, n);
+  t->T = 2.0f * dot3f(A, n);
+}
+
+/* Outputs the scaled quantities for callers that want them. */
+static int tri_test(const orc_ray *r, const float *v0, const float *v1, const float *v2, float *oU,
+                    float *oV, float *oW, float *oT) {
+  tri_rec t;
+  tri_record(r->org, v0, v1, v2, &t);
+  float U = dot3f(r->dir, t.u), V = dot3f(r->dir, t.v), W = dot3f(r->dir, t.w);
   if (oU) {
     *oU = U;
     *oV = V;
     *oW = W;
-    *oT = T;
+    *oT = t.T;
   }
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return 0;
+  float det = (U + V) + W;
   if (det == 0.0f) return 0;
   float ad = fabsf(det);
-  float Ts = det < 0.0f ? -T : T;
+  float Ts = det < 0.0f ? -t.T : t.T;
   return (Ts > 0.0f && Ts <= r->tfar * ad) ? 1 : 0; /* NaN anywhere => 0 (ray stays visible) */
 }
 
 int orc_ray_triangle(const orc_ray *ray, const float *v0, const float *v1, const float *v2) {
-  ray_shear s;
-  ray_prepare(ray, &s);
-  return tri_test(ray, &s, v0, v1, v2, 0, 0, 0, 0);
+  return tri_test(ray, v0, v1, v2, 0, 0, 0, 0);
 }
 
 /* flagged-epsilon classification of one (ray, triangle) pair, all in f64 on the f32 inputs */
@@ -517,11 +521,9 @@ orc_vis *orc_visibility_graph(const float *xyz, uint64_t nv, const uint32_t *tri
       orc_ray ray;
       orc_make_ray(center, p, &ray);
       if (endpoint_guard_rel) ray.tfar = ray.tfar * (1.0f - 3.814697265625e-06f); /* 2^-18 */
-      ray_shear sh;
-      ray_prepare(&ray, &sh);
       uint8_t occ = 0, flg = (want_flags && nb) ? ORC_FLAG_CULL : 0;
       for (uint64_t t = 0; t < ntri; ++t) {
-        if (tri_test(&ray, &sh, T[t].v, T[t].v + 3, T[t].v + 6, 0, 0, 0, 0)) {
+        if (tri_test(&ray, T[t].v, T[t].v + 3, T[t].v + 6, 0, 0, 0, 0)) {
           occ = 1;
           if (!want_flags) break;
         }

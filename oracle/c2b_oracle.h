@@ -14,8 +14,9 @@
  *     (Cargo.lock:278-279); neither Rust nor Embree exists in this image and the
  *     reference holds no golden visibility vectors, so this boundary is
  *     PARITY UNPINNED.  The oracle fixes ONE fully specified f32 predicate
- *     (Woop/Benthin/Wald watertight test, fixed operation order, no FMA
- *     contraction) and additionally reports the rays that lie within a stated
+ *     (watertight edge-function test in the form of Embree's robust "Pluecker"
+ *     intersector on origin-relative vertices, fixed operation order, explicit
+ *     fmaf only, no contraction) and additionally reports the rays that lie within a stated
  *     epsilon of an edge / a grazing face / the ray end point, where Embree's
  *     rounding could legitimately differ.
  *   - noise: the reference draws from rand 0.6.5 thread_rng() (unseedable); the

@@ -192,8 +192,6 @@ static int box_hit(const orc_ray *r, const float *inv, const bnode *nd) {
 static int bvh_occluded(const cpu_bvh *b, const orc_ray *r) {
   if (!b->n_nodes) return 0;
   if (!(r->tfar >= 0.0f)) return 0; /* NaN or negative tfar: nothing can satisfy 0 < t <= tfar */
-  ray_shear sh;
-  ray_prepare(r, &sh);
   float inv[3] = {1.0f / r->dir[0], 1.0f / r->dir[1], 1.0f / r->dir[2]};
   uint32_t stack[128];
   int sp = 0;
@@ -204,7 +202,7 @@ static int bvh_occluded(const cpu_bvh *b, const orc_ray *r) {
     if (nd->count) {
       for (uint32_t i = 0; i < nd->count; ++i) {
         const tri9 *t = &b->tris[nd->left + i];
-        if (tri_test(r, &sh, t->v, t->v + 3, t->v + 6, 0, 0, 0, 0)) return 1;
+        if (tri_test(r, t->v, t->v + 3, t->v + 6, 0, 0, 0, 0)) return 1;
       }
     } else if (sp + 2 <= 128) {
       stack[sp++] = nd->left;
