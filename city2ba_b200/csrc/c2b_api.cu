@@ -518,17 +518,21 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   // fused cull + occlusion
   C2B_CUDA(cudaMemsetAsync(ctx->vis_count.p, 0, (C + 1) * 4, st));
   {
-    const unsigned nb = blocks_for(C, FU_WARPS), nt = FU_WARPS * 32;
+    // persistent warps draw cameras from a ticket; more CTAs than can be resident is harmless
+    const unsigned nb = (unsigned)std::min<uint64_t>(blocks_for(C, FU_WARPS), (uint64_t)ctx->sm_count * 8), nt = FU_WARPS * 32;
     const bool cnt = opt.count_traversal != 0;
+    static const bool occ4 = getenv("C2B_FU_OCC3") == nullptr;  // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3)
     if (mesh) {
       if (cnt)
-        k_visibility_fused<FU_OCC_MESH, true><<<nb, nt, 0, st>>>(fa);
+        k_visibility_fused<FU_OCC_MESH, true, 3><<<nb, nt, 0, st>>>(fa);
+      else if (occ4)
+        k_visibility_fused<FU_OCC_MESH, false, 4><<<nb, nt, 0, st>>>(fa);
       else
-        k_visibility_fused<FU_OCC_MESH, false><<<nb, nt, 0, st>>>(fa);
+        k_visibility_fused<FU_OCC_MESH, false, 3><<<nb, nt, 0, st>>>(fa);
     } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
-      k_visibility_fused<FU_OCC_ANALYTIC, false><<<nb, nt, 0, st>>>(fa);
+      k_visibility_fused<FU_OCC_ANALYTIC, false, 2><<<nb, nt, 0, st>>>(fa);
     } else {
-      k_visibility_fused<FU_OCC_NONE, false><<<nb, nt, 0, st>>>(fa);
+      k_visibility_fused<FU_OCC_NONE, false, 3><<<nb, nt, 0, st>>>(fa);
     }
     C2B_KERNEL_CHECK();
   }

@@ -183,7 +183,7 @@ struct GridDesc {
 };
 
 __device__ __forceinline__ int grid_coord(const GridDesc &g, int k, double x) {
-  double t = floor((x - g.lo[k]) * g.inv_h);
+  double t = floor(dmul(dsub(x, g.lo[k]), g.inv_h));  // explicit rounding: binning and range queries agree
   int c = t < 0.0 ? 0 : (t >= (double)g.n[k] ? g.n[k] - 1 : (int)t);  // NaN -> comparisons false
   if (!(t == t)) c = 0;
   return c;

@@ -55,23 +55,22 @@ struct FusedArgs {
   uint32_t *scratch_idx;      // visible point indices, camera c at [ev_off[c], ev_off[c] + vis_count[c])
   uint32_t *vis_count;        // [C+1]
   unsigned long long *counters;  // [1] pairs evaluated, [2] list entries / nodes, [3] warp triangle tests,
-                                 // [4] candidates (rays), [5] scratch slice overflow flag
+                                 // [4] candidates (rays), [5] scratch slice overflow flag, [7] camera ticket
 };
 
-// camera_cell_range / row_span are __noinline__ on purpose: k_cam_plan sizes each camera's scratch
-// slice from the very rows k_visibility_fused later scans, so both must run the SAME machine code
-// (an FMA contracted in one inlined copy and not in the other could move a row end by one cell).
-
+// camera_cell_range / row_span run in BOTH k_cam_plan (which sizes each camera's scratch slice) and
+// k_visibility_fused (which scans the rows), so they must round identically in both inlined copies:
+// every operation is an explicit round-to-nearest intrinsic that the compiler cannot contract.
 // cells whose points can lie within max_dist of the centre; false = none
-__device__ __noinline__ bool camera_cell_range(const GridDesc &g, const double cc[3], double max_dist,
+__device__ __forceinline__ bool camera_cell_range(const GridDesc &g, const double cc[3], double max_dist,
                                                   int lo[3], int hi[3]) {
   bool empty = !(max_dist > 0.0);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     // every point with |p - c| < max_dist has c_k - r - eps < p_k < c_k + r + eps, and grid_coord is
     // monotone, so [coord(a0), coord(a1)] holds its cell; eps covers the rounding of a0 / a1
-    const double eps = 1e-9 * (fabs(cc[k]) + fabs(max_dist)) + 1e-300;
-    const double a0 = cc[k] - max_dist - eps, a1 = cc[k] + max_dist + eps;
+    const double eps = dadd(dmul(1e-9, dadd(fabs(cc[k]), fabs(max_dist))), 1e-300);
+    const double a0 = dsub(dsub(cc[k], max_dist), eps), a1 = dadd(dadd(cc[k], max_dist), eps);
     if (a0 > g.max_c[k] || a1 < g.min_c[k]) empty = true;  // ball misses the populated slab
     lo[k] = grid_coord(g, k, a0);
     hi[k] = grid_coord(g, k, a1);
@@ -83,36 +82,35 @@ __device__ __noinline__ bool camera_cell_range(const GridDesc &g, const double c
 // "in front of the camera" is pc.z = r2x*x + r2y*y + r2z*z + tz <= 0 (src/generate.rs:450): linear in
 // x along a row of cells, so the row [x0, x1] is trimmed to the x-range that can hold such a point.
 // false = nothing on this row can be in front.
-__device__ __noinline__ bool row_span(const GridDesc &g, double r2x, double r2y, double r2z, double tz,
-                                         double ccx, double max_dist, int y, int z, int &x0, int &x1) {
-  const double cell_h = 1.0 / g.inv_h;
+__device__ __forceinline__ bool row_span(const GridDesc &g, double cell_h, double r2x, double r2y, double r2z,
+                                         double tz, double xr, int y, int z, int &x0, int &x1) {
   // bounds of the row's cells in y and z; edge cells also hold the clamped coordinates, so they
   // extend to the data bounds
-  const double sl = 1e-6 * cell_h;
-  const double y0 = y == 0 ? g.min_c[1] : g.lo[1] + y * cell_h - sl;
-  const double y1 = y == g.n[1] - 1 ? g.max_c[1] : g.lo[1] + (y + 1) * cell_h + sl;
-  const double z0 = z == 0 ? g.min_c[2] : g.lo[2] + z * cell_h - sl;
-  const double z1 = z == g.n[2] - 1 ? g.max_c[2] : g.lo[2] + (z + 1) * cell_h + sl;
+  const double sl = dmul(1e-6, cell_h);
+  const double y0 = y == 0 ? g.min_c[1] : dsub(dadd(g.lo[1], dmul((double)y, cell_h)), sl);
+  const double y1 = y == g.n[1] - 1 ? g.max_c[1] : dadd(dadd(g.lo[1], dmul((double)(y + 1), cell_h)), sl);
+  const double z0 = z == 0 ? g.min_c[2] : dsub(dadd(g.lo[2], dmul((double)z, cell_h)), sl);
+  const double z1 = z == g.n[2] - 1 ? g.max_c[2] : dadd(dadd(g.lo[2], dmul((double)(z + 1), cell_h)), sl);
   // smallest value r2y*y + r2z*z + tz can take on the row (0 * inf is avoided explicitly)
-  const double my = r2y == 0.0 ? 0.0 : r2y * (r2y > 0.0 ? y0 : y1);
-  const double mz = r2z == 0.0 ? 0.0 : r2z * (r2z > 0.0 ? z0 : z1);
-  const double bmin = my + mz + tz;
-  const double xr = fabs(r2x) * (fabs(ccx) + fabs(max_dist));
-  const double mag = fabs(my) + fabs(mz) + fabs(tz) + xr;
+  const double my = r2y == 0.0 ? 0.0 : dmul(r2y, r2y > 0.0 ? y0 : y1);
+  const double mz = r2z == 0.0 ? 0.0 : dmul(r2z, r2z > 0.0 ? z0 : z1);
+  const double bmin = dadd(dadd(my, mz), tz);
+  const double mag = dadd(dadd(dadd(fabs(my), fabs(mz)), fabs(tz)), xr);
   if (bmin == bmin && fabs(bmin) < INFINITY) {
-    const double slack = 1e-9 * mag + 1e-300;
+    const double slack = dadd(dmul(1e-9, mag), 1e-300);
     if (xr <= slack) {
-      if (bmin > 2.0 * slack) return false;  // the whole row is behind the camera
+      if (bmin > dmul(2.0, slack)) return false;  // the whole row is behind the camera
     } else {
-      const double xlim = (-(bmin - slack)) / r2x;  // r2x*x <= -(bmin - slack)
+      const double xlim = ddiv(-dsub(bmin, slack), r2x);  // r2x*x <= -(bmin - slack)
       if (xlim == xlim) {
+        const double xs = dmul(1e-9, dadd(fabs(xlim), cell_h));
         if (r2x > 0.0) {
-          const double xe = xlim + 1e-9 * (fabs(xlim) + cell_h);
+          const double xe = dadd(xlim, xs);
           if (xe < g.lo[0]) return false;  // nothing in front on this row
           const int xc = grid_coord(g, 0, xe);
           x1 = xc < x1 ? xc : x1;
         } else {
-          const double xe = xlim - 1e-9 * (fabs(xlim) + cell_h);
+          const double xe = dsub(xlim, xs);
           if (xe > g.max_c[0]) return false;
           const int xc = grid_coord(g, 0, xe);
           x0 = xc > x0 ? xc : x0;
@@ -122,6 +120,48 @@ __device__ __noinline__ bool row_span(const GridDesc &g, double r2x, double r2y,
     }
   }
   return true;
+}
+
+// The cull predicate of src/generate.rs:450-454 with the two f64 divisions of `project` replaced by
+// a CLASSIFICATION: 1/pc.z is taken from the f32 reciprocal (relative error < 2e-7), (u, v) follow
+// in f64 with a propagated error bound, and only a pair whose |u| or |v| lies within that bound of
+// the frustum edge (or whose magnitudes leave the f32 range, or NaN) runs the exact operation
+// sequence.  The returned bool is therefore identical to cull_project_thr's; (u, v) themselves are
+// produced later by `observe` for the visible pairs only.
+__device__ __forceinline__ bool cull_predicate(const double *cam, V3 center, V3 p, double t_star) {
+  const V3 d{dsub(center.x, p.x), dsub(center.y, p.y), dsub(center.z, p.z)};
+  if (!(mag2(d) < t_star)) return false;
+  // project_world, z row first (same operation order as mat_vec)
+  const double pcz = dadd(dadd(dadd(dmul(cam[2], p.x), dmul(cam[5], p.y)), dmul(cam[8], p.z)), cam[11]);
+  if (!(pcz <= 0.0)) return false;
+  const double pcx = dadd(dadd(dadd(dmul(cam[0], p.x), dmul(cam[3], p.y)), dmul(cam[6], p.z)), cam[9]);
+  const double pcy = dadd(dadd(dadd(dmul(cam[1], p.x), dmul(cam[4], p.y)), dmul(cam[7], p.z)), cam[10]);
+  const double f = cam[12], k1 = cam[13], k2 = cam[14];
+  const double az = fabs(pcz);
+  if (az > 1e-30 && az < 1e30) {
+    const double iz = (double)__frcp_rn(__double2float_rn(pcz));
+    const double a = pcx * iz, b = pcy * iz;  // -(p_) up to 2e-7; only magnitudes matter below
+    double ua, va, bu, bv;
+    if (k1 == 0.0 && k2 == 0.0) {
+      ua = fabs(f * a);
+      va = fabs(f * b);
+      bu = 2e-6 * ua;
+      bv = 2e-6 * va;
+    } else {
+      const double m2p = a * a + b * b;
+      const double r = 1.0 + k1 * m2p + k2 * (m2p * m2p);
+      const double rb = 1.0 + fabs(k1) * m2p + fabs(k2) * (m2p * m2p);
+      ua = fabs(f * r * a);
+      va = fabs(f * r * b);
+      bu = 2e-6 * fabs(f * a) * rb;
+      bv = 2e-6 * fabs(f * b) * rb;
+    }
+    if (ua <= 1.0 - bu && va <= 1.0 - bv) return true;  // NaN falls through to the exact path
+    if (ua > 1.0 + bu || va > 1.0 + bv) return false;
+  }
+  double u, v;
+  project(f, k1, k2, V3{pcx, pcy, pcz}, u, v);
+  return u >= -1.0 && u <= 1.0 && v >= -1.0 && v <= 1.0;
 }
 
 // ---- plan -------------------------------------------------------------------------------------------
@@ -134,10 +174,12 @@ __global__ void __launch_bounds__(128) k_cam_plan(FusedArgs a) {
     if (camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
       const double *c = a.cams + 15 * cam;
       const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
+      const double cell_h = ddiv(1.0, a.g.inv_h);
+      const double xr = dmul(fabs(r2x), dadd(fabs(cc[0]), fabs(a.max_dist)));
       for (int z = lo[2]; z <= hi[2]; ++z)
         for (int y = lo[1]; y <= hi[1]; ++y) {
           int x0 = lo[0], x1 = hi[0];
-          if (!row_span(a.g, r2x, r2y, r2z, tz, cc[0], a.max_dist, y, z, x0, x1)) continue;
+          if (!row_span(a.g, cell_h, r2x, r2y, r2z, tz, xr, y, z, x0, x1)) continue;
           const uint32_t row = ((uint32_t)z * a.g.n[1] + y) * a.g.n[0];
           n += a.cell_start[row + x1 + 1] - a.cell_start[row + x0];
         }
@@ -166,8 +208,32 @@ __device__ __forceinline__ float ord2f(unsigned u) {
   return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
+__device__ __forceinline__ TriRec load_rec(const float4 *rec, int k) {
+  const float4 r0 = rec[3 * k], r1 = rec[3 * k + 1], r2 = rec[3 * k + 2];
+  TriRec t;
+  t.ux = r0.x; t.uy = r0.y; t.uz = r0.z;
+  t.vx = r0.w; t.vy = r1.x; t.vz = r1.y;
+  t.wx = r1.z; t.wy = r1.w; t.wz = r2.x;
+  t.T = r2.y;
+  return t;
+}
+
+// range of n . d over the direction box [dlo, dhi] (interval arithmetic; the caller adds slack)
+__device__ __forceinline__ void dot_range(float nx, float ny, float nz, float lx, float ly, float lz, float hx,
+                                          float hy, float hz, float &mn, float &mx) {
+  const float ax = nx * lx, bx = nx * hx, ay = ny * ly, by = ny * hy, az = nz * lz, bz = nz * hz;
+  mn = fminf(ax, bx) + fminf(ay, by) + fminf(az, bz);
+  mx = fmaxf(ax, bx) + fmaxf(ay, by) + fmaxf(az, bz);
+}
+
 // list-driven any-hit for a packet of rays that share the origin (ox, oy, oz).  rec = 32 x 3 float4
 // of this warp.  Returns true when this lane's ray is occluded.
+//
+// Two conservative filters run with lane = triangle before any ray is tested: (1) the leaf box must
+// overlap the bounding box of the packet's ray segments; (2) with the record in hand, the three edge
+// functions are bounded over the packet's direction box [dlo, dhi]: a ray can only hit if all three
+// are >= 0 or all three are <= 0, so a triangle for which some edge function is negative on the whole
+// box AND some edge function is positive on the whole box cannot be hit by any ray of the packet.
 template <bool COUNT>
 __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_t *__restrict__ mylist,
                                                uint32_t n_list, const Ray &ray, bool have, float ox,
@@ -175,8 +241,11 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
                                                unsigned &n_vis, unsigned &n_tri) {
   bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
   bool occ = false;
-  // bounding box of the packet's ray segments (origin + end points), conservatively padded
+  if (__ballot_sync(0xffffffffu, alive) == 0u) return false;
+  // bounding box of the packet's ray segments (origin + end points), conservatively padded, and of
+  // its directions
   float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+  float dlx = INFINITY, dly = INFINITY, dlz = INFINITY, dhx = -INFINITY, dhy = -INFINITY, dhz = -INFINITY;
   if (alive) {
     const float pad = conservative_pad(ox, oy, oz, a.scene_absmax) + 4e-6f * ray.tfar;
     const float ex = fmaf(ray.dx, ray.tfar, ox), ey = fmaf(ray.dy, ray.tfar, oy), ez = fmaf(ray.dz, ray.tfar, oz);
@@ -186,33 +255,54 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
     hx = fmaxf(ox, ex) + pad;
     hy = fmaxf(oy, ey) + pad;
     hz = fmaxf(oz, ez) + pad;
+    dlx = dhx = ray.dx;
+    dly = dhy = ray.dy;
+    dlz = dhz = ray.dz;
   }
-  if (__ballot_sync(0xffffffffu, alive) == 0u) return false;
   const float blx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx)));
   const float bly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly)));
   const float blz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz)));
   const float bhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
   const float bhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
   const float bhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
+  dlx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlx)));
+  dly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dly)));
+  dlz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlz)));
+  dhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhx)));
+  dhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhy)));
+  dhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhz)));
   for (uint32_t base = 0; base < n_list; base += 32) {
     const uint32_t j = base + lane;
     bool overlap = false;
-    int slot = 0;
+    TriRec t;
     if (j < n_list) {
       const uint32_t node = mylist[j];
       const float4 lo = __ldg(&a.nodes[2 * node]);
       const float4 hi = __ldg(&a.nodes[2 * node + 1]);
-      slot = __float_as_int(hi.w);
       overlap = !(lo.x > bhx || hi.x < blx || lo.y > bhy || hi.y < bly || lo.z > bhz || hi.z < blz);
+      if (overlap) {
+        const int slot = __float_as_int(hi.w);
+        const float4 v0 = __ldg(&a.tris[3 * slot]);
+        const float4 v1 = __ldg(&a.tris[3 * slot + 1]);
+        const float4 v2 = __ldg(&a.tris[3 * slot + 2]);
+        t = tri_record(ox, oy, oz, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z);
+        float umn, umx, vmn, vmx, wmn, wmx;
+        dot_range(t.ux, t.uy, t.uz, dlx, dly, dlz, dhx, dhy, dhz, umn, umx);
+        dot_range(t.vx, t.vy, t.vz, dlx, dly, dlz, dhx, dhy, dhz, vmn, vmx);
+        dot_range(t.wx, t.wy, t.wz, dlx, dly, dlz, dhx, dhy, dhz, wmn, wmx);
+        // slack: rounding of the per-ray FMA chain and of the interval sums, a few ulps of sum |n_k d_k|
+        const float su = 2e-6f * (fabsf(t.ux) + fabsf(t.uy) + fabsf(t.uz));
+        const float sv = 2e-6f * (fabsf(t.vx) + fabsf(t.vy) + fabsf(t.vz));
+        const float sw = 2e-6f * (fabsf(t.wx) + fabsf(t.wy) + fabsf(t.wz));
+        const bool some_neg = umx < -su || vmx < -sv || wmx < -sw;  // an edge function < 0 for every ray
+        const bool some_pos = umn > su || vmn > sv || wmn > sw;     // an edge function > 0 for every ray
+        overlap = !(some_neg && some_pos);                          // NaN bounds keep the triangle
+      }
     }
     const unsigned m = __ballot_sync(0xffffffffu, overlap);
     if (COUNT) n_vis += min(32u, n_list - base);
     if (m == 0u) continue;
     if (overlap) {
-      const float4 v0 = __ldg(&a.tris[3 * slot]);
-      const float4 v1 = __ldg(&a.tris[3 * slot + 1]);
-      const float4 v2 = __ldg(&a.tris[3 * slot + 2]);
-      const TriRec t = tri_record(ox, oy, oz, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z);
       float4 *r = rec + 3 * __popc(m & ((1u << lane) - 1u));
       r[0] = make_float4(t.ux, t.uy, t.uz, t.vx);
       r[1] = make_float4(t.vy, t.vz, t.wx, t.wy);
@@ -220,19 +310,24 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
     }
     __syncwarp();
     const int cnt = __popc(m);
-    for (int k = 0; k < cnt; ++k) {
-      const float4 r0 = rec[3 * k], r1 = rec[3 * k + 1], r2 = rec[3 * k + 2];
-      TriRec t;
-      t.ux = r0.x; t.uy = r0.y; t.uz = r0.z;
-      t.vx = r0.w; t.vy = r1.x; t.vz = r1.y;
-      t.wx = r1.z; t.wy = r1.w; t.wz = r2.x;
-      t.T = r2.y;
-      if (COUNT) ++n_tri;
-      if (alive && ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t)) {
+    if (COUNT) n_tri += cnt;
+    int k = 0;
+    for (; k + 1 < cnt; k += 2) {
+      const TriRec t0 = load_rec(rec, k), t1 = load_rec(rec, k + 1);
+      const bool h0 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
+      const bool h1 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t1);
+      if (alive && (h0 || h1)) {
         occ = true;
         alive = false;
       }
       if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+    }
+    if (k < cnt && (cnt & 1)) {
+      const TriRec t0 = load_rec(rec, cnt - 1);
+      if (alive && ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0)) {
+        occ = true;
+        alive = false;
+      }
     }
     __syncwarp();
     if (__ballot_sync(0xffffffffu, alive) == 0u) break;
@@ -240,109 +335,120 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
   return occ;
 }
 
-template <int OCC, bool COUNT>
-__global__ void __launch_bounds__(FU_WARPS * 32) k_visibility_fused(FusedArgs a) {
+// Persistent warps: every warp draws the next camera from a global ticket (counters[7]), so a warp
+// that drew a cheap camera (city edge, few points in range) immediately gets another one and no
+// warp idles waiting for the slowest camera of its block.
+template <int OCC, bool COUNT, int MIN_CTAS>
+__global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
   __shared__ double s_cam[FU_WARPS][16];
   __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
   __shared__ float4 s_rec[FU_WARPS][96];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t cam = (uint64_t)blockIdx.x * FU_WARPS + warp;
-  if (cam >= a.C) return;
   double *c = s_cam[warp];
   uint32_t *stage = s_stage[warp];
-  if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
-  __syncwarp();
-  const V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
-  const double cc[3] = {cen.x, cen.y, cen.z};
-  int lo[3], hi[3];
-  if (!camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
-    if (lane == 0) a.vis_count[cam] = 0;
-    return;
-  }
-  const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
-  uint32_t n_list = 0;
-  const uint32_t *mylist = nullptr;
-  if (OCC == FU_OCC_MESH) {
-    n_list = a.tri_count[cam];
-    mylist = a.tri_list + cam * a.tri_cap;
-  }
-  uint32_t *out = a.scratch_idx + a.ev_count[cam];
-  const uint32_t out_cap = a.ev_count[cam + 1] - a.ev_count[cam];
-  uint32_t nvis = 0, found = 0;
+  unsigned long long found_total = 0;
   unsigned n_vis_nodes = 0, n_tri = 0;
-  int qn = 0;  // warp-uniform number of staged survivors
-
-  auto resolve = [&](int count) {
-    const bool have = lane < count;
-    Ray ray;
-    ray.ox = ox; ray.oy = oy; ray.oz = oz;
-    ray.dx = ray.dy = ray.dz = 1.0f;
-    ray.tfar = -1.0f;
-    uint32_t pt = 0;
-    V3 p{0.0, 0.0, 0.0};
-    if (have) {
-      const uint32_t i = stage[lane];
-      p = V3{a.gx[i], a.gy[i], a.gz[i]};
-      pt = a.gidx[i];
-      if (OCC == FU_OCC_MESH) ray = make_ray(cen, p, a.endpoint_guard_rel != 0);
+  const double cell_h = ddiv(1.0, a.g.inv_h);
+  for (;;) {
+    unsigned long long ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&a.counters[7], 1ull);
+    const uint64_t cam = __shfl_sync(0xffffffffu, ticket, 0);
+    if (cam >= a.C) break;
+    __syncwarp();
+    if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
+    __syncwarp();
+    const V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
+    const double cc[3] = {cen.x, cen.y, cen.z};
+    int lo[3], hi[3];
+    if (!camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
+      if (lane == 0) a.vis_count[cam] = 0;
+      continue;
     }
-    bool occ = false;
+    const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
+    uint32_t n_list = 0;
+    const uint32_t *mylist = nullptr;
     if (OCC == FU_OCC_MESH) {
-      if (n_list == TRILIST_OVERFLOW)
-        occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
-      else
-        occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, s_rec[warp], lane, n_vis_nodes, n_tri);
-    } else if (OCC == FU_OCC_ANALYTIC) {
-      occ = have && hits_building(cen, p, a.block_length, a.block_inset);
+      n_list = a.tri_count[cam];
+      mylist = a.tri_list + cam * a.tri_cap;
     }
-    const bool vis = have && !occ;
-    const unsigned m = __ballot_sync(0xffffffffu, vis);
-    if (vis) {
-      const uint32_t pos = nvis + __popc(m & ((1u << lane) - 1u));
-      if (pos < out_cap)
-        out[pos] = pt;
-      else
-        a.counters[5] = 1ull;  // cannot happen (visible <= planned row points); reported as an error
-    }
-    nvis += __popc(m);
-  };
+    uint32_t *out = a.scratch_idx + a.ev_count[cam];
+    const uint32_t out_cap = a.ev_count[cam + 1] - a.ev_count[cam];
+    uint32_t nvis = 0;
+    int qn = 0;  // warp-uniform number of staged survivors
 
-  const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
-  for (int z = lo[2]; z <= hi[2]; ++z)
-    for (int y = lo[1]; y <= hi[1]; ++y) {
-      int x0 = lo[0], x1 = hi[0];
-      if (!row_span(a.g, r2x, r2y, r2z, tz, cc[0], a.max_dist, y, z, x0, x1)) continue;
-      const uint32_t row = ((uint32_t)z * a.g.n[1] + y) * a.g.n[0];
-      const uint32_t start = a.cell_start[row + x0], end = a.cell_start[row + x1 + 1];
-      for (uint32_t base = start; base < end; base += 32) {
-        const uint32_t i = base + lane;
-        bool pass = false;
-        if (i < end) {
-          double u, v;
-          pass = cull_project_thr(c, cen, V3{a.gx[i], a.gy[i], a.gz[i]}, a.t_star, u, v);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m == 0u) continue;
-        if (pass) stage[qn + __popc(m & ((1u << lane) - 1u))] = i;
-        qn += __popc(m);
-        found += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-          resolve(32);
-          const int rem = qn - 32;
-          uint32_t t = 0;
-          if (lane < rem) t = stage[32 + lane];
+    auto resolve = [&](int count) {
+      const bool have = lane < count;
+      Ray ray;
+      ray.ox = ox; ray.oy = oy; ray.oz = oz;
+      ray.dx = ray.dy = ray.dz = 1.0f;
+      ray.tfar = -1.0f;
+      uint32_t pt = 0;
+      V3 p{0.0, 0.0, 0.0};
+      if (have) {
+        const uint32_t i = stage[lane];
+        p = V3{a.gx[i], a.gy[i], a.gz[i]};
+        pt = a.gidx[i];
+        if (OCC == FU_OCC_MESH) ray = make_ray(cen, p, a.endpoint_guard_rel != 0);
+      }
+      bool occ = false;
+      if (OCC == FU_OCC_MESH) {
+        if (n_list == TRILIST_OVERFLOW)
+          occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
+        else
+          occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, s_rec[warp], lane, n_vis_nodes, n_tri);
+      } else if (OCC == FU_OCC_ANALYTIC) {
+        occ = have && hits_building(cen, p, a.block_length, a.block_inset);
+      }
+      const bool vis = have && !occ;
+      const unsigned m = __ballot_sync(0xffffffffu, vis);
+      if (vis) {
+        const uint32_t pos = nvis + __popc(m & ((1u << lane) - 1u));
+        if (pos < out_cap)
+          out[pos] = pt;
+        else
+          a.counters[5] = 1ull;  // cannot happen (visible <= planned row points); reported as an error
+      }
+      nvis += __popc(m);
+    };
+
+    const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
+    const double xr = dmul(fabs(r2x), dadd(fabs(cc[0]), fabs(a.max_dist)));
+    for (int z = lo[2]; z <= hi[2]; ++z)
+      for (int y = lo[1]; y <= hi[1]; ++y) {
+        int x0 = lo[0], x1 = hi[0];
+        if (!row_span(a.g, cell_h, r2x, r2y, r2z, tz, xr, y, z, x0, x1)) continue;
+        const uint32_t row = ((uint32_t)z * a.g.n[1] + y) * a.g.n[0];
+        const uint32_t start = a.cell_start[row + x0], end = a.cell_start[row + x1 + 1];
+        for (uint32_t base = start; base < end; base += 32) {
+          const uint32_t i = base + lane;
+          bool pass = false;
+          if (i < end) pass = cull_predicate(c, cen, V3{a.gx[i], a.gy[i], a.gz[i]}, a.t_star);
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (m == 0u) continue;
+          if (pass) stage[qn + __popc(m & ((1u << lane) - 1u))] = i;
+          qn += __popc(m);
           __syncwarp();
-          if (lane < rem) stage[lane] = t;
-          __syncwarp();
-          qn = rem;
+          if (qn >= 32) {
+            resolve(32);
+            const int rem = qn - 32;
+            uint32_t t = 0;
+            if (lane < rem) t = stage[32 + lane];
+            __syncwarp();
+            if (lane < rem) stage[lane] = t;
+            __syncwarp();
+            qn = rem;
+            found_total += 32;
+          }
         }
       }
+    if (qn > 0) {
+      resolve(qn);
+      found_total += qn;
     }
-  if (qn > 0) resolve(qn);
+    if (lane == 0) a.vis_count[cam] = nvis < out_cap ? nvis : out_cap;
+  }
   if (lane == 0) {
-    a.vis_count[cam] = nvis;
-    if (found) atomicAdd(&a.counters[4], (unsigned long long)found);
+    if (found_total) atomicAdd(&a.counters[4], found_total);
     if (COUNT) {
       atomicAdd(&a.counters[2], (unsigned long long)n_vis_nodes);
       atomicAdd(&a.counters[3], (unsigned long long)n_tri);
@@ -351,53 +457,70 @@ __global__ void __launch_bounds__(FU_WARPS * 32) k_visibility_fused(FusedArgs a)
 }
 
 // ---- per-camera sort + final write -------------------------------------------------------------------
-// Bitonic network over E*32 keys in registers, element index i = r*32 + lane (so that loads and the
-// final stores are coalesced): partner distance j < 32 is one __shfl_xor per register, j >= 32 a
-// register-to-register compare.  The (k, j) loops are NOT unrolled — only the E registers of a stage
-// are — which keeps the code a few hundred instructions (the fully unrolled network thrashed the
-// instruction cache: 8 of 12 stall cycles were no_instruction, profiles/r01c).
+// Bitonic network over E*32 keys in registers, element index i = lane*E + r: partner distance
+// j < E is a register-to-register compare, j >= E one __shfl_xor per register (15 of the 55 stages
+// at E = 32).  Descending blocks are handled by complementing the keys (x -> ~x reverses the order),
+// once per level k, so every compare-exchange is a plain (min, max) without direction selects.  The
+// (k, j) loops are NOT unrolled — only the E registers of a stage are — which keeps the code a few
+// hundred instructions (the fully unrolled network thrashed the instruction cache: 8 of 12 stall
+// cycles were no_instruction, profiles/r01c).
 template <int E, int RJ>
-__device__ __forceinline__ void bitonic_reg_stage(uint32_t (&a)[E], unsigned kr) {
-  // partner r ^ RJ; ascending when (r & kr) == 0, kr = k / 32 (kr == E: always ascending)
+__device__ __forceinline__ void bitonic_reg_stage(uint32_t (&a)[E]) {
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const int p = r ^ RJ;
     if (p > r) {
-      const bool up = ((unsigned)r & kr) == 0u;
       const uint32_t lo = min(a[r], a[p]), hi = max(a[r], a[p]);
-      a[r] = up ? lo : hi;
-      a[p] = up ? hi : lo;
+      a[r] = lo;
+      a[p] = hi;
     }
   }
 }
 
 template <int E>
-__device__ __forceinline__ void warp_bitonic_sort_rl(uint32_t (&a)[E], int lane) {
+__device__ __forceinline__ void warp_bitonic_sort(uint32_t (&a)[E], int lane) {
+  // flipped[r]: key r currently stored complemented.  Direction of element i at level k is
+  // ascending iff (i & k) == 0 (k == E*32: always ascending).
+  unsigned flipped = 0u;  // bit r
 #pragma unroll 1
   for (unsigned k = 2; k <= (unsigned)E * 32u; k <<= 1) {
+    // bring every key to the representation its direction at this level needs
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const unsigned i = (unsigned)lane * E + r;
+      const bool desc = (i & k) != 0u && k < (unsigned)E * 32u;
+      const bool is = (flipped >> r) & 1u;
+      if (desc != is) a[r] = ~a[r];
+    }
+    {
+      unsigned f = 0u;
+#pragma unroll
+      for (int r = 0; r < E; ++r) {
+        const unsigned i = (unsigned)lane * E + r;
+        if ((i & k) != 0u && k < (unsigned)E * 32u) f |= 1u << r;
+      }
+      flipped = f;
+    }
 #pragma unroll 1
     for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      if (j < 32u) {
-        // i & k: a lane bit when k < 32, a register bit otherwise
-        const bool lane_up = ((unsigned)lane & k) == 0u;
-        const bool lower = ((unsigned)lane & j) == 0u;
-        const unsigned kr = k >> 5;
+      if (j >= (unsigned)E) {
+        const int lj = (int)(j / E);
+        const bool lower = (lane & lj) == 0;
 #pragma unroll
         for (int r = 0; r < E; ++r) {
-          const bool up = k < 32u ? lane_up : (((unsigned)r & kr) == 0u);
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, a[r], (int)j);
-          a[r] = (lower == up) ? min(a[r], other) : max(a[r], other);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, a[r], lj);
+          a[r] = lower ? min(a[r], other) : max(a[r], other);
         }
       } else {
-        const unsigned rj = j >> 5, kr = k >> 5;
-        if constexpr (E > 1) { if (rj == 1u) bitonic_reg_stage<E, 1>(a, kr); }
-        if constexpr (E > 2) { if (rj == 2u) bitonic_reg_stage<E, 2>(a, kr); }
-        if constexpr (E > 4) { if (rj == 4u) bitonic_reg_stage<E, 4>(a, kr); }
-        if constexpr (E > 8) { if (rj == 8u) bitonic_reg_stage<E, 8>(a, kr); }
-        if constexpr (E > 16) { if (rj == 16u) bitonic_reg_stage<E, 16>(a, kr); }
+        if constexpr (E > 1) { if (j == 1u) bitonic_reg_stage<E, 1>(a); }
+        if constexpr (E > 2) { if (j == 2u) bitonic_reg_stage<E, 2>(a); }
+        if constexpr (E > 4) { if (j == 4u) bitonic_reg_stage<E, 4>(a); }
+        if constexpr (E > 8) { if (j == 8u) bitonic_reg_stage<E, 8>(a); }
+        if constexpr (E > 16) { if (j == 16u) bitonic_reg_stage<E, 16>(a); }
       }
     }
   }
+  // the last level is ascending everywhere: nothing is left complemented
 }
 
 struct SortWriteArgs {
@@ -417,22 +540,26 @@ constexpr uint32_t SW_BLOCK_MAX = 4096;  // shared-memory sort, one block per ca
 
 constexpr int SW_WARPS = 4;
 
+// sorted[] is indexed with one pad word per 32 (i + i/32), so that the lane*E + r stores and the
+// consecutive reads are both free of bank conflicts
+__device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
+
 template <int E>
 __device__ __forceinline__ void sort_warp_to_smem(const uint32_t *__restrict__ src, uint32_t n, int lane,
                                                   uint32_t *sorted) {
   uint32_t a[E];
 #pragma unroll
   for (int r = 0; r < E; ++r) {
-    const uint32_t t = r * 32 + lane;
+    const uint32_t t = r * 32 + lane;  // coalesced load; any starting permutation sorts
     a[r] = t < n ? src[t] : 0xffffffffu;
   }
-  warp_bitonic_sort_rl<E>(a, lane);
+  warp_bitonic_sort<E>(a, lane);
 #pragma unroll
-  for (int r = 0; r < E; ++r) sorted[r * 32 + lane] = a[r];
+  for (int r = 0; r < E; ++r) sorted[sw_pad((uint32_t)lane * E + r)] = a[r];
 }
 
 __global__ void __launch_bounds__(SW_WARPS * 32) k_sort_write(SortWriteArgs s) {
-  __shared__ uint32_t s_sorted[SW_WARPS][SW_WARP_MAX];
+  __shared__ uint32_t s_sorted[SW_WARPS][SW_WARP_MAX + SW_WARP_MAX / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
   if (cam >= s.C) return;
@@ -458,7 +585,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32) k_sort_write(SortWriteArgs s) {
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t pt = sorted[i];
+    const uint32_t pt = sorted[sw_pad(i)];
     const double *p = s.p_aos + 3 * (uint64_t)pt;
     s.out_idx[base + i] = pt;
     s.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
