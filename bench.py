@@ -52,6 +52,19 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(stage, workload, cull_mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel, per launch, from the
+    committed `ncu --set full` capture (profiles/traffic.json, written by profiles/summarize.py);
+    None when no capture matches this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        e = t[f"{workload}/{cull_mode}/{stage}"]
+        return float(e["dram_bytes"]), f'{e["kernel"]}: {e["source"]}'
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -326,19 +339,20 @@ def main():
     e2e_value = C * P * K / e2e_max
     # algorithmic bytes per stage (DESIGN.md "roofline bookkeeping"), whole job, per step
     n_words = (n_cand + 31) // 32
+    nodes_per_cam_sum = nodes / max(1.0, n_cand / 32.0) * C if n_cand else 0.0  # ~ one list per camera
     if args.cull_mode == "grid":
-        # segmented pipeline: keys-only pool, list-driven traversal,
-        # per-camera segment sort with (u, v) recomputed at the final write
-        b_cull = 28.0 * pairs_eval + 144.0 * C + 8.0 * n_cand   # grid-ordered point (24) + index (4) per
-        #                                                         evaluated pair, camera + centre, key written
-        b_trav = 56.0 * n_cand + 36.0 * nodes + 48.0 * tris_t + 4.0 * n_words  # key+centre+point per ray,
-        #            list entry (4) + its leaf box (32) per entry examined, 48 B per warp triangle test
+        # fused grid schedule: plan -> one fused pass per camera -> sort + write
+        b_cull = 144.0 * C + 4.0 * C * 2 + 4.0 * nodes_per_cam_sum  # plan: camera + centre, count + offset;
+        #                                                            leaf lists written (4 B per entry)
+        b_trav = (24.0 * pairs_eval + 4.0 * n_cand + 144.0 * C      # grid-ordered point per evaluated pair,
+                  + 36.0 * nodes + 48.0 * tris_t + 4.0 * n_obs)     # index per candidate, camera; list entry (4)
+        #            + leaf box (32) per entry examined, 48 B record per warp-triangle test, scratch index out
         b_sort = 0.0
-        b_comp = 24.0 * n_words + 16.0 * n_obs + 28.0 * n_obs + 24.0 * n_obs + 128.0 * C
-        #        words+first key (count, scatter), key read + index scattered/re-read, point gather + index,
-        #        CSR record written, camera record + offsets
+        b_comp = 4.0 * n_obs + 24.0 * n_obs + 24.0 * n_obs + 128.0 * C
+        #        scratch index read, point gather, CSR record written, camera record + offsets
     else:
-        b_cull = 28.0 * pairs_eval + 144.0 * C + 28.0 * n_cand
+        # exhaustive schedule: every pair -> pool (key, uv) -> radix sort -> ordered traversal -> compaction
+        b_cull = 24.0 * pairs_eval / 64.0 + 144.0 * C + 28.0 * n_cand  # a 64-camera tile reads each point once
         b_trav = 56.0 * n_cand + 32.0 * nodes + 48.0 * tris_t + 4.0 * n_words
         b_sort = 24.0 * n_cand * max(1, -(-(int(np.ceil(np.log2(max(C // world, 2)))) + int(np.ceil(np.log2(P)))) // 8))
         b_comp = 12.0 * n_cand + 8.0 * n_words + 24.0 * n_obs * 2 + 8.0 * (C + 1)
@@ -348,6 +362,11 @@ def main():
     }
     dom = max(stages, key=lambda k: stages[k][1])
     ach = stages[dom][0] / (stages[dom][1] * 1e-3) / 1e9 if stages[dom][1] > 0 else 0.0
+    kernel_of = ({"cull": "k_cam_plan + k_cam_trilist", "traverse": "k_visibility_fused (cull + ray build + occlusion)",
+                  "compact": "k_sort_write", "sort": "-"} if args.cull_mode == "grid" else
+                 {"cull": "k_cull_exhaustive", "sort": "k_rs_scatter (radix sort)", "traverse": "k_traverse",
+                  "compact": "k_compact_write"})
+    traffic, traffic_src = ncu_traffic(dom, args.workload, args.cull_mode)
     line = {
         "metric": "camera-point visibility tests/sec", "value": value, "unit": "tests/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev_max / K,
@@ -370,8 +389,8 @@ def main():
         "gpu_launches": int(launches_per_step * K),
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "roofline": {
-            "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak * world, "unit": "GB/s",
-            "frac": ach / (peak * world), "traffic": None, "peak_kind": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs x n_gpus)",
+            "bound": "hbm", "stage": dom, "kernel": kernel_of[dom], "achieved": ach, "peak": peak * world, "unit": "GB/s",
+            "frac": ach / (peak * world), "traffic": traffic, "traffic_source": traffic_src, "peak_kind": f"of {peak_kind} (MEASURED_PEAKS.json hbm_gbs x n_gpus)",
             "algorithmic_bytes_per_step": stages[dom][0],
             "all_stages_GBps": {k: (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else None) for k, v in stages.items()},
             "warp_node_visits": int(nodes), "warp_triangle_tests": int(tris_t),

@@ -501,6 +501,8 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     fa.tri_list = ctx->tri_list.as<uint32_t>();
     fa.tri_count = ctx->tri_count.as<uint32_t>();
     fa.tri_cap = trilist_cap;
+    fa.hoist_max = FU_HOIST;
+    if (const char *e = getenv("C2B_HOIST_MAX")) fa.hoist_max = (uint32_t)std::min(std::max(0, atoi(e)), FU_HOIST);
     k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
                                                      fa.scene_absmax, trilist_cap, ctx->tri_list.as<uint32_t>(),
                                                      ctx->tri_count.as<uint32_t>());

@@ -48,6 +48,7 @@ struct FusedArgs {
   const uint32_t *tri_list;   // [C * tri_cap] leaf node indices (k_cam_trilist)
   const uint32_t *tri_count;  // [C]
   uint32_t tri_cap;
+  uint32_t hoist_max;  // leaf lists up to this length (<= FU_HOIST) get per-camera records
   int endpoint_guard_rel;
   double block_length, block_inset;  // analytic occlusion (src/synthetic.rs:52-124)
   // plan + output
@@ -201,11 +202,11 @@ enum { FU_OCC_MESH = 0, FU_OCC_NONE = 1, FU_OCC_ANALYTIC = 2 };
 
 // float <-> unsigned with the same ordering (no NaNs), for REDUX min / max
 __device__ __forceinline__ unsigned f2ord(float f) {
-  const unsigned b = __float_as_uint(f);
-  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+  const int b = __float_as_int(f);
+  return (unsigned)b ^ ((unsigned)(b >> 31) | 0x80000000u);  // negative: ~b, else b ^ sign
 }
 __device__ __forceinline__ float ord2f(unsigned u) {
-  return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+  return __uint_as_float(u ^ ((unsigned)((int)~u >> 31) | 0x80000000u));
 }
 
 __device__ __forceinline__ TriRec load_rec(const float4 *rec, int k) {
@@ -226,6 +227,59 @@ __device__ __forceinline__ void dot_range(float nx, float ny, float nz, float lx
   mx = fmaxf(ax, bx) + fmaxf(ay, by) + fmaxf(az, bz);
 }
 
+// ---- per-camera triangle records ("hoisted" mode, the camera's leaf list has <= FU_HOIST entries) ----
+// Every ray of a camera starts at the same origin, so the origin-relative record of a triangle is a
+// per-(camera, triangle) constant.  The warp computes the records of its camera's whole leaf list
+// once, lane = triangle, into shared memory (SoA: four float4 planes of FU_HOIST entries, so that
+// both the lane = triangle reads and the broadcast reads of the test loop are conflict-free):
+//   plane 0 {ux uy uz vx}  plane 1 {vy vz wx wy}  plane 2 {wz T lo.x lo.y}  plane 3 {lo.z hi.x hi.y hi.z}
+constexpr int FU_HOIST = 64;
+
+__device__ __forceinline__ void hoist_records(const FusedArgs &a, const uint32_t *__restrict__ mylist,
+                                              uint32_t n_list, float ox, float oy, float oz, float4 *rec,
+                                              int lane) {
+  for (uint32_t j = lane; j < n_list; j += 32) {
+    const uint32_t node = mylist[j];
+    const float4 lo = __ldg(&a.nodes[2 * node]);
+    const float4 hi = __ldg(&a.nodes[2 * node + 1]);
+    const int slot = __float_as_int(hi.w);
+    const float4 v0 = __ldg(&a.tris[3 * slot]);
+    const float4 v1 = __ldg(&a.tris[3 * slot + 1]);
+    const float4 v2 = __ldg(&a.tris[3 * slot + 2]);
+    const TriRec t = tri_record(ox, oy, oz, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z);
+    rec[j] = make_float4(t.ux, t.uy, t.uz, t.vx);
+    rec[FU_HOIST + j] = make_float4(t.vy, t.vz, t.wx, t.wy);
+    rec[2 * FU_HOIST + j] = make_float4(t.wz, t.T, lo.x, lo.y);
+    rec[3 * FU_HOIST + j] = make_float4(lo.z, hi.x, hi.y, hi.z);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ TriRec unpack_rec(float4 r0, float4 r1, float4 r2) {
+  TriRec t;
+  t.ux = r0.x; t.uy = r0.y; t.uz = r0.z;
+  t.vx = r0.w; t.vy = r1.x; t.vz = r1.y;
+  t.wx = r1.z; t.wy = r1.w; t.wz = r2.x;
+  t.T = r2.y;
+  return t;
+}
+
+// can any direction of the box [dl, dh] give edge functions that are all >= 0 or all <= 0?
+__device__ __forceinline__ bool direction_box_may_hit(const TriRec &t, float dlx, float dly, float dlz,
+                                                      float dhx, float dhy, float dhz) {
+  float umn, umx, vmn, vmx, wmn, wmx;
+  dot_range(t.ux, t.uy, t.uz, dlx, dly, dlz, dhx, dhy, dhz, umn, umx);
+  dot_range(t.vx, t.vy, t.vz, dlx, dly, dlz, dhx, dhy, dhz, vmn, vmx);
+  dot_range(t.wx, t.wy, t.wz, dlx, dly, dlz, dhx, dhy, dhz, wmn, wmx);
+  // slack: rounding of the per-ray FMA chain and of the interval sums, a few ulps of sum |n_k d_k|
+  const float su = 2e-6f * (fabsf(t.ux) + fabsf(t.uy) + fabsf(t.uz));
+  const float sv = 2e-6f * (fabsf(t.vx) + fabsf(t.vy) + fabsf(t.vz));
+  const float sw = 2e-6f * (fabsf(t.wx) + fabsf(t.wy) + fabsf(t.wz));
+  const bool some_neg = umx < -su || vmx < -sv || wmx < -sw;  // an edge function < 0 for every ray
+  const bool some_pos = umn > su || vmn > sv || wmn > sw;     // an edge function > 0 for every ray
+  return !(some_neg && some_pos);                             // NaN bounds keep the triangle
+}
+
 // list-driven any-hit for a packet of rays that share the origin (ox, oy, oz).  rec = 32 x 3 float4
 // of this warp.  Returns true when this lane's ray is occluded.
 //
@@ -237,7 +291,7 @@ __device__ __forceinline__ void dot_range(float nx, float ny, float nz, float lx
 template <bool COUNT>
 __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_t *__restrict__ mylist,
                                                uint32_t n_list, const Ray &ray, bool have, float ox,
-                                               float oy, float oz, float4 *rec, int lane,
+                                               float oy, float oz, float4 *rec, bool hoisted, int lane,
                                                unsigned &n_vis, unsigned &n_tri) {
   bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
   bool occ = false;
@@ -271,6 +325,38 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
   dhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhx)));
   dhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhy)));
   dhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhz)));
+  if (hoisted) {
+    for (uint32_t base = 0; base < n_list; base += 32) {
+      const uint32_t j = base + lane;
+      bool overlap = false;
+      if (j < n_list) {
+        const float4 r2 = rec[2 * FU_HOIST + j], r3 = rec[3 * FU_HOIST + j];
+        overlap = !(r2.z > bhx || r3.y < blx || r2.w > bhy || r3.z < bly || r3.x > bhz || r3.w < blz);
+        if (overlap) overlap = direction_box_may_hit(unpack_rec(rec[j], rec[FU_HOIST + j], r2), dlx, dly, dlz, dhx, dhy, dhz);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, overlap);
+      if (COUNT) {
+        n_vis += min(32u, n_list - base);
+        n_tri += __popc(m);
+      }
+      while (m) {
+        const int k0 = (int)base + __ffs(m) - 1;
+        m &= m - 1;
+        bool h = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rec[k0], rec[FU_HOIST + k0], rec[2 * FU_HOIST + k0]));
+        if (m) {
+          const int k1 = (int)base + __ffs(m) - 1;
+          m &= m - 1;
+          h |= ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rec[k1], rec[FU_HOIST + k1], rec[2 * FU_HOIST + k1]));
+        }
+        if (alive && h) {
+          occ = true;
+          alive = false;
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u) return occ;
+      }
+    }
+    return occ;
+  }
   for (uint32_t base = 0; base < n_list; base += 32) {
     const uint32_t j = base + lane;
     bool overlap = false;
@@ -286,17 +372,7 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
         const float4 v1 = __ldg(&a.tris[3 * slot + 1]);
         const float4 v2 = __ldg(&a.tris[3 * slot + 2]);
         t = tri_record(ox, oy, oz, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z);
-        float umn, umx, vmn, vmx, wmn, wmx;
-        dot_range(t.ux, t.uy, t.uz, dlx, dly, dlz, dhx, dhy, dhz, umn, umx);
-        dot_range(t.vx, t.vy, t.vz, dlx, dly, dlz, dhx, dhy, dhz, vmn, vmx);
-        dot_range(t.wx, t.wy, t.wz, dlx, dly, dlz, dhx, dhy, dhz, wmn, wmx);
-        // slack: rounding of the per-ray FMA chain and of the interval sums, a few ulps of sum |n_k d_k|
-        const float su = 2e-6f * (fabsf(t.ux) + fabsf(t.uy) + fabsf(t.uz));
-        const float sv = 2e-6f * (fabsf(t.vx) + fabsf(t.vy) + fabsf(t.vz));
-        const float sw = 2e-6f * (fabsf(t.wx) + fabsf(t.wy) + fabsf(t.wz));
-        const bool some_neg = umx < -su || vmx < -sv || wmx < -sw;  // an edge function < 0 for every ray
-        const bool some_pos = umn > su || vmn > sv || wmn > sw;     // an edge function > 0 for every ray
-        overlap = !(some_neg && some_pos);                          // NaN bounds keep the triangle
+        overlap = direction_box_may_hit(t, dlx, dly, dlz, dhx, dhy, dhz);
       }
     }
     const unsigned m = __ballot_sync(0xffffffffu, overlap);
@@ -342,7 +418,7 @@ template <int OCC, bool COUNT, int MIN_CTAS>
 __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
   __shared__ double s_cam[FU_WARPS][16];
   __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
-  __shared__ float4 s_rec[FU_WARPS][96];
+  __shared__ float4 s_rec[FU_WARPS][4 * FU_HOIST];  // hoisted: 4 planes x FU_HOIST; chunked: 32 x 3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *c = s_cam[warp];
   uint32_t *stage = s_stage[warp];
@@ -371,6 +447,8 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       n_list = a.tri_count[cam];
       mylist = a.tri_list + cam * a.tri_cap;
     }
+    const bool hoisted = OCC == FU_OCC_MESH && n_list <= a.hoist_max;  // (OVERFLOW is 2^32 - 1)
+    if (hoisted) hoist_records(a, mylist, n_list, ox, oy, oz, s_rec[warp], lane);
     uint32_t *out = a.scratch_idx + a.ev_count[cam];
     const uint32_t out_cap = a.ev_count[cam + 1] - a.ev_count[cam];
     uint32_t nvis = 0;
@@ -395,7 +473,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
         if (n_list == TRILIST_OVERFLOW)
           occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
         else
-          occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, s_rec[warp], lane, n_vis_nodes, n_tri);
+          occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, s_rec[warp], hoisted, lane, n_vis_nodes, n_tri);
       } else if (OCC == FU_OCC_ANALYTIC) {
         occ = have && hits_building(cen, p, a.block_length, a.block_inset);
       }

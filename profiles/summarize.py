@@ -71,7 +71,39 @@ def launch_summary(path):
     return "\n".join(lines)
 
 
+def traffic_entries(path, workload, cull_mode, source):
+    """{workload/cull_mode/stage: dram bytes per launch} for bench.py's roofline.traffic"""
+    stage_of = {"k_visibility_fused": "traverse", "k_sort_write": "compact", "k_cam_plan": "cull",
+                "k_traverse": "traverse", "k_cull_exhaustive": "cull"}
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out = {}
+    for vals in rows[2:]:
+        d = dict(zip(hdr, vals))
+        u = dict(zip(hdr, units))
+        name = d.get("Kernel Name", "").split("(")[0].split("<")[0].replace("void ", "").strip()
+        if name not in stage_of:
+            continue
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u[m]]
+            tot += float(d[m].replace(",", "")) * scale
+        out[f"{workload}/{cull_mode}/{stage_of[name]}"] = {"dram_bytes": tot, "kernel": name, "source": source}
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--traffic":
+        # python profiles/summarize.py --traffic <rep> <workload> <cull_mode> <source label>
+        import json
+        here = os.path.dirname(os.path.abspath(__file__))
+        p = os.path.join(here, "traffic.json")
+        cur = json.load(open(p)) if os.path.exists(p) else {}
+        cur.update(traffic_entries(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5]))
+        json.dump(cur, open(p, "w"), indent=1, sort_keys=True)
+        print(json.dumps(cur, indent=1))
+        return
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     here = os.path.dirname(os.path.abspath(__file__))
     for rep in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):

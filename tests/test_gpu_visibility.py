@@ -273,3 +273,48 @@ def test_dense_mesh_overflows_triangle_lists(c2b, ctx, orc):
     assert 0 < ref.n_obs < ref.n_candidates
     for mode in MODES:
         assert_same_graph(c2b.visibility_graph(scene, cams, pts, 12.0, cull_mode=mode, ctx=ctx), ref, f"dense/{mode}")
+
+
+def test_list_modes_agree(c2b, ctx, orc, cfg2, monkeypatch):
+    """the three ways a packet finds its triangles — per-camera records in shared memory
+    (leaf list <= 64), per-packet records (<= 128, forced here with C2B_HOIST_MAX=0) and the
+    stackless BVH walk (list overflow, forced with C2B_TRILIST_CAP=1) — give the same graph"""
+    cams, pts, xyz, tri = cfg2
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
+    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "hoisted")
+    monkeypatch.setenv("C2B_HOIST_MAX", "0")
+    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-packet records")
+    monkeypatch.setenv("C2B_TRILIST_CAP", "1")
+    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "bvh walk")
+
+
+def test_frustum_edge_classification(c2b, ctx, orc):
+    """points constructed to project onto |u| = 1 or |v| = 1 (and a few ulps either side), with and
+    without radial distortion: the division-free classification of the cull kernel must fall back
+    to the exact operation sequence there and agree with the oracle bit for bit"""
+    rng = np.random.default_rng(4242)
+    cams = random_cameras(rng, 24, center=(0, 1, 0), spread=3.0)
+    cams[:8, 12:15] = (1.0, 0.0, 0.0)            # the BASELINE intrinsics
+    cams[8:16, 13:15] = 0.0                       # f != 1, no distortion
+    pts = []
+    for c in cams:
+        R = c[:9].reshape(3, 3).T                 # column-major record -> matrix
+        t = c[9:12]
+        f = c[12]
+        for _ in range(40):
+            z = -rng.uniform(0.5, 8.0)
+            edge = rng.choice([-1.0, 1.0])
+            other = rng.uniform(-1.2, 1.2)
+            # undistorted image-plane coordinates that land on the frustum edge when k1 = k2 = 0
+            a, b = (edge / f, other / f) if rng.uniform() < 0.5 else (other / f, edge / f)
+            pc = np.array([-a * z, -b * z, z])
+            p = R.T @ (pc - t)
+            for k in (-2, -1, 0, 1, 2):
+                pts.append(np.nextafter(p, p + k * np.array([1.0, 1.0, 1.0])) if k else p)
+    pts = np.array(pts)
+    empty = c2b.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), ctx=ctx)
+    ref = orc.visibility_graph(np.zeros((0, 3)), np.zeros((0, 3)), cams, pts, 20.0)
+    assert 0 < ref.n_obs < len(cams) * len(pts)
+    for mode in MODES:
+        assert_same_graph(c2b.visibility_graph(empty, cams, pts, 20.0, cull_mode=mode, ctx=ctx), ref, f"edge/{mode}")
