@@ -348,7 +348,7 @@ def main():
                   + 36.0 * nodes + 48.0 * tris_t + 4.0 * n_obs)     # index per candidate, camera; list entry (4)
         #            + leaf box (32) per entry examined, 48 B record per warp-triangle test, scratch index out
         b_sort = 0.0
-        b_comp = 4.0 * n_obs + 24.0 * n_obs + 24.0 * n_obs + 128.0 * C
+        b_comp = 4.0 * n_obs + 24.0 * n_obs + 20.0 * n_obs + 128.0 * C
         #        scratch index read, point gather, CSR record written, camera record + offsets
     else:
         # exhaustive schedule: every pair -> pool (key, uv) -> radix sort -> ordered traversal -> compaction

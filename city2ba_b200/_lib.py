@@ -37,7 +37,7 @@ class Obs(C.Structure):
         ("n_cameras", C.c_uint64),
         ("n_obs", C.c_uint64),
         ("offsets", C.POINTER(C.c_uint64)),
-        ("point_idx", C.POINTER(C.c_uint64)),
+        ("point_idx", C.POINTER(C.c_uint32)),
         ("uv", C.POINTER(C.c_double)),
         ("n_candidates", C.c_uint64),
         ("pairs_evaluated", C.c_uint64),

@@ -554,10 +554,10 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   nodes = h_cnt[2];
   tris_t = h_cnt[3];
   if (total_obs) {
-    C2B_TRY(ctx->out_idx[sel].ensure(total_obs * 8));
+    C2B_TRY(ctx->out_idx[sel].ensure(total_obs * 4));
     C2B_TRY(ctx->out_uv[sel].ensure(total_obs * 16));
     SortWriteArgs sw{fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, fa.cams, ctx->pts_aos.as<double>(),
-                     ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint64_t>(), ctx->out_uv[sel].as<double2>()};
+                     ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>()};
     if (max32 <= SW_BLOCK_MAX) {
       k_sort_write<<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
       C2B_KERNEL_CHECK();
@@ -568,17 +568,18 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     } else {
       // a camera sees more points than the shared-memory sort holds: radix-sort all visible keys
       C2B_TRY(ctx->sort_keys[0].ensure(total_obs * 8));
+      C2B_TRY(ctx->sort_keys[1].ensure(total_obs * 8));
       C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));
       C2B_TRY(ctx->sort_vals[1].ensure(total_obs * 4));
       k_expand_keys<<<blocks_for(C, 8), 256, 0, st>>>(fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, pbits,
                                                       ctx->sort_keys[0].as<uint64_t>());
       C2B_KERNEL_CHECK();
-      uint64_t *keys[2] = {ctx->sort_keys[0].as<uint64_t>(), ctx->out_idx[sel].as<uint64_t>()};
+      uint64_t *keys[2] = {ctx->sort_keys[0].as<uint64_t>(), ctx->sort_keys[1].as<uint64_t>()};
       uint32_t *vals[2] = {ctx->sort_vals[0].as<uint32_t>(), ctx->sort_vals[1].as<uint32_t>()};
       int res = 0;
       C2B_TRY(radix_sort_pairs(st, keys, vals, total_obs, pbits + cbits, ctx->sort_hist, ctx->scan_tmp, &res));
       k_write_sorted<<<blocks_for(total_obs, 256), 256, 0, st>>>(keys[res], total_obs, pbits, fa.cams,
-                                                                ctx->pts_aos.as<double>(), ctx->out_idx[sel].as<uint64_t>(),
+                                                                ctx->pts_aos.as<double>(), ctx->out_idx[sel].as<uint32_t>(),
                                                                 ctx->out_uv[sel].as<double2>());
       C2B_KERNEL_CHECK();
       k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C + 1,
@@ -760,7 +761,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
 
     C2B_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
     if (n_cand) {
-      C2B_TRY(ctx->out_idx[ctx->out_sel].ensure(n_cand * 8));
+      C2B_TRY(ctx->out_idx[ctx->out_sel].ensure(n_cand * 4));
       C2B_TRY(ctx->out_uv[ctx->out_sel].ensure(n_cand * 16));
       k_word_popc<<<blocks_for(n_words, 256), 256, 0, st>>>(ctx->vis_words.as<uint32_t>(), n_words,
                                                             ctx->word_prefix.as<uint32_t>());
@@ -769,7 +770,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
                                  n_words, d_total, ctx->scan_tmp));
       k_compact_write<<<blocks_for(n_cand, 256), 256, 0, st>>>(
           ctx->vis_words.as<uint32_t>(), ctx->word_prefix.as<uint32_t>(), keys[res], vals[res],
-          ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx[ctx->out_sel].as<uint64_t>(),
+          ctx->pool_uv.as<double2>(), n_cand, pbits, ctx->out_idx[ctx->out_sel].as<uint32_t>(),
           ctx->out_uv[ctx->out_sel].as<double2>());
       C2B_KERNEL_CHECK();
     }
@@ -800,13 +801,13 @@ int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out) {
   cudaStream_t st = ctx->stream;
   const uint64_t C = ctx->out_C, O = ctx->out_O;
   C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
-  C2B_TRY(ctx->h_idx.ensure(std::max<uint64_t>(O, 1) * 8));
+  C2B_TRY(ctx->h_idx.ensure(std::max<uint64_t>(O, 1) * 4));
   C2B_TRY(ctx->h_uv.ensure(std::max<uint64_t>(O, 1) * 16));
   cudaEvent_t e0 = ctx->ev[EV_COMPACT], e1 = ctx->ev[EV_D2H];
   C2B_CUDA(cudaEventRecord(e0, st));
   C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.p, ctx->out_offsets[ctx->out_sel].p, (C + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (O) {
-    C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.p, ctx->out_idx[ctx->out_sel].p, O * 8, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.p, ctx->out_idx[ctx->out_sel].p, O * 4, cudaMemcpyDeviceToHost, st));
     C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.p, ctx->out_uv[ctx->out_sel].p, O * 16, cudaMemcpyDeviceToHost, st));
   }
   C2B_CUDA(cudaEventRecord(e1, st));
@@ -814,9 +815,9 @@ int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out) {
   out->n_cameras = C;
   out->n_obs = O;
   out->offsets = ctx->h_offsets.as<uint64_t>();
-  out->point_idx = ctx->h_idx.as<uint64_t>();
+  out->point_idx = ctx->h_idx.as<uint32_t>();
   out->uv = ctx->h_uv.as<double>();
-  out->d2h_bytes = (C + 1) * 8 + O * 24;
+  out->d2h_bytes = (C + 1) * 8 + O * 20;
   float t = 0;
   cudaEventElapsedTime(&t, e0, e1);
   out->ms_d2h = t;
@@ -851,25 +852,37 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   CtxExtra *x = extra_of(ctx);
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
   // camera batches: the CSR slab of batch b travels to the host while batch b+1 is computed
-  uint64_t n_batches = 1;
-  if (C >= 16384) n_batches = std::min<uint64_t>(8, C / 8192);
-  if (const char *e = getenv("C2B_BATCHES")) n_batches = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)atoll(e)));
+  // The result transfer is the longest leg (20 B per observation over PCIe), so it should start as
+  // early as possible: the first batches are small (1/32, 1/32, 1/16, 1/8 of the cameras), the rest 1/8.
+  std::vector<uint64_t> bounds;  // batch b = cameras [bounds[b], bounds[b+1])
+  bounds.push_back(0);
+  if (const char *e = getenv("C2B_BATCHES")) {
+    const uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)atoll(e)));
+    for (uint64_t b = 1; b <= nb; ++b) bounds.push_back((b * C) / nb);
+  } else if (C >= 16384) {
+    for (uint64_t f : {1, 2, 4, 8, 12, 16, 20, 24, 28, 32}) bounds.push_back((f * C) / 32);
+  } else {
+    bounds.push_back(C);
+  }
+  const uint64_t n_batches = bounds.size() - 1;
 
-  cudaEvent_t u0, u1;
+  cudaEvent_t u0, u1, d0, d1;
   C2B_CUDA(cudaEventCreate(&u0));
   C2B_CUDA(cudaEventCreate(&u1));
+  C2B_CUDA(cudaEventCreate(&d0));
+  C2B_CUDA(cudaEventCreate(&d1));
   c2b_obs acc;
   memset(&acc, 0, sizeof acc);
   int rc = C2B_OK;
   uint64_t obs_base = 0;
-  float ms_upload = 0;
+  float ms_upload = 0, ms_copy = 0;
   auto run = [&]() -> int {
     C2B_CUDA(cudaEventRecord(u0, st));
     C2B_TRY(c2b_upload_points(ctx, pts, P));
     C2B_CUDA(cudaEventRecord(u1, st));
     C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
     for (uint64_t b = 0; b < n_batches; ++b) {
-      const uint64_t c0 = (b * C) / n_batches, c1 = ((b + 1) * C) / n_batches, nc = c1 - c0;
+      const uint64_t c0 = bounds[b], c1 = bounds[b + 1], nc = c1 - c0;
       const int sel = (int)(b & 1);
       ctx->out_sel = sel;
       if (b >= 2) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[sel], 0));  // set `sel` is free again
@@ -884,13 +897,14 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
       // pinned result arrays: sized from the first batch's density, grown if the guess was short
       size_t need = obs_base + O;
       if (b + 1 < n_batches) need = std::max<size_t>(need, (size_t)((double)(obs_base + O) * (double)C / (double)c1 * 1.05) + 1024);
-      C2B_TRY(grow_pinned(ctx, ctx->h_idx, std::max<size_t>(need, 1) * 8, obs_base * 8));
+      C2B_TRY(grow_pinned(ctx, ctx->h_idx, std::max<size_t>(need, 1) * 4, obs_base * 4));
       C2B_TRY(grow_pinned(ctx, ctx->h_uv, std::max<size_t>(need, 1) * 16, obs_base * 16));
       C2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sel], 0));
+      if (b == 0) C2B_CUDA(cudaEventRecord(d0, cs));
       C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.as<uint64_t>() + c0, ctx->out_offsets[sel].p, (nc + 1) * 8,
                                cudaMemcpyDeviceToHost, cs));
       if (O) {
-        C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.as<uint64_t>() + obs_base, ctx->out_idx[sel].p, O * 8,
+        C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.as<uint32_t>() + obs_base, ctx->out_idx[sel].p, O * 4,
                                  cudaMemcpyDeviceToHost, cs));
         C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.as<double>() + 2 * obs_base, ctx->out_uv[sel].p, O * 16,
                                  cudaMemcpyDeviceToHost, cs));
@@ -908,14 +922,18 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
       acc.ms_compact += s1.ms_compact;
       acc.ms_total += s1.ms_total;
     }
+    C2B_CUDA(cudaEventRecord(d1, cs));
     C2B_CUDA(cudaStreamSynchronize(cs));
     C2B_CUDA(cudaStreamSynchronize(st));
     C2B_CUDA(cudaEventElapsedTime(&ms_upload, u0, u1));
+    C2B_CUDA(cudaEventElapsedTime(&ms_copy, d0, d1));
     return C2B_OK;
   };
   rc = run();
   cudaEventDestroy(u0);
   cudaEventDestroy(u1);
+  cudaEventDestroy(d0);
+  cudaEventDestroy(d1);
   ctx->out_sel = 0;
   x->have_result = false;  // the resident state now holds the last batch only
   if (rc != C2B_OK) {
@@ -925,12 +943,12 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   acc.n_cameras = C;
   acc.n_obs = obs_base;
   acc.offsets = ctx->h_offsets.as<uint64_t>();
-  acc.point_idx = ctx->h_idx.as<uint64_t>();
+  acc.point_idx = ctx->h_idx.as<uint32_t>();
   acc.uv = ctx->h_uv.as<double>();
   acc.ms_h2d = ms_upload;
   acc.h2d_bytes = P * 24 + C * 120;
-  acc.d2h_bytes = (C + 1) * 8 + obs_base * 24;
-  acc.ms_d2h = 0;  // overlapped with compute on the copy stream
+  acc.d2h_bytes = (C + 1) * 8 + obs_base * 20;
+  acc.ms_d2h = ms_copy;  // first to last result copy on the copy stream; overlaps the compute of later batches
   acc.ms_total += ms_upload;
   *out = acc;
   return C2B_OK;
@@ -959,7 +977,7 @@ int c2b_reprojection_error_resident(c2b_ctx *ctx, double norm, double *out) {
   const double *px = ctx->pts.as<double>();
   k_reproj_partial<<<nb, ST_THREADS, 0, st>>>(ctx->cams.as<double>(), px, px + P, px + 2 * P,
                                               ctx->out_offsets[ctx->out_sel].as<uint64_t>(), C,
-                                              ctx->out_idx[ctx->out_sel].as<uint64_t>(), ctx->out_uv[ctx->out_sel].as<double2>(), O,
+                                              ctx->out_idx[ctx->out_sel].as<uint32_t>(), ctx->out_uv[ctx->out_sel].as<double2>(), O,
                                               norm, ctx->misc.as<double>());
   C2B_KERNEL_CHECK();
   std::vector<double> h(nb);

@@ -24,14 +24,14 @@ __global__ void k_compact_write(const uint32_t *__restrict__ words,
                                 const uint32_t *__restrict__ word_prefix,
                                 const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                 const double2 *__restrict__ pool_uv, uint64_t n_cand, int pbits,
-                                uint64_t *__restrict__ out_idx, double2 *__restrict__ out_uv) {
+                                uint32_t *__restrict__ out_idx, double2 *__restrict__ out_uv) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cand) return;
   uint32_t word = words[i >> 5];
   uint32_t bit = (uint32_t)(i & 31);
   if (!((word >> bit) & 1u)) return;
   uint64_t pos = (uint64_t)word_prefix[i >> 5] + __popc(word & ((1u << bit) - 1u));
-  out_idx[pos] = keys[i] & ((1ull << pbits) - 1ull);
+  out_idx[pos] = (uint32_t)(keys[i] & ((1ull << pbits) - 1ull));
   out_uv[pos] = pool_uv[vals[i]];
 }
 
@@ -84,17 +84,17 @@ __device__ __forceinline__ double2 observe(const double *cam, double x, double y
 // fallback for cameras that see more points than the shared-memory sort holds (SW_BLOCK_MAX): the scattered 64-bit keys were radix-sorted
 // globally; split each key and recompute (u, v)
 __global__ void k_write_sorted(const uint64_t *keys, uint64_t n, int pbits, const double *__restrict__ cams,
-                               const double *__restrict__ p_aos, uint64_t *out_idx,
+                               const double *__restrict__ p_aos, uint32_t *__restrict__ out_idx,
                                double2 *__restrict__ out_uv) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t key = keys[i];  // may alias out_idx: read before write, same slot
+  const uint64_t key = keys[i];
   const uint64_t cam = key >> pbits, pt = key & ((1ull << pbits) - 1ull);
   double c[15];
 #pragma unroll
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&cams[15 * cam + k]);
   out_uv[i] = observe(c, p_aos[3 * pt], p_aos[3 * pt + 1], p_aos[3 * pt + 2]);
-  out_idx[i] = pt;
+  out_idx[i] = (uint32_t)pt;
 }
 __global__ void k_widen_offsets(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

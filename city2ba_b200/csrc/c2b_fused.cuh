@@ -609,7 +609,7 @@ struct SortWriteArgs {
   const double *cams;
   const double *p_aos;  // xyz records, original point order
   uint64_t *out_offsets;
-  uint64_t *out_idx;
+  uint32_t *out_idx;
   double2 *out_uv;
 };
 

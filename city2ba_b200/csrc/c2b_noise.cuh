@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(ST_THREADS)
     k_reproj_partial(const double *__restrict__ cams, const double *__restrict__ px,
                      const double *__restrict__ py, const double *__restrict__ pz,
                      const uint64_t *__restrict__ offsets, uint64_t C,
-                     const uint64_t *__restrict__ idx, const double2 *__restrict__ uv, uint64_t O,
+                     const uint32_t *__restrict__ idx, const double2 *__restrict__ uv, uint64_t O,
                      double norm, double *__restrict__ partial) {
   double s = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < O;

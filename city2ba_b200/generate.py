@@ -182,7 +182,7 @@ def visibility_graph(scene, cameras, points, max_dist, verbose=False, *, cull_mo
         idx = np.ctypeslib.as_array(out.point_idx, shape=(O,)).copy()
         uv = np.ctypeslib.as_array(out.uv, shape=(2 * O,)).copy()
     else:
-        idx, uv = np.zeros(0, np.uint64), np.zeros(0, np.float64)
+        idx, uv = np.zeros(0, np.uint32), np.zeros(0, np.float64)
     st = _stats(out)
     lib().c2b_obs_free(ctx.handle, C.byref(out))
     return VisGraph(offsets, idx, uv, st)
@@ -223,7 +223,7 @@ class ResidentProblem:
         check(lib().c2b_download_obs(self.ctx.handle, C.byref(out)))
         Cn, O = int(out.n_cameras), int(out.n_obs)
         offsets = np.ctypeslib.as_array(out.offsets, shape=(Cn + 1,)).copy()
-        idx = np.ctypeslib.as_array(out.point_idx, shape=(O,)).copy() if O else np.zeros(0, np.uint64)
+        idx = np.ctypeslib.as_array(out.point_idx, shape=(O,)).copy() if O else np.zeros(0, np.uint32)
         uv = np.ctypeslib.as_array(out.uv, shape=(2 * O,)).copy() if O else np.zeros(0)
         return VisGraph(offsets, idx, uv, _stats(out))
 

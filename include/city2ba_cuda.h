@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define C2B_ABI_VERSION 1
+#define C2B_ABI_VERSION 2
 
 typedef enum {
   C2B_OK = 0,
@@ -114,7 +114,8 @@ typedef struct {
   uint64_t n_cameras;
   uint64_t n_obs;
   uint64_t *offsets;   /* [n_cameras+1] */
-  uint64_t *point_idx; /* [n_obs]       */
+  uint32_t *point_idx; /* [n_obs]; 32-bit on purpose: P < 2^32 is enforced, and the result crosses PCIe
+                          (20 instead of 24 bytes per observation); the binding widens to usize */
   double *uv;          /* [2*n_obs] u,v interleaved (normalised image coordinates) */
   /* statistics of this call */
   uint64_t n_candidates;    /* pairs that passed distance/front/frustum (= rays cast)      */
