@@ -37,7 +37,12 @@ WORKLOADS = {
     "cfg2": (4, 10, 10),
     "cfg3": (16, 9, 306),
     "cfg4": (64, 6, 200),
+    # config 5: the same 64x64 city with every wall tessellated 11 x 11 and displaced (4.96 M triangles),
+    # 49,920 lattice cameras, 4,992,000 points sampled on the mesh (area-weighted, seeded)
+    "cfg5": (64, 3, 100),
+    "cfg5s": (16, 3, 100),  # a 16x16-block cut of cfg5 (310 k triangles) for quick runs
 }
+TESS_K = 11
 MAX_DIST = 10.0
 BLOCK_LENGTH, BLOCK_INSET, CAM_H, PT_H, BUILDING_H = 20.0, 1.0, 1.0, 1.0, 10.0
 
@@ -115,9 +120,30 @@ def build_workload(name):
     from city2ba_b200 import synthetic
     n, cpb, ppb = WORKLOADS[name]
     cams = synthetic.grid_cameras(cpb, n, BLOCK_LENGTH, CAM_H)
+    if name.startswith("cfg5"):
+        xyz, tri = synthetic.city_mesh_tessellated(n, TESS_K, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)
+        pts = sample_points_on_walls(xyz, tri, int(synthetic.lib().c2b_grid_num_points(ppb, n)))
+        return cams, pts, xyz, tri
     pts = synthetic.grid_points(ppb, n, BLOCK_LENGTH, BLOCK_INSET, PT_H)
     xyz, tri = synthetic.city_mesh(n, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)
     return cams, pts, xyz, tri
+
+
+def sample_points_on_walls(xyz, tri, n, seed=0xC17B2A):
+    """n world points on the mesh, area-weighted over the triangles that reach below 3 m (what
+    street-level cameras can see), uniform inside each triangle — the rule of src/generate.rs:370-408 with a
+    seeded generator (the reference's thread_rng cannot be seeded)."""
+    rng = np.random.default_rng(seed)
+    a, b, c = (xyz[tri[:, k]].astype(np.float64) for k in range(3))
+    low = np.minimum(np.minimum(a[:, 1], b[:, 1]), c[:, 1]) <= 3.0
+    a, b, c = a[low], b[low], c[low]
+    area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1)
+    cdf = np.cumsum(area)
+    pick = np.minimum(np.searchsorted(cdf, rng.uniform(0, cdf[-1], n)), len(cdf) - 1)
+    r1, r2 = rng.uniform(size=n), rng.uniform(size=n)
+    flip = r1 + r2 > 1
+    r1[flip], r2[flip] = 1 - r1[flip], 1 - r2[flip]
+    return np.ascontiguousarray(a[pick] + r1[:, None] * (b[pick] - a[pick]) + r2[:, None] * (c[pick] - a[pick]))
 
 
 def shard(C, rank, world):
@@ -169,8 +195,8 @@ def run_reference(args):
         "ms_per_step": 1e3 * C * P / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: synthetic {WORKLOADS[args.workload][0]}x"
-                               f"{WORKLOADS[args.workload][0]}-block city, {C} cameras x {P} points, "
-                               f"max_dist {MAX_DIST}", "cameras": C, "points": P,
+                               f"{WORKLOADS[args.workload][0]}-block city{', walls tessellated' if args.workload.startswith('cfg5') else ''}, "
+                               f"{C} cameras x {P} points, max_dist {MAX_DIST}", "cameras": C, "points": P,
                    "triangles": int(len(tri)), "note": "reference binary (Rust + Embree 3.8) cannot be "
                    "built here; this is the oracle's C restatement of its algorithm: OpenMP over "
                    "cameras, brute-force point loop, CPU BVH any-hit; ms_per_step extrapolates the "
@@ -374,7 +400,8 @@ def main():
         "data": "synthetic",
         "config": {
             "workload": f"{args.workload}: synthetic {WORKLOADS[args.workload][0]}x"
-                        f"{WORKLOADS[args.workload][0]}-block city, {C} cameras x {P} points, max_dist {MAX_DIST}",
+                        f"{WORKLOADS[args.workload][0]}-block city{', walls tessellated' if args.workload.startswith('cfg5') else ''}, "
+                        f"{C} cameras x {P} points, max_dist {MAX_DIST}",
             "cameras": C, "points": P, "triangles": int(len(tri)), "bvh_nodes": scene.num_nodes,
             "cull_mode": args.cull_mode, "parallelism": f"camera ranges over {world} GPU(s), mesh/BVH/points replicated",
             "l2": "256 MB buffer written between timed steps (L2 flush)",

@@ -502,14 +502,16 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     fa.tri_count = ctx->tri_count.as<uint32_t>();
     fa.tri_cap = trilist_cap;
     fa.hoist_max = FU_HOIST;
+    fa.packet_bvh = getenv("C2B_NO_PACKET_BVH") == nullptr;
     if (const char *e = getenv("C2B_HOIST_MAX")) fa.hoist_max = (uint32_t)std::min(std::max(0, atoi(e)), FU_HOIST);
     k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
                                                      fa.scene_absmax, trilist_cap, ctx->tri_list.as<uint32_t>(),
-                                                     ctx->tri_count.as<uint32_t>());
+                                                     ctx->tri_count.as<uint32_t>(), fa.counters + 0);
     C2B_KERNEL_CHECK();
   }
   C2B_TRY(read_counters(ctx, h_cnt));
   pairs_eval = h_cnt[1];
+  const bool any_overflow = h_cnt[0] != 0;  // cameras whose leaf list exceeded the cap
   if (pairs_eval >= 0xffffffffull)
     return set_error(C2B_ERR_INVALID, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
   C2B_TRY(ctx->scratch_idx.ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
@@ -526,15 +528,17 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     static const bool occ4 = getenv("C2B_FU_OCC3") == nullptr;  // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3)
     if (mesh) {
       if (cnt)
-        k_visibility_fused<FU_OCC_MESH, true, 3><<<nb, nt, 0, st>>>(fa);
+        k_visibility_fused<FU_OCC_MESH, true, 3, true><<<nb, nt, 0, st>>>(fa);
+      else if (any_overflow)
+        k_visibility_fused<FU_OCC_MESH, false, 4, true><<<nb, nt, 0, st>>>(fa);
       else if (occ4)
-        k_visibility_fused<FU_OCC_MESH, false, 4><<<nb, nt, 0, st>>>(fa);
+        k_visibility_fused<FU_OCC_MESH, false, 4, false><<<nb, nt, 0, st>>>(fa);
       else
-        k_visibility_fused<FU_OCC_MESH, false, 3><<<nb, nt, 0, st>>>(fa);
+        k_visibility_fused<FU_OCC_MESH, false, 3, false><<<nb, nt, 0, st>>>(fa);
     } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
-      k_visibility_fused<FU_OCC_ANALYTIC, false, 2><<<nb, nt, 0, st>>>(fa);
+      k_visibility_fused<FU_OCC_ANALYTIC, false, 2, false><<<nb, nt, 0, st>>>(fa);
     } else {
-      k_visibility_fused<FU_OCC_NONE, false, 3><<<nb, nt, 0, st>>>(fa);
+      k_visibility_fused<FU_OCC_NONE, false, 3, false><<<nb, nt, 0, st>>>(fa);
     }
     C2B_KERNEL_CHECK();
   }

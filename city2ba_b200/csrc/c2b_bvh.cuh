@@ -227,7 +227,14 @@ __global__ void k_bvh_layout(int64_t n, const uint32_t *__restrict__ left,
   uint64_t size = 2ull * (l - f + 1) - 1;
   const float *b = leaf ? leaf_box + 6 * (uint64_t)k_self : int_box + 6 * (uint64_t)k_self;
   int esc = (int)(pre + size);
-  int leaf_slot = leaf ? (int)k_self : -1;
+  // second w field: leaf -> triangle slot (>= 0); internal -> -(pre-order index of the RIGHT child) - 1
+  // (<= -3; the left child is pre + 1), which lane = node traversals need to push both children
+  int leaf_slot = (int)k_self;
+  if (!leaf) {
+    const uint32_t lc = left[k_self];
+    const uint32_t split = (lc & LEAF_BIT) ? (lc & ~LEAF_BIT) : last[lc];
+    leaf_slot = -(int)(pre + 2ull * (split - f + 1)) - 1;
+  }
   nodes[2 * pre] = make_float4(b[0], b[1], b[2], __int_as_float(esc));
   nodes[2 * pre + 1] = make_float4(b[3], b[4], b[5], __int_as_float(leaf_slot));
 }

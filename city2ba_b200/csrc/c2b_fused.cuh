@@ -49,6 +49,7 @@ struct FusedArgs {
   const uint32_t *tri_count;  // [C]
   uint32_t tri_cap;
   uint32_t hoist_max;  // leaf lists up to this length (<= FU_HOIST) get per-camera records
+  int packet_bvh;      // list overflow: 1 = lane = node packet traversal, 0 = per-ray stackless walk
   int endpoint_guard_rel;
   double block_length, block_inset;  // analytic occlusion (src/synthetic.rs:52-124)
   // plan + output
@@ -280,8 +281,105 @@ __device__ __forceinline__ bool direction_box_may_hit(const TriRec &t, float dlx
   return !(some_neg && some_pos);                             // NaN bounds keep the triangle
 }
 
-// list-driven any-hit for a packet of rays that share the origin (ox, oy, oz).  rec = 32 x 3 float4
-// of this warp.  Returns true when this lane's ray is occluded.
+// bounding box of a packet's ray segments (origin + end points, conservatively padded) and of its
+// directions, reduced over the warp with REDUX on order-preserving integer images of the floats
+struct PacketBounds {
+  float blx, bly, blz, bhx, bhy, bhz;  // segments
+  float dlx, dly, dlz, dhx, dhy, dhz;  // directions
+};
+
+
+__device__ __forceinline__ PacketBounds packet_bounds(const Ray &ray, bool alive, float ox, float oy,
+                                                      float oz, float scene_absmax) {
+  float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+  float dlx = INFINITY, dly = INFINITY, dlz = INFINITY, dhx = -INFINITY, dhy = -INFINITY, dhz = -INFINITY;
+  if (alive) {
+    const float pad = conservative_pad(ox, oy, oz, scene_absmax) + 4e-6f * ray.tfar;
+    const float ex = fmaf(ray.dx, ray.tfar, ox), ey = fmaf(ray.dy, ray.tfar, oy), ez = fmaf(ray.dz, ray.tfar, oz);
+    lx = fminf(ox, ex) - pad;
+    ly = fminf(oy, ey) - pad;
+    lz = fminf(oz, ez) - pad;
+    hx = fmaxf(ox, ex) + pad;
+    hy = fmaxf(oy, ey) + pad;
+    hz = fmaxf(oz, ez) + pad;
+    dlx = dhx = ray.dx;
+    dly = dhy = ray.dy;
+    dlz = dhz = ray.dz;
+  }
+  PacketBounds b;
+  b.blx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx)));
+  b.bly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly)));
+  b.blz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz)));
+  b.bhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
+  b.bhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
+  b.bhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
+  b.dlx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlx)));
+  b.dly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dly)));
+  b.dlz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlz)));
+  b.dhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhx)));
+  b.dhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhy)));
+  b.dhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhz)));
+  return b;
+}
+
+__device__ __forceinline__ bool box_meets_packet(const PacketBounds &b, float4 lo, float4 hi) {
+  // written so that NaN compares keep the box (conservative)
+  return !(lo.x > b.bhx || hi.x < b.blx || lo.y > b.bhy || hi.y < b.bly || lo.z > b.bhz || hi.z < b.blz);
+}
+
+// lane = triangle: lanes with `want` load triangle `slot`, build its record for the origin, drop it
+// if the direction box cannot hit it, and park the survivors' records in rec[0..3*cnt);
+// then lane = ray: every record is tested.  Returns false when no ray of the packet is left alive.
+template <bool COUNT>
+__device__ __forceinline__ bool test_leaf_chunk(const FusedArgs &a, const PacketBounds &pb, int slot, bool want,
+                                                const Ray &ray, bool &alive, bool &occ, float ox, float oy,
+                                                float oz, float4 *rec, int lane, unsigned &n_tri) {
+  TriRec t;
+  if (want) {
+    const float4 v0 = __ldg(&a.tris[3 * slot]);
+    const float4 v1 = __ldg(&a.tris[3 * slot + 1]);
+    const float4 v2 = __ldg(&a.tris[3 * slot + 2]);
+    t = tri_record(ox, oy, oz, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z);
+    want = direction_box_may_hit(t, pb.dlx, pb.dly, pb.dlz, pb.dhx, pb.dhy, pb.dhz);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (m == 0u) return true;
+  if (want) {
+    float4 *r = rec + 3 * __popc(m & ((1u << lane) - 1u));
+    r[0] = make_float4(t.ux, t.uy, t.uz, t.vx);
+    r[1] = make_float4(t.vy, t.vz, t.wx, t.wy);
+    r[2] = make_float4(t.wz, t.T, 0.0f, 0.0f);
+  }
+  __syncwarp();
+  const int cnt = __popc(m);
+  if (COUNT) n_tri += cnt;
+  bool any_alive = true;
+  int k = 0;
+  for (; k + 1 < cnt; k += 2) {
+    const TriRec t0 = load_rec(rec, k), t1 = load_rec(rec, k + 1);
+    const bool h0 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
+    const bool h1 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t1);
+    if (alive && (h0 || h1)) {
+      occ = true;
+      alive = false;
+    }
+    any_alive = __ballot_sync(0xffffffffu, alive) != 0u;
+    if (!any_alive) break;
+  }
+  if (any_alive && (cnt & 1)) {
+    const TriRec t0 = load_rec(rec, cnt - 1);
+    if (alive && ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0)) {
+      occ = true;
+      alive = false;
+    }
+    any_alive = __ballot_sync(0xffffffffu, alive) != 0u;
+  }
+  __syncwarp();
+  return any_alive;
+}
+
+// list-driven any-hit for a packet of rays that share the origin (ox, oy, oz).  Returns true when
+// this lane's ray is occluded.
 //
 // Two conservative filters run with lane = triangle before any ray is tested: (1) the leaf box must
 // overlap the bounding box of the packet's ray segments; (2) with the record in hand, the three edge
@@ -296,43 +394,17 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
   bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
   bool occ = false;
   if (__ballot_sync(0xffffffffu, alive) == 0u) return false;
-  // bounding box of the packet's ray segments (origin + end points), conservatively padded, and of
-  // its directions
-  float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
-  float dlx = INFINITY, dly = INFINITY, dlz = INFINITY, dhx = -INFINITY, dhy = -INFINITY, dhz = -INFINITY;
-  if (alive) {
-    const float pad = conservative_pad(ox, oy, oz, a.scene_absmax) + 4e-6f * ray.tfar;
-    const float ex = fmaf(ray.dx, ray.tfar, ox), ey = fmaf(ray.dy, ray.tfar, oy), ez = fmaf(ray.dz, ray.tfar, oz);
-    lx = fminf(ox, ex) - pad;
-    ly = fminf(oy, ey) - pad;
-    lz = fminf(oz, ez) - pad;
-    hx = fmaxf(ox, ex) + pad;
-    hy = fmaxf(oy, ey) + pad;
-    hz = fmaxf(oz, ez) + pad;
-    dlx = dhx = ray.dx;
-    dly = dhy = ray.dy;
-    dlz = dhz = ray.dz;
-  }
-  const float blx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx)));
-  const float bly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly)));
-  const float blz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz)));
-  const float bhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
-  const float bhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
-  const float bhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
-  dlx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlx)));
-  dly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dly)));
-  dlz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlz)));
-  dhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhx)));
-  dhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhy)));
-  dhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhz)));
+  const PacketBounds pb = packet_bounds(ray, alive, ox, oy, oz, a.scene_absmax);
   if (hoisted) {
     for (uint32_t base = 0; base < n_list; base += 32) {
       const uint32_t j = base + lane;
       bool overlap = false;
       if (j < n_list) {
         const float4 r2 = rec[2 * FU_HOIST + j], r3 = rec[3 * FU_HOIST + j];
-        overlap = !(r2.z > bhx || r3.y < blx || r2.w > bhy || r3.z < bly || r3.x > bhz || r3.w < blz);
-        if (overlap) overlap = direction_box_may_hit(unpack_rec(rec[j], rec[FU_HOIST + j], r2), dlx, dly, dlz, dhx, dhy, dhz);
+        overlap = box_meets_packet(pb, make_float4(r2.z, r2.w, r3.x, 0.0f), make_float4(r3.y, r3.z, r3.w, 0.0f));
+        if (overlap)
+          overlap = direction_box_may_hit(unpack_rec(rec[j], rec[FU_HOIST + j], r2), pb.dlx, pb.dly, pb.dlz, pb.dhx,
+                                          pb.dhy, pb.dhz);
       }
       unsigned m = __ballot_sync(0xffffffffu, overlap);
       if (COUNT) {
@@ -360,61 +432,96 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
   for (uint32_t base = 0; base < n_list; base += 32) {
     const uint32_t j = base + lane;
     bool overlap = false;
-    TriRec t;
+    int slot = 0;
     if (j < n_list) {
       const uint32_t node = mylist[j];
       const float4 lo = __ldg(&a.nodes[2 * node]);
       const float4 hi = __ldg(&a.nodes[2 * node + 1]);
-      overlap = !(lo.x > bhx || hi.x < blx || lo.y > bhy || hi.y < bly || lo.z > bhz || hi.z < blz);
-      if (overlap) {
-        const int slot = __float_as_int(hi.w);
-        const float4 v0 = __ldg(&a.tris[3 * slot]);
-        const float4 v1 = __ldg(&a.tris[3 * slot + 1]);
-        const float4 v2 = __ldg(&a.tris[3 * slot + 2]);
-        t = tri_record(ox, oy, oz, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z);
-        overlap = direction_box_may_hit(t, dlx, dly, dlz, dhx, dhy, dhz);
-      }
+      overlap = box_meets_packet(pb, lo, hi);
+      slot = __float_as_int(hi.w);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, overlap);
     if (COUNT) n_vis += min(32u, n_list - base);
-    if (m == 0u) continue;
-    if (overlap) {
-      float4 *r = rec + 3 * __popc(m & ((1u << lane) - 1u));
-      r[0] = make_float4(t.ux, t.uy, t.uz, t.vx);
-      r[1] = make_float4(t.vy, t.vz, t.wx, t.wy);
-      r[2] = make_float4(t.wz, t.T, 0.0f, 0.0f);
-    }
-    __syncwarp();
-    const int cnt = __popc(m);
-    if (COUNT) n_tri += cnt;
-    int k = 0;
-    for (; k + 1 < cnt; k += 2) {
-      const TriRec t0 = load_rec(rec, k), t1 = load_rec(rec, k + 1);
-      const bool h0 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
-      const bool h1 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t1);
-      if (alive && (h0 || h1)) {
-        occ = true;
-        alive = false;
-      }
-      if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-    }
-    if (k < cnt && (cnt & 1)) {
-      const TriRec t0 = load_rec(rec, cnt - 1);
-      if (alive && ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0)) {
-        occ = true;
-        alive = false;
-      }
-    }
-    __syncwarp();
-    if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+    if (!test_leaf_chunk<COUNT>(a, pb, slot, overlap, ray, alive, occ, ox, oy, oz, rec, lane, n_tri)) break;
   }
   return occ;
+}
+
+// ---- packet traversal of the BVH, lane = node --------------------------------------------------------
+// For cameras whose leaf list overflows (fine meshes).  The warp keeps a LIFO of node indices in
+// shared memory; each step pops up to 32 nodes, every lane tests ONE node's box against the
+// packet's segment box (two LDG.128, six compares — no per-ray slab test), overlapping leaves go to
+// a pending-leaf buffer, overlapping internal nodes push both children (left = node + 1, right =
+// -hi.w - 1).  Whenever 32 leaves are pending (or the LIFO is empty) they are resolved with
+// test_leaf_chunk.  The per-warp 4 KB region is split: records [0, 96) float4, pending leaves 64 u32,
+// LIFO FU_LIFO u32.  Returns 2 if the LIFO would overflow (the caller falls back to the per-ray
+// stackless walk, which needs no memory), else 0 / 1 = this lane's ray is occluded.
+constexpr int FU_LIFO = 576;
+
+template <bool COUNT>
+__device__ __forceinline__ int packet_bvh_hit(const FusedArgs &a, const Ray &ray, bool have, float ox, float oy,
+                                              float oz, float4 *region, int lane, unsigned &n_vis,
+                                              unsigned &n_tri) {
+  bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
+  bool occ = false;
+  if (__ballot_sync(0xffffffffu, alive) == 0u) return 0;
+  const PacketBounds pb = packet_bounds(ray, alive, ox, oy, oz, a.scene_absmax);
+  float4 *rec = region;
+  uint32_t *pending = reinterpret_cast<uint32_t *>(region + 96);
+  uint32_t *lifo = pending + 64;
+  int sp = 1, np = 0;
+  if (lane == 0) lifo[0] = 0u;
+  __syncwarp();
+  while (sp > 0 || np > 0) {
+    if (sp > 0 && np <= 32) {
+      const int take = sp < 32 ? sp : 32;
+      const bool mine = lane < take;
+      bool leaf = false, inner = false;
+      int slot = 0;
+      uint32_t node = 0, right = 0;
+      if (mine) {
+        node = lifo[sp - take + lane];
+        const float4 lo = __ldg(&a.nodes[2 * node]);
+        const float4 hi = __ldg(&a.nodes[2 * node + 1]);
+        if (box_meets_packet(pb, lo, hi)) {
+          slot = __float_as_int(hi.w);
+          leaf = slot >= 0;
+          inner = !leaf;
+          right = (uint32_t)(-slot - 1);
+        }
+      }
+      __syncwarp();  // every lane has read its node before anyone pushes into the same slots
+      sp -= take;
+      if (COUNT) n_vis += take;
+      const unsigned lm = __ballot_sync(0xffffffffu, leaf), im = __ballot_sync(0xffffffffu, inner);
+      if (sp + 2 * __popc(im) > FU_LIFO) return 2;
+      const unsigned lt = (1u << lane) - 1u;
+      if (leaf) pending[np + __popc(lm & lt)] = (uint32_t)slot;
+      if (inner) {
+        const int pos = sp + 2 * __popc(im & lt);
+        lifo[pos] = node + 1u;
+        lifo[pos + 1] = right;
+      }
+      np += __popc(lm);
+      sp += 2 * __popc(im);
+      __syncwarp();
+    } else {
+      const int cnt = np < 32 ? np : 32;
+      const bool want = lane < cnt;
+      const int slot = want ? (int)pending[np - cnt + lane] : 0;
+      np -= cnt;
+      if (!test_leaf_chunk<COUNT>(a, pb, slot, want, ray, alive, occ, ox, oy, oz, rec, lane, n_tri)) break;
+    }
+  }
+  return occ ? 1 : 0;
 }
 
 // Persistent warps: every warp draws the next camera from a global ticket (counters[7]), so a warp
 // that drew a cheap camera (city edge, few points in range) immediately gets another one and no
 // warp idles waiting for the slowest camera of its block.
-template <int OCC, bool COUNT, int MIN_CTAS>
+// WALK = the BVH traversals for cameras whose leaf list overflowed are compiled in; the host picks
+// the variant without them when k_cam_trilist reported no overflow (coarse meshes), which keeps
+// their registers out of the list-driven fast path.
+template <int OCC, bool COUNT, int MIN_CTAS, bool WALK>
 __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
   __shared__ double s_cam[FU_WARPS][16];
   __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
@@ -470,9 +577,11 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       }
       bool occ = false;
       if (OCC == FU_OCC_MESH) {
-        if (n_list == TRILIST_OVERFLOW)
-          occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
-        else
+        if (WALK && n_list == TRILIST_OVERFLOW) {
+          const int r = a.packet_bvh ? packet_bvh_hit<COUNT>(a, ray, have, ox, oy, oz, s_rec[warp], lane, n_vis_nodes, n_tri) : 2;
+          occ = r == 2 ? warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters)
+                       : r == 1;
+        } else
           occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, s_rec[warp], hoisted, lane, n_vis_nodes, n_tri);
       } else if (OCC == FU_OCC_ANALYTIC) {
         occ = have && hits_building(cen, p, a.block_length, a.block_inset);

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128)
     k_cam_trilist(const float4 *__restrict__ nodes, int n_nodes, const double *__restrict__ cen_x,
                   const double *__restrict__ cen_y, const double *__restrict__ cen_z, uint64_t C,
                   float rmax, float scene_absmax, uint32_t cap, uint32_t *__restrict__ list,
-                  uint32_t *__restrict__ count) {
+                  uint32_t *__restrict__ count, unsigned long long *__restrict__ n_overflow) {
   const uint64_t cam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (cam >= C) return;
   const float ox = __double2float_rn(cen_x[cam]), oy = __double2float_rn(cen_y[cam]),
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(128)
     }
   }
   count[cam] = n <= cap ? n : TRILIST_OVERFLOW;
+  if (n > cap) atomicAdd(n_overflow, 1ull);
 }
 
 // ---- Embree-shaped ray batch (parity tooling): AoS 48-byte rays, tfar = -inf on hit ---------------

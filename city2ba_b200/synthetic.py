@@ -47,6 +47,50 @@ def city_mesh(num_blocks, block_length=20.0, block_inset=1.0, height=10.0):
     return xyz, tri
 
 
+def city_mesh_tessellated(num_blocks, k, block_length=20.0, block_inset=1.0, height=10.0, amplitude=0.05):
+    """The city-block boxes with every wall and roof tessellated into k x k quads (2 k^2 triangles per
+    face, 10 k^2 per block) and the INTERIOR vertices of each face displaced along the face normal by
+    a deterministic hash of their lattice position (borders stay put, so the boxes remain closed).
+    This is BASELINE config 5's "large OBJ city mesh": 64 blocks x k = 11 gives 4.96 M triangles.
+    A new artefact (the reference has no synthetic mesh); plain numpy, no RNG."""
+    n, L, ins, H = int(num_blocks), float(block_length), float(block_inset), float(height)
+    g = np.arange(k + 1, dtype=np.float64) / k
+    a, b = np.meshgrid(g, g, indexing="ij")                      # face parameters in [0, 1]^2
+    interior = ((a > 0) & (a < 1) & (b > 0) & (b < 1)).astype(np.float64)
+    ia, ib = np.meshgrid(np.arange(k + 1), np.arange(k + 1), indexing="ij")
+    vid = np.arange((k + 1) * (k + 1)).reshape(k + 1, k + 1)
+    q00, q10, q11, q01 = vid[:-1, :-1].ravel(), vid[1:, :-1].ravel(), vid[1:, 1:].ravel(), vid[:-1, 1:].ravel()
+    face_tri = np.concatenate([np.stack([q00, q10, q11], 1), np.stack([q00, q11, q01], 1)])
+    bx, bz = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    bx, bz = bx.ravel()[:, None, None], bz.ravel()[:, None, None]  # (blocks, 1, 1)
+    x0, x1 = bx * L + ins, (bx + 1) * L - ins
+    z0, z1 = bz * L + ins, (bz + 1) * L - ins
+    A, B = a[None], b[None]
+
+    def disp(face):
+        # integer hash of (block, face, lattice position) -> [-1, 1]
+        h = (bx * 73856093) ^ (bz * 19349663) ^ (face * 83492791) ^ (ia[None] * 2654435761) ^ (ib[None] * 40503)
+        h = (h ^ (h >> 13)) * 1274126177 & 0xffffffff
+        return ((h & 0xffff) / 32767.5 - 1.0) * amplitude * interior[None]
+
+    faces = []
+    one = np.ones_like(A)
+    faces.append((x0 + A * (x1 - x0), B * H * one, z0 * one - disp(0)))            # z lo wall
+    faces.append((x0 + A * (x1 - x0), B * H * one, z1 * one + disp(1)))            # z hi wall
+    faces.append((x0 * one - disp(2), B * H * one, z0 + A * (z1 - z0)))            # x lo wall
+    faces.append((x1 * one + disp(3), B * H * one, z0 + A * (z1 - z0)))            # x hi wall
+    faces.append((x0 + A * (x1 - x0), H * one + disp(4), z0 + B * (z1 - z0)))      # roof
+    nv_face = (k + 1) * (k + 1)
+    xyz = np.empty((n * n, 5, nv_face, 3), np.float32)
+    for f, (X, Y, Z) in enumerate(faces):
+        xyz[:, f, :, 0] = np.broadcast_to(X, (n * n, k + 1, k + 1)).reshape(n * n, -1)
+        xyz[:, f, :, 1] = np.broadcast_to(Y, (n * n, k + 1, k + 1)).reshape(n * n, -1)
+        xyz[:, f, :, 2] = np.broadcast_to(Z, (n * n, k + 1, k + 1)).reshape(n * n, -1)
+    base = (np.arange(n * n * 5, dtype=np.int64) * nv_face)[:, None, None]
+    tri = (face_tri[None].astype(np.int64) + base).reshape(-1, 3).astype(np.uint32)
+    return xyz.reshape(-1, 3), tri
+
+
 def synthetic_grid(num_cameras_per_block, num_points_per_block, num_blocks, block_length,
                    block_inset, camera_height, point_height, max_dist, verbose=False, *,
                    occlusion="analytic", building_height=10.0, cull=True, cull_mode="grid",

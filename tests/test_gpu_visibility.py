@@ -276,9 +276,10 @@ def test_dense_mesh_overflows_triangle_lists(c2b, ctx, orc):
 
 
 def test_list_modes_agree(c2b, ctx, orc, cfg2, monkeypatch):
-    """the three ways a packet finds its triangles — per-camera records in shared memory
-    (leaf list <= 64), per-packet records (<= 128, forced here with C2B_HOIST_MAX=0) and the
-    stackless BVH walk (list overflow, forced with C2B_TRILIST_CAP=1) — give the same graph"""
+    """the four ways a packet finds its triangles — per-camera records in shared memory (leaf list
+    <= 64), per-packet records (<= 128, forced here with C2B_HOIST_MAX=0), the lane = node packet
+    traversal of the BVH (list overflow, forced with C2B_TRILIST_CAP=1) and the per-ray stackless
+    walk (C2B_NO_PACKET_BVH) — give the same graph"""
     cams, pts, xyz, tri = cfg2
     scene = c2b.Scene(xyz, tri, ctx=ctx)
     ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
@@ -286,7 +287,9 @@ def test_list_modes_agree(c2b, ctx, orc, cfg2, monkeypatch):
     monkeypatch.setenv("C2B_HOIST_MAX", "0")
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-packet records")
     monkeypatch.setenv("C2B_TRILIST_CAP", "1")
-    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "bvh walk")
+    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "packet bvh")
+    monkeypatch.setenv("C2B_NO_PACKET_BVH", "1")
+    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-ray walk")
 
 
 def test_frustum_edge_classification(c2b, ctx, orc):
@@ -318,3 +321,22 @@ def test_frustum_edge_classification(c2b, ctx, orc):
     assert 0 < ref.n_obs < len(cams) * len(pts)
     for mode in MODES:
         assert_same_graph(c2b.visibility_graph(empty, cams, pts, 20.0, cull_mode=mode, ctx=ctx), ref, f"edge/{mode}")
+
+
+@pytest.mark.parametrize("k", [2, 4, 11])
+def test_tessellated_city(c2b, ctx, orc, k):
+    """BASELINE config 5 in the small: city blocks whose walls are tessellated k x k and displaced,
+    points sampled on the mesh.  k = 2 keeps the per-camera leaf lists short (records hoisted per
+    camera), k = 4 lands between 64 and 128 entries for many cameras (per-packet records), k = 11
+    overflows the lists (stackless BVH walk).  All must reproduce the brute-force oracle."""
+    from city2ba_b200 import synthetic
+    import bench
+    n = 3
+    xyz, tri = synthetic.city_mesh_tessellated(n, k)
+    cams = synthetic.grid_cameras(4, n, 20.0, 1.0)
+    pts = bench.sample_points_on_walls(xyz, tri, 6000, seed=k)
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
+    assert 0 < ref.n_obs < ref.n_candidates
+    for mode in MODES:
+        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, cull_mode=mode, ctx=ctx), ref, f"tess{k}/{mode}")
