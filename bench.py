@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--cull-mode", default="grid", choices=["grid", "exhaustive"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exhaustive", action="store_true")
+    ap.add_argument("--no-noise", action="store_true")
     args = ap.parse_args()
     if args.workload is None:
         # the metric's target is quoted on the 64x64-block city (cfg4); it fits one GPU
@@ -317,6 +318,40 @@ def main():
     h2d, d2h = int(out.h2d_bytes), int(out.d2h_bytes)
     n_obs_local = int(out.n_obs)
     e2e_stage = {k: float(getattr(out, k)) for k in ("ms_h2d", "ms_prep", "ms_cull", "ms_sort", "ms_traverse", "ms_compact", "ms_d2h")}
+
+    # ---- noise pass on the generated problem (config 2 / 5: drift + Gaussian noise), rank 0 only ------
+    noise = None
+    if not args.no_noise and rank == 0:
+        O = int(out.n_obs)
+        pd_ = Ct.POINTER(Ct.c_double)
+        # pinned host arrays (what a host program that cares about transfer time would hand over)
+        t_uv = torch.from_numpy(np.ctypeslib.as_array(out.uv, shape=(2 * O,)).copy() if O else np.zeros(0)).pin_memory()
+        t_cam = torch.from_numpy(np.ascontiguousarray(cams[c0:c1]).copy()).pin_memory()
+        t_pts = torch.from_numpy(pts.copy()).pin_memory()
+        uv, ncam, npts = t_uv.numpy(), t_cam.numpy(), t_pts.numpy()
+        ms3 = (Ct.c_float * 3)()
+        noise = {}
+        for name, call, nbytes in (
+            ("add_drift_normalized", lambda: L.c2b_add_drift_normalized(
+                ctx.handle, ncam.ctypes.data_as(pd_), len(ncam), npts.ctypes.data_as(pd_), len(npts),
+                0.001, 0.0, 0.0, 1), 2 * (120 * len(ncam) + 24 * len(npts)) + 3 * 24 * (len(ncam) + len(npts))),
+            ("add_noise", lambda: L.c2b_add_noise(
+                ctx.handle, ncam.ctypes.data_as(pd_), len(ncam), npts.ctypes.data_as(pd_), len(npts),
+                uv.ctypes.data_as(pd_), O, 0.0, 0.0001, 0.01, 0.001, 42),
+             2 * (120 * len(ncam) + 24 * len(npts) + 16 * O) + 2 * 24 * (len(ncam) + len(npts))),
+        ):
+            best_wall, kern = 1e9, 0.0
+            for _ in range(3):
+                t0 = time.perf_counter()
+                _lib.check(call())
+                best_wall = min(best_wall, time.perf_counter() - t0)
+                _lib.check(L.c2b_noise_timing(ctx.handle, ms3))
+                kern = float(ms3[1])
+            noise[name] = {"elements": len(ncam) + len(npts) + (O if name == "add_noise" else 0),
+                           "ms_host_to_host": 1e3 * best_wall, "ms_kernels": kern,
+                           "algorithmic_bytes": nbytes, "kernel_GBps": nbytes / (kern * 1e-3) / 1e9 if kern > 0 else None,
+                           "note": "pinned host arrays in and out (H2D + D2H inside ms_host_to_host); "
+                                   "ms_kernels = statistics reductions + elementwise kernels (CUDA events)"}
 
     # ---- traversal counters (one untimed instrumented run) and the exhaustive arm ------------------
     _, stc = resident_arm(args.cull_mode, 1, 0, count=True)
@@ -424,6 +459,8 @@ def main():
         },
         "clocks": clocks,
     }
+    if noise is not None:
+        line["noise"] = noise
     if ex is not None:
         line["exhaustive"] = {"value": C * P / ex_t, "unit": "tests/s", "ms_per_step": 1e3 * ex_t,
                               "cull_ms": ex_cull, "steps": ex[2],

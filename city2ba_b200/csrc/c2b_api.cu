@@ -1006,6 +1006,27 @@ struct NoiseBufs {
   }
 };
 
+// device time of the last noise call: [0] upload, [1] statistics + kernels, [2] download
+struct NoiseTimer {
+  c2b_ctx *ctx;
+  cudaEvent_t ev[4] = {};
+  explicit NoiseTimer(c2b_ctx *c) : ctx(c) {
+    for (auto &e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], ctx->stream);
+  }
+  void mark(int k) { cudaEventRecord(ev[k], ctx->stream); }
+  void finish() {
+    for (int k = 0; k < 3; ++k) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, ev[k], ev[k + 1]) != cudaSuccess) (void)cudaGetLastError();
+      ctx->noise_ms[k] = t;
+    }
+  }
+  ~NoiseTimer() {
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
+};
+
 // mean / std / nearest-origin of the chained sequence on the device.  scratch layout (doubles):
 // [0..2] mean, [3..5] sumsq, [6..8] origin, then partials.
 int device_stats(c2b_ctx *ctx, NoiseBufs &nb, uint64_t C, uint64_t P, double mean[3], double sd[3],
@@ -1073,7 +1094,9 @@ int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, 
   C2B_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   NoiseBufs nb;
+  NoiseTimer tm(ctx);
   C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
+  tm.mark(1);
   double mean[3], sd[3];
   C2B_TRY(device_stats(ctx, nb, C, P, mean, sd, true));
   V3 dir;
@@ -1092,14 +1115,17 @@ int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, 
     k_drift_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, origin, dir, strength,
                                                      angle_strength, std_, seed);
     C2B_KERNEL_CHECK();
-    C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
   }
   if (P) {
     k_drift_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, origin, dir, strength, std_, seed);
     C2B_KERNEL_CHECK();
-    C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
   }
+  tm.mark(2);
+  if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
+  if (P) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
   C2B_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
   return C2B_OK;
 }
 }  // namespace
@@ -1124,7 +1150,9 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
   C2B_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   NoiseBufs nb;
+  NoiseTimer tm(ctx);
   C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, uv, O));
+  tm.mark(1);
   double mean[3], sd[3];
   C2B_TRY(device_stats(ctx, nb, C, P, mean, sd, false));
   double bal_std = std::sqrt((sd[0] * sd[0] + sd[1] * sd[1]) + sd[2] * sd[2]);
@@ -1132,19 +1160,76 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
     k_noise_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, bal_std, translation_std,
                                                      rotation_std, seed);
     C2B_KERNEL_CHECK();
-    C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
   }
   if (P) {
     k_noise_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, point_std, seed);
     C2B_KERNEL_CHECK();
-    C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
   }
   if (O) {
     k_noise_obs<<<blocks_for(O, 256), 256, 0, st>>>(nb.uv.as<double2>(), O, observations_std, seed);
     C2B_KERNEL_CHECK();
-    C2B_CUDA(cudaMemcpyAsync(uv, nb.uv.p, O * 16, cudaMemcpyDeviceToHost, st));
   }
+  tm.mark(2);
+  if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
+  if (P) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  if (O) C2B_CUDA(cudaMemcpyAsync(uv, nb.uv.p, O * 16, cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
   C2B_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return C2B_OK;
+}
+
+int c2b_add_sin_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, const double dir[3],
+                      const double noise_dir[3], double strength, double frequency) {
+  if (!ctx || (C && !cams) || (P && !pts) || !dir || !noise_dir)
+    return set_error(C2B_ERR_INVALID, "c2b_add_sin_noise: null argument");
+  if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_sin_noise: problem has no cameras and no points");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  NoiseBufs nb;
+  NoiseTimer tm(ctx);
+  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
+  tm.mark(1);
+  const uint64_t n = C + P;
+  int blocks = (int)std::min<uint64_t>(std::max<uint64_t>(blocks_for(n, ST_THREADS), 1), ST_BLOCKS);
+  C2B_TRY(nb.scratch.ensure((size_t)(8 + 6 * blocks) * 8));
+  double *s = nb.scratch.as<double>();
+  const double *cx = nb.centers.as<double>();
+  k_extent_partial<<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, nb.pts.as<double>(), P, s + 8);
+  C2B_KERNEL_CHECK();
+  k_extent_final<<<1, 32, 0, st>>>(s + 8, blocks, s);
+  C2B_KERNEL_CHECK();
+  double ext[6];
+  C2B_CUDA(cudaMemcpyAsync(ext, s, 48, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  V3 dim{ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
+  // "Add epsilon to nonexistent dimensions" (src/noise.rs:395-396)
+  if (dim.x == 0.0) dim.x = 1e-8;
+  if (dim.y == 0.0) dim.y = 1e-8;
+  if (dim.z == 0.0) dim.z = 1e-8;
+  const double nm = std::sqrt((noise_dir[0] * noise_dir[0] + noise_dir[1] * noise_dir[1]) + noise_dir[2] * noise_dir[2]);
+  const double inv = 1.0 / nm;
+  const V3 nd{noise_dir[0] * inv, noise_dir[1] * inv, noise_dir[2] * inv}, d{dir[0], dir[1], dir[2]};
+  if (C) {
+    k_sin_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, dim, d, nd, strength, frequency);
+    C2B_KERNEL_CHECK();
+  }
+  if (P) {
+    k_sin_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, dim, d, nd, strength, frequency);
+    C2B_KERNEL_CHECK();
+  }
+  tm.mark(2);
+  if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
+  if (P) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  tm.mark(3);
+  C2B_CUDA(cudaStreamSynchronize(st));
+  tm.finish();
+  return C2B_OK;
+}
+
+int c2b_noise_timing(c2b_ctx *ctx, float ms[3]) {
+  if (!ctx || !ms) return set_error(C2B_ERR_INVALID, "c2b_noise_timing: null argument");
+  for (int k = 0; k < 3; ++k) ms[k] = ctx->noise_ms[k];
   return C2B_OK;
 }
 

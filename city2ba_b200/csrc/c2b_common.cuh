@@ -186,6 +186,8 @@ struct c2b_ctx {
   // fused grid schedule: per-camera plan (row points -> scratch slice), visible counts, CSR offsets
   c2b::DevBuf ev_off, vis_count, seg_off, scratch_idx;
 
+  float noise_ms[3] = {0, 0, 0};  // last noise call: upload, statistics + kernels, download
+
   // host results
   c2b::PinBuf h_offsets, h_idx, h_uv, h_small;
 };

@@ -270,6 +270,84 @@ __global__ void k_noise_obs(double2 *__restrict__ uv, uint64_t O, double observa
   uv[i] = q;
 }
 
+// ---- add_sin_noise, src/noise.rs:388-416 --------------------------------------------------------------
+// extent of the chained sequence (BAProblem::extent, src/baproblem.rs:307-330): partial[6*block + k]
+__global__ void __launch_bounds__(ST_THREADS)
+    k_extent_partial(const double *__restrict__ cx, const double *__restrict__ cy,
+                     const double *__restrict__ cz, uint64_t C, const double *__restrict__ pts,
+                     uint64_t P, double *__restrict__ partial) {
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  uint64_t n = C + P;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    V3 e = chain_element(cx, cy, cz, C, pts, i);
+    // f64::min / f64::max semantics (a NaN operand is ignored), like fmin / fmax
+    lo[0] = fmin(lo[0], e.x); lo[1] = fmin(lo[1], e.y); lo[2] = fmin(lo[2], e.z);
+    hi[0] = fmax(hi[0], e.x); hi[1] = fmax(hi[1], e.y); hi[2] = fmax(hi[2], e.z);
+  }
+  __shared__ double sh[6][ST_THREADS / 32];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      sh[k][threadIdx.x >> 5] = lo[k];
+      sh[3 + k][threadIdx.x >> 5] = hi[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double r = sh[threadIdx.x][0];
+    for (int w = 1; w < ST_THREADS / 32; ++w)
+      r = threadIdx.x < 3 ? fmin(r, sh[threadIdx.x][w]) : fmax(r, sh[threadIdx.x][w]);
+    partial[6 * (uint64_t)blockIdx.x + threadIdx.x] = r;
+  }
+}
+// out6 = min xyz, max xyz
+__global__ void k_extent_final(const double *__restrict__ partial, int nb, double *__restrict__ out6) {
+  if (threadIdx.x < 6) {
+    double r = partial[threadIdx.x];
+    for (int b = 1; b < nb; ++b)
+      r = threadIdx.x < 3 ? fmin(r, partial[6 * b + threadIdx.x]) : fmax(r, partial[6 * b + threadIdx.x]);
+    out6[threadIdx.x] = r;
+  }
+}
+
+// noise(x) = sin(dot(x / dimension, dir) * frequency * pi) * strength * normalize(noise_dir)
+__device__ __forceinline__ V3 sin_noise(V3 x, V3 dim, V3 dir, V3 nd, double strength, double frequency) {
+  const V3 q{ddiv(x.x, dim.x), ddiv(x.y, dim.y), ddiv(x.z, dim.z)};
+  const double dot = dadd(dadd(dmul(q.x, dir.x), dmul(q.y, dir.y)), dmul(q.z, dir.z));
+  const double amp = dmul(sin(dmul(dmul(dot, frequency), 3.14159265358979323846)), strength);
+  return V3{dmul(nd.x, amp), dmul(nd.y, amp), dmul(nd.z, amp)};
+}
+
+__global__ void k_sin_cams(double *__restrict__ cams, uint64_t C, V3 dim, V3 dir, V3 nd, double strength,
+                           double frequency) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  double cam[15], out[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) cam[k] = cams[15 * i + k];
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // Basis3::one()
+  camera_transform(cam, I, sin_noise(camera_center(cam), dim, dir, nd, strength, frequency), out);
+#pragma unroll
+  for (int k = 0; k < 15; ++k) cams[15 * i + k] = out[k];
+}
+
+__global__ void k_sin_pts(double *__restrict__ pts, uint64_t P, V3 dim, V3 dir, V3 nd, double strength,
+                          double frequency) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  const V3 d = sin_noise(p, dim, dir, nd, strength, frequency);
+  pts[3 * i] = dadd(p.x, d.x);
+  pts[3 * i + 1] = dadd(p.y, d.y);
+  pts[3 * i + 2] = dadd(p.z, d.z);
+}
+
 // ---- total_reprojection_error, src/baproblem.rs:265-279 (one thread per observation, two-stage sum)
 __global__ void __launch_bounds__(ST_THREADS)
     k_reproj_partial(const double *__restrict__ cams, const double *__restrict__ px,

@@ -57,3 +57,22 @@ def add_noise(bal: BAProblem, translation_std, rotation_std, point_std, observat
                               float(translation_std), float(rotation_std), float(point_std),
                               float(observations_std), _seed(seed)))
     return BAProblem(cams, pts, VisGraph(g.offsets, g.point_idx, uv))
+
+
+def add_sin_noise(bal: BAProblem, dir, noise_dir, strength, frequency, ctx=None) -> BAProblem:
+    """src/noise.rs:388-416"""
+    ctx = ctx or context()
+    cams, pts = bal.cameras.copy(), bal.points.copy()
+    d = np.ascontiguousarray(dir, np.float64)
+    nd = np.ascontiguousarray(noise_dir, np.float64)
+    check(lib().c2b_add_sin_noise(ctx.handle, _p(cams), len(cams), _p(pts), len(pts), _p(d), _p(nd),
+                                  float(strength), float(frequency)))
+    return BAProblem(cams, pts, bal.vis_graph)
+
+
+def last_timing(ctx=None):
+    """device milliseconds of the last noise call: (upload, statistics + kernels, download)"""
+    ctx = ctx or context()
+    ms = (C.c_float * 3)()
+    check(lib().c2b_noise_timing(ctx.handle, ms))
+    return tuple(float(x) for x in ms)

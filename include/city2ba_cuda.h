@@ -161,6 +161,14 @@ int c2b_add_drift_normalized(c2b_ctx *ctx, double *cams, uint64_t C, double *pts
 int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double *uv,
                   uint64_t O, double translation_std, double rotation_std, double point_std,
                   double observations_std, uint64_t seed);
+/* replaces noise::add_sin_noise (src/noise.rs:388-416): every camera centre / point x moves by
+ * sin(dot(x / dimensions, dir) * frequency * pi) * strength * normalize(noise_dir), dimensions =
+ * BAProblem::dimensions (src/baproblem.rs:307-337; zero extents count as 1e-8).  Deterministic. */
+int c2b_add_sin_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, const double dir[3],
+                      const double noise_dir[3], double strength, double frequency);
+/* device time of the last noise call on this ctx (CUDA events on its stream), milliseconds:
+ * ms[0] upload, ms[1] statistics + elementwise kernels, ms[2] download */
+int c2b_noise_timing(c2b_ctx *ctx, float ms[3]);
 /* BAProblem::mean / std (src/baproblem.rs:282-304) */
 int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts, uint64_t P,
                  double mean[3], double std[3]);

@@ -932,6 +932,50 @@ void orc_add_noise(double *cams, uint64_t C, double *pts, uint64_t P, double *uv
   }
 }
 
+/* src/noise.rs:388-416 with BAProblem::extent / dimensions (src/baproblem.rs:307-337) */
+void orc_add_sin_noise(double *cams, uint64_t C, double *pts, uint64_t P, const double *dir,
+                       const double *noise_dir, double strength, double frequency) {
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint64_t i = 0; i < C; ++i) {
+    double c[3];
+    orc_center(cams + ORC_CAM_STRIDE * i, c);
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fmin(lo[k], c[k]);
+      hi[k] = fmax(hi[k], c[k]);
+    }
+  }
+  for (uint64_t i = 0; i < P; ++i)
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fmin(lo[k], pts[3 * i + k]);
+      hi[k] = fmax(hi[k], pts[3 * i + k]);
+    }
+  double dim[3], nd[3];
+  for (int k = 0; k < 3; ++k) {
+    dim[k] = hi[k] - lo[k];
+    if (dim[k] == 0.0) dim[k] = 1e-8; /* "Add epsilon to nonexistent dimensions" */
+  }
+  normalize3(noise_dir, nd);
+  static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (uint64_t i = 0; i < C + P; ++i) {
+    double x[3];
+    if (i < C)
+      orc_center(cams + ORC_CAM_STRIDE * i, x);
+    else
+      memcpy(x, pts + 3 * (i - C), 24);
+    double q[3] = {x[0] / dim[0], x[1] / dim[1], x[2] / dim[2]};
+    double dot = (q[0] * dir[0] + q[1] * dir[1]) + q[2] * dir[2];
+    double amp = sin(dot * frequency * 3.14159265358979323846) * strength;
+    double d[3] = {nd[0] * amp, nd[1] * amp, nd[2] * amp};
+    if (i < C) {
+      double out[ORC_CAM_STRIDE];
+      orc_transform(cams + ORC_CAM_STRIDE * i, I, d, out);
+      memcpy(cams + ORC_CAM_STRIDE * i, out, sizeof out);
+    } else {
+      for (int k = 0; k < 3; ++k) pts[3 * (i - C) + k] = x[k] + d[k];
+    }
+  }
+}
+
 /* src/baproblem.rs:265-279 */
 double orc_total_reprojection_error(const double *cams, uint64_t C, const double *pts,
                                     const uint64_t *offsets, const uint64_t *point_idx,

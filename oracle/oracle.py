@@ -350,6 +350,13 @@ def add_noise(cams, pts, uv, translation_std, rotation_std, point_std, observati
     return cams, pts, uv
 
 
+def add_sin_noise(cams, pts, dir, noise_dir, strength, frequency):
+    cams, pts = _d(cams).copy().reshape(-1, CAM), _d(pts).copy().reshape(-1, 3)
+    lib().orc_add_sin_noise(_p(cams), _u64(len(cams)), _p(pts), _u64(len(pts)), _p(_d(dir)), _p(_d(noise_dir)),
+                            C.c_double(strength), C.c_double(frequency))
+    return cams, pts
+
+
 def total_reprojection_error(cams, pts, offsets, point_idx, uv, norm):
     cams, pts, uv = _d(cams).reshape(-1), _d(pts).reshape(-1), _d(uv).reshape(-1)
     off = np.ascontiguousarray(offsets, dtype=np.uint64)

@@ -80,3 +80,31 @@ def test_reference_library_properties(c2b, ctx):
     e0 = ba.total_reprojection_error(2.0)
     assert c2b.noise.add_drift_normalized(ba, 0.1, 0.1, 0.1, seed=3, ctx=ctx).total_reprojection_error(2.0) > e0
     assert c2b.noise.add_noise(ba, 0.1, 0.1, 0.1, 0.1, seed=3, ctx=ctx).total_reprojection_error(2.0) > e0
+
+
+def test_sin_noise_matches_oracle(c2b, problem, orc, ctx):
+    # the two calls of run_noise (src/bin/city2ba.rs:319-332): dir x then z, displacement along +y
+    for d in ([1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.3, -0.2, 0.9]):
+        out = c2b.noise.add_sin_noise(problem, d, [0.0, 2.0, 0.0], 0.05, 1.5, ctx=ctx)
+        oc, op = orc.add_sin_noise(problem.cameras, problem.points, d, [0.0, 2.0, 0.0], 0.05, 1.5)
+        assert np.allclose(out.cameras, oc, rtol=RTOL, atol=ATOL) and np.allclose(out.points, op, rtol=RTOL, atol=ATOL)
+        assert not np.allclose(out.points, problem.points)
+        assert np.array_equal(out.points[:, [0, 2]], problem.points[:, [0, 2]])  # +y only
+    up, kern, down = c2b.noise.last_timing(ctx)
+    assert up >= 0 and kern > 0 and down >= 0
+
+
+def test_sin_noise_flat_dimension_and_property(c2b, ctx):
+    """a problem with zero extent in y divides by 1e-8 there (src/noise.rs:395-396), and
+    tests/main.rs:185-195: sin noise must increase the total reprojection error"""
+    from city2ba_b200 import synthetic
+    ba = synthetic.synthetic_grid(10, 20, 3, 5.0, 1.0, 1.0, 1.0, 10.0, False, ctx=ctx)
+    e0 = ba.total_reprojection_error(2.0)
+    assert c2b.noise.add_sin_noise(ba, [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], 0.1, 1.0, ctx=ctx).total_reprojection_error(2.0) > e0
+    cams = np.zeros((2, 15))
+    cams[:, [0, 4, 8, 12]] = 1.0
+    cams[1, 9] = -3.0                              # centre (3, 0, 0)
+    pts = np.array([[1.0, 0.0, 2.0], [2.0, 0.0, -1.0]])
+    g = c2b.VisGraph(np.array([0, 0, 0], np.uint64), np.zeros(0, np.uint64), np.zeros((0, 2)))
+    out = c2b.noise.add_sin_noise(c2b.BAProblem(cams, pts, g), [0.0, 1.0, 0.0], [1.0, 0.0, 0.0], 0.5, 1.0, ctx=ctx)
+    assert np.allclose(out.points, pts)            # y = 0 everywhere: sin(0) = 0
