@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exhaustive", action="store_true")
     ap.add_argument("--no-noise", action="store_true")
+    ap.add_argument("--replicate-points", action="store_true",
+                    help="N > 1: every rank uploads all points itself instead of 1/N + NCCL all-gather")
     args = ap.parse_args()
     if args.workload is None:
         # the metric's target is quoted on the 64x64-block city (cfg4); it fits one GPU
@@ -298,15 +300,36 @@ def main():
     e2e_t = 0.0
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
     mine = torch.zeros(1, dtype=torch.int64, device=dev)
+    # N > 1: every rank uploads 1/N of the points over its own PCIe link and the shards are
+    # all-gathered over NVLink (NCCL) instead of N full uploads — the path's point exchange.
+    # (world == 1: the plain host-pointer call.)
+    shard_pts = world > 1 and not args.replicate_points
+    if shard_pts:
+        per = -(-P // world)
+        lo_p, hi_p = min(P, rank * per), min(P, (rank + 1) * per)
+        pin_shard = torch.zeros(per * 3, dtype=torch.float64).pin_memory()
+        pin_shard[:(hi_p - lo_p) * 3] = torch.from_numpy(pts[lo_p:hi_p].reshape(-1))
+        d_shard = torch.empty(per * 3, dtype=torch.float64, device=dev)
+        d_full = torch.empty(world * per * 3, dtype=torch.float64, device=dev)
+    h2d_pts = 0
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
             barrier()
         flush_l2()
         t0 = time.perf_counter()
-        _lib.check(L.c2b_visibility_graph(ctx.handle, scene.handle, my_cams.data_ptr(), Cr,
-                                          pin_pts.data_ptr(), P, MAX_DIST, Ct.byref(opt), Ct.byref(out)))
+        if shard_pts:
+            d_shard.copy_(pin_shard, non_blocking=True)
+            dist.all_gather_into_tensor(d_full, d_shard)
+            torch.cuda.synchronize()
+            _lib.check(L.c2b_upload_points_device(ctx.handle, d_full.data_ptr(), P))
+            h2d_pts = per * 24
+            _lib.check(L.c2b_visibility_graph(ctx.handle, scene.handle, my_cams.data_ptr(), Cr,
+                                              None, P, MAX_DIST, Ct.byref(opt), Ct.byref(out)))
+        else:
+            _lib.check(L.c2b_visibility_graph(ctx.handle, scene.handle, my_cams.data_ptr(), Cr,
+                                              pin_pts.data_ptr(), P, MAX_DIST, Ct.byref(opt), Ct.byref(out)))
         if world > 1:
-            # the path's one exchange: per-rank observation counts -> global CSR offsets
+            # per-rank observation counts -> global CSR offsets
             mine[0] = int(out.n_obs)
             dist.all_gather_into_tensor(counts, mine)
             counts_host = counts.cpu()
@@ -315,7 +338,7 @@ def main():
             e2e_t += dt
     barrier()
     clocks = sampler.stop() if sampler else None
-    h2d, d2h = int(out.h2d_bytes), int(out.d2h_bytes)
+    h2d, d2h = int(out.h2d_bytes) + h2d_pts, int(out.d2h_bytes)
     n_obs_local = int(out.n_obs)
     e2e_stage = {k: float(getattr(out, k)) for k in ("ms_h2d", "ms_prep", "ms_cull", "ms_sort", "ms_traverse", "ms_compact", "ms_d2h")}
 
@@ -438,7 +461,8 @@ def main():
                         f"{WORKLOADS[args.workload][0]}-block city{', walls tessellated' if args.workload.startswith('cfg5') else ''}, "
                         f"{C} cameras x {P} points, max_dist {MAX_DIST}",
             "cameras": C, "points": P, "triangles": int(len(tri)), "bvh_nodes": scene.num_nodes,
-            "cull_mode": args.cull_mode, "parallelism": f"camera ranges over {world} GPU(s), mesh/BVH/points replicated",
+            "cull_mode": args.cull_mode, "parallelism": f"camera ranges over {world} GPU(s), mesh/BVH/points replicated"
+                           + ("; e2e: points uploaded 1/N per rank + NCCL all-gather" if shard_pts else ""),
             "l2": "256 MB buffer written between timed steps (L2 flush)",
             "candidates": int(n_cand), "observations": int(n_obs),
             "pairs_evaluated_per_step": int(pairs_eval),

@@ -72,7 +72,7 @@ EXPORTS = [
     "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version", "c2b_kernel_launches",
     "c2b_scene_create", "c2b_scene_bounds", "c2b_scene_num_triangles", "c2b_scene_num_nodes",
     "c2b_scene_destroy", "c2b_occluded", "c2b_intersect1", "c2b_vis_options_default",
-    "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_cameras",
+    "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_points_device", "c2b_upload_cameras",
     "c2b_visibility_graph_resident", "c2b_download_obs", "c2b_reprojection_error_resident",
     "c2b_add_drift", "c2b_add_drift_normalized", "c2b_add_noise", "c2b_add_sin_noise", "c2b_noise_timing",
     "c2b_mean_std",
@@ -119,6 +119,7 @@ def lib():
     L.c2b_obs_free.argtypes = [vp, C.POINTER(Obs)]
     L.c2b_obs_free.restype = None
     L.c2b_upload_points.argtypes = [vp, vp, u64]
+    L.c2b_upload_points_device.argtypes = [vp, vp, u64]
     L.c2b_upload_cameras.argtypes = [vp, vp, u64]
     L.c2b_visibility_graph_resident.argtypes = [vp, vp, dbl, C.POINTER(VisOptions), C.POINTER(Obs)]
     L.c2b_download_obs.argtypes = [vp, C.POINTER(Obs)]

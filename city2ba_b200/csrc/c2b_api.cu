@@ -271,7 +271,7 @@ void c2b_vis_options_default(c2b_vis_options *opt) {
   opt->block_inset = 1.0;
 }
 
-int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
+static int upload_points_impl(c2b_ctx *ctx, const double *pts, uint64_t P, cudaMemcpyKind kind) {
   if (!ctx || (P && !pts)) return set_error(C2B_ERR_INVALID, "c2b_upload_points: null argument");
   if (P >= 0xffffffffull) return set_error(C2B_ERR_INVALID, "too many points (%llu)", (unsigned long long)P);
   CtxExtra *x = extra_of(ctx);
@@ -284,7 +284,7 @@ int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
   if (P == 0) return C2B_OK;
   C2B_TRY(ctx->pts_aos.ensure(P * 24));
   C2B_TRY(ctx->pts.ensure(P * 24));
-  C2B_CUDA(cudaMemcpyAsync(ctx->pts_aos.p, pts, P * 24, cudaMemcpyHostToDevice, ctx->stream));
+  C2B_CUDA(cudaMemcpyAsync(ctx->pts_aos.p, pts, P * 24, kind, ctx->stream));
   double *px = ctx->pts.as<double>(), *py = px + P, *pz = py + P;
   k_aos_to_soa3<<<blocks_for(P, 256), 256, 0, ctx->stream>>>(ctx->pts_aos.as<double>(), P, px, py, pz);
   C2B_KERNEL_CHECK();
@@ -298,6 +298,14 @@ int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
   C2B_KERNEL_CHECK();
   C2B_CUDA(cudaMemcpyAsync(x->pts_bounds, ctx->misc.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
   return C2B_OK;
+}
+
+int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
+  return upload_points_impl(ctx, pts, P, cudaMemcpyHostToDevice);
+}
+
+int c2b_upload_points_device(c2b_ctx *ctx, const double *d_pts, uint64_t P) {
+  return upload_points_impl(ctx, d_pts, P, cudaMemcpyDeviceToDevice);
 }
 
 int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C) {
@@ -851,9 +859,14 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
                          const double *pts, uint64_t P, double max_dist, const c2b_vis_options *opt,
                          c2b_obs *out) {
   if (!ctx || !out) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null argument");
-  if ((C && !cams) || (P && !pts)) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null input array");
+  if (C && !cams) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: null camera array");
   C2B_CUDA(cudaSetDevice(ctx->device));
   CtxExtra *x = extra_of(ctx);
+  // pts == NULL: use the points already resident on the device (c2b_upload_points[_device])
+  const bool resident_pts = P && !pts;
+  if (resident_pts && !(x->have_points && ctx->P == P))
+    return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: pts is null and no %llu resident points were uploaded",
+                     (unsigned long long)P);
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
   // camera batches: the CSR slab of batch b travels to the host while batch b+1 is computed
   // The result transfer is the longest leg (20 B per observation over PCIe), so it should start as
@@ -882,7 +895,7 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   float ms_upload = 0, ms_copy = 0;
   auto run = [&]() -> int {
     C2B_CUDA(cudaEventRecord(u0, st));
-    C2B_TRY(c2b_upload_points(ctx, pts, P));
+    if (!resident_pts) C2B_TRY(c2b_upload_points(ctx, pts, P));
     C2B_CUDA(cudaEventRecord(u1, st));
     C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
     for (uint64_t b = 0; b < n_batches; ++b) {
@@ -950,7 +963,7 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   acc.point_idx = ctx->h_idx.as<uint32_t>();
   acc.uv = ctx->h_uv.as<double>();
   acc.ms_h2d = ms_upload;
-  acc.h2d_bytes = P * 24 + C * 120;
+  acc.h2d_bytes = (resident_pts ? 0 : P * 24) + C * 120;
   acc.d2h_bytes = (C + 1) * 8 + obs_base * 20;
   acc.ms_d2h = ms_copy;  // first to last result copy on the copy stream; overlaps the compute of later batches
   acc.ms_total += ms_upload;

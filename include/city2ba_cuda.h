@@ -128,7 +128,8 @@ typedef struct {
 } c2b_obs;
 
 /* one call, host buffers in, host CSR out (what the Rust visibility_graph body would call).
- * cams: C x 15 doubles; pts: P x 3 doubles (cgmath Point3<f64> is repr(C)). */
+ * cams: C x 15 doubles; pts: P x 3 doubles (cgmath Point3<f64> is repr(C)).  pts == NULL with P equal to
+ * the number of points already resident (c2b_upload_points / c2b_upload_points_device) reuses them. */
 int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cams, uint64_t C,
                          const double *pts, uint64_t P, double max_dist,
                          const c2b_vis_options *opt, c2b_obs *out);
@@ -137,6 +138,10 @@ void c2b_obs_free(c2b_ctx *ctx, c2b_obs *obs);
 /* the same path split in three so a caller can keep inputs/outputs resident in HBM
  * (bench `value`, multi-pass pipelines).  upload -> run (device CSR stays in the ctx) -> download. */
 int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P);
+/* the same from a DEVICE pointer on the ctx's GPU (e.g. the output of an NCCL all-gather when every
+ * rank uploaded 1/N of the points over its own PCIe link); the caller's stream must have finished
+ * writing d_pts.  The data is copied; d_pts may be reused afterwards. */
+int c2b_upload_points_device(c2b_ctx *ctx, const double *d_pts, uint64_t P);
 int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C);
 int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
                                   const c2b_vis_options *opt, c2b_obs *stats_out);

@@ -340,3 +340,33 @@ def test_tessellated_city(c2b, ctx, orc, k):
     assert 0 < ref.n_obs < ref.n_candidates
     for mode in MODES:
         assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, cull_mode=mode, ctx=ctx), ref, f"tess{k}/{mode}")
+
+
+def test_device_resident_points_entry(c2b, ctx, orc, cfg2):
+    """c2b_upload_points_device + c2b_visibility_graph(pts = NULL): the multi-GPU flow where the
+    points arrive on the device through an all-gather instead of a host upload"""
+    import ctypes as C
+    import torch
+    from city2ba_b200 import _lib
+    from city2ba_b200.generate import _options
+    cams, pts, xyz, tri = cfg2
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
+    L = _lib.lib()
+    d_pts = torch.from_numpy(pts).to("cuda:0")
+    torch.cuda.synchronize()
+    _lib.check(L.c2b_upload_points_device(ctx.handle, d_pts.data_ptr(), len(pts)))
+    opt = _options("grid", "mesh", False, False, 20.0, 1.0)
+    out = _lib.Obs()
+    cam_arr = np.ascontiguousarray(cams)
+    _lib.check(L.c2b_visibility_graph(ctx.handle, scene.handle, cam_arr.ctypes.data, len(cams), None, len(pts),
+                                      10.0, C.byref(opt), C.byref(out)))
+    O = int(out.n_obs)
+    assert O == ref.n_obs
+    assert np.array_equal(np.ctypeslib.as_array(out.offsets, shape=(len(cams) + 1,)), ref.offsets)
+    assert np.array_equal(np.ctypeslib.as_array(out.point_idx, shape=(O,)).astype(np.uint64), ref.point_idx)
+    assert np.array_equal(np.ctypeslib.as_array(out.uv, shape=(2 * O,)).reshape(-1, 2), ref.uv)
+    # a point count that does not match what is resident is refused
+    rc = L.c2b_visibility_graph(ctx.handle, scene.handle, cam_arr.ctypes.data, len(cams), None, len(pts) + 1,
+                                10.0, C.byref(opt), C.byref(out))
+    assert rc != 0 and b"resident" in L.c2b_last_error()
