@@ -71,7 +71,7 @@ OCC_MESH, OCC_NONE, OCC_ANALYTIC = 0, 1, 2
 EXPORTS = [
     "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version", "c2b_kernel_launches",
     "c2b_scene_create", "c2b_scene_bounds", "c2b_scene_num_triangles", "c2b_scene_num_nodes",
-    "c2b_scene_destroy", "c2b_occluded", "c2b_intersect1", "c2b_vis_options_default",
+    "c2b_scene_destroy", "c2b_occluded", "c2b_intersect", "c2b_intersect1", "c2b_vis_options_default",
     "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_points_device", "c2b_upload_cameras",
     "c2b_visibility_graph_resident", "c2b_download_obs", "c2b_reprojection_error_resident",
     "c2b_add_drift", "c2b_add_drift_normalized", "c2b_add_noise", "c2b_add_sin_noise", "c2b_noise_timing",
@@ -111,6 +111,7 @@ def lib():
     L.c2b_scene_destroy.argtypes = [vp]
     L.c2b_scene_destroy.restype = None
     L.c2b_occluded.argtypes = [vp, vp, C.POINTER(Ray48), u64]
+    L.c2b_intersect.argtypes = [vp, vp, C.POINTER(Ray48), u64]
     L.c2b_intersect1.argtypes = [vp, vp, pf, pf, C.POINTER(i32), pf]
     L.c2b_vis_options_default.argtypes = [C.POINTER(VisOptions)]
     L.c2b_vis_options_default.restype = None

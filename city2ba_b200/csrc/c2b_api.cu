@@ -89,6 +89,15 @@ static CtxExtra *extra_of(c2b_ctx *ctx) {
   return nullptr;
 }
 
+static float scene_abs_max(const c2b_scene *scene) {
+  float m = 0.0f;
+  if (scene)
+    for (int k = 0; k < 3; ++k) m = std::max(m, std::max(std::fabs(scene->lo[k]), std::fabs(scene->hi[k])));
+  if (!std::isfinite(m)) m = 3.0e38f;
+  return m;
+}
+
+
 extern "C" {
 
 const char *c2b_last_error(void) { return last_error_ref().c_str(); }
@@ -233,30 +242,41 @@ int c2b_occluded(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t
   return C2B_OK;
 }
 
+int c2b_intersect(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t n) {
+  if (!ctx || !scene || (n && !rays)) return set_error(C2B_ERR_INVALID, "c2b_intersect: null argument");
+  if (n == 0) return C2B_OK;
+  if (scene->n_nodes == 0) {
+    for (uint64_t i = 0; i < n; ++i) rays[i].flags = 0;
+    return C2B_OK;
+  }
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  C2B_TRY(ctx->stage.ensure(n * sizeof(c2b_ray48)));
+  C2B_CUDA(cudaMemcpyAsync(ctx->stage.p, rays, n * sizeof(c2b_ray48), cudaMemcpyHostToDevice, ctx->stream));
+  k_intersect_rays<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(scene->nodes.as<float4>(), scene->tris.as<float4>(),
+                                                                (int)scene->n_nodes, ctx->stage.as<c2b_ray48>(), n,
+                                                                scene_abs_max(scene));
+  C2B_KERNEL_CHECK();
+  C2B_CUDA(cudaMemcpyAsync(rays, ctx->stage.p, n * sizeof(c2b_ray48), cudaMemcpyDeviceToHost, ctx->stream));
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
+  return C2B_OK;
+}
+
 int c2b_intersect1(c2b_ctx *ctx, const c2b_scene *scene, const float org[3], const float dir[3],
                    int *hit, float *tfar) {
   if (!ctx || !scene || !org || !dir || !hit || !tfar)
     return set_error(C2B_ERR_INVALID, "c2b_intersect1: null argument");
-  *hit = 0;
-  *tfar = INFINITY;
-  if (scene->n_tris == 0) return C2B_OK;
-  C2B_CUDA(cudaSetDevice(ctx->device));
-  C2B_TRY(ctx->misc.ensure(64));
-  Ray r;
-  r.ox = org[0];
-  r.oy = org[1];
-  r.oz = org[2];
-  r.dx = dir[0];
-  r.dy = dir[1];
-  r.dz = dir[2];
-  r.tfar = INFINITY;
-  k_intersect1<<<1, 32, 0, ctx->stream>>>(scene->tris.as<float4>(), scene->n_tris, r, ctx->misc.as<float>());
-  C2B_KERNEL_CHECK();
-  float h[2];
-  C2B_CUDA(cudaMemcpyAsync(h, ctx->misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
-  *hit = h[0] != 0.0f;
-  *tfar = h[1];
+  c2b_ray48 r;
+  memset(&r, 0, sizeof r);
+  r.org_x = org[0];
+  r.org_y = org[1];
+  r.org_z = org[2];
+  r.dir_x = dir[0];
+  r.dir_y = dir[1];
+  r.dir_z = dir[2];
+  r.tfar = INFINITY;  // Ray::new(org, dir): tnear 0, tfar +inf
+  C2B_TRY(c2b_intersect(ctx, scene, &r, 1));
+  *hit = r.flags != 0;
+  *tfar = r.flags ? r.tfar : INFINITY;
   return C2B_OK;
 }
 
@@ -399,14 +419,6 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
 }
 
 namespace {
-
-float scene_abs_max(const c2b_scene *scene) {
-  float m = 0.0f;
-  if (scene)
-    for (int k = 0; k < 3; ++k) m = std::max(m, std::max(std::fabs(scene->lo[k]), std::fabs(scene->hi[k])));
-  if (!std::isfinite(m)) m = 3.0e38f;
-  return m;
-}
 
 void fill_stats(c2b_ctx *ctx, c2b_obs *stats, uint64_t C, uint64_t n_cand, uint64_t pairs_eval,
                 uint64_t nodes, uint64_t tris) {

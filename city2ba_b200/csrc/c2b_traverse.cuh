@@ -229,22 +229,71 @@ __global__ void __launch_bounds__(256) k_occluded_rays(const float4 *__restrict_
   if (have && occ) rays[i].tfar = -INFINITY;
 }
 
-// closest hit for ONE ray (camera placement, src/generate.rs:253-262): a single warp strides the
-// triangle list; the watertight test reports t = T/det.
-__global__ void k_intersect1(const float4 *__restrict__ tris, uint64_t n_tris, Ray ray,
-                             float *__restrict__ out /* [0]=hit flag, [1]=t */) {
+// ---- closest hit (Embree rtcIntersect1, src/generate.rs:253-262: camera placement rays) -----------
+// Same warp-cooperative stackless walk as warp_any_hit, but a lane keeps walking after a hit and
+// remembers the smallest t.  Every triangle is tested against the ray's ORIGINAL tfar and the
+// result is min over the hits of T/det, so it equals the brute-force minimum over all triangles bit
+// for bit; the running best only tightens the (conservative) box test.
+__device__ __forceinline__ float warp_closest_hit(const float4 *__restrict__ nodes,
+                                                  const float4 *__restrict__ tris, int n_nodes,
+                                                  const Ray &ray, bool alive, float scene_absmax) {
+  BoxRay br = make_box_ray(ray, scene_absmax);
+  alive = alive && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
   float best = INFINITY;
-  for (uint64_t t = threadIdx.x; t < n_tris; t += 32) {
-    const float4 v0 = tris[3 * t], v1 = tris[3 * t + 1], v2 = tris[3 * t + 2];
-    float tt;
-    if (ray_triangle(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, &tt))
-      best = fminf(best, tt);
+  int node = 0;
+  while (node < n_nodes) {
+    const float4 lo = __ldg(&nodes[2 * node]);
+    const float4 hi = __ldg(&nodes[2 * node + 1]);
+    const bool hit = alive && box_overlap(br, lo, hi);
+    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+    const int esc = __float_as_int(lo.w);
+    if (hm == 0u) {
+      node = esc;
+      continue;
+    }
+    const int leaf = __float_as_int(hi.w);
+    if (leaf >= 0) {
+      const float4 v0 = __ldg(&tris[3 * leaf]);
+      const float4 v1 = __ldg(&tris[3 * leaf + 1]);
+      const float4 v2 = __ldg(&tris[3 * leaf + 2]);
+      float t;
+      if (hit && ray_triangle(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, &t) && t < best) {
+        best = t;
+        br.tfar = fminf(ray.tfar, best);
+      }
+      node = esc;  // == node + 1 for a leaf
+    } else {
+      node = node + 1;
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if (threadIdx.x == 0) {
-    out[0] = best < INFINITY ? 1.0f : 0.0f;
-    out[1] = best;
+  return best;
+}
+
+// Embree-shaped closest-hit batch: on a hit tfar = t and flags = 1, otherwise flags = 0
+__global__ void __launch_bounds__(256) k_intersect_rays(const float4 *__restrict__ nodes,
+                                                        const float4 *__restrict__ tris, int n_nodes,
+                                                        c2b_ray48 *rays, uint64_t n, float scene_absmax) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((i & ~31ull) >= n) return;
+  const bool have = i < n;
+  Ray ray;
+  ray.ox = ray.oy = ray.oz = 0.0f;
+  ray.dx = ray.dy = ray.dz = 1.0f;
+  ray.tfar = -1.0f;
+  if (have) {
+    ray.ox = rays[i].org_x;
+    ray.oy = rays[i].org_y;
+    ray.oz = rays[i].org_z;
+    ray.dx = rays[i].dir_x;
+    ray.dy = rays[i].dir_y;
+    ray.dz = rays[i].dir_z;
+    ray.tfar = rays[i].tfar;
+  }
+  const float t = warp_closest_hit(nodes, tris, n_nodes, ray, have, scene_absmax);
+  if (have) {
+    const bool hit = t < INFINITY;
+    if (hit) rays[i].tfar = t;
+    rays[i].flags = hit ? 1u : 0u;
   }
 }
 

@@ -92,6 +92,21 @@ class Scene:
                                  rays.ctypes.data_as(C.POINTER(_lib.Ray48)), n))
         return np.isneginf(rays["tfar"])
 
+    def intersect(self, org, dirs, tfar=np.inf):
+        """Embree-shaped closest hit on explicit f32 rays: (hit bool array, distance array; inf = miss)."""
+        org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = org.shape[0]
+        rays = np.zeros(n, dtype=np.dtype([
+            ("org", np.float32, 3), ("tnear", np.float32), ("dir", np.float32, 3),
+            ("time", np.float32), ("tfar", np.float32), ("mask", np.uint32), ("id", np.uint32),
+            ("flags", np.uint32)]))
+        rays["org"], rays["dir"] = org, dirs
+        rays["tfar"] = np.broadcast_to(np.asarray(tfar, np.float32), (n,))
+        check(lib().c2b_intersect(self.ctx.handle, self._h, rays.ctypes.data_as(C.POINTER(_lib.Ray48)), n))
+        hit = rays["flags"] != 0
+        return hit, np.where(hit, rays["tfar"], np.float32(np.inf))
+
     def intersect1(self, org, direction):
         """Closest hit of one ray: (hit, distance) — scene.intersect, src/generate.rs:253-262."""
         o = np.ascontiguousarray(org, np.float32)

@@ -75,6 +75,9 @@ typedef struct {
   uint32_t mask, id, flags;
 } c2b_ray48;
 int c2b_occluded(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t n_rays);
+/* Embree rtcIntersect1 as a batch: closest hit of every ray through the BVH.  On a hit tfar = distance
+ * and flags = 1; otherwise the ray is left untouched and flags = 0. */
+int c2b_intersect(c2b_ctx *ctx, const c2b_scene *scene, c2b_ray48 *rays, uint64_t n_rays);
 /* replaces CommittedScene::intersect on a single ray (src/generate.rs:253-262): closest hit;
  * *hit = 1 and *tfar = distance when something is hit, else *hit = 0. */
 int c2b_intersect1(c2b_ctx *ctx, const c2b_scene *scene, const float org[3], const float dir[3],

@@ -370,3 +370,46 @@ def test_device_resident_points_entry(c2b, ctx, orc, cfg2):
     rc = L.c2b_visibility_graph(ctx.handle, scene.handle, cam_arr.ctypes.data, len(cams), None, len(pts) + 1,
                                 10.0, C.byref(opt), C.byref(out))
     assert rc != 0 and b"resident" in L.c2b_last_error()
+
+
+def test_closest_hit_batch_matches_brute_force(c2b, ctx, orc):
+    """c2b_intersect (Embree rtcIntersect1 as a batch, BVH walk) against the brute-force minimum of
+    the oracle predicate's t over all triangles; rays that miss stay untouched"""
+    rng = np.random.default_rng(9)
+    xyz, tri = procedural_scene(3)
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    n = 3000
+    org = rng.uniform(-20, 20, (n, 3)).astype(np.float32) * np.array([1, 0.2, 1], np.float32) + np.array([0, 3, 0], np.float32)
+    d = rng.normal(size=(n, 3))
+    d[: n // 3] = [0, -1, 0]                      # the downward placement rays of generate_cameras_poisson
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    hit, t = scene.intersect(org, d)
+    # brute force in numpy with the SAME f32 formula as c2b_math.cuh tri_record / ray_tri_record
+    valid = tri[(tri[:, 0] != tri[:, 1]) & (tri[:, 1] != tri[:, 2]) & (tri[:, 0] != tri[:, 2])]
+    best = np.full(n, np.inf, np.float32)
+    f = np.float32
+    for a_, b_, c_ in valid:
+        A, B, Cc = (xyz[a_] - org).astype(f), (xyz[b_] - org).astype(f), (xyz[c_] - org).astype(f)
+        e0, e1, e2 = Cc - A, A - B, B - Cc
+
+        def cross(p, q):
+            return np.stack([p[:, 1] * q[:, 2] - p[:, 2] * q[:, 1], p[:, 2] * q[:, 0] - p[:, 0] * q[:, 2],
+                             p[:, 0] * q[:, 1] - p[:, 1] * q[:, 0]], 1).astype(f)
+
+        def dot(p, q):  # fmaf chain: exact products accumulated in f64 then rounded once per step
+            s0 = (p[:, 0] * q[:, 0]).astype(f)
+            s1 = (p[:, 1].astype(np.float64) * q[:, 1].astype(np.float64) + s0.astype(np.float64)).astype(f)
+            return (p[:, 2].astype(np.float64) * q[:, 2].astype(np.float64) + s1.astype(np.float64)).astype(f)
+
+        U, V, W = dot(d, cross(e0, Cc + A)), dot(d, cross(e1, A + B)), dot(d, cross(e2, B + Cc))
+        T = (f(2.0) * dot(A, cross(e0, e1))).astype(f)
+        det = ((U + V).astype(f) + W).astype(f)
+        mixed = ((U < 0) | (V < 0) | (W < 0)) & ((U > 0) | (V > 0) | (W > 0))
+        Ts = np.where(det < 0, -T, T)
+        ok = ~mixed & (det != 0) & (Ts > 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tt = (Ts / np.abs(det)).astype(f)
+        best = np.where(ok & (tt < best), tt, best)
+    assert np.array_equal(hit, np.isfinite(best))
+    assert hit.sum() > n // 4 and (~hit).sum() > 0
+    assert np.array_equal(t[hit], best[hit])
