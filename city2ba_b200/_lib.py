@@ -75,7 +75,7 @@ EXPORTS = [
     "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_points_device", "c2b_upload_cameras",
     "c2b_visibility_graph_resident", "c2b_download_obs", "c2b_reprojection_error_resident",
     "c2b_add_drift", "c2b_add_drift_normalized", "c2b_add_noise", "c2b_add_sin_noise", "c2b_noise_timing",
-    "c2b_mean_std",
+    "c2b_mean_std", "c2b_generate_world_points_uniform",
     "c2b_grid_num_cameras", "c2b_grid_num_points", "c2b_grid_cameras", "c2b_grid_points",
     "c2b_line_cameras", "c2b_line_points", "c2b_city_mesh", "c2b_camera_center",
     "c2b_camera_project_world", "c2b_camera_project", "c2b_camera_from_position_direction",
@@ -131,6 +131,8 @@ def lib():
     L.c2b_add_sin_noise.argtypes = [vp, pd, u64, pd, u64, pd, pd, dbl, dbl]
     L.c2b_noise_timing.argtypes = [vp, pf]
     L.c2b_mean_std.argtypes = [vp, pd, u64, pd, u64, pd, pd]
+    L.c2b_generate_world_points_uniform.argtypes = [vp, pf, u64, pu32, u64, pd, u64, u64, dbl, u64, pd,
+                                                    C.POINTER(u64)]
     L.c2b_grid_num_cameras.argtypes = [u64, u64]
     L.c2b_grid_num_cameras.restype = u64
     L.c2b_grid_num_points.argtypes = [u64, u64]

@@ -14,6 +14,7 @@
 #include "c2b_fused.cuh"
 #include "c2b_math.cuh"
 #include "c2b_noise.cuh"
+#include "c2b_sample.cuh"
 #include "c2b_sort.cuh"
 #include "c2b_traverse.cuh"
 
@@ -1256,6 +1257,157 @@ int c2b_noise_timing(c2b_ctx *ctx, float ms[3]) {
   if (!ctx || !ms) return set_error(C2B_ERR_INVALID, "c2b_noise_timing: null argument");
   for (int k = 0; k < 3; ++k) ms[k] = ctx->noise_ms[k];
   return C2B_OK;
+}
+
+// ---- input generation: world points (src/generate.rs:356-420) -----------------------------------------
+int c2b_generate_world_points_uniform(c2b_ctx *ctx, const float *xyz, uint64_t nv, const uint32_t *tri,
+                                      uint64_t nt, const double *cams, uint64_t C, uint64_t num_points,
+                                      double max_dist, uint64_t seed, double *pts_out, uint64_t *n_out) {
+  if (!ctx || !n_out || (nv && !xyz) || (nt && !tri) || (C && !cams) || (num_points && !pts_out))
+    return set_error(C2B_ERR_INVALID, "c2b_generate_world_points_uniform: null argument");
+  *n_out = 0;
+  if (C == 0)
+    return set_error(C2B_ERR_INVALID, "Cannot generate world points with 0 cameras. Try increasing the number of "
+                                      "cameras generated (via --cameras).");
+  if (num_points == 0) return C2B_OK;
+  if (num_points >= 0x7fffffffull) return set_error(C2B_ERR_INVALID, "too many points requested");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // areas and their running sum (sequential f64, the WeightedIndex table); vertices as float4 triples
+  std::vector<double> cdf(nt);
+  std::vector<float4> tv(3 * nt);
+  double run = 0.0;
+  for (uint64_t i = 0; i < nt; ++i) {
+    V3 v[3];
+    for (int j = 0; j < 3; ++j) {
+      const uint64_t k = tri[3 * i + j];
+      if (k >= nv) return set_error(C2B_ERR_INVALID, "triangle %llu references vertex >= %llu", (unsigned long long)i,
+                                    (unsigned long long)nv);
+      tv[3 * i + j] = make_float4(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], 0.0f);
+      v[j] = V3{(double)xyz[3 * k], (double)xyz[3 * k + 1], (double)xyz[3 * k + 2]};
+    }
+    const V3 e1{v[1].x - v[0].x, v[1].y - v[0].y, v[1].z - v[0].z}, e2{v[2].x - v[0].x, v[2].y - v[0].y, v[2].z - v[0].z};
+    run += mag(cross(e1, e2)) / 2.0;
+    cdf[i] = run;
+  }
+  if (nt == 0 || !(run > 0.0) || !std::isfinite(run))
+    return set_error(C2B_ERR_INVALID, "mesh has no triangle of positive area to sample points on");
+  // camera centres -> uniform grid with cells of side >= max_dist
+  std::vector<double> cen(3 * C);
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint64_t i = 0; i < C; ++i) {
+    const V3 c = camera_center(cams + 15 * i);
+    const double a[3] = {c.x, c.y, c.z};
+    for (int k = 0; k < 3; ++k) {
+      cen[3 * i + k] = a[k];
+      if (a[k] < lo[k]) lo[k] = a[k];
+      if (a[k] > hi[k]) hi[k] = a[k];
+    }
+  }
+  CamGrid g;
+  double h = (max_dist > 0.0 && std::isfinite(max_dist)) ? max_dist : 1.0;
+  for (int k = 0; k < 3; ++k) {
+    if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) lo[k] = hi[k] = 0.0;  // NaN / inf centres: one cell
+    h = std::max(h, (hi[k] - lo[k]) / 128.0);
+  }
+  if (!std::isfinite(max_dist) && max_dist > 0.0) h = INFINITY;  // everything is near: a single cell
+  uint64_t cells = 1;
+  for (int k = 0; k < 3; ++k) {
+    g.lo[k] = lo[k];
+    g.n[k] = std::isfinite(h) ? (int)std::floor((hi[k] - lo[k]) / h) + 1 : 1;
+    cells *= (uint64_t)g.n[k];
+  }
+  g.inv_h = std::isfinite(h) ? 1.0 / h : 0.0;
+  std::vector<uint32_t> cell_start(cells + 1, 0), cell_of(C);
+  for (uint64_t i = 0; i < C; ++i) {
+    const int cx = cam_grid_coord(g, 0, cen[3 * i]), cy = cam_grid_coord(g, 1, cen[3 * i + 1]),
+              cz = cam_grid_coord(g, 2, cen[3 * i + 2]);
+    cell_of[i] = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
+    cell_start[cell_of[i] + 1]++;
+  }
+  for (uint64_t c = 0; c < cells; ++c) cell_start[c + 1] += cell_start[c];
+  std::vector<double> cen_sorted(3 * C);
+  {
+    std::vector<uint32_t> cur(cell_start.begin(), cell_start.end() - 1);
+    for (uint64_t i = 0; i < C; ++i) {
+      const uint32_t p = cur[cell_of[i]]++;
+      for (int k = 0; k < 3; ++k) cen_sorted[3 * p + k] = cen[3 * i + k];
+    }
+  }
+  DevBuf d_tv, d_cdf, d_cs, d_cen, d_cand, d_keep, d_rank, d_out, d_small;
+  auto cleanup = [&]() {
+    for (DevBuf *b : {&d_tv, &d_cdf, &d_cs, &d_cen, &d_cand, &d_keep, &d_rank, &d_out, &d_small}) b->release();
+  };
+  int rc = [&]() -> int {
+    C2B_TRY(d_tv.ensure(tv.size() * 16));
+    C2B_TRY(d_cdf.ensure(nt * 8));
+    C2B_TRY(d_cs.ensure((cells + 1) * 4));
+    C2B_TRY(d_cen.ensure(C * 24));
+    C2B_TRY(d_out.ensure(num_points * 24));
+    C2B_TRY(d_small.ensure(64));
+    C2B_CUDA(cudaMemcpyAsync(d_tv.p, tv.data(), tv.size() * 16, cudaMemcpyHostToDevice, st));
+    C2B_CUDA(cudaMemcpyAsync(d_cdf.p, cdf.data(), nt * 8, cudaMemcpyHostToDevice, st));
+    C2B_CUDA(cudaMemcpyAsync(d_cs.p, cell_start.data(), (cells + 1) * 4, cudaMemcpyHostToDevice, st));
+    C2B_CUDA(cudaMemcpyAsync(d_cen.p, cen_sorted.data(), C * 24, cudaMemcpyHostToDevice, st));
+    SampleArgs a;
+    a.tri_v = d_tv.as<float4>();
+    a.cdf = d_cdf.as<double>();
+    a.nt = nt;
+    a.total = run;
+    a.g = g;
+    a.cell_start = d_cs.as<uint32_t>();
+    a.cen = d_cen.as<double>();
+    a.max_d2 = max_dist * max_dist;
+    a.seed = seed;
+    const uint64_t threshold = 10 * num_points;
+    uint64_t got = 0, consumed = 0;
+    while (got < num_points) {
+      const uint64_t want = num_points - got;
+      const uint64_t n = std::min<uint64_t>(want + want / 4 + 1024, 1ull << 26);
+      C2B_TRY(d_cand.ensure(n * 24));
+      C2B_TRY(d_keep.ensure((n + 1) * 4));
+      C2B_TRY(d_rank.ensure((n + 1) * 4));
+      a.first = consumed;
+      a.n = n;
+      a.cand = d_cand.as<double>();
+      a.keep = d_keep.as<uint32_t>();
+      C2B_CUDA(cudaMemsetAsync(d_small.p, 0, 64, st));
+      k_sample_points<<<blocks_for(n, 256), 256, 0, st>>>(a);
+      C2B_KERNEL_CHECK();
+      uint32_t *d_total = d_small.as<uint32_t>() + 4;
+      C2B_TRY(exclusive_scan_u32(st, a.keep, d_rank.as<uint32_t>(), n, d_total, ctx->scan_tmp));
+      k_sample_compact<<<blocks_for(n, 256), 256, 0, st>>>(a.cand, a.keep, d_rank.as<uint32_t>(), n, got, num_points,
+                                                           d_out.as<double>(), d_small.as<unsigned long long>());
+      C2B_KERNEL_CHECK();
+      unsigned long long h[4];
+      C2B_CUDA(cudaMemcpyAsync(h, d_small.p, 32, cudaMemcpyDeviceToHost, st));
+      C2B_CUDA(cudaStreamSynchronize(st));
+      uint32_t accepted;
+      memcpy(&accepted, reinterpret_cast<const char *>(h) + 16, 4);
+      if (got + accepted >= num_points) {
+        // h[0] = round-local index of the candidate that completed the request
+        const uint64_t used = consumed + h[0] + 1;
+        if (used - num_points >= threshold)
+          return set_error(C2B_ERR_INVALID, "Failed to generate enough points. %llu successes, %llu failures, %llu "
+                                            "requested points.", (unsigned long long)num_points,
+                           (unsigned long long)(used - num_points), (unsigned long long)num_points);
+        got = num_points;
+        break;
+      }
+      got += accepted;
+      consumed += n;
+      if (consumed - got >= threshold)
+        return set_error(C2B_ERR_INVALID, "Failed to generate enough points. %llu successes, %llu failures, %llu "
+                                          "requested points.", (unsigned long long)got,
+                         (unsigned long long)(consumed - got), (unsigned long long)num_points);
+    }
+    C2B_CUDA(cudaMemcpyAsync(pts_out, d_out.p, num_points * 24, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaStreamSynchronize(st));
+    return C2B_OK;
+  }();
+  cleanup();
+  if (rc == C2B_OK) *n_out = num_points;
+  return rc;
 }
 
 int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts, uint64_t P,

@@ -252,3 +252,24 @@ class ResidentProblem:
         v = C.c_double(0)
         check(lib().c2b_reprojection_error_resident(self.ctx.handle, float(norm), C.byref(v)))
         return v.value
+
+
+def generate_world_points_uniform(xyz, tri, cameras, num_points, max_dist, seed=None, ctx=None) -> np.ndarray:
+    """src/generate.rs:356-420 on the GPU: `num_points` points on the mesh (area-weighted triangle,
+    uniform inside it) that lie within `max_dist` of some camera.  `xyz`/`tri` are all models'
+    vertices / index triples concatenated.  The reference draws from thread_rng(); here the sample is a
+    pure function of `seed` (default: a fresh one from os.urandom)."""
+    import os
+    ctx = ctx or context()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    tri = np.ascontiguousarray(tri, dtype=np.uint32).reshape(-1, 3)
+    cams = _cam_array(cameras)
+    seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2 ** 64 - 1)
+    out = np.empty((int(num_points), 3))
+    n = C.c_uint64(0)
+    check(lib().c2b_generate_world_points_uniform(
+        ctx.handle, xyz.ctypes.data_as(C.POINTER(C.c_float)), xyz.shape[0],
+        tri.ctypes.data_as(C.POINTER(C.c_uint32)), tri.shape[0], cams.ctypes.data_as(C.POINTER(C.c_double)),
+        cams.shape[0], int(num_points), float(max_dist), seed, out.ctypes.data_as(C.POINTER(C.c_double)),
+        C.byref(n)))
+    return out[: n.value]

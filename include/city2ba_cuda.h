@@ -181,6 +181,19 @@ int c2b_noise_timing(c2b_ctx *ctx, float ms[3]);
 int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts, uint64_t P,
                  double mean[3], double std[3]);
 
+/* ---- input generation on the GPU -------------------------------------------------------------------
+ * replaces generate_world_points_uniform (src/generate.rs:356-420): num_points world points, each
+ * on an area-weighted random triangle (all index triples of all models, concatenated), uniform
+ * inside it (random_point_in_triangle, :314-326), kept only if some camera centre lies within
+ * max_dist (the R-tree query at :396-400, dist^2 <= max_dist^2).  Candidate k is a pure function of
+ * (seed, k) — Philox4x32-10 — and accepted candidates are returned in candidate order, so the result is
+ * deterministic (the reference's thread_rng() is not seedable: parity with it is distributional, with
+ * the oracle exact).  Errors mirror the reference's panics: no cameras; more than 10 * num_points
+ * rejections before num_points acceptances ("Failed to generate enough points ..."). */
+int c2b_generate_world_points_uniform(c2b_ctx *ctx, const float *xyz, uint64_t nv, const uint32_t *tri,
+                                      uint64_t nt, const double *cams, uint64_t C, uint64_t num_points,
+                                      double max_dist, uint64_t seed, double *pts_out, uint64_t *n_out);
+
 /* ---- host-side input generators (no GPU work) ----------------------------------------------------
  * camera/point lattices of synthetic_grid / synthetic_line (src/synthetic.rs:178-258, 323-344)
  * and the city-block box mesh used as the synthetic triangle scene. */

@@ -932,6 +932,72 @@ void orc_add_noise(double *cams, uint64_t C, double *pts, uint64_t P, double *uv
   }
 }
 
+/* src/generate.rs:356-420 with the candidate stream of the CUDA path: candidate k draws the
+ * triangle variate from Philox(seed, stream 16, index k, slot 0) and (rx, ry) from slot 1; accepted
+ * candidates are kept in order.  Returns the number of points written (num_points), or 0 when more
+ * than 10 * num_points candidates were rejected first (the reference panics). */
+uint64_t orc_generate_world_points_uniform(const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt,
+                                           const double *cams, uint64_t C, uint64_t num_points,
+                                           double max_dist, uint64_t seed, double *out) {
+  if (!C || !nt || !num_points) return 0;
+  double *cdf = (double *)malloc(8 * nt), *cen = (double *)malloc(24 * C);
+  double run = 0.0;
+  for (uint64_t i = 0; i < nt; ++i) {
+    double v[3][3], e1[3], e2[3], n[3];
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) v[j][k] = (double)xyz[3 * (uint64_t)tri[3 * i + j] + k];
+    for (int k = 0; k < 3; ++k) {
+      e1[k] = v[1][k] - v[0][k];
+      e2[k] = v[2][k] - v[0][k];
+    }
+    cross3(e1, e2, n);
+    run += mag3(n) / 2.0;
+    cdf[i] = run;
+  }
+  for (uint64_t i = 0; i < C; ++i) orc_center(cams + ORC_CAM_STRIDE * i, cen + 3 * i);
+  const double max_d2 = max_dist * max_dist;
+  uint64_t got = 0, fails = 0;
+  for (uint64_t k = 0; got < num_points && fails < 10 * num_points && run > 0.0; ++k) {
+    uint32_t c0[4] = {(uint32_t)k, (uint32_t)(k >> 32), 16u, 0u}, c1[4] = {(uint32_t)k, (uint32_t)(k >> 32), 16u, 1u};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4], q[4];
+    orc_philox4x32_10(c0, key, o);
+    orc_philox4x32_10(c1, key, q);
+    double u = (double)((((uint64_t)o[0]) | ((uint64_t)o[1] << 32)) >> 11) * 1.1102230246251565e-16;
+    double rx = (double)((((uint64_t)q[0]) | ((uint64_t)q[1] << 32)) >> 11) * 1.1102230246251565e-16;
+    double ry = (double)((((uint64_t)q[2]) | ((uint64_t)q[3] << 32)) >> 11) * 1.1102230246251565e-16;
+    double target = u * run;
+    uint64_t lo = 0, hi = nt - 1;
+    while (lo < hi) {
+      uint64_t mid = (lo + hi) >> 1;
+      if (cdf[mid] > target) hi = mid; else lo = mid + 1;
+    }
+    if (rx + ry > 1.0) {
+      rx = 1.0 - rx;
+      ry = 1.0 - ry;
+    }
+    double p[3];
+    for (int d = 0; d < 3; ++d) {
+      double v0 = (double)xyz[3 * (uint64_t)tri[3 * lo] + d], v1 = (double)xyz[3 * (uint64_t)tri[3 * lo + 1] + d],
+             v2 = (double)xyz[3 * (uint64_t)tri[3 * lo + 2] + d];
+      p[d] = (v0 + rx * (v1 - v0)) + ry * (v2 - v0);
+    }
+    int near = 0;
+    for (uint64_t c = 0; c < C && !near; ++c) {
+      double dx = cen[3 * c] - p[0], dy = cen[3 * c + 1] - p[1], dz = cen[3 * c + 2] - p[2];
+      if ((dx * dx + dy * dy) + dz * dz <= max_d2) near = 1;
+    }
+    if (near) {
+      memcpy(out + 3 * got, p, 24);
+      ++got;
+    } else {
+      ++fails;
+    }
+  }
+  free(cdf);
+  free(cen);
+  return got == num_points ? got : 0;
+}
+
 /* src/noise.rs:388-416 with BAProblem::extent / dimensions (src/baproblem.rs:307-337) */
 void orc_add_sin_noise(double *cams, uint64_t C, double *pts, uint64_t P, const double *dir,
                        const double *noise_dir, double strength, double frequency) {

@@ -138,6 +138,9 @@ void orc_add_noise(double *cams, uint64_t C, double *pts, uint64_t P, double *uv
                    double translation_std, double rotation_std, double point_std,
                    double observations_std, uint64_t seed);
 /* total_reprojection_error (src/baproblem.rs:265-279) on CSR observations */
+uint64_t orc_generate_world_points_uniform(const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt,
+                                           const double *cams, uint64_t C, uint64_t num_points,
+                                           double max_dist, uint64_t seed, double *out);
 void orc_add_sin_noise(double *cams, uint64_t C, double *pts, uint64_t P, const double *dir,
                        const double *noise_dir, double strength, double frequency);
 double orc_total_reprojection_error(const double *cams, uint64_t C, const double *pts,

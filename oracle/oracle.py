@@ -350,6 +350,18 @@ def add_noise(cams, pts, uv, translation_std, rotation_std, point_std, observati
     return cams, pts, uv
 
 
+def generate_world_points_uniform(xyz, tri, cams, num_points, max_dist, seed):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    tri = np.ascontiguousarray(tri, dtype=np.uint32).reshape(-1, 3)
+    cams = _d(cams).reshape(-1, CAM)
+    out = np.empty((int(num_points), 3))
+    f = lib().orc_generate_world_points_uniform
+    f.restype = C.c_uint64
+    n = f(_p(xyz, C.c_float), _u64(len(xyz)), _p(tri, C.c_uint32), _u64(len(tri)), _p(cams), _u64(len(cams)),
+          _u64(num_points), C.c_double(max_dist), _u64(seed), _p(out))
+    return out[:int(n)]
+
+
 def add_sin_noise(cams, pts, dir, noise_dir, strength, frequency):
     cams, pts = _d(cams).copy().reshape(-1, CAM), _d(pts).copy().reshape(-1, 3)
     lib().orc_add_sin_noise(_p(cams), _u64(len(cams)), _p(pts), _u64(len(pts)), _p(_d(dir)), _p(_d(noise_dir)),
