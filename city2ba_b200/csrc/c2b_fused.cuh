@@ -606,10 +606,15 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
         if (!row_span(a.g, cell_h, r2x, r2y, r2z, tz, xr, y, z, x0, x1)) continue;
         const uint32_t row = ((uint32_t)z * a.g.n[1] + y) * a.g.n[0];
         const uint32_t start = a.cell_start[row + x0], end = a.cell_start[row + x1 + 1];
+        // software pipeline: the next 32 points are in flight while the current ones are evaluated
+        V3 pn{0.0, 0.0, 0.0};
+        if (start + lane < end) pn = V3{a.gx[start + lane], a.gy[start + lane], a.gz[start + lane]};
         for (uint32_t base = start; base < end; base += 32) {
           const uint32_t i = base + lane;
+          const V3 pcur = pn;
+          if (i + 32 < end) pn = V3{a.gx[i + 32], a.gy[i + 32], a.gz[i + 32]};
           bool pass = false;
-          if (i < end) pass = cull_predicate(c, cen, V3{a.gx[i], a.gy[i], a.gz[i]}, a.t_star);
+          if (i < end) pass = cull_predicate(c, cen, pcur, a.t_star);
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (m == 0u) continue;
           if (pass) stage[qn + __popc(m & ((1u << lane) - 1u))] = i;

@@ -429,3 +429,20 @@ def test_closest_hit_batch_matches_brute_force(c2b, ctx, orc):
     assert np.array_equal(hit, np.isfinite(best))
     assert hit.sum() > n // 4 and (~hit).sum() > 0
     assert np.array_equal(t[hit], best[hit])
+
+
+@pytest.mark.parametrize("name", ["cfg1_test_scene.npz", "box_obj.npz"])
+@pytest.mark.parametrize("mode", MODES)
+def test_reference_meshes_golden(c2b, ctx, name, mode):
+    """BASELINE config 1: the reference's own test_scene.obj (100 cameras, 200 points, max_dist 100)
+    and tests/box.obj, arrays derived by tests/golden/make_golden_obj.py"""
+    from city2ba_b200.generate import generate_world_points_uniform
+    g = np.load(os.path.join(GOLDEN, name))
+    md = float(g["max_dist"])
+    scene = c2b.Scene(g["xyz"], g["tri"], ctx=ctx)           # includes the degenerate `l` triples
+    v = c2b.visibility_graph(scene, g["cams"], g["pts"], md, cull_mode=mode, ctx=ctx)
+    assert np.array_equal(v.offsets, g["offsets"]) and np.array_equal(v.point_idx, g["idx"])
+    assert np.array_equal(v.uv, g["uv"])
+    assert v.stats["n_candidates"] == len(g["cand_idx"])
+    seed = {"cfg1_test_scene.npz": 20261017, "box_obj.npz": 7}[name]
+    assert np.array_equal(generate_world_points_uniform(g["xyz"], g["tri"], g["cams"], len(g["pts"]), md, seed=seed, ctx=ctx), g["pts"])

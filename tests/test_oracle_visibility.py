@@ -129,3 +129,25 @@ def test_hits_building_quirk(orc):
     # a view segment crossing a building is blocked; along a street it is not (src/synthetic.rs:100-124)
     assert orc.hits_building([0, 1, 10], [20, 1, 10], 20.0, 1.0) == 1
     assert orc.hits_building([0, 1, 0], [19, 1, 0], 20.0, 1.0) == 0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["cfg1_test_scene.npz", "box_obj.npz"])
+def test_golden_reference_meshes(orc, name):
+    """BASELINE config 1 on the reference's own test_scene.obj (and tests/box.obj): the committed
+    arrays were derived from the OBJ files by tests/golden/make_golden_obj.py; the oracle must
+    reproduce the stored graph, and its seeded point generator the stored points"""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, name))
+    md = float(g["max_dist"])
+    v = orc.visibility_graph(g["xyz"], g["tri"], g["cams"], g["pts"], md)
+    assert np.array_equal(v.offsets, g["offsets"]) and np.array_equal(v.point_idx, g["idx"])
+    assert np.array_equal(v.uv, g["uv"]) and np.array_equal(v.cand_occluded, g["cand_occluded"])
+    seed = {"cfg1_test_scene.npz": 20261017, "box_obj.npz": 7}[name]
+    assert np.array_equal(orc.generate_world_points_uniform(g["xyz"], g["tri"], g["cams"], len(g["pts"]), md, seed), g["pts"])
+    # every world point lies ON a triangle, so every ray is an end-point case (SURVEY finding 3)
+    assert g["flag_counts"][2] >= 0.99 * len(g["cand_idx"])
