@@ -351,7 +351,10 @@ class BAProblem:
 
     def largest_connected_component(self):
         """src/baproblem.rs:456-534 (union-find over cameras + points; largest set wins; ties are
-        hash-map order in the reference, lowest label here)."""
+        hash-map order in the reference, lowest label here).  Kept as written there, including the
+        observation filter at :523 that looks up sets[point index] WITHOUT the camera offset: an
+        observation of point i by a camera of the component is dropped when entity i of the combined
+        (cameras, then points) numbering lies outside the component."""
         if self.num_cameras() == 0:
             return self
         from scipy.sparse import coo_matrix
@@ -361,13 +364,20 @@ class BAProblem:
         counts = g.counts()
         cam_of = np.repeat(np.arange(nc), counts)
         n = nc + npt
-        A = coo_matrix((np.ones(len(cam_of), np.int8), (cam_of, g.point_idx.astype(np.int64) + nc)),
-                       shape=(n, n))
+        idx = g.point_idx.astype(np.int64)
+        A = coo_matrix((np.ones(len(cam_of), np.int8), (cam_of, idx + nc)), shape=(n, n))
         _, labels = connected_components(A, directed=False)
         sizes = np.bincount(labels)
         lcc = int(np.argmax(sizes))
         ci = np.nonzero(labels[:nc] == lcc)[0]
         pi = np.nonzero(labels[nc:] == lcc)[0]
+        keep = labels[idx] == lcc                          # the reference's sets[x.0] (no + num_cameras)
+        if not np.all(keep):
+            new_counts = np.bincount(cam_of[keep], minlength=nc)
+            offsets = np.zeros(nc + 1, np.uint64)
+            offsets[1:] = np.cumsum(new_counts)
+            filtered = BAProblem(self.cameras, self.points, VisGraph(offsets, g.point_idx[keep], g.uv[keep]))
+            return filtered.subset(ci, pi)
         return self.subset(ci, pi)
 
     def cull(self):

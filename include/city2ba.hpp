@@ -1,0 +1,714 @@
+// city2ba.hpp — C++17 host mirror of the reference's library surface for the visibility / noise
+// hot path, over the C ABI of libcity2ba_cuda.so (include/city2ba_cuda.h).
+//
+// The reference is a Rust crate (tkonolige/city2ba); this image has no rustc, so the host side a
+// Rust maintainer would keep is restated here in C++ with the SAME names, argument order and error
+// behaviour, so that tests written against it read like the reference's own (tests/cpp/).
+//   city2ba::SnavelyCamera            src/baproblem.rs:107-225   (project_world, project, center,
+//                                     from_position_direction, transform, from_vec / to_vec)
+//   city2ba::BAProblem                src/baproblem.rs:256-801   (from_visibility, cull, BAL text/binary I/O)
+//   city2ba::generate::*              src/generate.rs:356-481    (visibility_graph, generate_world_points_uniform)
+//   city2ba::synthetic::*             src/synthetic.rs:163-381   (synthetic_grid, synthetic_line)
+//   city2ba::noise::*                 src/noise.rs:47-177,388-416 (add_drift*, add_noise, add_sin_noise)
+// Precondition failures that `panic!`/`assert!` in the reference throw std::logic_error here;
+// city2ba::Error carries the reference's Error kinds (src/baproblem.rs:32-62).  Randomness: the
+// reference draws from thread_rng(); every noise function here takes a seed (Philox4x32-10 stream).
+// There is no CPU fallback: everything that computes goes through the GPU library.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "city2ba_cuda.h"
+
+namespace city2ba {
+
+using Vector3 = std::array<double, 3>;
+using Point3 = std::array<double, 3>;
+using Observation = std::pair<size_t, std::pair<double, double>>;  // (point index, (u, v))
+using VisGraph = std::vector<std::vector<Observation>>;
+
+// city2ba::Error, src/baproblem.rs:32-62
+struct Error : std::runtime_error {
+  enum Kind { ParseError, EmptyProblem, IOError, Gpu } kind;
+  Error(Kind k, const std::string &what) : std::runtime_error(what), kind(k) {}
+};
+
+namespace detail {
+inline void check(int rc) {
+  if (rc == C2B_OK) return;
+  throw Error(rc == C2B_ERR_EMPTY ? Error::EmptyProblem : Error::Gpu, c2b_last_error());
+}
+inline void require(bool ok, const char *what) {
+  if (!ok) throw std::logic_error(what);  // the reference's assert! / panic!
+}
+}  // namespace detail
+
+// ---- rotations in cgmath's conventions (column-major 3x3 as 9 doubles) ------------------------------
+using Basis3 = std::array<double, 9>;
+inline Basis3 basis_one() { return {1, 0, 0, 0, 1, 0, 0, 0, 1}; }
+inline Basis3 from_angle_y(double rad) {
+  const double s = std::sin(rad), c = std::cos(rad);
+  return {c, 0, -s, 0, 1, 0, s, 0, c};
+}
+inline Basis3 from_angle_x(double rad) {
+  const double s = std::sin(rad), c = std::cos(rad);
+  return {1, 0, 0, 0, c, s, 0, -s, c};
+}
+inline Basis3 from_axis_angle(const Vector3 &a, double rad) {
+  const double s = std::sin(rad), c = std::cos(rad), k = 1.0 - c;
+  return {k * a[0] * a[0] + c,        k * a[0] * a[1] + s * a[2], k * a[0] * a[2] - s * a[1],
+          k * a[0] * a[1] - s * a[2], k * a[1] * a[1] + c,        k * a[1] * a[2] + s * a[0],
+          k * a[0] * a[2] + s * a[1], k * a[1] * a[2] - s * a[0], k * a[2] * a[2] + c};
+}
+namespace detail {
+// cgmath Quaternion::from(Matrix3) (Shepperd branches); m column-major, returns (s, x, y, z)
+inline std::array<double, 4> quat_from_mat(const Basis3 &m) {
+  auto M = [&](int c, int r) { return m[c * 3 + r]; };
+  const double trace = (M(0, 0) + M(1, 1)) + M(2, 2);
+  if (trace >= 0.0) {
+    double s = std::sqrt(1.0 + trace);
+    const double w = 0.5 * s;
+    s = 0.5 / s;
+    return {w, (M(1, 2) - M(2, 1)) * s, (M(2, 0) - M(0, 2)) * s, (M(0, 1) - M(1, 0)) * s};
+  }
+  if (M(0, 0) > M(1, 1) && M(0, 0) > M(2, 2)) {
+    double s = std::sqrt(((M(0, 0) - M(1, 1)) - M(2, 2)) + 1.0);
+    const double x = 0.5 * s;
+    s = 0.5 / s;
+    return {(M(1, 2) - M(2, 1)) * s, x, (M(1, 0) + M(0, 1)) * s, (M(0, 2) + M(2, 0)) * s};
+  }
+  if (M(1, 1) > M(2, 2)) {
+    double s = std::sqrt(((M(1, 1) - M(0, 0)) - M(2, 2)) + 1.0);
+    const double y = 0.5 * s;
+    s = 0.5 / s;
+    return {(M(2, 0) - M(0, 2)) * s, (M(1, 0) + M(0, 1)) * s, y, (M(2, 1) + M(1, 2)) * s};
+  }
+  double s = std::sqrt(((M(2, 2) - M(0, 0)) - M(1, 1)) + 1.0);
+  const double z = 0.5 * s;
+  s = 0.5 / s;
+  return {(M(0, 1) - M(1, 0)) * s, (M(0, 2) + M(2, 0)) * s, (M(2, 1) + M(1, 2)) * s, z};
+}
+inline Basis3 mat_from_quat(const std::array<double, 4> &q) {
+  const double s = q[0], x = q[1], y = q[2], z = q[3];
+  const double x2 = x + x, y2 = y + y, z2 = z + z;
+  const double xx2 = x2 * x, xy2 = x2 * y, xz2 = x2 * z, yy2 = y2 * y, yz2 = y2 * z, zz2 = z2 * z;
+  const double sy2 = y2 * s, sz2 = z2 * s, sx2 = x2 * s;
+  return {1.0 - yy2 - zz2, xy2 + sz2, xz2 - sy2, xy2 - sz2, 1.0 - xx2 - zz2, yz2 + sx2,
+          xz2 + sy2, yz2 - sx2, 1.0 - xx2 - yy2};
+}
+}  // namespace detail
+
+// src/baproblem.rs:78-90
+inline Basis3 from_rodrigues(const Vector3 &x) {
+  const double theta2 = (x[0] * x[0] + x[1] * x[1]) + x[2] * x[2];
+  if (theta2 > 2.220446049250313e-16) {
+    const double angle = std::sqrt(theta2), inv = 1.0 / angle;
+    return from_axis_angle({x[0] * inv, x[1] * inv, x[2] * inv}, angle);
+  }
+  return detail::mat_from_quat(detail::quat_from_mat({1.0, x[2], -x[1], -x[2], 1.0, x[0], x[1], -x[0], 1.0}));
+}
+// src/baproblem.rs:93-102
+inline Vector3 to_rodrigues(const Basis3 &R) {
+  const auto q = detail::quat_from_mat(R);
+  const double angle = 2.0 * std::acos(std::max(-1.0, std::min(1.0, q[0])));
+  const double d = 1.0 - q[0] * q[0];
+  if (d < 2.220446049250313e-16) return {0.0, 0.0, 0.0};
+  const double sd = std::sqrt(d);
+  const Vector3 a{q[1] / sd, q[2] / sd, q[3] / sd};
+  const double inv = 1.0 / std::sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
+  return {a[0] * inv * angle, a[1] * inv * angle, a[2] * inv * angle};
+}
+
+// ---- SnavelyCamera, src/baproblem.rs:130-225 -------------------------------------------------------
+struct SnavelyCamera {
+  // the C ABI's record: dir as column-major 3x3 [0..9), loc [9..12), intrin f,k1,k2 [12..15)
+  double rec[C2B_CAM_STRIDE];
+
+  // src/baproblem.rs:153-159
+  static SnavelyCamera from_position_direction(const Point3 &position, const Basis3 &dir) {
+    SnavelyCamera c;
+    c2b_camera_from_position_direction(position.data(), dir.data(), c.rec);
+    return c;
+  }
+  // src/baproblem.rs:180-190: [rodrigues 3, translation 3, f, k1, k2]
+  static SnavelyCamera from_vec(const std::array<double, 9> &x) {
+    SnavelyCamera c;
+    const Basis3 R = from_rodrigues({x[0], x[1], x[2]});
+    std::copy(R.begin(), R.end(), c.rec);
+    for (int k = 0; k < 6; ++k) c.rec[9 + k] = x[3 + k];
+    return c;
+  }
+  // src/baproblem.rs:192-202
+  std::array<double, 9> to_vec() const {
+    Basis3 R;
+    std::copy(rec, rec + 9, R.begin());
+    const Vector3 r = to_rodrigues(R);
+    return {r[0], r[1], r[2], rec[9], rec[10], rec[11], rec[12], rec[13], rec[14]};
+  }
+  // src/baproblem.rs:141-143
+  Point3 project_world(const Point3 &p) const {
+    Point3 o;
+    c2b_camera_project_world(rec, p.data(), o.data());
+    return o;
+  }
+  // src/baproblem.rs:145-151
+  std::array<double, 2> project(const Point3 &pc) const {
+    std::array<double, 2> uv;
+    c2b_camera_project(rec, pc.data(), uv.data());
+    return uv;
+  }
+  // Camera::to_world, src/baproblem.rs:117-119: dir^-1 * (p - loc), through the centre helper's
+  // general inverse: R^-1 (p - t) = R^-1 p + centre
+  Point3 to_world(const Point3 &pc) const {
+    // solve R x = pc - t with the cofactor inverse used everywhere else (c2b_camera_center does
+    // -(R^-1 t)); x = R^-1 pc + centre
+    SnavelyCamera probe = *this;
+    probe.rec[9] = -pc[0];
+    probe.rec[10] = -pc[1];
+    probe.rec[11] = -pc[2];
+    const Point3 rinv_pc = probe.center();  // -(R^-1 (-pc)) = R^-1 pc
+    const Point3 c = center();
+    return {rinv_pc[0] + c[0], rinv_pc[1] + c[1], rinv_pc[2] + c[2]};
+  }
+  // src/baproblem.rs:161-163
+  Point3 center() const {
+    Point3 o;
+    c2b_camera_center(rec, o.data());
+    return o;
+  }
+  // src/baproblem.rs:165-171
+  SnavelyCamera transform(const Basis3 &delta_dir, const Vector3 &delta_loc) const {
+    SnavelyCamera c;
+    c2b_camera_transform(rec, delta_dir.data(), delta_loc.data(), c.rec);
+    return c;
+  }
+  Basis3 rotation() const {
+    Basis3 R;
+    std::copy(rec, rec + 9, R.begin());
+    return R;
+  }
+};
+
+// ---- GPU context and scene (where embree_rs::Device / CommittedScene stood) ------------------------
+class Context {
+ public:
+  explicit Context(int device = 0) { detail::check(c2b_init(device, &h_)); }
+  ~Context() { c2b_shutdown(h_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  c2b_ctx *handle() const { return h_; }
+
+ private:
+  c2b_ctx *h_ = nullptr;
+};
+
+class Scene {
+ public:
+  // Scene::new + model_to_geometry per model + attach + commit (src/bin/city2ba.rs:515-521);
+  // xyz: 3 floats per vertex, tri: 3 indices per triple, all models concatenated
+  Scene(const Context &ctx, const std::vector<float> &xyz, const std::vector<uint32_t> &tri) : ctx_(&ctx) {
+    detail::check(c2b_scene_create(ctx.handle(), xyz.data(), xyz.size() / 3, tri.data(), tri.size() / 3, &h_));
+  }
+  ~Scene() { c2b_scene_destroy(h_); }
+  Scene(const Scene &) = delete;
+  Scene &operator=(const Scene &) = delete;
+  const Context &context() const { return *ctx_; }
+  c2b_scene *handle() const { return h_; }
+  uint64_t num_triangles() const { return c2b_scene_num_triangles(h_); }
+  // scene.bounds(), src/generate.rs:237
+  std::pair<std::array<float, 3>, std::array<float, 3>> bounds() const {
+    std::array<float, 3> lo, hi;
+    detail::check(c2b_scene_bounds(h_, lo.data(), hi.data()));
+    return {lo, hi};
+  }
+  // scene.intersect on one ray, src/generate.rs:253-262: (hit, tfar)
+  std::pair<bool, float> intersect(const std::array<float, 3> &org, const std::array<float, 3> &dir) const {
+    int hit = 0;
+    float t = 0;
+    detail::check(c2b_intersect1(ctx_->handle(), h_, org.data(), dir.data(), &hit, &t));
+    return {hit != 0, t};
+  }
+
+ private:
+  const Context *ctx_;
+  c2b_scene *h_ = nullptr;
+};
+
+namespace detail {
+inline std::vector<double> flatten(const std::vector<SnavelyCamera> &cams) {
+  std::vector<double> f(cams.size() * C2B_CAM_STRIDE);
+  for (size_t i = 0; i < cams.size(); ++i) std::memcpy(&f[i * C2B_CAM_STRIDE], cams[i].rec, sizeof cams[i].rec);
+  return f;
+}
+inline VisGraph unpack(const c2b_obs &o) {
+  VisGraph g(o.n_cameras);
+  for (uint64_t c = 0; c < o.n_cameras; ++c) {
+    g[c].reserve(o.offsets[c + 1] - o.offsets[c]);
+    for (uint64_t i = o.offsets[c]; i < o.offsets[c + 1]; ++i)
+      g[c].push_back({(size_t)o.point_idx[i], {o.uv[2 * i], o.uv[2 * i + 1]}});
+  }
+  return g;
+}
+inline VisGraph run_visibility(const Context &ctx, const Scene *scene, const std::vector<SnavelyCamera> &cameras,
+                               const std::vector<Point3> &points, double max_dist, int occlusion,
+                               double block_length, double block_inset) {
+  const std::vector<double> cams = flatten(cameras);
+  c2b_vis_options opt;
+  c2b_vis_options_default(&opt);
+  opt.occlusion = occlusion;
+  opt.block_length = block_length;
+  opt.block_inset = block_inset;
+  c2b_obs out;
+  std::memset(&out, 0, sizeof out);
+  check(c2b_visibility_graph(ctx.handle(), scene ? scene->handle() : nullptr, cams.data(), cameras.size(),
+                             points.empty() ? nullptr : points[0].data(), points.size(), max_dist, &opt, &out));
+  VisGraph g = unpack(out);
+  c2b_obs_free(ctx.handle(), &out);
+  return g;
+}
+}  // namespace detail
+
+namespace generate {
+// src/generate.rs:424-481.  Per camera: every point within max_dist, in front, inside the frustum and
+// not occluded by the scene, in ascending point order, with its projection.
+inline VisGraph visibility_graph(const Scene &scene, const std::vector<SnavelyCamera> &cameras,
+                                 const std::vector<Point3> &points, double max_dist, bool /*verbose*/) {
+  return detail::run_visibility(scene.context(), &scene, cameras, points, max_dist, C2B_OCC_MESH, 20.0, 1.0);
+}
+
+// src/generate.rs:356-420 (seeded; the reference draws from thread_rng())
+inline std::vector<Point3> generate_world_points_uniform(const Context &ctx, const std::vector<float> &xyz,
+                                                         const std::vector<uint32_t> &tri,
+                                                         const std::vector<SnavelyCamera> &cameras,
+                                                         size_t num_points, double max_dist, uint64_t seed) {
+  detail::require(!cameras.empty(), "Cannot generate world points with 0 cameras. Try increasing the number of "
+                                    "cameras generated (via --cameras).");
+  const std::vector<double> cams = detail::flatten(cameras);
+  std::vector<Point3> pts(num_points);
+  uint64_t n = 0;
+  const int rc = c2b_generate_world_points_uniform(ctx.handle(), xyz.data(), xyz.size() / 3, tri.data(), tri.size() / 3,
+                                                   cams.data(), cameras.size(), num_points, max_dist, seed,
+                                                   num_points ? pts[0].data() : nullptr, &n);
+  if (rc != C2B_OK) throw std::logic_error(c2b_last_error());  // the reference panics
+  pts.resize(n);
+  return pts;
+}
+}  // namespace generate
+
+// ---- BAProblem, src/baproblem.rs:256-801 --------------------------------------------------------------
+struct BAProblem {
+  std::vector<SnavelyCamera> cameras;
+  std::vector<Point3> points;
+  VisGraph vis_graph;
+
+  // src/baproblem.rs:360-376
+  static BAProblem from_visibility(std::vector<SnavelyCamera> cams, std::vector<Point3> points, VisGraph obs) {
+    detail::require(cams.size() == obs.size(), "assertion failed: cams.len() == obs.len()");
+    for (const auto &o : obs)
+      for (const auto &e : o) detail::require(e.first < points.size(), "assertion failed: ci < &points.len()");
+    return BAProblem{std::move(cams), std::move(points), std::move(obs)};
+  }
+  size_t num_points() const { return points.size(); }
+  size_t num_cameras() const { return cameras.size(); }
+  size_t num_observations() const {
+    size_t n = 0;
+    for (const auto &v : vis_graph) n += v.size();
+    return n;
+  }
+
+  // src/baproblem.rs:265-279
+  double total_reprojection_error(double norm) const {
+    double total = 0.0;
+    for (size_t c = 0; c < cameras.size(); ++c) {
+      double s = 0.0;
+      for (const auto &[o, uv] : vis_graph[c]) {
+        const auto p = cameras[c].project(cameras[c].project_world(points[o]));
+        s += std::pow(std::fabs(p[0] - uv.first), norm) + std::pow(std::fabs(p[1] - uv.second), norm);
+      }
+      total += s;
+    }
+    return std::pow(total, 1.0 / norm);
+  }
+
+  // src/baproblem.rs:282-304 (sequential folds over camera centres, then points)
+  Vector3 mean() const {
+    const double num = (double)(cameras.size() + points.size());
+    Vector3 a{0, 0, 0};
+    auto add = [&](const Point3 &b) {
+      for (int k = 0; k < 3; ++k) a[k] = a[k] + b[k] / num;
+    };
+    for (const auto &c : cameras) add(c.center());
+    for (const auto &p : points) add(p);
+    return a;
+  }
+  Vector3 std() const {
+    const double num = (double)(cameras.size() + points.size());
+    const Vector3 m = mean();
+    Vector3 a{0, 0, 0};
+    auto add = [&](const Point3 &x) {
+      for (int k = 0; k < 3; ++k) a[k] = a[k] + (x[k] - m[k]) * (x[k] - m[k]);
+    };
+    for (const auto &c : cameras) add(c.center());
+    for (const auto &p : points) add(p);
+    return {std::sqrt(a[0] / num), std::sqrt(a[1] / num), std::sqrt(a[2] / num)};
+  }
+  // src/baproblem.rs:307-337
+  std::pair<Vector3, Vector3> extent() const {
+    Vector3 lo{INFINITY, INFINITY, INFINITY}, hi{-INFINITY, -INFINITY, -INFINITY};
+    auto add = [&](const Point3 &x) {
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = std::fmin(lo[k], x[k]);
+        hi[k] = std::fmax(hi[k], x[k]);
+      }
+    };
+    for (const auto &c : cameras) add(c.center());
+    for (const auto &p : points) add(p);
+    return {lo, hi};
+  }
+  Vector3 dimensions() const {
+    const auto e = extent();
+    return {e.second[0] - e.first[0], e.second[1] - e.first[1], e.second[2] - e.first[2]};
+  }
+
+  // src/baproblem.rs:394-423
+  BAProblem subset(const std::vector<size_t> &ci, const std::vector<size_t> &pi) const {
+    BAProblem out;
+    for (size_t i : ci) out.cameras.push_back(cameras[i]);
+    for (size_t i : pi) out.points.push_back(points[i]);
+    std::vector<int64_t> point_indices(points.size(), -1);
+    for (size_t i = 0; i < pi.size(); ++i) point_indices[pi[i]] = (int64_t)i;
+    for (size_t i : ci) {
+      std::vector<Observation> o;
+      for (const auto &e : vis_graph[i])
+        if (point_indices[e.first] >= 0) o.push_back({(size_t)point_indices[e.first], e.second});
+      out.vis_graph.push_back(std::move(o));
+    }
+    return out;
+  }
+  // src/baproblem.rs:426-453: cameras need > 3 observations, points > 1
+  BAProblem remove_singletons() const {
+    std::vector<size_t> ci, pi;
+    for (size_t i = 0; i < vis_graph.size(); ++i)
+      if (vis_graph[i].size() > 3) ci.push_back(i);
+    std::vector<int64_t> count(points.size(), 0);
+    for (const auto &obs : vis_graph)
+      for (const auto &e : obs) count[e.first] += 1;
+    for (size_t i = 0; i < count.size(); ++i)
+      if (count[i] > 1) pi.push_back(i);
+    return subset(ci, pi);
+  }
+  // src/baproblem.rs:456-534.  Kept as written there, including the observation filter at :523 that
+  // looks up sets[point index] WITHOUT the camera offset: an observation of point i by a camera of
+  // the component is dropped when entity i of the combined (cameras, then points) numbering lies
+  // outside the component.  Ties between equally large components: lowest set label here (hash-map
+  // order in the reference, i.e. unspecified).
+  BAProblem largest_connected_component() const {
+    if (num_cameras() == 0) return *this;
+    const size_t nc = num_cameras(), np = num_points();
+    std::vector<size_t> parent(nc + np);
+    std::iota(parent.begin(), parent.end(), 0);
+    auto find = [&](size_t x) {
+      while (parent[x] != x) {
+        parent[x] = parent[parent[x]];
+        x = parent[x];
+      }
+      return x;
+    };
+    for (size_t i = 0; i < nc; ++i)
+      for (const auto &e : vis_graph[i]) {
+        const size_t a = find(i), b = find(e.first + nc);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+      }
+    std::vector<size_t> sets(nc + np);
+    std::unordered_map<size_t, size_t> size_of;
+    for (size_t i = 0; i < nc + np; ++i) size_of[sets[i] = find(i)] += 1;
+    size_t lcc = 0, best = 0;
+    for (const auto &[label, n] : size_of)
+      if (n > best || (n == best && label < lcc)) {
+        best = n;
+        lcc = label;
+      }
+    BAProblem out;
+    std::unordered_map<size_t, size_t> point_map;
+    for (size_t i = 0; i < np; ++i)
+      if (sets[nc + i] == lcc) {
+        point_map[i] = out.points.size();
+        out.points.push_back(points[i]);
+      }
+    for (size_t i = 0; i < nc; ++i) {
+      if (sets[i] != lcc) continue;
+      out.cameras.push_back(cameras[i]);
+      std::vector<Observation> o;
+      for (const auto &e : vis_graph[i])
+        if (sets[e.first] == lcc) o.push_back({point_map.at(e.first), e.second});
+      out.vis_graph.push_back(std::move(o));
+    }
+    return out;
+  }
+  // src/baproblem.rs:538-549
+  BAProblem cull() const {
+    size_t nc = num_cameras(), np = num_points();
+    BAProblem culled = largest_connected_component().remove_singletons();
+    while (culled.num_cameras() != nc || culled.num_points() != np) {
+      nc = culled.num_cameras();
+      np = culled.num_points();
+      culled = culled.largest_connected_component().remove_singletons();
+    }
+    return culled;
+  }
+
+  // ---- BAL I/O, src/baproblem.rs:580-785 ----
+  // Rust's `{}` for f64: shortest digits that round-trip, positional (never an exponent)
+  static std::string fmt(double x) {
+    char buf[400];
+    const auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+  }
+  // src/baproblem.rs:709-733
+  void write_text(const std::string &path) const {
+    std::ofstream f(path);
+    if (!f) throw Error(Error::IOError, "cannot create " + path);
+    f << num_cameras() << ' ' << num_points() << ' ' << num_observations() << '\n';
+    for (size_t c = 0; c < vis_graph.size(); ++c)
+      for (const auto &[p, uv] : vis_graph[c]) f << c << ' ' << p << ' ' << fmt(uv.first) << ' ' << fmt(uv.second) << '\n';
+    for (const auto &c : cameras) {
+      const auto v = c.to_vec();
+      for (int k = 0; k < 9; ++k) f << (k ? " " : "") << fmt(v[k]);
+      f << '\n';
+    }
+    for (const auto &p : points) f << fmt(p[0]) << ' ' << fmt(p[1]) << ' ' << fmt(p[2]) << '\n';
+    if (!f) throw Error(Error::IOError, "write failed: " + path);
+  }
+  // src/baproblem.rs:736-764: big-endian u64 / f64, per-camera count-prefixed observation lists
+  void write_binary(const std::string &path) const {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Error(Error::IOError, "cannot create " + path);
+    auto put64 = [&](uint64_t v) {
+      unsigned char b[8];
+      for (int k = 0; k < 8; ++k) b[k] = (unsigned char)(v >> (56 - 8 * k));
+      f.write(reinterpret_cast<const char *>(b), 8);
+    };
+    auto putf = [&](double d) {
+      uint64_t v;
+      std::memcpy(&v, &d, 8);
+      put64(v);
+    };
+    put64(num_cameras());
+    put64(num_points());
+    put64(num_observations());
+    for (const auto &obs : vis_graph) {
+      put64(obs.size());
+      for (const auto &[p, uv] : obs) {
+        put64(p);
+        putf(uv.first);
+        putf(uv.second);
+      }
+    }
+    for (const auto &c : cameras)
+      for (double v : c.to_vec()) putf(v);
+    for (const auto &p : points)
+      for (double v : p) putf(v);
+    if (!f) throw Error(Error::IOError, "write failed: " + path);
+  }
+  // src/baproblem.rs:768-785: the extension picks the format
+  void write(const std::string &path) const {
+    const auto dot = path.rfind('.');
+    const std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
+    if (ext == "bal")
+      write_text(path);
+    else if (ext == "bbal")
+      write_binary(path);
+    else
+      throw Error(Error::IOError, "unknown file extension: " + path);
+  }
+  // src/baproblem.rs:580-706
+  static BAProblem from_file(const std::string &path) {
+    const auto dot = path.rfind('.');
+    const std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
+    BAProblem ba;
+    if (ext == "bal") {
+      std::ifstream f(path);
+      if (!f) throw Error(Error::IOError, "cannot open " + path);
+      size_t nc, np, no;
+      if (!(f >> nc >> np >> no)) throw Error(Error::ParseError, "bad BAL header");
+      ba.vis_graph.assign(nc, {});
+      for (size_t i = 0; i < no; ++i) {
+        size_t c, p;
+        double u, v;
+        if (!(f >> c >> p >> u >> v)) throw Error(Error::ParseError, "bad observation line");
+        detail::require(c < nc && p < np, "observation index out of range");
+        ba.vis_graph[c].push_back({p, {u, v}});
+      }
+      for (size_t i = 0; i < nc; ++i) {
+        std::array<double, 9> x;
+        for (auto &t : x)
+          if (!(f >> t)) throw Error(Error::ParseError, "bad camera line");
+        ba.cameras.push_back(SnavelyCamera::from_vec(x));
+      }
+      for (size_t i = 0; i < np; ++i) {
+        Point3 p;
+        for (auto &t : p)
+          if (!(f >> t)) throw Error(Error::ParseError, "bad point line");
+        ba.points.push_back(p);
+      }
+    } else if (ext == "bbal") {
+      std::ifstream f(path, std::ios::binary);
+      if (!f) throw Error(Error::IOError, "cannot open " + path);
+      auto get64 = [&]() {
+        unsigned char b[8];
+        if (!f.read(reinterpret_cast<char *>(b), 8)) throw Error(Error::ParseError, "truncated binary BAL file");
+        uint64_t v = 0;
+        for (int k = 0; k < 8; ++k) v = (v << 8) | b[k];
+        return v;
+      };
+      auto getf = [&]() {
+        const uint64_t v = get64();
+        double d;
+        std::memcpy(&d, &v, 8);
+        return d;
+      };
+      const uint64_t nc = get64(), np = get64(), no = get64();
+      size_t seen = 0;
+      ba.vis_graph.assign(nc, {});
+      for (uint64_t c = 0; c < nc; ++c) {
+        const uint64_t n = get64();
+        for (uint64_t i = 0; i < n; ++i) {
+          const uint64_t p = get64();
+          const double u = getf(), v = getf();
+          detail::require(p < np, "observation index out of range");
+          ba.vis_graph[c].push_back({(size_t)p, {u, v}});
+        }
+        seen += n;
+      }
+      if (seen != no) throw Error(Error::ParseError, "observation count does not match the header");
+      for (uint64_t i = 0; i < nc; ++i) {
+        std::array<double, 9> x;
+        for (auto &t : x) t = getf();
+        ba.cameras.push_back(SnavelyCamera::from_vec(x));
+      }
+      for (uint64_t i = 0; i < np; ++i) {
+        Point3 p;
+        for (auto &t : p) t = getf();
+        ba.points.push_back(p);
+      }
+    } else {
+      throw Error(Error::IOError, "unknown file extension: " + path);
+    }
+    if (ba.cameras.empty() || ba.points.empty()) throw Error(Error::EmptyProblem, "Bundle adjustment problem is empty");
+    return ba;
+  }
+  // impl Display, src/baproblem.rs:788-801
+  std::string to_string() const {
+    std::ostringstream s;
+    s << "Bundle Adjustment Problem with " << num_cameras() << " cameras, " << num_points() << " points, "
+      << "and " << num_observations() << " observations";
+    return s.str();
+  }
+};
+
+namespace synthetic {
+// src/synthetic.rs:163-300.  Occlusion by the analytic 2-D wall test of the reference (src/synthetic.rs:52-124).
+inline BAProblem synthetic_grid(const Context &ctx, size_t num_cameras_per_block, size_t num_points_per_block,
+                                size_t num_blocks, double block_length, double block_inset, double camera_height,
+                                double point_height, double max_dist, bool /*verbose*/) {
+  detail::require(block_inset * 2.0 < block_length,
+                  "Block inset must be less than half the block length, to not violate physical constraints.");
+  std::vector<SnavelyCamera> cams(c2b_grid_num_cameras(num_cameras_per_block, num_blocks));
+  std::vector<Point3> pts(c2b_grid_num_points(num_points_per_block, num_blocks));
+  static_assert(sizeof(SnavelyCamera) == sizeof(double) * C2B_CAM_STRIDE, "camera records must be contiguous");
+  detail::check(c2b_grid_cameras(num_cameras_per_block, num_blocks, block_length, camera_height,
+                                 cams.empty() ? nullptr : cams[0].rec));
+  detail::check(c2b_grid_points(num_points_per_block, num_blocks, block_length, block_inset, point_height,
+                                pts.empty() ? nullptr : pts[0].data()));
+  VisGraph g = detail::run_visibility(ctx, nullptr, cams, pts, max_dist, C2B_OCC_ANALYTIC, block_length, block_inset);
+  return BAProblem::from_visibility(std::move(cams), std::move(pts), std::move(g)).cull();
+}
+
+// src/synthetic.rs:313-381 (no occlusion test)
+inline BAProblem synthetic_line(const Context &ctx, size_t num_cameras, size_t num_points, double length,
+                                double point_offset, double camera_height, double point_height, double max_dist,
+                                bool /*verbose*/) {
+  std::vector<SnavelyCamera> cams(num_cameras);
+  std::vector<Point3> pts(num_points);
+  detail::check(c2b_line_cameras(num_cameras, length, camera_height, cams.empty() ? nullptr : cams[0].rec));
+  detail::check(c2b_line_points(num_points, length, point_offset, point_height, pts.empty() ? nullptr : pts[0].data()));
+  VisGraph g = detail::run_visibility(ctx, nullptr, cams, pts, max_dist, C2B_OCC_NONE, 20.0, 1.0);
+  return BAProblem::from_visibility(std::move(cams), std::move(pts), std::move(g)).cull();
+}
+}  // namespace synthetic
+
+namespace noise {
+namespace detail_n {
+struct Flat {
+  std::vector<double> cams, pts, uv;
+  explicit Flat(const BAProblem &ba) : cams(detail::flatten(ba.cameras)) {
+    pts.reserve(ba.points.size() * 3);
+    for (const auto &p : ba.points) pts.insert(pts.end(), p.begin(), p.end());
+    for (const auto &o : ba.vis_graph)
+      for (const auto &e : o) {
+        uv.push_back(e.second.first);
+        uv.push_back(e.second.second);
+      }
+  }
+  BAProblem rebuild(const BAProblem &ba) const {
+    BAProblem out = ba;
+    for (size_t i = 0; i < out.cameras.size(); ++i) std::memcpy(out.cameras[i].rec, &cams[i * C2B_CAM_STRIDE], sizeof out.cameras[i].rec);
+    for (size_t i = 0; i < out.points.size(); ++i) out.points[i] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    size_t k = 0;
+    for (auto &o : out.vis_graph)
+      for (auto &e : o) {
+        e.second = {uv[2 * k], uv[2 * k + 1]};
+        ++k;
+      }
+    return out;
+  }
+};
+}  // namespace detail_n
+
+// src/noise.rs:68-116
+inline BAProblem add_drift(const Context &ctx, const BAProblem &ba, double strength, double angle_strength, double std_,
+                           const Vector3 &dir, uint64_t seed) {
+  detail_n::Flat f(ba);
+  detail::check(c2b_add_drift(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(), strength,
+                              angle_strength, std_, dir.data(), seed));
+  return f.rebuild(ba);
+}
+// src/noise.rs:47-56
+inline BAProblem add_drift_normalized(const Context &ctx, const BAProblem &ba, double strength, double angle_strength,
+                                      double std_, uint64_t seed) {
+  detail_n::Flat f(ba);
+  detail::check(c2b_add_drift_normalized(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(),
+                                         strength, angle_strength, std_, seed));
+  return f.rebuild(ba);
+}
+// src/noise.rs:119-177
+inline BAProblem add_noise(const Context &ctx, const BAProblem &ba, double translation_std, double rotation_std,
+                           double point_std, double observations_std, uint64_t seed) {
+  detail_n::Flat f(ba);
+  detail::check(c2b_add_noise(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(), f.uv.data(),
+                              f.uv.size() / 2, translation_std, rotation_std, point_std, observations_std, seed));
+  return f.rebuild(ba);
+}
+// src/noise.rs:388-416
+inline BAProblem add_sin_noise(const Context &ctx, const BAProblem &ba, const Vector3 &dir, const Vector3 &noise_dir,
+                               double strength, double frequency) {
+  detail_n::Flat f(ba);
+  detail::check(c2b_add_sin_noise(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(),
+                                  dir.data(), noise_dir.data(), strength, frequency));
+  return f.rebuild(ba);
+}
+}  // namespace noise
+
+}  // namespace city2ba
