@@ -22,6 +22,10 @@ using namespace c2b;
 
 namespace {
 
+// internal status of the resident pipeline: the camera batch holds more than 2^32 pairs / candidates.
+// c2b_visibility_graph halves the batch and retries; the public resident entry reports C2B_ERR_INVALID.
+constexpr int ERR_TOO_LARGE = -100;
+
 inline int bit_length(uint64_t v) {
   int b = 0;
   while (v) {
@@ -533,8 +537,10 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_TRY(read_counters(ctx, h_cnt));
   pairs_eval = h_cnt[1];
   const bool any_overflow = h_cnt[0] != 0;  // cameras whose leaf list exceeded the cap
-  if (pairs_eval >= 0xffffffffull)
-    return set_error(C2B_ERR_INVALID, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
+  uint64_t max_pairs = 0xffffffffull;  // 32-bit scratch offsets
+  if (const char *e = getenv("C2B_MAX_PAIRS")) max_pairs = std::min<uint64_t>(max_pairs, (uint64_t)atoll(e));  // test hook
+  if (pairs_eval >= max_pairs)
+    return set_error(ERR_TOO_LARGE, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
   C2B_TRY(ctx->scratch_idx.ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
   fa.scratch_idx = ctx->scratch_idx.as<uint32_t>();
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_CULL], st));
@@ -627,8 +633,17 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
 
 }  // namespace
 
+static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
+                                    const c2b_vis_options *opt_in, c2b_obs *stats);
+
 int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
                                   const c2b_vis_options *opt_in, c2b_obs *stats) {
+  const int rc = visibility_resident_impl(ctx, scene, max_dist, opt_in, stats);
+  return rc == ERR_TOO_LARGE ? C2B_ERR_INVALID : rc;
+}
+
+static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
+                                    const c2b_vis_options *opt_in, c2b_obs *stats) {
   if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_visibility_graph_resident: null ctx");
   CtxExtra *x = extra_of(ctx);
   if (!x->have_points || !x->have_cameras)
@@ -710,7 +725,7 @@ int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double m
       ctx->pool_capacity = pool_n + pool_n / 16 + 1024;  // exact count is known now: re-run once
     }
     if (pool_n >= 0xffffffffull)
-      return set_error(C2B_ERR_INVALID, "more than 2^32 candidates in one call; shard the cameras");
+      return set_error(ERR_TOO_LARGE, "more than 2^32 candidates in one call; shard the cameras");
   } else {
     C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
     C2B_CUDA(cudaMemsetAsync(ctx->cam_count.p, 0, (C + 1) * 4, st));
@@ -911,14 +926,25 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
     if (!resident_pts) C2B_TRY(c2b_upload_points(ctx, pts, P));
     C2B_CUDA(cudaEventRecord(u1, st));
     C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
-    for (uint64_t b = 0; b < n_batches; ++b) {
-      const uint64_t c0 = bounds[b], c1 = bounds[b + 1], nc = c1 - c0;
+    // camera ranges still to do, in order; a range that turns out too large for 32-bit offsets is halved
+    std::vector<std::pair<uint64_t, uint64_t>> todo;
+    for (uint64_t b = n_batches; b-- > 0;) todo.push_back({bounds[b], bounds[b + 1]});
+    for (uint64_t b = 0; !todo.empty(); ++b) {
+      const uint64_t c0 = todo.back().first, c1 = todo.back().second, nc = c1 - c0;
+      todo.pop_back();
       const int sel = (int)(b & 1);
       ctx->out_sel = sel;
       if (b >= 2) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[sel], 0));  // set `sel` is free again
       C2B_TRY(c2b_upload_cameras(ctx, cams ? cams + 15 * c0 : nullptr, nc));
       c2b_obs s1;
-      C2B_TRY(c2b_visibility_graph_resident(ctx, scene, max_dist, opt, &s1));
+      const int rcb = visibility_resident_impl(ctx, scene, max_dist, opt, &s1);
+      if (rcb == ERR_TOO_LARGE && nc > 1) {
+        todo.push_back({c0 + nc / 2, c1});
+        todo.push_back({c0, c0 + nc / 2});
+        --b;  // the buffer set was not used
+        continue;
+      }
+      if (rcb != C2B_OK) return rcb == ERR_TOO_LARGE ? C2B_ERR_INVALID : rcb;
       const uint64_t O = ctx->out_O;
       if (obs_base)
         k_add_u64<<<blocks_for(nc + 1, 256), 256, 0, st>>>(ctx->out_offsets[sel].as<uint64_t>(), nc + 1, obs_base);
@@ -926,7 +952,7 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
       C2B_CUDA(cudaEventRecord(ctx->ev_ready[sel], st));
       // pinned result arrays: sized from the first batch's density, grown if the guess was short
       size_t need = obs_base + O;
-      if (b + 1 < n_batches) need = std::max<size_t>(need, (size_t)((double)(obs_base + O) * (double)C / (double)c1 * 1.05) + 1024);
+      if (!todo.empty()) need = std::max<size_t>(need, (size_t)((double)(obs_base + O) * (double)C / (double)c1 * 1.05) + 1024);
       C2B_TRY(grow_pinned(ctx, ctx->h_idx, std::max<size_t>(need, 1) * 4, obs_base * 4));
       C2B_TRY(grow_pinned(ctx, ctx->h_uv, std::max<size_t>(need, 1) * 16, obs_base * 16));
       C2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sel], 0));

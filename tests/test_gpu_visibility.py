@@ -446,3 +446,17 @@ def test_reference_meshes_golden(c2b, ctx, name, mode):
     assert v.stats["n_candidates"] == len(g["cand_idx"])
     seed = {"cfg1_test_scene.npz": 20261017, "box_obj.npz": 7}[name]
     assert np.array_equal(generate_world_points_uniform(g["xyz"], g["tri"], g["cams"], len(g["pts"]), md, seed=seed, ctx=ctx), g["pts"])
+
+
+def test_oversized_batches_are_split(c2b, ctx, orc, cfg2, monkeypatch):
+    """a camera batch whose row points exceed the 32-bit scratch offsets is halved and retried
+    (C2B_MAX_PAIRS lowers the limit so that the path runs at test size); the graph is unchanged"""
+    cams, pts, xyz, tri = cfg2
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
+    monkeypatch.setenv("C2B_MAX_PAIRS", "20000")          # 800 cameras x ~90 row points: several splits
+    g = c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx)
+    assert_same_graph(g, ref, "split batches")
+    monkeypatch.setenv("C2B_MAX_PAIRS", "10")             # not even one camera fits: a clean error
+    with pytest.raises(c2b.C2BError, match="shard the cameras"):
+        c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx)
