@@ -480,6 +480,12 @@ def main():
             "algorithmic_bytes_per_step": stages[dom][0],
             "all_stages_GBps": {k: (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else None) for k, v in stages.items()},
             "warp_node_visits": int(nodes), "warp_triangle_tests": int(tris_t),
+            # the whole pass by BASELINE.md section 5's single formula (node visits and triangle tests are
+            # per 32-ray packet here: one fetch serves the packet)
+            "pipeline": (lambda b: {"algorithmic_bytes_per_step": b, "achieved": b / (t_dev_max / K) / 1e9,
+                                    "frac": b / (t_dev_max / K) / 1e9 / (peak * world),
+                                    "formula": "24*pairs_evaluated + 120*C + 64*node_visits + 48*triangle_tests + 24*O + 8*(C+1)"})(
+                24.0 * pairs_eval + 120.0 * C + 64.0 * nodes + 48.0 * tris_t + 24.0 * n_obs + 8.0 * (C + 1)),
         },
         "clocks": clocks,
     }
