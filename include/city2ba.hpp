@@ -7,9 +7,14 @@
 //   city2ba::SnavelyCamera            src/baproblem.rs:107-225   (project_world, project, center,
 //                                     from_position_direction, transform, from_vec / to_vec)
 //   city2ba::BAProblem                src/baproblem.rs:256-801   (from_visibility, cull, BAL text/binary I/O)
-//   city2ba::generate::*              src/generate.rs:356-481    (visibility_graph, generate_world_points_uniform)
+//   city2ba::tobj::load_obj           tobj 0.1.12 (Cargo.lock:1149-1150) as called at src/bin/city2ba.rs:481
+//   city2ba::generate::*              src/generate.rs:109-544    (generate_cameras_{path,path_step,poisson},
+//                                     generate_world_points_uniform, visibility_graph, move_to_origin,
+//                                     modify_intrinsics)
 //   city2ba::synthetic::*             src/synthetic.rs:163-381   (synthetic_grid, synthetic_line)
-//   city2ba::noise::*                 src/noise.rs:47-177,388-416 (add_drift*, add_noise, add_sin_noise)
+//   city2ba::noise::*                 src/noise.rs:47-416        (add_drift*, add_noise, add_sin_noise on the GPU;
+//                                     add_incorrect_correspondences, drop_features, split_landmarks,
+//                                     join_landmarks: sequential graph edits, host)
 // Precondition failures that `panic!`/`assert!` in the reference throw std::logic_error here;
 // city2ba::Error carries the reference's Error kinds (src/baproblem.rs:32-62).  Randomness: the
 // reference draws from thread_rng(); every noise function here takes a seed (Philox4x32-10 stream).
@@ -23,6 +28,7 @@
 #include <cstring>
 #include <fstream>
 #include <numeric>
+#include <optional>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -129,6 +135,104 @@ inline Vector3 to_rodrigues(const Basis3 &R) {
   const Vector3 a{q[1] / sd, q[2] / sd, q[3] / sd};
   const double inv = 1.0 / std::sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
   return {a[0] * inv * angle, a[1] * inv * angle, a[2] * inv * angle};
+}
+
+namespace detail {
+// approx::ulps_eq! with its defaults (epsilon = f64::EPSILON, max_ulps = 4), as cgmath 0.17 uses it
+inline bool ulps_eq(double a, double b) {
+  if (std::fabs(a - b) <= 2.220446049250313e-16) return true;
+  if (std::signbit(a) != std::signbit(b)) return false;
+  int64_t ia, ib;
+  std::memcpy(&ia, &a, 8);
+  std::memcpy(&ib, &b, 8);
+  return (ia > ib ? ia - ib : ib - ia) <= 4;
+}
+inline Vector3 cross(const Vector3 &a, const Vector3 &b) {
+  return {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+}
+inline double dot(const Vector3 &a, const Vector3 &b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+inline double magnitude(const Vector3 &a) { return std::sqrt(dot(a, a)); }
+inline Vector3 normalize(const Vector3 &a) {
+  const double inv = 1.0 / magnitude(a);
+  return {a[0] * inv, a[1] * inv, a[2] * inv};
+}
+inline Vector3 sub(const Point3 &a, const Point3 &b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
+
+// The reference draws from rand 0.6.5's thread_rng() (OS-seeded, no seed option anywhere); the
+// sequential host-side procedures here take a seed and draw from SplitMix64 instead, so parity with
+// the reference is distributional by construction.
+struct Rng {
+  uint64_t s;
+  explicit Rng(uint64_t seed) : s(seed) {}
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  double uniform() { return (double)(next() >> 11) * 0x1.0p-53; }          // gen_range(0.0, 1.0)
+  double range(double lo, double hi) { return lo + (hi - lo) * uniform(); }  // gen_range(lo, hi)
+  size_t below(size_t n) {                                                   // gen_range(0, n)
+    const size_t k = (size_t)(uniform() * (double)n);
+    return k < n ? k : n - 1;
+  }
+  bool coin() { return (next() >> 63) != 0; }  // rand::random::<bool>()
+  // WeightedIndex::new(w).unwrap().sample(): panics on an empty list, a negative weight or a zero total
+  size_t weighted(const std::vector<double> &w) {
+    double total = 0.0;
+    for (double x : w) {
+      if (!(x >= 0.0)) throw std::logic_error("called `Result::unwrap()` on an `Err` value: NegativeWeight");
+      total += x;
+    }
+    if (w.empty()) throw std::logic_error("called `Result::unwrap()` on an `Err` value: NoItem");
+    if (!(total > 0.0)) throw std::logic_error("called `Result::unwrap()` on an `Err` value: AllWeightsZero");
+    const double t = uniform() * total;
+    double acc = 0.0;
+    for (size_t i = 0; i < w.size(); ++i) {
+      acc += w[i];
+      if (t < acc) return i;
+    }
+    size_t last = w.size() - 1;
+    while (last > 0 && w[last] == 0.0) --last;
+    return last;
+  }
+  template <class T>
+  void shuffle(std::vector<T> &v) {  // SliceRandom::shuffle (Fisher-Yates from the back)
+    for (size_t i = v.size(); i > 1; --i) std::swap(v[i - 1], v[below(i)]);
+  }
+  // IteratorRandom::choose_multiple over 0..len: reservoir sampling, at most `amount` values, order arbitrary
+  std::vector<size_t> choose_multiple(size_t len, size_t amount) {
+    std::vector<size_t> r;
+    r.reserve(std::min(len, amount));
+    for (size_t i = 0; i < len; ++i) {
+      if (r.size() < amount)
+        r.push_back(i);
+      else {
+        const size_t k = below(i + 1);
+        if (k < amount) r[k] = i;
+      }
+    }
+    return r;
+  }
+};
+}  // namespace detail
+
+// cgmath 0.17 Basis3::between_vectors (through Quaternion::between_vectors), used by the path cameras
+// (src/generate.rs:144,200)
+inline Basis3 between_vectors(const Vector3 &a, const Vector3 &b) {
+  const double k_cos_theta = detail::dot(a, b);
+  if (detail::ulps_eq(k_cos_theta, 1.0)) return basis_one();  // same direction
+  const double k = std::sqrt(detail::dot(a, a) * detail::dot(b, b));
+  if (detail::ulps_eq(k_cos_theta / k, -1.0)) {  // opposite direction: half a turn about an orthogonal axis
+    Vector3 orthogonal = detail::cross({1.0, 0.0, 0.0}, a);
+    if (detail::ulps_eq(detail::dot(orthogonal, orthogonal), 0.0)) orthogonal = detail::cross({0.0, 1.0, 0.0}, a);
+    const Vector3 o = detail::normalize(orthogonal);
+    return detail::mat_from_quat({0.0, o[0], o[1], o[2]});
+  }
+  const Vector3 v = detail::cross(a, b);
+  const double s = k + k_cos_theta;
+  const double inv = 1.0 / std::sqrt(s * s + detail::dot(v, v));
+  return detail::mat_from_quat({s * inv, v[0] * inv, v[1] * inv, v[2] * inv});
 }
 
 // ---- SnavelyCamera, src/baproblem.rs:130-225 -------------------------------------------------------
@@ -240,6 +344,10 @@ class Scene {
     detail::check(c2b_intersect1(ctx_->handle(), h_, org.data(), dir.data(), &hit, &t));
     return {hit != 0, t};
   }
+  // the same closest-hit query for a whole batch of rays in one launch (flags = 1 and tfar = distance on a hit)
+  void intersect(std::vector<c2b_ray48> &rays) const {
+    detail::check(c2b_intersect(ctx_->handle(), h_, rays.data(), rays.size()));
+  }
 
  private:
   const Context *ctx_;
@@ -280,6 +388,203 @@ inline VisGraph run_visibility(const Context &ctx, const Scene *scene, const std
 }
 }  // namespace detail
 
+// ---- OBJ ingest with the rules of tobj 0.1.12 (Cargo.lock:1149-1150; src/bin/city2ba.rs:481) --------------
+// One Model per `o` / `g` statement that is followed by elements; per-model vertex arrays holding only
+// the vertices its elements use, in order of first use (de-duplicated by the v/vt/vn index triple);
+// triangles as they are, quads as (a,b,c),(a,c,d), larger polygons as a fan from their first vertex;
+// `l` records with two vertices append TWO indices and `p` records one (so a model of lines is a list of
+// index pairs: what generate_cameras_path reads, and what model_to_geometry regroups into harmless
+// degenerate triples when --path is not given, src/generate.rs:74-105).  Materials are not read.
+namespace tobj {
+struct Mesh {
+  std::vector<float> positions;   // 3 per vertex
+  std::vector<uint32_t> indices;  // into positions / 3
+};
+struct Model {
+  Mesh mesh;
+  std::string name;
+};
+
+inline std::vector<Model> load_obj(const std::string &path) {
+  std::ifstream f(path);
+  if (!f) throw Error(Error::IOError, "Could not open file \"" + path + "\"");
+  std::vector<float> pos;
+  size_t n_vt = 0, n_vn = 0;
+  struct Key {
+    int64_t v, vt, vn;
+    bool operator==(const Key &o) const { return v == o.v && vt == o.vt && vn == o.vn; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key &k) const {
+      return std::hash<int64_t>()(k.v * 1000003 ^ (k.vt + 1) * 10007 ^ (k.vn + 1));
+    }
+  };
+  std::vector<std::vector<Key>> faces;  // elements of the model being read
+  std::string name = "unnamed_object";
+  std::vector<Model> models;
+  auto flush = [&]() {
+    if (faces.empty()) return;
+    Model m;
+    m.name = name;
+    std::unordered_map<Key, uint32_t, KeyHash> seen;
+    auto add = [&](const Key &k) {
+      auto it = seen.find(k);
+      if (it == seen.end()) {
+        it = seen.emplace(k, (uint32_t)(m.mesh.positions.size() / 3)).first;
+        for (int c = 0; c < 3; ++c) m.mesh.positions.push_back(pos[3 * (size_t)k.v + c]);
+      }
+      m.mesh.indices.push_back(it->second);
+    };
+    for (const auto &e : faces) {
+      if (e.size() <= 3) {  // point, line, triangle
+        for (const auto &k : e) add(k);
+      } else if (e.size() == 4) {
+        for (int i : {0, 1, 2, 0, 2, 3}) add(e[i]);
+      } else {
+        for (size_t i = 1; i + 1 < e.size(); ++i) {
+          add(e[0]);
+          add(e[i]);
+          add(e[i + 1]);
+        }
+      }
+    }
+    models.push_back(std::move(m));
+    faces.clear();
+  };
+  std::string line;
+  size_t lineno = 0;
+  auto bad = [&](const char *what) {
+    return Error(Error::IOError, "Load error: " + std::string(what) + " (" + path + ":" + std::to_string(lineno) + ")");
+  };
+  while (std::getline(f, line)) {
+    ++lineno;
+    std::istringstream ls(line);
+    std::string tag;
+    if (!(ls >> tag) || tag[0] == '#') continue;
+    if (tag == "v") {
+      float x, y, z;
+      if (!(ls >> x >> y >> z)) throw bad("position parse error");
+      pos.insert(pos.end(), {x, y, z});
+    } else if (tag == "vt") {
+      ++n_vt;
+    } else if (tag == "vn") {
+      ++n_vn;
+    } else if (tag == "f" || tag == "l" || tag == "p") {
+      std::vector<Key> e;
+      std::string tok;
+      while (ls >> tok) {
+        int64_t idx[3] = {0, 0, 0};
+        size_t k = 0, start = 0;
+        while (k < 3 && start <= tok.size()) {
+          const size_t slash = tok.find('/', start);
+          const std::string part = tok.substr(start, slash == std::string::npos ? std::string::npos : slash - start);
+          if (!part.empty()) {
+            char *end = nullptr;
+            idx[k] = std::strtoll(part.c_str(), &end, 10);
+            if (*end) throw bad("face parse error");
+          }
+          ++k;
+          if (slash == std::string::npos) break;
+          start = slash + 1;
+        }
+        // 1-based; negative = relative to what has been read so far; 0 = absent
+        auto fix = [&](int64_t i, size_t n) -> int64_t { return i > 0 ? i - 1 : i < 0 ? (int64_t)n + i : -1; };
+        const Key key{fix(idx[0], pos.size() / 3), fix(idx[1], n_vt), fix(idx[2], n_vn)};
+        if (key.v < 0 || (size_t)key.v >= pos.size() / 3) throw bad("face vertex index out of range");
+        e.push_back(key);
+      }
+      if (e.empty()) throw bad("face parse error");
+      faces.push_back(std::move(e));
+    } else if (tag == "o" || tag == "g") {
+      flush();
+      std::string rest;
+      std::getline(ls, rest);
+      const size_t a = rest.find_first_not_of(" \t\r"), b = rest.find_last_not_of(" \t\r");
+      name = a == std::string::npos ? "unnamed_object" : rest.substr(a, b - a + 1);
+    }
+    // mtllib / usemtl / s and anything else: ignored
+  }
+  flush();
+  return models;
+}
+}  // namespace tobj
+
+namespace detail {
+// all models as ONE vertex / index-triple array for c2b_scene_create and the point sampler: each model's
+// index list is regrouped into triples on its own (num_tri = indices.len() / 3, src/generate.rs:78) and
+// offset by the vertices that precede it
+inline void concat_models(const std::vector<tobj::Model> &models, std::vector<float> &xyz, std::vector<uint32_t> &tri) {
+  xyz.clear();
+  tri.clear();
+  for (const auto &m : models) {
+    const uint32_t base = (uint32_t)(xyz.size() / 3);
+    xyz.insert(xyz.end(), m.mesh.positions.begin(), m.mesh.positions.end());
+    const size_t n = m.mesh.indices.size() / 3 * 3;
+    for (size_t i = 0; i < n; ++i) tri.push_back(base + m.mesh.indices[i]);
+  }
+}
+// Poisson-disk samples in the unit square.  The reference asks the `poisson` crate (0.10.1, Ebeida's
+// maximal sampler) for `samples` points at relative radius 1.0, i.e. the largest radius at which that
+// many discs could still be packed; the crate is not vendored, so this is Bridson's dart throwing
+// (30 attempts per active sample) at the hexagonal-packing radius for `samples` discs.  Like the
+// crate it yields noticeably fewer than `samples` points ("x2 seems to get us closer to the desired
+// amount", src/generate.rs:230).  Distributional parity only.
+inline std::vector<std::array<double, 2>> poisson_disk(size_t samples, Rng &rng) {
+  std::vector<std::array<double, 2>> out;
+  if (samples == 0) return out;
+  const double r = 2.0 * std::sqrt(0.9068996821171089 / ((double)samples * 3.141592653589793));
+  const double cell = r / std::sqrt(2.0);
+  const int n = std::max(1, (int)std::ceil(1.0 / cell));
+  std::vector<int> grid((size_t)n * n, -1);
+  auto cell_of = [&](double x) { return std::min(n - 1, (int)(x / cell)); };
+  auto fits = [&](double x, double y) {
+    const int cx = cell_of(x), cy = cell_of(y);
+    for (int j = std::max(0, cy - 2); j <= std::min(n - 1, cy + 2); ++j)
+      for (int i = std::max(0, cx - 2); i <= std::min(n - 1, cx + 2); ++i) {
+        const int k = grid[(size_t)j * n + i];
+        if (k >= 0) {
+          const double dx = out[k][0] - x, dy = out[k][1] - y;
+          if (dx * dx + dy * dy < r * r) return false;
+        }
+      }
+    return true;
+  };
+  std::vector<int> active;
+  auto push = [&](double x, double y) {
+    grid[(size_t)cell_of(y) * n + cell_of(x)] = (int)out.size();
+    active.push_back((int)out.size());
+    out.push_back({x, y});
+  };
+  push(rng.uniform(), rng.uniform());
+  while (!active.empty()) {
+    const size_t a = rng.below(active.size());
+    const auto base = out[active[a]];
+    bool placed = false;
+    for (int attempt = 0; attempt < 30 && !placed; ++attempt) {
+      const double ang = rng.range(0.0, 6.283185307179586), rad = r * std::sqrt(rng.range(1.0, 4.0));
+      const double x = base[0] + rad * std::cos(ang), y = base[1] + rad * std::sin(ang);
+      if (x < 0.0 || x >= 1.0 || y < 0.0 || y >= 1.0 || !fits(x, y)) continue;
+      push(x, y);
+      placed = true;
+    }
+    if (!placed) {
+      active[a] = active.back();
+      active.pop_back();
+    }
+  }
+  return out;
+}
+inline std::vector<std::pair<Point3, Point3>> path_segments(const tobj::Model &path) {
+  std::vector<Point3> v;
+  for (size_t i = 0; i + 2 < path.mesh.positions.size(); i += 3)
+    v.push_back({(double)path.mesh.positions[i], (double)path.mesh.positions[i + 1], (double)path.mesh.positions[i + 2]});
+  std::vector<std::pair<Point3, Point3>> seg;
+  for (size_t i = 0; i + 1 < path.mesh.indices.size(); i += 2)
+    seg.push_back({v.at(path.mesh.indices[i]), v.at(path.mesh.indices[i + 1])});
+  return seg;
+}
+}  // namespace detail
+
 namespace generate {
 // src/generate.rs:424-481.  Per camera: every point within max_dist, in front, inside the frustum and
 // not occluded by the scene, in ascending point order, with its projection.
@@ -304,6 +609,148 @@ inline std::vector<Point3> generate_world_points_uniform(const Context &ctx, con
   if (rc != C2B_OK) throw std::logic_error(c2b_last_error());  // the reference panics
   pts.resize(n);
   return pts;
+}
+
+// the call sequence of src/bin/city2ba.rs:515-521 (Device::new, Scene::new, model_to_geometry per model,
+// attach_geometry, commit) in one step
+inline Scene commit_scene(const Context &ctx, const std::vector<tobj::Model> &models) {
+  std::vector<float> xyz;
+  std::vector<uint32_t> tri;
+  detail::concat_models(models, xyz, tri);
+  return Scene(ctx, xyz, tri);
+}
+
+// src/generate.rs:356-420 with the reference's `&[tobj::Model]` argument
+inline std::vector<Point3> generate_world_points_uniform(const Context &ctx, const std::vector<tobj::Model> &models,
+                                                         const std::vector<SnavelyCamera> &cameras,
+                                                         size_t num_points, double max_dist, uint64_t seed) {
+  std::vector<float> xyz;
+  std::vector<uint32_t> tri;
+  detail::concat_models(models, xyz, tri);
+  return generate_world_points_uniform(ctx, xyz, tri, cameras, num_points, max_dist, seed);
+}
+
+// src/generate.rs:109-148: cameras at random positions along a path (segments weighted by length),
+// looking along the direction of travel
+inline std::vector<SnavelyCamera> generate_cameras_path(const Scene & /*scene*/, const tobj::Model &path,
+                                                        size_t num_cameras, uint64_t seed) {
+  const auto paths = detail::path_segments(path);
+  std::vector<double> lengths;
+  for (const auto &[x, y] : paths) lengths.push_back(detail::magnitude(detail::sub(y, x)));
+  detail::Rng rng(seed);
+  std::vector<SnavelyCamera> cams;
+  for (size_t n = 0; n < num_cameras; ++n) {
+    const size_t i = rng.weighted(lengths);
+    const auto &[x, y] = paths[i];
+    const double d = rng.uniform();
+    const Vector3 dir = detail::sub(y, x);
+    const Point3 pos{x[0] + d * dir[0], x[1] + d * dir[1], x[2] + d * dir[2]};
+    cams.push_back(SnavelyCamera::from_position_direction(pos, between_vectors(detail::normalize(dir), {0.0, 0.0, -1.0})));
+  }
+  return cams;
+}
+
+// src/generate.rs:152-213: fixed steps from the start of the path
+inline std::vector<SnavelyCamera> generate_cameras_path_step(const Scene & /*scene*/, const tobj::Model &path,
+                                                             size_t num_cameras, double step_size,
+                                                             std::ostream *log = nullptr) {
+  const auto paths = detail::path_segments(path);
+  double total_length = 0.0;
+  for (const auto &[x, y] : paths) total_length += detail::magnitude(detail::sub(y, x));
+  if (!((double)num_cameras * step_size <= total_length)) {
+    std::ostringstream m;
+    m << "Length of path " << total_length << " is less than the number of cameras (" << num_cameras
+      << ") times the step size (" << step_size << ") " << (double)num_cameras * step_size;
+    throw std::logic_error(m.str());
+  }
+  if (log)
+    *log << "Generating cameras along path. Path length: " << total_length << ", using "
+         << (double)num_cameras * step_size << " of it.\n";
+  size_t segment_index = 0;
+  double dist = 0.0;
+  std::vector<SnavelyCamera> cams;
+  for (size_t n = 0; n < num_cameras; ++n) {
+    detail::require(segment_index < paths.size(), "index out of bounds: the path ended before the last camera");
+    Vector3 dir = detail::sub(paths[segment_index].second, paths[segment_index].first);
+    const Point3 &start = paths[segment_index].first;
+    const double t = dist / detail::magnitude(dir);
+    cams.push_back(SnavelyCamera::from_position_direction({start[0] + t * dir[0], start[1] + t * dir[1], start[2] + t * dir[2]},
+                                                          between_vectors(detail::normalize(dir), {0.0, 0.0, -1.0})));
+    dist += step_size;
+    while (dist >= detail::magnitude(dir)) {
+      segment_index += 1;
+      dist -= detail::magnitude(dir);
+      // the reference indexes paths[segment_index] here, so a last step that lands exactly on the end of
+      // the path panics there as well
+      detail::require(segment_index < paths.size(), "index out of bounds: the path ended before the last camera");
+      dir = detail::sub(paths[segment_index].second, paths[segment_index].first);
+    }
+  }
+  return cams;
+}
+
+// src/generate.rs:217-280: Poisson-disk positions over the scene's (x, z) bounds, each dropped onto the
+// tallest surface below it (closest hit of a ray straight down — ALL rays in one GPU batch instead of
+// one rtcIntersect1 per sample) and raised by `height`; kept if pt[2] < lower_y + ground (the
+// reference compares z, not y, :264 — kept as written); random yaw about y.
+inline std::vector<SnavelyCamera> generate_cameras_poisson(const Scene &scene, size_t num_points, double height,
+                                                           double ground, uint64_t seed) {
+  detail::Rng rng(seed);
+  const auto samples = detail::poisson_disk(num_points * 2, rng);
+  const auto [lo, hi] = scene.bounds();
+  const Point3 start{(double)hi[0], (double)hi[1] + 0.1, (double)hi[2]};
+  const Vector3 delta{(double)(hi[0] - lo[0]), 0.0, (double)(hi[2] - lo[2])};
+  std::vector<Point3> origins;
+  std::vector<c2b_ray48> rays;
+  for (const auto &smp : samples) {
+    const Point3 o{start[0] - delta[0] * smp[0], start[1] - delta[1] * 0.0, start[2] - delta[2] * smp[1]};
+    origins.push_back(o);
+    c2b_ray48 r;
+    std::memset(&r, 0, sizeof r);
+    r.org_x = (float)o[0];
+    r.org_y = (float)o[1];
+    r.org_z = (float)o[2];
+    r.dir_y = -1.0f;
+    r.tfar = INFINITY;
+    r.mask = 0xffffffffu;
+    rays.push_back(r);
+  }
+  if (!rays.empty()) scene.intersect(rays);
+  std::vector<SnavelyCamera> cams;
+  for (size_t i = 0; i < rays.size(); ++i) {
+    if (!rays[i].flags) continue;
+    const Point3 pt{origins[i][0], origins[i][1] - (double)rays[i].tfar + height, origins[i][2]};
+    if (pt[2] < (double)lo[1] + ground)
+      cams.push_back(SnavelyCamera::from_position_direction(pt, from_angle_y(rng.range(0.0, 2.0 * 3.141592653589793))));
+  }
+  return cams;
+}
+
+// src/generate.rs:484-527: translate all models so that the minimum corner of their bounding box is the origin
+inline std::vector<tobj::Model> move_to_origin(std::vector<tobj::Model> models) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY};
+  bool any = false;
+  for (const auto &m : models)
+    for (size_t i = 0; i + 2 < m.mesh.positions.size(); i += 3) {
+      any = true;
+      for (int k = 0; k < 3; ++k) mn[k] = std::fmin(mn[k], m.mesh.positions[i + k]);
+    }
+  detail::require(any, "called `Option::unwrap()` on a `None` value");  // fold1 of nothing
+  for (auto &m : models)
+    for (size_t i = 0; i + 2 < m.mesh.positions.size(); i += 3)
+      for (int k = 0; k < 3; ++k) m.mesh.positions[i + k] -= mn[k];
+  return models;
+}
+
+// src/generate.rs:530-544: intrinsics uniform in [intrinsic_start, intrinsic_end)
+inline void modify_intrinsics(std::vector<SnavelyCamera> &cameras, const Vector3 &intrinsic_start,
+                              const Vector3 &intrinsic_end, uint64_t seed) {
+  detail::Rng rng(seed);
+  for (auto &c : cameras)
+    for (int k = 0; k < 3; ++k) {
+      const double v = rng.uniform();
+      c.rec[12 + k] = intrinsic_start[k] + v * (intrinsic_end[k] - intrinsic_start[k]);
+    }
 }
 }  // namespace generate
 
@@ -708,6 +1155,141 @@ inline BAProblem add_sin_noise(const Context &ctx, const BAProblem &ba, const Ve
   detail::check(c2b_add_sin_noise(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(),
                                   dir.data(), noise_dir.data(), strength, frequency));
   return f.rebuild(ba);
+}
+
+// ---- graph-editing noise (src/noise.rs:180-378): sequential, data-dependent edits of the observation
+// graph, host side like the reference's (they are O(observations) and not on the data-parallel path).
+// Seeded; parity with the reference's thread_rng() draws is distributional.
+
+// src/noise.rs:180-226: with probability mismatch_chance an observation trades its point index with
+// another observation of the same camera, chosen with weight (largest image distance) - (its image
+// distance) — as written there, which also gives the observation itself the largest weight.
+inline BAProblem add_incorrect_correspondences(const BAProblem &bal, double mismatch_chance, uint64_t seed) {
+  BAProblem out = bal;
+  detail::Rng rng(seed);
+  for (auto &obs : out.vis_graph) {
+    if (obs.size() <= 1) continue;
+    for (size_t i = 0; i < obs.size(); ++i) {
+      if (!(rng.uniform() <= mismatch_chance)) continue;
+      std::vector<double> weights(obs.size());
+      for (size_t j = 0; j < obs.size(); ++j) {
+        const double dx = obs[i].second.first - obs[j].second.first, dy = obs[i].second.second - obs[j].second.second;
+        weights[j] = -std::sqrt(dx * dx + dy * dy);
+      }
+      weights[i] = 0.0;
+      double m = INFINITY;
+      for (double w : weights) m = std::fmin(m, w);
+      for (double &w : weights) w -= m;
+      const size_t j = rng.weighted(weights);
+      std::swap(obs[i].first, obs[j].first);
+    }
+  }
+  return out;
+}
+
+// src/noise.rs:229-250: every camera keeps floor(len * drop_percent) of its observations, chosen by a shuffle
+inline BAProblem drop_features(const BAProblem &bal, double drop_percent, uint64_t seed) {
+  BAProblem out = bal;
+  detail::Rng rng(seed);
+  for (auto &o : out.vis_graph) {
+    const size_t l = (size_t)((double)o.size() * drop_percent);
+    rng.shuffle(o);
+    if (l < o.size()) o.resize(l);
+  }
+  return out;
+}
+
+// src/noise.rs:254-288: floor(split_percent * points) landmarks get a copy at the same location; each of
+// their observations moves to the copy with probability 1/2
+inline BAProblem split_landmarks(const BAProblem &bal, double split_percent, uint64_t seed) {
+  BAProblem out = bal;
+  detail::Rng rng(seed);
+  const size_t l = bal.points.size();
+  const size_t n = (size_t)(split_percent * (double)l);
+  const std::vector<size_t> inds = rng.choose_multiple(l, n);
+  std::unordered_map<size_t, size_t> split_inds;
+  for (size_t k = 0; k < inds.size(); ++k) {
+    out.points.push_back(bal.points[inds[k]]);
+    split_inds[inds[k]] = l + k;
+  }
+  for (auto &obs : out.vis_graph)
+    for (auto &e : obs) {
+      const auto it = split_inds.find(e.first);
+      if (it != split_inds.end() && rng.coin()) e.first = it->second;
+    }
+  return out;
+}
+
+namespace detail_n {
+// k nearest neighbours over the points (the reference's rstar R-tree, nearest_neighbor_iter): a k-d tree
+struct KdTree {
+  const std::vector<Point3> &pts;
+  std::vector<uint32_t> order;
+  explicit KdTree(const std::vector<Point3> &p) : pts(p), order(p.size()) {
+    std::iota(order.begin(), order.end(), 0u);
+    build(0, order.size(), 0);
+  }
+  void build(size_t lo, size_t hi, int axis) {
+    if (hi - lo <= 1) return;
+    const size_t mid = (lo + hi) / 2;
+    std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi,
+                     [&](uint32_t a, uint32_t b) { return pts[a][axis] < pts[b][axis]; });
+    build(lo, mid, (axis + 1) % 3);
+    build(mid + 1, hi, (axis + 1) % 3);
+  }
+  // (squared distance, index) of the k nearest points to q, ascending (ties by index)
+  std::vector<std::pair<double, uint32_t>> nearest(const Point3 &q, size_t k) const {
+    std::vector<std::pair<double, uint32_t>> heap;  // max-heap on (distance, index)
+    search(0, order.size(), 0, q, k, heap);
+    std::sort_heap(heap.begin(), heap.end());
+    return heap;
+  }
+  void search(size_t lo, size_t hi, int axis, const Point3 &q, size_t k,
+              std::vector<std::pair<double, uint32_t>> &heap) const {
+    if (lo >= hi) return;
+    const size_t mid = (lo + hi) / 2;
+    const uint32_t id = order[mid];
+    const Vector3 d = detail::sub(pts[id], q);
+    const std::pair<double, uint32_t> cand{detail::dot(d, d), id};
+    if (heap.size() < k) {
+      heap.push_back(cand);
+      std::push_heap(heap.begin(), heap.end());
+    } else if (cand < heap.front()) {
+      std::pop_heap(heap.begin(), heap.end());
+      heap.back() = cand;
+      std::push_heap(heap.begin(), heap.end());
+    }
+    const double delta = q[axis] - pts[id][axis];
+    const int next = (axis + 1) % 3;
+    if (delta < 0.0) {
+      search(lo, mid, next, q, k, heap);
+      if (heap.size() < k || delta * delta <= heap.front().first) search(mid + 1, hi, next, q, k, heap);
+    } else {
+      search(mid + 1, hi, next, q, k, heap);
+      if (heap.size() < k || delta * delta <= heap.front().first) search(lo, mid, next, q, k, heap);
+    }
+  }
+};
+}  // namespace detail_n
+
+// src/noise.rs:323-378: floor(join_percent * points) observations (drawn over ALL observations) are
+// re-pointed at one of the 10 nearest other landmarks of the landmark they see
+inline BAProblem join_landmarks(const BAProblem &bal, double join_percent, uint64_t seed) {
+  BAProblem out = bal;
+  detail::Rng rng(seed);
+  const detail_n::KdTree tree(bal.points);
+  const size_t n = (size_t)(join_percent * (double)bal.points.size());
+  const std::vector<size_t> inds = rng.choose_multiple(bal.num_observations(), n);
+  std::vector<size_t> starts(bal.vis_graph.size() + 1, 0);  // linear observation index -> (camera, slot)
+  for (size_t c = 0; c < bal.vis_graph.size(); ++c) starts[c + 1] = starts[c] + bal.vis_graph[c].size();
+  for (size_t i : inds) {
+    const size_t c = (size_t)(std::upper_bound(starts.begin(), starts.end(), i) - starts.begin()) - 1;
+    auto &e = out.vis_graph[c][i - starts[c]];
+    const auto near = tree.nearest(bal.points[e.first], 11);  // .skip(1).take(10)
+    detail::require(near.size() > 1, "No neighbors?!");
+    e.first = near[1 + rng.below(near.size() - 1)].second;
+  }
+  return out;
 }
 }  // namespace noise
 
