@@ -588,9 +588,16 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     C2B_TRY(ctx->out_idx[sel].ensure(total_obs * 4));
     C2B_TRY(ctx->out_uv[sel].ensure(total_obs * 16));
     SortWriteArgs sw{fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, fa.cams, ctx->pts_aos.as<double>(),
-                     ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>()};
+                     ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>(),
+                     std::max(pbits, 1)};
     if (max32 <= SW_BLOCK_MAX) {
-      k_sort_write<<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+      static const int sw_occ = getenv("C2B_SW_OCC") ? atoi(getenv("C2B_SW_OCC")) : 8;  // CTAs/SM the registers are capped for
+      if (sw_occ >= 8)
+        k_sort_write<8><<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+      else if (sw_occ >= 6)
+        k_sort_write<6><<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+      else
+        k_sort_write<4><<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
       C2B_KERNEL_CHECK();
       if (max32 > SW_WARP_MAX) {
         k_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);

@@ -60,7 +60,7 @@ struct FusedArgs {
                                  // [4] candidates (rays), [5] scratch slice overflow flag, [7] camera ticket
 };
 
-// camera_cell_range / row_span run in BOTH k_cam_plan (which sizes each camera's scratch slice) and
+// camera_cell_range / camera_row run in BOTH k_cam_plan (which sizes each camera's scratch slice) and
 // k_visibility_fused (which scans the rows), so they must round identically in both inlined copies:
 // every operation is an explicit round-to-nearest intrinsic that the compiler cannot contract.
 // cells whose points can lie within max_dist of the centre; false = none
@@ -81,34 +81,40 @@ __device__ __forceinline__ bool camera_cell_range(const GridDesc &g, const doubl
   return !empty;
 }
 
-// "in front of the camera" is pc.z = r2x*x + r2y*y + r2z*z + tz <= 0 (src/generate.rs:450): linear in
-// x along a row of cells, so the row [x0, x1] is trimmed to the x-range that can hold such a point.
-// false = nothing on this row can be in front.
-__device__ __forceinline__ bool row_span(const GridDesc &g, double cell_h, double r2x, double r2y, double r2z,
-                                         double tz, double xr, int y, int z, int &x0, int &x1) {
-  // bounds of the row's cells in y and z; edge cells also hold the clamped coordinates, so they
-  // extend to the data bounds
-  const double sl = dmul(1e-6, cell_h);
-  const double y0 = y == 0 ? g.min_c[1] : dsub(dadd(g.lo[1], dmul((double)y, cell_h)), sl);
-  const double y1 = y == g.n[1] - 1 ? g.max_c[1] : dadd(dadd(g.lo[1], dmul((double)(y + 1), cell_h)), sl);
-  const double z0 = z == 0 ? g.min_c[2] : dsub(dadd(g.lo[2], dmul((double)z, cell_h)), sl);
-  const double z1 = z == g.n[2] - 1 ? g.max_c[2] : dadd(dadd(g.lo[2], dmul((double)(z + 1), cell_h)), sl);
-  // smallest value r2y*y + r2z*z + tz can take on the row (0 * inf is avoided explicitly)
-  const double my = r2y == 0.0 ? 0.0 : dmul(r2y, r2y > 0.0 ? y0 : y1);
-  const double mz = r2z == 0.0 ? 0.0 : dmul(r2z, r2z > 0.0 ? z0 : z1);
-  const double bmin = dadd(dadd(my, mz), tz);
-  const double mag = dadd(dadd(dadd(fabs(my), fabs(mz)), fabs(tz)), xr);
+// ---- per-row trimming ---------------------------------------------------------------------------------
+// A camera scans rows of x-contiguous cells.  Everything a visible point must satisfy that is LINEAR in
+// x along a row trims the row's cell range before any point is read:
+//   in front of the camera      pc.z = r2.p + tz <= 0                                (src/generate.rs:450)
+//   inside the image            |f pc.x| <= -pc.z and |f pc.y| <= -pc.z, i.e. the four half-spaces
+//                               (+-f r0 + r2).p + (+-f tx + tz) <= 0, (+-f r1 + r2).p + (+-f ty + tz) <= 0
+//                               (src/generate.rs:454 with `project`, src/baproblem.rs:145-151; only when
+//                               k1 = k2 = 0, otherwise the image bound is not a plane)
+//   within max_dist             |x - cx| <= sqrt(R^2 - d^2), d = distance of the centre from the row's
+//                               (y, z) rectangle
+// All of it is conservative (slack of 1e-9 of the magnitudes involved against rounding of ~1e-16), the
+// exact predicate still runs on every point that is read.
+
+// trims [x0, x1] to the cells that can hold a point with nx*x + ny*y + nz*z + off <= 0 for y in [y0, y1],
+// z in [z0, z1]; xr bounds |nx*x| over the camera's ball; false = nothing on this row qualifies
+__device__ __forceinline__ bool trim_halfspace(const GridDesc &g, double cell_h, double nx, double ny, double nz,
+                                               double off, double xr, double mag_floor, double y0, double y1,
+                                               double z0, double z1, int &x0, int &x1) {
+  // smallest value ny*y + nz*z + off can take on the row (0 * inf is avoided explicitly)
+  const double my = ny == 0.0 ? 0.0 : dmul(ny, ny > 0.0 ? y0 : y1);
+  const double mz = nz == 0.0 ? 0.0 : dmul(nz, nz > 0.0 ? z0 : z1);
+  const double bmin = dadd(dadd(my, mz), off);
+  const double mag = dadd(dadd(dadd(dadd(fabs(my), fabs(mz)), fabs(off)), xr), mag_floor);
   if (bmin == bmin && fabs(bmin) < INFINITY) {
     const double slack = dadd(dmul(1e-9, mag), 1e-300);
     if (xr <= slack) {
-      if (bmin > dmul(2.0, slack)) return false;  // the whole row is behind the camera
+      if (bmin > dmul(2.0, slack)) return false;  // the whole row is outside
     } else {
-      const double xlim = ddiv(-dsub(bmin, slack), r2x);  // r2x*x <= -(bmin - slack)
+      const double xlim = ddiv(-dsub(bmin, slack), nx);  // nx*x <= -(bmin - slack)
       if (xlim == xlim) {
         const double xs = dmul(1e-9, dadd(fabs(xlim), cell_h));
-        if (r2x > 0.0) {
+        if (nx > 0.0) {
           const double xe = dadd(xlim, xs);
-          if (xe < g.lo[0]) return false;  // nothing in front on this row
+          if (xe < g.lo[0]) return false;
           const int xc = grid_coord(g, 0, xe);
           x1 = xc < x1 ? xc : x1;
         } else {
@@ -122,6 +128,71 @@ __device__ __forceinline__ bool row_span(const GridDesc &g, double cell_h, doubl
     }
   }
   return true;
+}
+
+struct RowRange {
+  uint32_t start, end;  // grid-ordered points [start, end) of the trimmed row; start >= end: nothing
+};
+
+// The trimmed point range of row (y, z) for the camera record c (15 doubles) with centre cc.  Runs in BOTH
+// k_cam_plan (which sizes each camera's scratch slice) and k_visibility_fused (which scans the rows), so it
+// must round identically in both inlined copies: every operation is an explicit round-to-nearest intrinsic
+// that the compiler cannot contract.
+__device__ __forceinline__ RowRange camera_row(const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                               const double *c, const double cc[3], double max_dist,
+                                               const int lo[3], const int hi[3], double cell_h, int y, int z) {
+  RowRange r{0u, 0u};
+  int x0 = lo[0], x1 = hi[0];
+  // bounds of the row's cells in y and z; edge cells also hold the clamped coordinates, so they
+  // extend to the data bounds
+  const double sl = dmul(1e-6, cell_h);
+  const double y0 = y == 0 ? g.min_c[1] : dsub(dadd(g.lo[1], dmul((double)y, cell_h)), sl);
+  const double y1 = y == g.n[1] - 1 ? g.max_c[1] : dadd(dadd(g.lo[1], dmul((double)(y + 1), cell_h)), sl);
+  const double z0 = z == 0 ? g.min_c[2] : dsub(dadd(g.lo[2], dmul((double)z, cell_h)), sl);
+  const double z1 = z == g.n[2] - 1 ? g.max_c[2] : dadd(dadd(g.lo[2], dmul((double)(z + 1), cell_h)), sl);
+  const double reach = dadd(fabs(cc[0]), fabs(max_dist));
+  // the ball
+  {
+    const double dy = fmax(fmax(dsub(y0, cc[1]), dsub(cc[1], y1)), 0.0);
+    const double dz = fmax(fmax(dsub(z0, cc[2]), dsub(cc[2], z1)), 0.0);
+    const double rem = dsub(dmul(dmul(max_dist, max_dist), 1.000000001), dadd(dmul(dy, dy), dmul(dz, dz)));
+    if (rem < 0.0) return r;
+    if (rem == rem && rem < INFINITY) {
+      const double w = dadd(dmul(dsqrt(rem), 1.000000001), dmul(1e-9, reach));
+      const double xa = dsub(cc[0], w), xb = dadd(cc[0], w);
+      if (xa > g.max_c[0] || xb < g.min_c[0]) return r;
+      const int ca = grid_coord(g, 0, xa), cb = grid_coord(g, 0, xb);
+      x0 = ca > x0 ? ca : x0;
+      x1 = cb < x1 ? cb : x1;
+      if (x0 > x1) return r;
+    }
+  }
+  // magnitudes the rounding errors of the exact predicate scale with: (|f| + 1) (|R| |p| + |t|)
+  const double f = c[12];
+  const bool planar_image = c[13] == 0.0 && c[14] == 0.0 && fabs(f) < INFINITY;
+  double rmax = 0.0;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) rmax = fmax(rmax, fabs(c[k]));
+  const double span = dadd(dadd(dadd(fabs(cc[0]), fabs(cc[1])), fabs(cc[2])), dmul(3.0, fabs(max_dist)));
+  const double mag_floor = dmul(dadd(planar_image ? fabs(f) : 0.0, 1.0), dmul(rmax, dadd(span, 1.0)));
+  // in front of the camera
+  if (!trim_halfspace(g, cell_h, c[2], c[5], c[8], c[11], dmul(fabs(c[2]), reach), mag_floor, y0, y1, z0, z1, x0, x1))
+    return r;
+  if (planar_image) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = k >> 1;  // 0: u (camera x), 1: v (camera y)
+      const double sf = (k & 1) ? -f : f;
+      const double nx = dadd(dmul(sf, c[row]), c[2]), ny = dadd(dmul(sf, c[3 + row]), c[5]);
+      const double nz = dadd(dmul(sf, c[6 + row]), c[8]), off = dadd(dmul(sf, c[9 + row]), c[11]);
+      if (!trim_halfspace(g, cell_h, nx, ny, nz, off, dmul(fabs(nx), reach), mag_floor, y0, y1, z0, z1, x0, x1))
+        return r;
+    }
+  }
+  const uint32_t rowbase = ((uint32_t)z * g.n[1] + y) * g.n[0];
+  r.start = cell_start[rowbase + x0];
+  r.end = cell_start[rowbase + x1 + 1];
+  return r;
 }
 
 // The cull predicate of src/generate.rs:450-454 with the two f64 divisions of `project` replaced by
@@ -166,33 +237,40 @@ __device__ __forceinline__ bool cull_predicate(const double *cam, V3 center, V3 
   return u >= -1.0 && u <= 1.0 && v >= -1.0 && v <= 1.0;
 }
 
+// out-of-line copy for the fused kernel: called once per 32 rows, and kept out of the register
+// allocation of its 64-register hot loops (same operations, same results)
+__device__ __noinline__ RowRange camera_row_call(const GridDesc &g, const uint32_t *__restrict__ cell_start,
+                                                 const double *c, const double *cc, double max_dist, const int *lo,
+                                                 const int *hi, double cell_h, int y, int z) {
+  return camera_row(g, cell_start, c, cc, max_dist, lo, hi, cell_h, y, z);
+}
+
 // ---- plan -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_cam_plan(FusedArgs a) {
+// one thread per camera, rows in sequence (a warp per camera with lane = row leaves most lanes idle and
+// measured 0.19 ms at cfg4 against 0.03 ms for this form)
+__global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
   const uint64_t cam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t n = 0;
+  unsigned long long n = 0;
   if (cam < a.C) {
     const double cc[3] = {a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
     int lo[3], hi[3];
     if (camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
-      const double *c = a.cams + 15 * cam;
-      const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
+      double c[15];
+#pragma unroll
+      for (int k = 0; k < 15; ++k) c[k] = a.cams[15 * cam + k];
       const double cell_h = ddiv(1.0, a.g.inv_h);
-      const double xr = dmul(fabs(r2x), dadd(fabs(cc[0]), fabs(a.max_dist)));
       for (int z = lo[2]; z <= hi[2]; ++z)
         for (int y = lo[1]; y <= hi[1]; ++y) {
-          int x0 = lo[0], x1 = hi[0];
-          if (!row_span(a.g, cell_h, r2x, r2y, r2z, tz, xr, y, z, x0, x1)) continue;
-          const uint32_t row = ((uint32_t)z * a.g.n[1] + y) * a.g.n[0];
-          n += a.cell_start[row + x1 + 1] - a.cell_start[row + x0];
+          const RowRange rr = camera_row(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, y, z);
+          if (rr.end > rr.start) n += rr.end - rr.start;
         }
     }
   }
   if (cam <= a.C) a.ev_count[cam] = (uint32_t)n;  // n <= P < 2^32; slot C = 0 closes the scan
   // 64-bit total, so the host can tell when the u32 scan would wrap
-  unsigned long long s = n;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&a.counters[1], s);
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(&a.counters[1], n);
 }
 
 // ---- the fused pass ---------------------------------------------------------------------------------
@@ -598,14 +676,20 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       nvis += __popc(m);
     };
 
-    const double r2x = c[2], r2y = c[5], r2z = c[8], tz = c[11];
-    const double xr = dmul(fabs(r2x), dadd(fabs(cc[0]), fabs(a.max_dist)));
-    for (int z = lo[2]; z <= hi[2]; ++z)
-      for (int y = lo[1]; y <= hi[1]; ++y) {
-        int x0 = lo[0], x1 = hi[0];
-        if (!row_span(a.g, cell_h, r2x, r2y, r2z, tz, xr, y, z, x0, x1)) continue;
-        const uint32_t row = ((uint32_t)z * a.g.n[1] + y) * a.g.n[0];
-        const uint32_t start = a.cell_start[row + x0], end = a.cell_start[row + x1 + 1];
+    // lane = row: the trimmed point ranges of up to 32 rows at a time (their cell_start loads in parallel),
+    // then the warp scans the non-empty ones
+    const int ny = hi[1] - lo[1] + 1, nrows = ny * (hi[2] - lo[2] + 1);
+    for (int rb = 0; rb < nrows; rb += 32) {
+      RowRange rr{0u, 0u};
+      if (rb + lane < nrows) {
+        const int ri = rb + lane;
+        rr = camera_row_call(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, lo[1] + ri % ny, lo[2] + ri / ny);
+      }
+      unsigned live = __ballot_sync(0xffffffffu, rr.end > rr.start);
+      while (live) {
+        const int j = __ffs(live) - 1;
+        live &= live - 1;
+        const uint32_t start = __shfl_sync(0xffffffffu, rr.start, j), end = __shfl_sync(0xffffffffu, rr.end, j);
         // software pipeline: the next 32 points are in flight while the current ones are evaluated
         V3 pn{0.0, 0.0, 0.0};
         if (start + lane < end) pn = V3{a.gx[start + lane], a.gy[start + lane], a.gz[start + lane]};
@@ -633,6 +717,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
           }
         }
       }
+    }
     if (qn > 0) {
       resolve(qn);
       found_total += qn;
@@ -725,33 +810,110 @@ struct SortWriteArgs {
   uint64_t *out_offsets;
   uint32_t *out_idx;
   double2 *out_uv;
+  int key_bits;  // bits of the largest point index: the radix passes cover exactly these
 };
 
-constexpr uint32_t SW_WARP_MAX = 1024;   // register sort, one warp per camera
+constexpr uint32_t SW_WARP_MAX = 1024;   // one warp per camera
 constexpr uint32_t SW_BLOCK_MAX = 4096;  // shared-memory sort, one block per camera
 
 constexpr int SW_WARPS = 4;
+constexpr int SW_RADIX_BITS = 8;
+constexpr int SW_BINS = 1 << SW_RADIX_BITS;
 
 // sorted[] is indexed with one pad word per 32 (i + i/32), so that the lane*E + r stores and the
 // consecutive reads are both free of bank conflicts
 __device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
 
+// Warp-private LSD radix sort of n <= 32*E keys, 8-bit digits.  Keys live in registers in list order
+// (a[r] = key r*32 + lane); one pass = digit histogram in shared memory (ATOMS), exclusive scan of the
+// 256 counters (8 per lane + one warp scan), then a stable scatter chunk by chunk: the rank of a key
+// among the equal digits of its chunk is popc(__match_any_sync & lanes below), the chunk's first lane
+// per digit advances the counter.  A pass whose keys all share the digit is skipped (common for the top
+// digit: a camera's points are usually close in index).  About 0.4k warp instructions per pass at
+// n = 532 against ~3k for the 1024-key bitonic network this replaces (profiles/r01h: k_sort_write spent
+// 878 M warp instructions, 16.5 per observation).  The sorted keys end up in `sorted` (padded layout).
 template <int E>
 __device__ __forceinline__ void sort_warp_to_smem(const uint32_t *__restrict__ src, uint32_t n, int lane,
-                                                  uint32_t *sorted) {
+                                                  uint32_t *sorted, uint32_t *hist, int key_bits) {
   uint32_t a[E];
 #pragma unroll
   for (int r = 0; r < E; ++r) {
-    const uint32_t t = r * 32 + lane;  // coalesced load; any starting permutation sorts
+    const uint32_t t = r * 32 + lane;
     a[r] = t < n ? src[t] : 0xffffffffu;
   }
-  warp_bitonic_sort<E>(a, lane);
+  const unsigned lt = (1u << lane) - 1u;
+  bool in_smem = false;
+  for (int shift = 0; shift < key_bits; shift += SW_RADIX_BITS) {
 #pragma unroll
-  for (int r = 0; r < E; ++r) sorted[sw_pad((uint32_t)lane * E + r)] = a[r];
+    for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+      if ((uint32_t)(r * 32 + lane) < n) atomicAdd(&hist[(a[r] >> shift) & (SW_BINS - 1)], 1u);
+    __syncwarp();
+    // exclusive scan: lane owns counters [8*lane, 8*lane + 8)
+    uint32_t c[SW_BINS / 32];
+    uint32_t sum = 0;
+    bool one_bin = false;
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      c[k] = hist[lane * (SW_BINS / 32) + k];
+      one_bin |= c[k] == n;
+      sum += c[k];
+    }
+    if (__any_sync(0xffffffffu, one_bin)) continue;  // every key has the same digit: order unchanged
+    uint32_t pre = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    pre -= sum;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      hist[lane * (SW_BINS / 32) + k] = pre;
+      pre += c[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      if ((uint32_t)(r * 32) < n) {  // warp-uniform
+        const bool valid = (uint32_t)(r * 32 + lane) < n;
+        const uint32_t d = valid ? (a[r] >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & lt);
+        uint32_t base = 0;
+        if (valid) base = hist[d];
+        __syncwarp();
+        if (valid && rank == 0) hist[d] = base + __popc(peers);
+        if (valid) sorted[sw_pad(base + rank)] = a[r];
+        __syncwarp();
+      }
+    }
+    in_smem = true;
+    if (shift + SW_RADIX_BITS < key_bits) {
+#pragma unroll
+      for (int r = 0; r < E; ++r) {
+        const uint32_t t = r * 32 + lane;
+        if (t < n) a[r] = sorted[sw_pad(t)];
+      }
+      __syncwarp();
+    }
+  }
+  if (!in_smem) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const uint32_t t = r * 32 + lane;
+      if (t < n) sorted[sw_pad(t)] = a[r];
+    }
+  }
 }
 
-__global__ void __launch_bounds__(SW_WARPS * 32) k_sort_write(SortWriteArgs s) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWriteArgs s) {
   __shared__ uint32_t s_sorted[SW_WARPS][SW_WARP_MAX + SW_WARP_MAX / 32];
+  __shared__ uint32_t s_hist[SW_WARPS][SW_BINS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
   if (cam >= s.C) return;
@@ -764,13 +926,15 @@ __global__ void __launch_bounds__(SW_WARPS * 32) k_sort_write(SortWriteArgs s) {
   const uint32_t *src = s.scratch_idx + s.ev_off[cam];
   uint32_t *sorted = s_sorted[warp];
   if (n <= 128)
-    sort_warp_to_smem<4>(src, n, lane, sorted);
+    sort_warp_to_smem<4>(src, n, lane, sorted, s_hist[warp], s.key_bits);
   else if (n <= 256)
-    sort_warp_to_smem<8>(src, n, lane, sorted);
+    sort_warp_to_smem<8>(src, n, lane, sorted, s_hist[warp], s.key_bits);
   else if (n <= 512)
-    sort_warp_to_smem<16>(src, n, lane, sorted);
+    sort_warp_to_smem<16>(src, n, lane, sorted, s_hist[warp], s.key_bits);
+  else if (n <= 768)
+    sort_warp_to_smem<24>(src, n, lane, sorted, s_hist[warp], s.key_bits);
   else
-    sort_warp_to_smem<32>(src, n, lane, sorted);
+    sort_warp_to_smem<32>(src, n, lane, sorted, s_hist[warp], s.key_bits);
   __syncwarp();
   double c[15];
 #pragma unroll
