@@ -828,7 +828,9 @@ __device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
 // (a[r] = key r*32 + lane); one pass = digit histogram in shared memory (ATOMS), exclusive scan of the
 // 256 counters (8 per lane + one warp scan), then a stable scatter chunk by chunk: the rank of a key
 // among the equal digits of its chunk is popc(__match_any_sync & lanes below), the chunk's first lane
-// per digit advances the counter.  A pass whose keys all share the digit is skipped (common for the top
+// per digit advances the counter with one shared-memory atomic and hands the old value to its peers
+// by shuffle (no warp barrier inside the chunk loop: they cost a quarter of the kernel's instructions
+// in the first version, profiles/r01j).  A pass whose keys all share the digit is skipped (common for the top
 // digit: a camera's points are usually close in index).  About 0.4k warp instructions per pass at
 // n = 532 against ~3k for the 1024-key bitonic network this replaces (profiles/r01h: k_sort_write spent
 // 878 M warp instructions, 16.5 per observation).  The sorted keys end up in `sorted` (padded layout).
@@ -861,7 +863,10 @@ __device__ __forceinline__ void sort_warp_to_smem(const uint32_t *__restrict__ s
       one_bin |= c[k] == n;
       sum += c[k];
     }
-    if (__any_sync(0xffffffffu, one_bin)) continue;  // every key has the same digit: order unchanged
+    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
+      __syncwarp();                          // (the counters are cleared again by the next pass)
+      continue;
+    }
     uint32_t pre = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -883,14 +888,14 @@ __device__ __forceinline__ void sort_warp_to_smem(const uint32_t *__restrict__ s
         const uint32_t d = valid ? (a[r] >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const uint32_t rank = __popc(peers & lt);
-        uint32_t base = 0;
-        if (valid) base = hist[d];
-        __syncwarp();
-        if (valid && rank == 0) hist[d] = base + __popc(peers);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
+        const uint32_t base = __shfl_sync(0xffffffffu, old, leader);
         if (valid) sorted[sw_pad(base + rank)] = a[r];
-        __syncwarp();
       }
     }
+    __syncwarp();
     in_smem = true;
     if (shift + SW_RADIX_BITS < key_bits) {
 #pragma unroll
