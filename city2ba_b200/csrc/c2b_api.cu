@@ -476,9 +476,19 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     return C2B_OK;
   }
 
-  C2B_TRY(ctx->ev_off.ensure((C + 1) * 4));
-  C2B_TRY(ctx->vis_count.ensure((C + 1) * 4));
-  C2B_TRY(ctx->seg_off.ensure((C + 1) * 4));
+  // Tickets per camera: with fewer cameras than persistent warps a camera's rows are split over 2 or 4
+  // tickets (a ticket repeats the per-camera set-up, so it only pays on warps that would otherwise idle).
+  int parts_log2 = 0;
+  {
+    const uint64_t warps = (uint64_t)ctx->sm_count * 4 * FU_WARPS;
+    if (2 * C <= warps) parts_log2 = 1;
+    if (4 * C <= warps) parts_log2 = 2;
+    if (const char *e = getenv("C2B_PARTS_LOG2")) parts_log2 = std::min(std::max(0, atoi(e)), 2);  // test hook
+  }
+  const uint64_t slots = C << parts_log2;
+  C2B_TRY(ctx->ev_off.ensure((slots + 1) * 4));
+  C2B_TRY(ctx->vis_count.ensure((slots + 1) * 4));
+  C2B_TRY(ctx->seg_off.ensure((slots + 1) * 4));
   const double *cxp = ctx->cam_center.as<double>();
   const bool mesh = opt.occlusion == C2B_OCC_MESH && scene && scene->n_nodes > 0;
   FusedArgs fa;
@@ -500,6 +510,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   fa.endpoint_guard_rel = opt.endpoint_guard_rel;
   fa.block_length = opt.block_length;
   fa.block_inset = opt.block_inset;
+  fa.parts_log2 = parts_log2;
   fa.ev_count = ctx->ev_off.as<uint32_t>();
   fa.vis_count = ctx->vis_count.as<uint32_t>();
   fa.counters = ctx->counters.as<unsigned long long>();
@@ -511,7 +522,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   // plan: row points per camera -> scratch slices
   k_cam_plan<<<blocks_for(C + 1, 128), 128, 0, st>>>(fa);
   C2B_KERNEL_CHECK();
-  C2B_TRY(exclusive_scan_u32(st, fa.ev_count, fa.ev_count, C + 1, nullptr, ctx->scan_tmp));
+  C2B_TRY(exclusive_scan_u32(st, fa.ev_count, fa.ev_count, slots + 1, nullptr, ctx->scan_tmp));
   if (mesh) {
     uint32_t trilist_cap = 128;
     if (const char *e = getenv("C2B_TRILIST_CAP")) trilist_cap = (uint32_t)std::max(1, atoi(e));
@@ -529,9 +540,15 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     fa.hoist_max = FU_HOIST;
     fa.packet_bvh = getenv("C2B_NO_PACKET_BVH") == nullptr;
     if (const char *e = getenv("C2B_HOIST_MAX")) fa.hoist_max = (uint32_t)std::min(std::max(0, atoi(e)), FU_HOIST);
-    k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
-                                                     fa.scene_absmax, trilist_cap, ctx->tri_list.as<uint32_t>(),
-                                                     ctx->tri_count.as<uint32_t>(), fa.counters + 0);
+    const bool tl_warp = getenv("C2B_TRILIST_WARP") ? atoi(getenv("C2B_TRILIST_WARP")) != 0 : C < 32768;  // env: test hook
+    if (tl_warp)
+      k_cam_trilist_warp<<<blocks_for(C, TL_WARPS), TL_WARPS * 32, 0, st>>>(
+          fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax, fa.scene_absmax, trilist_cap,
+          ctx->tri_list.as<uint32_t>(), ctx->tri_count.as<uint32_t>(), fa.counters + 0);
+    else
+      k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
+                                                       fa.scene_absmax, trilist_cap, ctx->tri_list.as<uint32_t>(),
+                                                       ctx->tri_count.as<uint32_t>(), fa.counters + 0);
     C2B_KERNEL_CHECK();
   }
   C2B_TRY(read_counters(ctx, h_cnt));
@@ -547,10 +564,10 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
 
   // fused cull + occlusion
-  C2B_CUDA(cudaMemsetAsync(ctx->vis_count.p, 0, (C + 1) * 4, st));
+  C2B_CUDA(cudaMemsetAsync(ctx->vis_count.p, 0, (slots + 1) * 4, st));
   {
     // persistent warps draw cameras from a ticket; more CTAs than can be resident is harmless
-    const unsigned nb = (unsigned)std::min<uint64_t>(blocks_for(C, FU_WARPS), (uint64_t)ctx->sm_count * 8), nt = FU_WARPS * 32;
+    const unsigned nb = (unsigned)std::min<uint64_t>(blocks_for(slots, FU_WARPS), (uint64_t)ctx->sm_count * 8), nt = FU_WARPS * 32;
     const bool cnt = opt.count_traversal != 0;
     static const bool occ4 = getenv("C2B_FU_OCC3") == nullptr;  // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3)
     if (mesh) {
@@ -572,9 +589,9 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
 
   // visible counts -> CSR offsets
-  k_max_u32<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(fa.vis_count, C, d_max);
+  C2B_TRY(exclusive_scan_u32(st, fa.vis_count, ctx->seg_off.as<uint32_t>(), slots + 1, d_total, ctx->scan_tmp));
+  k_max_cam<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C, parts_log2, d_max);
   C2B_KERNEL_CHECK();
-  C2B_TRY(exclusive_scan_u32(st, fa.vis_count, ctx->seg_off.as<uint32_t>(), C + 1, d_total, ctx->scan_tmp));
   C2B_TRY(read_counters(ctx, h_cnt));
   if (h_cnt[5]) return set_error(C2B_ERR_CUDA, "internal: a camera's scratch slice overflowed");
   uint32_t total32, max32;
@@ -589,15 +606,18 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     C2B_TRY(ctx->out_uv[sel].ensure(total_obs * 16));
     SortWriteArgs sw{fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, fa.cams, ctx->pts_aos.as<double>(),
                      ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>(),
-                     std::max(pbits, 1)};
+                     std::max(pbits, 1), parts_log2};
     if (max32 <= SW_BLOCK_MAX) {
       static const int sw_occ = getenv("C2B_SW_OCC") ? atoi(getenv("C2B_SW_OCC")) : 8;  // CTAs/SM the registers are capped for
-      if (sw_occ >= 8)
-        k_sort_write<8><<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+      const unsigned swb = (unsigned)blocks_for(C, SW_WARPS), swt = SW_WARPS * 32;
+      if (parts_log2 > 0)
+        k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
+      else if (sw_occ >= 8)
+        k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
       else if (sw_occ >= 6)
-        k_sort_write<6><<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+        k_sort_write<6, false><<<swb, swt, 0, st>>>(sw);
       else
-        k_sort_write<4><<<blocks_for(C, SW_WARPS), SW_WARPS * 32, 0, st>>>(sw);
+        k_sort_write<4, false><<<swb, swt, 0, st>>>(sw);
       C2B_KERNEL_CHECK();
       if (max32 > SW_WARP_MAX) {
         k_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);
@@ -609,8 +629,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
       C2B_TRY(ctx->sort_keys[1].ensure(total_obs * 8));
       C2B_TRY(ctx->sort_vals[0].ensure(total_obs * 4));
       C2B_TRY(ctx->sort_vals[1].ensure(total_obs * 4));
-      k_expand_keys<<<blocks_for(C, 8), 256, 0, st>>>(fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, pbits,
-                                                      ctx->sort_keys[0].as<uint64_t>());
+      k_expand_keys<<<blocks_for(C, 8), 256, 0, st>>>(sw, pbits, ctx->sort_keys[0].as<uint64_t>());
       C2B_KERNEL_CHECK();
       uint64_t *keys[2] = {ctx->sort_keys[0].as<uint64_t>(), ctx->sort_keys[1].as<uint64_t>()};
       uint32_t *vals[2] = {ctx->sort_vals[0].as<uint32_t>(), ctx->sort_vals[1].as<uint32_t>()};
@@ -620,8 +639,8 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
                                                                 ctx->pts_aos.as<double>(), ctx->out_idx[sel].as<uint32_t>(),
                                                                 ctx->out_uv[sel].as<double2>());
       C2B_KERNEL_CHECK();
-      k_widen_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C + 1,
-                                                             ctx->out_offsets[sel].as<uint64_t>());
+      k_widen_cam_offsets<<<blocks_for(C + 1, 256), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C + 1, parts_log2,
+                                                                 ctx->out_offsets[sel].as<uint64_t>());
       C2B_KERNEL_CHECK();
     }
   } else {

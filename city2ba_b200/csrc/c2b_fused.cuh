@@ -52,10 +52,14 @@ struct FusedArgs {
   int packet_bvh;      // list overflow: 1 = lane = node packet traversal, 0 = per-ray stackless walk
   int endpoint_guard_rel;
   double block_length, block_inset;  // analytic occlusion (src/synthetic.rs:52-124)
-  // plan + output
-  uint32_t *ev_count;         // [C+1] points on the camera's rows (k_cam_plan), then its exclusive scan
-  uint32_t *scratch_idx;      // visible point indices, camera c at [ev_off[c], ev_off[c] + vis_count[c])
-  uint32_t *vis_count;        // [C+1]
+  // plan + output.  A camera's rows are split into 2^parts_log2 contiguous blocks, one TICKET each (1, 2
+  // or 4: more than one only when there are fewer cameras than persistent warps, so that the extra
+  // per-ticket work runs on warps that would otherwise idle); slot = (camera << parts_log2) | part owns
+  // its own scratch slice and visible count.  Part p holds rows [nrows*p >> log2, nrows*(p+1) >> log2).
+  int parts_log2;
+  uint32_t *ev_count;         // [slots+1] points on the slot's rows (k_cam_plan), then its exclusive scan
+  uint32_t *scratch_idx;      // visible point indices, slot s at [ev_off[s], ev_off[s] + vis_count[s])
+  uint32_t *vis_count;        // [slots+1]
   unsigned long long *counters;  // [1] pairs evaluated, [2] list entries / nodes, [3] warp triangle tests,
                                  // [4] candidates (rays), [5] scratch slice overflow flag, [7] camera ticket
 };
@@ -250,7 +254,8 @@ __device__ __noinline__ RowRange camera_row_call(const GridDesc &g, const uint32
 // measured 0.19 ms at cfg4 against 0.03 ms for this form)
 __global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
   const uint64_t cam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long n = 0;
+  const int S = 1 << a.parts_log2;
+  unsigned long long n0 = 0, n1 = 0, n2 = 0, n3 = 0;
   if (cam < a.C) {
     const double cc[3] = {a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
     int lo[3], hi[3];
@@ -259,15 +264,34 @@ __global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
 #pragma unroll
       for (int k = 0; k < 15; ++k) c[k] = a.cams[15 * cam + k];
       const double cell_h = ddiv(1.0, a.g.inv_h);
+      const int nrows = (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+      int ri = 0;
       for (int z = lo[2]; z <= hi[2]; ++z)
-        for (int y = lo[1]; y <= hi[1]; ++y) {
+        for (int y = lo[1]; y <= hi[1]; ++y, ++ri) {
           const RowRange rr = camera_row(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, y, z);
-          if (rr.end > rr.start) n += rr.end - rr.start;
+          if (rr.end > rr.start) {
+            const unsigned long long m = rr.end - rr.start;
+            int part = 0;  // the block of rows ri falls in (same split as k_visibility_fused)
+            for (int q = 1; q < S; ++q)
+              if (ri >= (nrows * q) >> a.parts_log2) part = q;
+            n0 += part == 0 ? m : 0ull;
+            n1 += part == 1 ? m : 0ull;
+            n2 += part == 2 ? m : 0ull;
+            n3 += part == 3 ? m : 0ull;
+          }
         }
     }
+    uint32_t *out = a.ev_count + (cam << a.parts_log2);  // each < 2^32 (<= P)
+    out[0] = (uint32_t)n0;
+    if (S > 1) out[1] = (uint32_t)n1;
+    if (S > 2) {
+      out[2] = (uint32_t)n2;
+      out[3] = (uint32_t)n3;
+    }
   }
-  if (cam <= a.C) a.ev_count[cam] = (uint32_t)n;  // n <= P < 2^32; slot C = 0 closes the scan
+  if (cam == a.C) a.ev_count[cam << a.parts_log2] = 0u;  // closes the scan
   // 64-bit total, so the host can tell when the u32 scan would wrap
+  unsigned long long n = n0 + n1 + n2 + n3;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(&a.counters[1], n);
@@ -276,6 +300,10 @@ __global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
 // ---- the fused pass ---------------------------------------------------------------------------------
 constexpr int FU_WARPS = 8;
 constexpr int FU_STAGE = 64;
+#ifndef C2B_STAGE_COORDS
+#define C2B_STAGE_COORDS 0  // 1: survivors' coordinates staged in shared memory (48 KB/CTA, measured 3.11 ms at
+                            // cfg4); 0: re-read through L1 at ray set-up (36 KB/CTA, 3.07 ms)
+#endif
 
 enum { FU_OCC_MESH = 0, FU_OCC_NONE = 1, FU_OCC_ANALYTIC = 2 };
 
@@ -602,19 +630,29 @@ __device__ __forceinline__ int packet_bvh_hit(const FusedArgs &a, const Ray &ray
 template <int OCC, bool COUNT, int MIN_CTAS, bool WALK>
 __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
   __shared__ double s_cam[FU_WARPS][16];
+  // survivors of the cull wait here for their packet: a ring of FU_STAGE entries per warp holding the
+  // grid position and the coordinates just read (so that the ray set-up needs no second trip to global memory)
   __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
+#if C2B_STAGE_COORDS
+  __shared__ double s_px[FU_WARPS][FU_STAGE], s_py[FU_WARPS][FU_STAGE], s_pz[FU_WARPS][FU_STAGE];
+#endif
   __shared__ float4 s_rec[FU_WARPS][4 * FU_HOIST];  // hoisted: 4 planes x FU_HOIST; chunked: 32 x 3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *c = s_cam[warp];
   uint32_t *stage = s_stage[warp];
+#if C2B_STAGE_COORDS
+  double *stx = s_px[warp], *sty = s_py[warp], *stz = s_pz[warp];
+#endif
   unsigned long long found_total = 0;
   unsigned n_vis_nodes = 0, n_tri = 0;
   const double cell_h = ddiv(1.0, a.g.inv_h);
   for (;;) {
     unsigned long long ticket = 0;
     if (lane == 0) ticket = atomicAdd(&a.counters[7], 1ull);
-    const uint64_t cam = __shfl_sync(0xffffffffu, ticket, 0);
+    const uint64_t slot = __shfl_sync(0xffffffffu, ticket, 0);
+    const uint64_t cam = slot >> a.parts_log2;
     if (cam >= a.C) break;
+    const int part = (int)(slot & ((1u << a.parts_log2) - 1u));
     __syncwarp();
     if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
     __syncwarp();
@@ -622,7 +660,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     const double cc[3] = {cen.x, cen.y, cen.z};
     int lo[3], hi[3];
     if (!camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
-      if (lane == 0) a.vis_count[cam] = 0;
+      if (lane == 0) a.vis_count[slot] = 0;
       continue;
     }
     const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
@@ -634,10 +672,10 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     }
     const bool hoisted = OCC == FU_OCC_MESH && n_list <= a.hoist_max;  // (OVERFLOW is 2^32 - 1)
     if (hoisted) hoist_records(a, mylist, n_list, ox, oy, oz, s_rec[warp], lane);
-    uint32_t *out = a.scratch_idx + a.ev_count[cam];
-    const uint32_t out_cap = a.ev_count[cam + 1] - a.ev_count[cam];
+    uint32_t *out = a.scratch_idx + a.ev_count[slot];
+    const uint32_t out_cap = a.ev_count[slot + 1] - a.ev_count[slot];
     uint32_t nvis = 0;
-    int qn = 0;  // warp-uniform number of staged survivors
+    int qn = 0, head = 0;  // warp-uniform: number of staged survivors, ring position of the oldest
 
     auto resolve = [&](int count) {
       const bool have = lane < count;
@@ -648,9 +686,14 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       uint32_t pt = 0;
       V3 p{0.0, 0.0, 0.0};
       if (have) {
-        const uint32_t i = stage[lane];
-        p = V3{a.gx[i], a.gy[i], a.gz[i]};
+        const int e = (head + lane) & (FU_STAGE - 1);
+        const uint32_t i = stage[e];
         pt = a.gidx[i];
+#if C2B_STAGE_COORDS
+        p = V3{stx[e], sty[e], stz[e]};
+#else
+        p = V3{a.gx[i], a.gy[i], a.gz[i]};
+#endif
         if (OCC == FU_OCC_MESH) ray = make_ray(cen, p, a.endpoint_guard_rel != 0);
       }
       bool occ = false;
@@ -678,51 +721,73 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
 
     // lane = row: the trimmed point ranges of up to 32 rows at a time (their cell_start loads in parallel),
     // then the warp scans the non-empty ones
+    // this ticket's block of rows
     const int ny = hi[1] - lo[1] + 1, nrows = ny * (hi[2] - lo[2] + 1);
-    for (int rb = 0; rb < nrows; rb += 32) {
+    const int row0 = (nrows * part) >> a.parts_log2, row1 = (nrows * (part + 1)) >> a.parts_log2;
+    for (int rb = row0; rb < row1; rb += 32) {
       RowRange rr{0u, 0u};
-      if (rb + lane < nrows) {
+      if (rb + lane < row1) {
         const int ri = rb + lane;
         rr = camera_row_call(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, lo[1] + ri % ny, lo[2] + ri / ny);
       }
       unsigned live = __ballot_sync(0xffffffffu, rr.end > rr.start);
-      while (live) {
-        const int j = __ffs(live) - 1;
-        live &= live - 1;
-        const uint32_t start = __shfl_sync(0xffffffffu, rr.start, j), end = __shfl_sync(0xffffffffu, rr.end, j);
-        // software pipeline: the next 32 points are in flight while the current ones are evaluated
-        V3 pn{0.0, 0.0, 0.0};
-        if (start + lane < end) pn = V3{a.gx[start + lane], a.gy[start + lane], a.gz[start + lane]};
-        for (uint32_t base = start; base < end; base += 32) {
-          const uint32_t i = base + lane;
-          const V3 pcur = pn;
-          if (i + 32 < end) pn = V3{a.gx[i + 32], a.gy[i + 32], a.gz[i + 32]};
-          bool pass = false;
-          if (i < end) pass = cull_predicate(c, cen, pcur, a.t_star);
-          const unsigned m = __ballot_sync(0xffffffffu, pass);
-          if (m == 0u) continue;
-          if (pass) stage[qn + __popc(m & ((1u << lane) - 1u))] = i;
+      if (live == 0u) continue;
+      int j = __ffs(live) - 1;
+      live &= live - 1;
+      uint32_t base = __shfl_sync(0xffffffffu, rr.start, j), end = __shfl_sync(0xffffffffu, rr.end, j);
+      // software pipeline over 32-point chunks, ACROSS rows: the next chunk (the next row's first one at a
+      // row end) is in flight while the current one is evaluated
+      V3 pn{0.0, 0.0, 0.0};
+      if (base + lane < end) pn = V3{a.gx[base + lane], a.gy[base + lane], a.gz[base + lane]};
+      for (;;) {
+        uint32_t nbase = base + 32, nend = end;
+        bool more = true;
+        if (nbase >= end) {
+          if (live) {
+            j = __ffs(live) - 1;
+            live &= live - 1;
+            nbase = __shfl_sync(0xffffffffu, rr.start, j);
+            nend = __shfl_sync(0xffffffffu, rr.end, j);
+          } else {
+            more = false;
+          }
+        }
+        const uint32_t i = base + lane;
+        const V3 pcur = pn;
+        if (more && nbase + lane < nend) pn = V3{a.gx[nbase + lane], a.gy[nbase + lane], a.gz[nbase + lane]};
+        bool pass = false;
+        if (i < end) pass = cull_predicate(c, cen, pcur, a.t_star);
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m != 0u) {
+          if (pass) {
+            const int e = (head + qn + __popc(m & ((1u << lane) - 1u))) & (FU_STAGE - 1);
+            stage[e] = i;
+#if C2B_STAGE_COORDS
+            stx[e] = pcur.x;
+            sty[e] = pcur.y;
+            stz[e] = pcur.z;
+#endif
+          }
           qn += __popc(m);
           __syncwarp();
           if (qn >= 32) {
             resolve(32);
-            const int rem = qn - 32;
-            uint32_t t = 0;
-            if (lane < rem) t = stage[32 + lane];
             __syncwarp();
-            if (lane < rem) stage[lane] = t;
-            __syncwarp();
-            qn = rem;
+            head = (head + 32) & (FU_STAGE - 1);
+            qn -= 32;
             found_total += 32;
           }
         }
+        if (!more) break;
+        base = nbase;
+        end = nend;
       }
     }
     if (qn > 0) {
       resolve(qn);
       found_total += qn;
     }
-    if (lane == 0) a.vis_count[cam] = nvis < out_cap ? nvis : out_cap;
+    if (lane == 0) a.vis_count[slot] = nvis < out_cap ? nvis : out_cap;
   }
   if (lane == 0) {
     if (found_total) atomicAdd(&a.counters[4], found_total);
@@ -810,8 +875,49 @@ struct SortWriteArgs {
   uint64_t *out_offsets;
   uint32_t *out_idx;
   double2 *out_uv;
-  int key_bits;  // bits of the largest point index: the radix passes cover exactly these
+  int key_bits;    // bits of the largest point index: the radix passes cover exactly these
+  int parts_log2;  // slots per camera (FusedArgs::parts_log2); ev_off / seg_off are indexed by slot
 };
+
+// a camera's visible list is the concatenation of its slots' scratch slices
+struct CamSlices {
+  uint32_t base, n;         // CSR segment of the camera
+  uint32_t sub[4], eo[4];   // slot q starts at list position sub[q] and at scratch_idx[eo[q]]
+};
+// MULTI = false: one slot per camera (parts_log2 == 0), the common case, compiled without the slot search
+template <bool MULTI>
+__device__ __forceinline__ CamSlices cam_slices(const SortWriteArgs &s, uint64_t cam) {
+  CamSlices cs;
+  if (!MULTI) {
+    cs.base = s.seg_off[cam];
+    cs.n = s.seg_off[cam + 1] - cs.base;
+    cs.sub[0] = 0u;
+    cs.eo[0] = s.ev_off[cam];
+    return cs;
+  }
+  const uint64_t slot0 = cam << s.parts_log2;
+  const int S = 1 << s.parts_log2;
+  cs.base = s.seg_off[slot0];
+  cs.n = s.seg_off[slot0 + S] - cs.base;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cs.sub[q] = q < S ? s.seg_off[slot0 + q] - cs.base : 0xffffffffu;
+    cs.eo[q] = q < S ? s.ev_off[slot0 + q] : 0u;
+  }
+  return cs;
+}
+template <bool MULTI>
+__device__ __forceinline__ uint32_t cam_key(const SortWriteArgs &s, const CamSlices &cs, uint32_t t) {
+  if (!MULTI) return s.scratch_idx[cs.eo[0] + t];
+  uint32_t sub = cs.sub[0], eo = cs.eo[0];
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (t >= cs.sub[q]) {
+      sub = cs.sub[q];
+      eo = cs.eo[q];
+    }
+  return s.scratch_idx[eo + (t - sub)];
+}
 
 constexpr uint32_t SW_WARP_MAX = 1024;   // one warp per camera
 constexpr uint32_t SW_BLOCK_MAX = 4096;  // shared-memory sort, one block per camera
@@ -834,14 +940,16 @@ __device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
 // digit: a camera's points are usually close in index).  About 0.4k warp instructions per pass at
 // n = 532 against ~3k for the 1024-key bitonic network this replaces (profiles/r01h: k_sort_write spent
 // 878 M warp instructions, 16.5 per observation).  The sorted keys end up in `sorted` (padded layout).
-template <int E>
-__device__ __forceinline__ void sort_warp_to_smem(const uint32_t *__restrict__ src, uint32_t n, int lane,
-                                                  uint32_t *sorted, uint32_t *hist, int key_bits) {
+template <int E, bool MULTI>
+__device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const CamSlices &cs, int lane,
+                                                  uint32_t *sorted, uint32_t *hist) {
+  const uint32_t n = cs.n;
+  const int key_bits = s.key_bits;
   uint32_t a[E];
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const uint32_t t = r * 32 + lane;
-    a[r] = t < n ? src[t] : 0xffffffffu;
+    a[r] = t < n ? cam_key<MULTI>(s, cs, t) : 0xffffffffu;
   }
   const unsigned lt = (1u << lane) - 1u;
   bool in_smem = false;
@@ -915,35 +1023,36 @@ __device__ __forceinline__ void sort_warp_to_smem(const uint32_t *__restrict__ s
   }
 }
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool MULTI>
 __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWriteArgs s) {
   __shared__ uint32_t s_sorted[SW_WARPS][SW_WARP_MAX + SW_WARP_MAX / 32];
   __shared__ uint32_t s_hist[SW_WARPS][SW_BINS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
   if (cam >= s.C) return;
-  const uint32_t base = s.seg_off[cam], n = s.seg_off[cam + 1] - base;
+  const CamSlices cs = cam_slices<MULTI>(s, cam);
+  const uint32_t base = cs.base, n = cs.n;
   if (lane == 0) {
     s.out_offsets[cam] = base;
-    if (cam == s.C - 1) s.out_offsets[s.C] = s.seg_off[s.C];
+    if (cam == s.C - 1) s.out_offsets[s.C] = s.seg_off[s.C << s.parts_log2];
   }
   if (n == 0 || n > SW_WARP_MAX) return;
-  const uint32_t *src = s.scratch_idx + s.ev_off[cam];
   uint32_t *sorted = s_sorted[warp];
   if (n <= 128)
-    sort_warp_to_smem<4>(src, n, lane, sorted, s_hist[warp], s.key_bits);
+    sort_warp_to_smem<4, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   else if (n <= 256)
-    sort_warp_to_smem<8>(src, n, lane, sorted, s_hist[warp], s.key_bits);
+    sort_warp_to_smem<8, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   else if (n <= 512)
-    sort_warp_to_smem<16>(src, n, lane, sorted, s_hist[warp], s.key_bits);
+    sort_warp_to_smem<16, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   else if (n <= 768)
-    sort_warp_to_smem<24>(src, n, lane, sorted, s_hist[warp], s.key_bits);
+    sort_warp_to_smem<24, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   else
-    sort_warp_to_smem<32>(src, n, lane, sorted, s_hist[warp], s.key_bits);
+    sort_warp_to_smem<32, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   __syncwarp();
   double c[15];
 #pragma unroll
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
+  // (an explicit software pipeline of the point gathers measured 0.85 ms against 0.83 ms for this form)
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t pt = sorted[sw_pad(i)];
@@ -957,12 +1066,12 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
 __global__ void __launch_bounds__(256) k_sort_write_block(SortWriteArgs s) {
   __shared__ uint32_t s_sort[SW_BLOCK_MAX];
   const uint64_t cam = blockIdx.x;
-  const uint32_t base = s.seg_off[cam], n = s.seg_off[cam + 1] - base;
+  const CamSlices cs = cam_slices<true>(s, cam);
+  const uint32_t base = cs.base, n = cs.n;
   if (n <= SW_WARP_MAX || n > SW_BLOCK_MAX) return;
-  const uint32_t *src = s.scratch_idx + s.ev_off[cam];
   uint32_t n2 = 2;
   while (n2 < n) n2 <<= 1;
-  for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) s_sort[t] = t < n ? src[t] : 0xffffffffu;
+  for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) s_sort[t] = t < n ? cam_key<true>(s, cs, t) : 0xffffffffu;
   __syncthreads();
   for (uint32_t k = 2; k <= n2; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -993,16 +1102,27 @@ __global__ void __launch_bounds__(256) k_sort_write_block(SortWriteArgs s) {
 
 // fallback for cameras that see more than SW_BLOCK_MAX points: 64-bit (camera, point) keys of ALL
 // visible entries, radix-sorted globally, then k_write_sorted
-__global__ void __launch_bounds__(256) k_expand_keys(const uint32_t *__restrict__ ev_off,
-                                                     const uint32_t *__restrict__ seg_off, uint64_t C,
-                                                     const uint32_t *__restrict__ scratch_idx, int pbits,
-                                                     uint64_t *__restrict__ keys) {
+__global__ void __launch_bounds__(256) k_expand_keys(SortWriteArgs s, int pbits, uint64_t *__restrict__ keys) {
   const int lane = threadIdx.x & 31;
   const uint64_t cam = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (cam >= C) return;
-  const uint32_t base = seg_off[cam], n = seg_off[cam + 1] - base;
-  const uint32_t *src = scratch_idx + ev_off[cam];
-  for (uint32_t t = lane; t < n; t += 32) keys[base + t] = (cam << pbits) | (uint64_t)src[t];
+  if (cam >= s.C) return;
+  const CamSlices cs = cam_slices<true>(s, cam);
+  for (uint32_t t = lane; t < cs.n; t += 32) keys[cs.base + t] = (cam << pbits) | (uint64_t)cam_key<true>(s, cs, t);
+}
+
+// per-camera maximum of the visible counts (slots summed) and CSR offsets widened to u64
+__global__ void k_max_cam(const uint32_t *__restrict__ seg_off, uint64_t C, int parts_log2, uint32_t *__restrict__ out) {
+  uint32_t m = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (uint64_t)gridDim.x * blockDim.x)
+    m = max(m, seg_off[(i + 1) << parts_log2] - seg_off[i << parts_log2]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__global__ void k_widen_cam_offsets(const uint32_t *__restrict__ seg_off, uint64_t n, int parts_log2,
+                                    uint64_t *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = seg_off[i << parts_log2];
 }
 
 }  // namespace c2b

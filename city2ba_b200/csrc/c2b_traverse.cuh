@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
 // ---- per-camera triangle lists ------------------------------------------------------------------------
 // All rays of a camera start at its centre and are shorter than max_dist, so every triangle any of
 // them can hit lies in the cube [c - R, c + R]^3.  k_cam_trilist walks the tree once per camera
-// (one thread each, stackless) and records the leaves whose box overlaps that cube, up to `cap`
+// (one warp each, lane = node) and records the leaves whose box overlaps that cube, up to `cap`
 // per camera (more => TRILIST_OVERFLOW, the camera's packets use the generic walk).  A packet then
 // needs no tree walk at all (packet_any_hit, c2b_fused.cuh): lanes test 32 list entries at a time
 // against the packet's bounding box (lane = triangle), and only the surviving triangles are run
@@ -170,17 +170,10 @@ __device__ __forceinline__ float conservative_pad(float ox, float oy, float oz, 
   return 4e-6f * (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + scene_absmax) + 1e-30f;
 }
 
-__global__ void __launch_bounds__(128)
-    k_cam_trilist(const float4 *__restrict__ nodes, int n_nodes, const double *__restrict__ cen_x,
-                  const double *__restrict__ cen_y, const double *__restrict__ cen_z, uint64_t C,
-                  float rmax, float scene_absmax, uint32_t cap, uint32_t *__restrict__ list,
-                  uint32_t *__restrict__ count, unsigned long long *__restrict__ n_overflow) {
-  const uint64_t cam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cam >= C) return;
-  const float ox = __double2float_rn(cen_x[cam]), oy = __double2float_rn(cen_y[cam]),
-              oz = __double2float_rn(cen_z[cam]);
-  const float r = rmax + conservative_pad(ox, oy, oz, scene_absmax);
-  const float lx = ox - r, ly = oy - r, lz = oz - r, hx = ox + r, hy = oy + r, hz = oz + r;
+// serial stackless walk (one thread): the fall-back of the warp version below
+__device__ __forceinline__ uint32_t trilist_serial(const float4 *__restrict__ nodes, int n_nodes, float lx, float ly,
+                                                   float lz, float hx, float hy, float hz, uint32_t cap,
+                                                   uint32_t *__restrict__ mylist) {
   uint32_t n = 0;
   int node = 0;
   while (node < n_nodes) {
@@ -191,7 +184,7 @@ __global__ void __launch_bounds__(128)
     if (outside) {
       node = __float_as_int(lo.w);
     } else if (__float_as_int(hi.w) >= 0) {
-      if (n < cap) list[cam * cap + n] = (uint32_t)node;
+      if (n < cap) mylist[n] = (uint32_t)node;
       ++n;
       if (n > cap) break;
       node = __float_as_int(lo.w);
@@ -199,8 +192,102 @@ __global__ void __launch_bounds__(128)
       node = node + 1;
     }
   }
+  return n;
+}
+
+// one thread per camera: the cheapest form when there are enough cameras to fill the GPU (cfg4, one GPU:
+// 0.075 ms for 99,840 cameras against 0.15 ms for the warp form below)
+__global__ void __launch_bounds__(128)
+    k_cam_trilist(const float4 *__restrict__ nodes, int n_nodes, const double *__restrict__ cen_x,
+                  const double *__restrict__ cen_y, const double *__restrict__ cen_z, uint64_t C,
+                  float rmax, float scene_absmax, uint32_t cap, uint32_t *__restrict__ list,
+                  uint32_t *__restrict__ count, unsigned long long *__restrict__ n_overflow) {
+  const uint64_t cam = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cam >= C) return;
+  const float ox = __double2float_rn(cen_x[cam]), oy = __double2float_rn(cen_y[cam]),
+              oz = __double2float_rn(cen_z[cam]);
+  const float r = rmax + conservative_pad(ox, oy, oz, scene_absmax);
+  const uint32_t n = trilist_serial(nodes, n_nodes, ox - r, oy - r, oz - r, ox + r, oy + r, oz + r, cap, list + cam * cap);
   count[cam] = n <= cap ? n : TRILIST_OVERFLOW;
   if (n > cap) atomicAdd(n_overflow, 1ull);
+}
+
+// One warp per camera, lane = node, for calls with few cameras (multi-GPU shards, early batches), where
+// the serial walk is a chain of dependent loads that takes the same 0.07 ms for 12,480 cameras as for
+// 99,840: the warp keeps a LIFO of node indices in shared memory, pops up to 32 per step, every lane
+// tests one node's box against the camera's cube, overlapping leaves are appended to the list (ballot
+// order), overlapping inner nodes push both children (left = node + 1, right child index in the node's
+// second w).
+constexpr int TL_WARPS = 4;
+constexpr int TL_LIFO = 320;
+
+__global__ void __launch_bounds__(TL_WARPS * 32)
+    k_cam_trilist_warp(const float4 *__restrict__ nodes, int n_nodes, const double *__restrict__ cen_x,
+                  const double *__restrict__ cen_y, const double *__restrict__ cen_z, uint64_t C,
+                  float rmax, float scene_absmax, uint32_t cap, uint32_t *__restrict__ list,
+                  uint32_t *__restrict__ count, unsigned long long *__restrict__ n_overflow) {
+  __shared__ uint32_t s_lifo[TL_WARPS][TL_LIFO];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t cam = (uint64_t)blockIdx.x * TL_WARPS + warp;
+  if (cam >= C) return;
+  const float ox = __double2float_rn(cen_x[cam]), oy = __double2float_rn(cen_y[cam]),
+              oz = __double2float_rn(cen_z[cam]);
+  const float r = rmax + conservative_pad(ox, oy, oz, scene_absmax);
+  const float lx = ox - r, ly = oy - r, lz = oz - r, hx = ox + r, hy = oy + r, hz = oz + r;
+  uint32_t *mylist = list + cam * cap;
+  uint32_t *lifo = s_lifo[warp];
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t n = 0;
+  int sp = n_nodes > 0 ? 1 : 0;
+  bool serial = false;
+  if (lane == 0) lifo[0] = 0u;
+  __syncwarp();
+  while (sp > 0) {
+    const int take = sp < 32 ? sp : 32;
+    bool leaf = false, inner = false;
+    uint32_t node = 0, right = 0;
+    if (lane < take) {
+      node = lifo[sp - take + lane];
+      const float4 lo = __ldg(&nodes[2 * node]);
+      const float4 hi = __ldg(&nodes[2 * node + 1]);
+      // written so that NaN compares keep the node (conservative)
+      const bool outside = lo.x > hx || hi.x < lx || lo.y > hy || hi.y < ly || lo.z > hz || hi.z < lz;
+      if (!outside) {
+        const int slot = __float_as_int(hi.w);
+        leaf = slot >= 0;
+        inner = !leaf;
+        right = (uint32_t)(-slot - 1);
+      }
+    }
+    __syncwarp();  // every lane has read its node before anyone pushes into the same slots
+    sp -= take;
+    const unsigned lm = __ballot_sync(0xffffffffu, leaf), im = __ballot_sync(0xffffffffu, inner);
+    if (leaf) {
+      const uint32_t pos = n + __popc(lm & lt);
+      if (pos < cap) mylist[pos] = node;
+    }
+    n += __popc(lm);
+    if (n > cap) break;
+    if (sp + 2 * __popc(im) > TL_LIFO) {
+      serial = true;
+      break;
+    }
+    if (inner) {
+      const int pos = sp + 2 * __popc(im & lt);
+      lifo[pos] = node + 1u;
+      lifo[pos + 1] = right;
+    }
+    sp += 2 * __popc(im);
+    __syncwarp();
+  }
+  if (serial) {  // the LIFO would overflow: one lane walks the tree without memory
+    if (lane == 0) n = trilist_serial(nodes, n_nodes, lx, ly, lz, hx, hy, hz, cap, mylist);
+    n = __shfl_sync(0xffffffffu, n, 0);
+  }
+  if (lane == 0) {
+    count[cam] = n <= cap ? n : TRILIST_OVERFLOW;
+    if (n > cap) atomicAdd(n_overflow, 1ull);
+  }
 }
 
 // ---- Embree-shaped ray batch (parity tooling): AoS 48-byte rays, tfar = -inf on hit ---------------

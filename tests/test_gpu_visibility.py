@@ -300,12 +300,44 @@ def test_list_modes_agree(c2b, ctx, orc, cfg2, monkeypatch):
     scene = c2b.Scene(xyz, tri, ctx=ctx)
     ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "hoisted")
+    for form in ("0", "1"):      # leaf lists built by one thread per camera / one warp per camera (lane = node)
+        monkeypatch.setenv("C2B_TRILIST_WARP", form)
+        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, f"trilist form {form}")
+    monkeypatch.delenv("C2B_TRILIST_WARP")
     monkeypatch.setenv("C2B_HOIST_MAX", "0")
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-packet records")
     monkeypatch.setenv("C2B_TRILIST_CAP", "1")
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "packet bvh")
     monkeypatch.setenv("C2B_NO_PACKET_BVH", "1")
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-ray walk")
+
+
+@pytest.mark.parametrize("parts_log2", ["0", "1", "2"])
+def test_camera_tickets_agree(c2b, ctx, orc, cfg2, monkeypatch, parts_log2):
+    """a camera's rows dealt to 1, 2 or 4 tickets (own scratch slice and visible count each, stitched
+    back together by the sort/write pass) give the same graph — mesh, analytic and no occlusion, and the
+    block-sort / global-sort fallbacks of cameras that see more than 1,024 / 4,096 points"""
+    cams, pts, xyz, tri = cfg2
+    monkeypatch.setenv("C2B_PARTS_LOG2", parts_log2)
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), orc.visibility_graph(xyz, tri, cams, pts, 10.0),
+                      f"mesh/{parts_log2}")
+    for analytic in (True, False):
+        ref = orc.synthetic_visibility(cams, pts, 10.0, analytic)
+        g = c2b.visibility_graph(None, cams, pts, 10.0, occlusion="analytic" if analytic else "none", ctx=ctx)
+        assert_same_graph(g, ref, f"analytic={analytic}/{parts_log2}")
+    # dense points around a few cameras, no occluders: per-camera lists beyond the warp and the block sort
+    rng = np.random.default_rng(11)
+    few = cams[:6].copy()
+    dense = np.array([orc.center(c) for c in few]).repeat(1500, axis=0) + rng.uniform(-6, 6, (9000, 3)) * [1, 0.1, 1]
+    ref = orc.synthetic_visibility(few, dense, 10.0, False)
+    counts = np.diff(ref.offsets)
+    assert counts.max() > 1024
+    assert_same_graph(c2b.visibility_graph(None, few, dense, 10.0, occlusion="none", ctx=ctx), ref, f"dense/{parts_log2}")
+    far = np.concatenate([dense, dense + 1e-3, dense - 1e-3, dense + 2e-3])
+    ref = orc.synthetic_visibility(few[:2], far, 30.0, False)
+    assert np.diff(ref.offsets).max() > 4096
+    assert_same_graph(c2b.visibility_graph(None, few[:2], far, 30.0, occlusion="none", ctx=ctx), ref, f"global sort/{parts_log2}")
 
 
 def test_frustum_edge_classification(c2b, ctx, orc):
