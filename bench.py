@@ -495,6 +495,14 @@ def main():
         line["exhaustive"] = {"value": C * P / ex_t, "unit": "tests/s", "ms_per_step": 1e3 * ex_t,
                               "cull_ms": ex_cull, "steps": ex[2],
                               "note": "every camera x point pair tested on the GPU (the reference's loop)"}
+        # secondary bound: the exhaustive cull's hot loop issues 7 FP64-pipe instructions per
+        # pair (3 DADD + DMUL + 2 DFMA + DSETP); the probe is a loop of independent DFMAs on the same device
+        import ctypes as _C
+        rate = _C.c_double(0.0)
+        if _lib.lib().c2b_probe_fp64(ctx.handle, _C.byref(rate)) == 0 and rate.value > 0 and ex_cull > 0:
+            per_rank_pairs = C * P / world
+            line["exhaustive"]["fp64_probe_dfma_per_s"] = rate.value
+            line["exhaustive"]["fp64_pipe_frac"] = 7.0 * per_rank_pairs / (ex_cull * 1e-3) / rate.value
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle as orc
         orc.build()

@@ -69,7 +69,7 @@ OCC_MESH, OCC_NONE, OCC_ANALYTIC = 0, 1, 2
 
 # every symbol include/city2ba_cuda.h declares
 EXPORTS = [
-    "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version", "c2b_kernel_launches",
+    "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version", "c2b_kernel_launches", "c2b_probe_fp64",
     "c2b_scene_create", "c2b_scene_bounds", "c2b_scene_num_triangles", "c2b_scene_num_nodes",
     "c2b_scene_destroy", "c2b_occluded", "c2b_intersect", "c2b_intersect1", "c2b_vis_options_default",
     "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_points_device", "c2b_upload_cameras",
@@ -131,6 +131,7 @@ def lib():
     L.c2b_add_sin_noise.argtypes = [vp, pd, u64, pd, u64, pd, pd, dbl, dbl]
     L.c2b_noise_timing.argtypes = [vp, pf]
     L.c2b_mean_std.argtypes = [vp, pd, u64, pd, u64, pd, pd]
+    L.c2b_probe_fp64.argtypes = [vp, pd]
     L.c2b_generate_world_points_uniform.argtypes = [vp, pf, u64, pu32, u64, pd, u64, u64, dbl, u64, pd,
                                                     C.POINTER(u64)]
     L.c2b_grid_num_cameras.argtypes = [u64, u64]

@@ -1462,6 +1462,32 @@ int c2b_generate_world_points_uniform(c2b_ctx *ctx, const float *xyz, uint64_t n
   return rc;
 }
 
+int c2b_probe_fp64(c2b_ctx *ctx, double *dfma_per_s) {
+  if (!ctx || !dfma_per_s) return set_error(C2B_ERR_INVALID, "c2b_probe_fp64: null argument");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  C2B_TRY(ctx->misc.ensure(8));
+  cudaStream_t st = ctx->stream;
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  C2B_CUDA(cudaEventCreate(&e0));
+  C2B_CUDA(cudaEventCreate(&e1));
+  float best = 0.0f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    C2B_CUDA(cudaEventRecord(e0, st));
+    k_probe_dfma<<<blocks, threads, 0, st>>>(ctx->misc.as<double>(), iters, 1.0000001);
+    C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaEventRecord(e1, st));
+    C2B_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    C2B_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep && (best == 0.0f || ms < best)) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *dfma_per_s = (double)blocks * threads * iters * PROBE_CHAINS / (best * 1e-3);
+  return C2B_OK;
+}
+
 int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts, uint64_t P,
                  double mean[3], double sd[3]) {
   if (!ctx || (C && !cams) || (P && !pts) || !mean || !sd)

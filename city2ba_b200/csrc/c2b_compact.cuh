@@ -62,6 +62,23 @@ __global__ void k_words_all_visible(const uint64_t *__restrict__ keys, uint32_t 
   if ((threadIdx.x & 31) == 0) words[i >> 5] = m;
 }
 
+// ---- FP64 issue-rate probe (c2b_probe_fp64): PROBE_CHAINS independent DFMA chains per thread ---------
+constexpr int PROBE_CHAINS = 8;
+__global__ void __launch_bounds__(256) k_probe_dfma(double *__restrict__ sink, int iters, double m) {
+  double a[PROBE_CHAINS];
+#pragma unroll
+  for (int k = 0; k < PROBE_CHAINS; ++k) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < PROBE_CHAINS; ++k) a[k] = __fma_rn(a[k], m, 1e-12);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < PROBE_CHAINS; ++k) s += a[k];
+  if (s == 12345.678) *sink = s;  // keeps the chains alive; never true
+}
+
 // ---- helpers shared with the grid schedule (c2b_fused.cuh) ----------------------------------------
 __global__ void k_max_u32(const uint32_t *__restrict__ v, uint64_t n, uint32_t *__restrict__ out) {
   uint32_t m = 0;

@@ -49,6 +49,10 @@ const char *c2b_last_error(void);
 int c2b_abi_version(void);
 /* number of CUDA kernels this library has launched in this process so far */
 uint64_t c2b_kernel_launches(void);
+/* measurement aid: sustained rate of independent f64 FMAs on this device, in DFMA/s
+ * (one fused multiply-add per thread counted as one).  The secondary bound of the exhaustive cull, whose
+ * hot loop is FP64-issue-bound; not part of the reference's surface. */
+int c2b_probe_fp64(c2b_ctx *ctx, double *dfma_per_s);
 
 /* ---- scene (triangle mesh -> GPU LBVH) ----------------------------------------------------------
  * replaces Scene::new + model_to_geometry + attach_geometry + commit
