@@ -155,7 +155,7 @@ void c2b_shutdown(c2b_ctx *ctx) {
                     &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets[0], &ctx->out_idx[0],
                     &ctx->out_uv[0], &ctx->out_offsets[1], &ctx->out_idx[1], &ctx->out_uv[1],
                     &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos, &ctx->ev_off,
-                    &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx};
+                    &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx, &ctx->plan_rows, &ctx->plan_row_count};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
@@ -511,6 +511,10 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   fa.block_length = opt.block_length;
   fa.block_inset = opt.block_inset;
   fa.parts_log2 = parts_log2;
+  C2B_TRY(ctx->plan_rows.ensure(C * FU_ROWS * sizeof(uint2)));
+  C2B_TRY(ctx->plan_row_count.ensure(C * 4));
+  fa.rows = ctx->plan_rows.as<uint2>();
+  fa.row_count = ctx->plan_row_count.as<uint32_t>();
   fa.ev_count = ctx->ev_off.as<uint32_t>();
   fa.vis_count = ctx->vis_count.as<uint32_t>();
   fa.counters = ctx->counters.as<unsigned long long>();

@@ -184,7 +184,7 @@ struct c2b_ctx {
   c2b::DevBuf misc;  // small scratch (reductions)
   c2b::DevBuf tri_list, tri_count;  // per-camera leaf lists for list-driven traversal
   // fused grid schedule: per-camera plan (row points -> scratch slice), visible counts, CSR offsets
-  c2b::DevBuf ev_off, vis_count, seg_off, scratch_idx;
+  c2b::DevBuf ev_off, vis_count, seg_off, scratch_idx, plan_rows, plan_row_count;
 
   float noise_ms[3] = {0, 0, 0};  // last noise call: upload, statistics + kernels, download
 

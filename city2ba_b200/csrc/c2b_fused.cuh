@@ -57,6 +57,10 @@ struct FusedArgs {
   // per-ticket work runs on warps that would otherwise idle); slot = (camera << parts_log2) | part owns
   // its own scratch slice and visible count.  Part p holds rows [nrows*p >> log2, nrows*(p+1) >> log2).
   int parts_log2;
+  // the plan also leaves every camera's trimmed row ranges behind (cameras with <= FU_ROWS rows), so that
+  // the fused pass starts a camera with one coalesced load instead of recomputing them
+  uint2 *rows;          // [C * FU_ROWS] (start, end) of row r of the camera, r = (z - lo.z) * ny + (y - lo.y)
+  uint32_t *row_count;  // [C] number of rows; 0 = nothing to scan; FU_ROWS_MANY = more than FU_ROWS (recompute)
   uint32_t *ev_count;         // [slots+1] points on the slot's rows (k_cam_plan), then its exclusive scan
   uint32_t *scratch_idx;      // visible point indices, slot s at [ev_off[s], ev_off[s] + vis_count[s])
   uint32_t *vis_count;        // [slots+1]
@@ -133,6 +137,9 @@ __device__ __forceinline__ bool trim_halfspace(const GridDesc &g, double cell_h,
   }
   return true;
 }
+
+constexpr int FU_ROWS = 32;
+constexpr uint32_t FU_ROWS_MANY = 0xffffffffu;
 
 struct RowRange {
   uint32_t start, end;  // grid-ordered points [start, end) of the trimmed row; start >= end: nothing
@@ -259,16 +266,20 @@ __global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
   if (cam < a.C) {
     const double cc[3] = {a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
     int lo[3], hi[3];
+    a.row_count[cam] = 0u;
     if (camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
       double c[15];
 #pragma unroll
       for (int k = 0; k < 15; ++k) c[k] = a.cams[15 * cam + k];
       const double cell_h = ddiv(1.0, a.g.inv_h);
       const int nrows = (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1);
+      const bool keep = nrows <= FU_ROWS;
+      a.row_count[cam] = keep ? (uint32_t)nrows : FU_ROWS_MANY;
       int ri = 0;
       for (int z = lo[2]; z <= hi[2]; ++z)
         for (int y = lo[1]; y <= hi[1]; ++y, ++ri) {
           const RowRange rr = camera_row(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, y, z);
+          if (keep) a.rows[cam * FU_ROWS + ri] = make_uint2(rr.start, rr.end);
           if (rr.end > rr.start) {
             const unsigned long long m = rr.end - rr.start;
             int part = 0;  // the block of rows ri falls in (same split as k_visibility_fused)
@@ -342,11 +353,14 @@ __device__ __forceinline__ void dot_range(float nx, float ny, float nz, float lx
 //   plane 0 {ux uy uz vx}  plane 1 {vy vz wx wy}  plane 2 {wz T lo.x lo.y}  plane 3 {lo.z hi.x hi.y hi.z}
 constexpr int FU_HOIST = 64;
 
-__device__ __forceinline__ void hoist_records(const FusedArgs &a, const uint32_t *__restrict__ mylist,
+// (l0, l1: this lane's list entries lane and lane + 32, loaded by the caller together with the camera's other
+// per-camera words so that their latencies overlap)
+__device__ __forceinline__ void hoist_records(const FusedArgs &a, uint32_t l0, uint32_t l1,
                                               uint32_t n_list, float ox, float oy, float oz, float4 *rec,
                                               int lane) {
+  static_assert(FU_HOIST == 64, "two list entries per lane");
   for (uint32_t j = lane; j < n_list; j += 32) {
-    const uint32_t node = mylist[j];
+    const uint32_t node = j < 32 ? l0 : l1;
     const float4 lo = __ldg(&a.nodes[2 * node]);
     const float4 hi = __ldg(&a.nodes[2 * node + 1]);
     const int slot = __float_as_int(hi.w);
@@ -654,26 +668,34 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     if (cam >= a.C) break;
     const int part = (int)(slot & ((1u << a.parts_log2) - 1u));
     __syncwarp();
-    if (lane < 15) c[lane] = __ldg(&a.cams[15 * cam + lane]);
-    __syncwarp();
+    // everything that depends on the camera index only is loaded back to back, before the first use, so
+    // that the round trips overlap (the per-camera set-up is a latency chain: 0.31 ms of the 3.08 ms at cfg4
+    // before this and the stored row ranges, 0.16 ms after; profiles/shard_probe.py --max-dist 0.3)
+    double creg = 0.0;
+    if (lane < 15) creg = __ldg(&a.cams[15 * cam + lane]);
     const V3 cen{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
-    const double cc[3] = {cen.x, cen.y, cen.z};
-    int lo[3], hi[3];
-    if (!camera_cell_range(a.g, cc, a.max_dist, lo, hi)) {
-      if (lane == 0) a.vis_count[slot] = 0;
-      continue;
-    }
-    const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
-    uint32_t n_list = 0;
+    const uint32_t planned_rows = a.row_count[cam];
+    const uint32_t ev0 = a.ev_count[slot], ev1 = a.ev_count[slot + 1];
+    const uint2 myrow = a.rows[cam * FU_ROWS + lane];  // meaningful for lane < planned_rows <= FU_ROWS
+    uint32_t n_list = 0, l0 = 0, l1 = 0;
     const uint32_t *mylist = nullptr;
     if (OCC == FU_OCC_MESH) {
       n_list = a.tri_count[cam];
       mylist = a.tri_list + cam * a.tri_cap;
+      if ((uint32_t)lane < a.tri_cap) l0 = mylist[lane];
+      if ((uint32_t)lane + 32u < a.tri_cap) l1 = mylist[lane + 32];
     }
+    if (lane < 15) c[lane] = creg;
+    __syncwarp();
+    if (planned_rows == 0u) {  // the plan found nothing to scan (ball outside the data, NaN centre, ...)
+      if (lane == 0) a.vis_count[slot] = 0;
+      continue;
+    }
+    const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
     const bool hoisted = OCC == FU_OCC_MESH && n_list <= a.hoist_max;  // (OVERFLOW is 2^32 - 1)
-    if (hoisted) hoist_records(a, mylist, n_list, ox, oy, oz, s_rec[warp], lane);
-    uint32_t *out = a.scratch_idx + a.ev_count[slot];
-    const uint32_t out_cap = a.ev_count[slot + 1] - a.ev_count[slot];
+    if (hoisted) hoist_records(a, l0, l1, n_list, ox, oy, oz, s_rec[warp], lane);
+    uint32_t *out = a.scratch_idx + ev0;
+    const uint32_t out_cap = ev1 - ev0;
     uint32_t nvis = 0;
     int qn = 0, head = 0;  // warp-uniform: number of staged survivors, ring position of the oldest
 
@@ -721,14 +743,26 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
 
     // lane = row: the trimmed point ranges of up to 32 rows at a time (their cell_start loads in parallel),
     // then the warp scans the non-empty ones
-    // this ticket's block of rows
-    const int ny = hi[1] - lo[1] + 1, nrows = ny * (hi[2] - lo[2] + 1);
+    // this ticket's block of rows: ranges as the plan left them (one coalesced load), or — a camera with
+    // more than FU_ROWS rows — recomputed with lane = row, 32 at a time
+    int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, ny = 1, nrows = (int)planned_rows;
+    double cc[3] = {cen.x, cen.y, cen.z};
+    if (planned_rows == FU_ROWS_MANY) {
+      camera_cell_range(a.g, cc, a.max_dist, lo, hi);  // true: the plan got past it
+      ny = hi[1] - lo[1] + 1;
+      nrows = ny * (hi[2] - lo[2] + 1);
+    }
     const int row0 = (nrows * part) >> a.parts_log2, row1 = (nrows * (part + 1)) >> a.parts_log2;
-    for (int rb = row0; rb < row1; rb += 32) {
+    for (int rb = planned_rows != FU_ROWS_MANY ? 0 : row0; rb < row1; rb += 32) {
       RowRange rr{0u, 0u};
-      if (rb + lane < row1) {
-        const int ri = rb + lane;
-        rr = camera_row_call(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, lo[1] + ri % ny, lo[2] + ri / ny);
+      const int ri = rb + lane;
+      if (ri >= row0 && ri < row1) {
+        if (planned_rows != FU_ROWS_MANY) {  // at most FU_ROWS = 32 rows, one trip: lane = row index
+          rr.start = myrow.x;
+          rr.end = myrow.y;
+        } else {
+          rr = camera_row_call(a.g, a.cell_start, c, cc, a.max_dist, lo, hi, cell_h, lo[1] + ri % ny, lo[2] + ri / ny);
+        }
       }
       unsigned live = __ballot_sync(0xffffffffu, rr.end > rr.start);
       if (live == 0u) continue;

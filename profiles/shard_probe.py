@@ -22,7 +22,9 @@ def main():
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--shard", default="0/8")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--max-dist", type=float, default=None, help="override the workload's max_dist (startup-cost probe)")
     a = ap.parse_args()
+    md = bench.MAX_DIST if a.max_dist is None else a.max_dist
     r, n = (int(x) for x in a.shard.split("/"))
     ctx = c2b.context(0)
     cams, pts, xyz, tri = bench.build_workload(a.workload)
@@ -38,11 +40,11 @@ def main():
     for s in range(3 + a.steps):
         flush.zero_()
         torch.cuda.synchronize()
-        st = rp.run(scene, bench.MAX_DIST, cull_mode="grid", count_traversal=False)
+        st = rp.run(scene, md, cull_mode="grid", count_traversal=False)
         if s >= 3:
             for k in ("ms_total", "ms_cull", "ms_traverse", "ms_compact"):
                 tot[k] = tot.get(k, 0.0) + st[k] / a.steps
-    print(json.dumps({"shard": a.shard, "cameras": c1 - c0, **{k: round(v, 4) for k, v in tot.items()}}))
+    print(json.dumps({"shard": a.shard, "max_dist": md, "cameras": c1 - c0, "pairs": int(st["pairs_evaluated"]), "rays": int(st["n_candidates"]), **{k: round(v, 4) for k, v in tot.items()}}))
 
 
 if __name__ == "__main__":

@@ -334,6 +334,14 @@ def test_camera_tickets_agree(c2b, ctx, orc, cfg2, monkeypatch, parts_log2):
     counts = np.diff(ref.offsets)
     assert counts.max() > 1024
     assert_same_graph(c2b.visibility_graph(None, few, dense, 10.0, occlusion="none", ctx=ctx), ref, f"dense/{parts_log2}")
+    # points filling a volume: the max_dist ball covers up to 9 x 9 rows of cells, more than the 32 row ranges
+    # the plan stores per camera, so the fused pass recomputes them (the FU_ROWS_MANY path)
+    vol = rng.uniform(-14, 14, (20000, 3))
+    vcams = random_cameras(rng, 30, center=(0, 0, 0), spread=10.0)
+    vcams[:, 10] += rng.uniform(-8, 8, 30)                 # move the cameras in y as well
+    ref = orc.synthetic_visibility(vcams, vol, 10.0, False)
+    assert ref.n_obs > 1000
+    assert_same_graph(c2b.visibility_graph(None, vcams, vol, 10.0, occlusion="none", ctx=ctx), ref, f"volume/{parts_log2}")
     far = np.concatenate([dense, dense + 1e-3, dense - 1e-3, dense + 2e-3])
     ref = orc.synthetic_visibility(few[:2], far, 30.0, False)
     assert np.diff(ref.offsets).max() > 4096
