@@ -479,19 +479,16 @@ __device__ __forceinline__ bool test_leaf_chunk(const FusedArgs &a, const Packet
     const TriRec t0 = load_rec(rec, k), t1 = load_rec(rec, k + 1);
     const bool h0 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
     const bool h1 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t1);
-    if (alive && (h0 || h1)) {
-      occ = true;
-      alive = false;
-    }
+    occ |= alive & (h0 | h1);
+    alive &= !(h0 | h1);
     any_alive = __ballot_sync(0xffffffffu, alive) != 0u;
     if (!any_alive) break;
   }
   if (any_alive && (cnt & 1)) {
     const TriRec t0 = load_rec(rec, cnt - 1);
-    if (alive && ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0)) {
-      occ = true;
-      alive = false;
-    }
+    const bool h = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
+    occ |= alive & h;
+    alive &= !h;
     any_alive = __ballot_sync(0xffffffffu, alive) != 0u;
   }
   __syncwarp();
@@ -540,10 +537,8 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
           m &= m - 1;
           h |= ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rec[k1], rec[FU_HOIST + k1], rec[2 * FU_HOIST + k1]));
         }
-        if (alive && h) {
-          occ = true;
-          alive = false;
-        }
+        occ |= alive & h;
+        alive &= !h;
         if (__ballot_sync(0xffffffffu, alive) == 0u) return occ;
       }
     }
@@ -1064,7 +1059,12 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
   if (cam >= s.C) return;
-  const CamSlices cs = cam_slices<MULTI>(s, cam);
+  CamSlices cs = cam_slices<MULTI>(s, cam);
+  // n is the same in every lane, but the compiler cannot know (it comes from memory through a per-thread
+  // address); REDUX leaves it in a uniform register, so that the branches on it below are uniform branches
+  // and the warp collectives inside them need no divergence scaffolding (BRA.DIV + WARPSYNC.COLLECTIVE
+  // around every MATCH / SHFL were a fifth of this kernel's instructions, profiles/r01l)
+  cs.n = __reduce_max_sync(0xffffffffu, cs.n);
   const uint32_t base = cs.base, n = cs.n;
   if (lane == 0) {
     s.out_offsets[cam] = base;

@@ -279,13 +279,14 @@ C2B_HD bool ray_tri_record(float dx, float dy, float dz, float tfar, const TriRe
   const float U = dot3f(dx, dy, dz, t.ux, t.uy, t.uz);
   const float V = dot3f(dx, dy, dz, t.vx, t.vy, t.vz);
   const float W = dot3f(dx, dy, dz, t.wx, t.wy, t.wz);
-  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  // one boolean expression without early exits (they cost a convergence barrier per test on the GPU):
+  // miss if the edge functions have mixed signs or det == 0; NaN anywhere fails the last compare
+  const bool mixed = ((U < 0.0f) | (V < 0.0f) | (W < 0.0f)) & ((U > 0.0f) | (V > 0.0f) | (W > 0.0f));
   const float det = fadd(fadd(U, V), W);
-  if (det == 0.0f) return false;
   const float ad = fabsf(det);
   const float Ts = det < 0.0f ? -t.T : t.T;
-  const bool hit = Ts > 0.0f && Ts <= fmul(tfar, ad);
-  if (hit && t_out) *t_out = fdiv(Ts, ad);
+  const bool hit = !mixed & (det != 0.0f) & (Ts > 0.0f) & (Ts <= fmul(tfar, ad));
+  if (t_out && hit) *t_out = fdiv(Ts, ad);
   return hit;
 }
 
