@@ -573,7 +573,9 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     // persistent warps draw cameras from a ticket; more CTAs than can be resident is harmless
     const unsigned nb = (unsigned)std::min<uint64_t>(blocks_for(slots, FU_WARPS), (uint64_t)ctx->sm_count * 8), nt = FU_WARPS * 32;
     const bool cnt = opt.count_traversal != 0;
-    static const bool occ4 = getenv("C2B_FU_OCC3") == nullptr;  // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3)
+    // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3).  Measured at cfg4: 2.68 ms; 3 CTAs/SM 2.69 ms; 5 CTAs/SM at
+    // 48 registers 2.74 ms
+    static const bool occ4 = getenv("C2B_FU_OCC3") == nullptr;
     if (mesh) {
       if (cnt)
         k_visibility_fused<FU_OCC_MESH, true, 3, true><<<nb, nt, 0, st>>>(fa);
@@ -1233,6 +1235,9 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
   cudaStream_t st = ctx->stream;
   NoiseBufs nb;
   NoiseTimer tm(ctx);
+  // a zero standard deviation adds unit_random() * 0 (src/noise.rs:149,159-168): the array is unchanged, so
+  // its kernel — and for the observations the round trip over PCIe — is skipped
+  if (observations_std == 0.0) O = 0;
   C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, uv, O));
   tm.mark(1);
   double mean[3], sd[3];
@@ -1243,7 +1248,8 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
                                                      rotation_std, seed);
     C2B_KERNEL_CHECK();
   }
-  if (P) {
+  const bool move_points = P && point_std != 0.0;
+  if (move_points) {
     k_noise_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, point_std, seed);
     C2B_KERNEL_CHECK();
   }
@@ -1253,7 +1259,7 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
   }
   tm.mark(2);
   if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
-  if (P) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  if (move_points) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
   if (O) C2B_CUDA(cudaMemcpyAsync(uv, nb.uv.p, O * 16, cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   C2B_CUDA(cudaStreamSynchronize(st));

@@ -188,8 +188,8 @@ __global__ void k_drift_cams(double *__restrict__ cams, uint64_t C, const double
   V3 c = camera_center(cam);
   V3 d{dsub(c.x, origin[0]), dsub(c.y, origin[1]), dsub(c.z, origin[2])};
   double distance = mag(d);
-  double z0, z1;
-  normal_pair(seed, ST_DRIFT_CAM, i, 0, z0, z1);
+  double z0 = 0.0, z1 = 0.0;
+  if (std != 0.0) normal_pair(seed, ST_DRIFT_CAM, i, 0, z0, z1);  // Normal(1, 0) is 1 whatever the draw
   double v1 = dadd(1.0, dmul(std, z0)), v2 = dadd(1.0, dmul(std, z1));
   double angle = dmul(dmul(angle_strength, v1), pow(distance, 1.2));
   V3 dl{dmul(dmul(dmul(dmul(dir.x, strength), v2), distance), distance),
@@ -209,8 +209,8 @@ __global__ void k_drift_pts(double *__restrict__ pts, uint64_t P, const double *
   V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
   V3 d{dsub(p.x, origin[0]), dsub(p.y, origin[1]), dsub(p.z, origin[2])};
   double distance = mag(d);
-  double z0, z1;
-  normal_pair(seed, ST_DRIFT_PT, i, 0, z0, z1);
+  double z0 = 0.0, z1 = 0.0;
+  if (std != 0.0) normal_pair(seed, ST_DRIFT_PT, i, 0, z0, z1);  // Normal(1, 0) is 1 whatever the draw
   double v = dadd(1.0, dmul(std, z0));
   pts[3 * i] = dadd(p.x, dmul(dmul(dmul(dmul(dir.x, strength), v), distance), distance));
   pts[3 * i + 1] = dadd(p.y, dmul(dmul(dmul(dmul(dir.y, strength), v), distance), distance));
