@@ -614,16 +614,12 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
                      ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>(),
                      std::max(pbits, 1), parts_log2};
     if (max32 <= SW_BLOCK_MAX) {
-      static const int sw_occ = getenv("C2B_SW_OCC") ? atoi(getenv("C2B_SW_OCC")) : 8;  // CTAs/SM the registers are capped for
+      // registers capped for 8 CTAs/SM (measured at cfg4: 0.81 ms; 6 CTAs/SM 0.91 ms, 4 CTAs/SM 1.12 ms)
       const unsigned swb = (unsigned)blocks_for(C, SW_WARPS), swt = SW_WARPS * 32;
       if (parts_log2 > 0)
         k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
-      else if (sw_occ >= 8)
-        k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
-      else if (sw_occ >= 6)
-        k_sort_write<6, false><<<swb, swt, 0, st>>>(sw);
       else
-        k_sort_write<4, false><<<swb, swt, 0, st>>>(sw);
+        k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
       C2B_KERNEL_CHECK();
       if (max32 > SW_WARP_MAX) {
         k_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);

@@ -2,21 +2,22 @@
 // cull + projection (src/generate.rs:446-454), ray construction (:456-464), occlusion (:472) and
 // the visible-point list (:473-478) without a candidate pool in between.
 //
-//   k_cam_plan          one thread per camera: how many grid-ordered points its rows hold (an upper
-//                       bound of its visible count) -> exclusive scan -> the camera's slice of the
-//                       scratch index array.
-//   k_visibility_fused  one warp per camera.  The warp scans the x-contiguous cell rows its
-//                       max_dist ball touches (each row trimmed to the half-space in front of the
-//                       camera), evaluates the exact f64 predicate per lane and stages the
-//                       survivors' grid positions in shared memory.  Every 32 survivors form a ray
-//                       packet that is resolved at once: the rays are built from the coordinates
-//                       just read (L1 hits), the camera's leaf list (k_cam_trilist) is filtered
-//                       against the packet's bounding box with lane = triangle, the survivors'
-//                       origin-relative triangle records (TriRec, 3 x float4) are computed ONCE for
-//                       the packet and parked in shared memory, and then lane = ray runs the 9-FMA
-//                       edge-function test per record.  Visible point indices go to the camera's
-//                       scratch slice; the camera's visible count needs no atomics.
-//   k_sort_write        one warp per camera: register bitonic sort of the visible indices
+//   k_cam_plan          one thread per camera: the x-contiguous cell rows its max_dist ball touches, each
+//                       trimmed by what is linear in x along a row (in front of the camera, the four
+//                       side planes of the image, the ball); the trimmed (start, end) point ranges are
+//                       kept for the fused pass, their total (an upper bound of the camera's visible
+//                       count) -> exclusive scan -> the camera's slice of the scratch index array.
+//   k_visibility_fused  persistent warps drawing cameras from a ticket.  Per camera the warp scans the
+//                       planned rows 32 grid-ordered points at a time, evaluates the exact f64 predicate
+//                       per lane and stages the survivors in shared memory.  Every 32 survivors form a
+//                       ray packet that is resolved at once: the rays are built from the coordinates
+//                       just read (L1 hits), the camera's leaf list (k_cam_trilist) is filtered against
+//                       the packet's segment box and direction box with lane = triangle, and lane = ray
+//                       runs the 9-FMA edge-function test on the survivors' origin-relative records
+//                       (TriRec; computed once per camera when the list has <= 64 entries, else once per
+//                       packet; cameras whose list overflows traverse the BVH with lane = node).
+//                       Visible point indices go to the camera's scratch slice; no atomics.
+//   k_sort_write        one warp per camera: warp-private LSD radix sort of the visible indices
 //                       (ascending point index, src/generate.rs:446), (u, v) recomputed with the
 //                       cull kernel's device function (bit-identical), CSR records written coalesced.
 #pragma once
