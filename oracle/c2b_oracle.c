@@ -392,10 +392,16 @@ static unsigned tri_flags(const orc_ray *r, const float *v0, const float *v1, co
   if (!(den != 0.0)) return 0;
   double bv = (d22 * h1 - d12 * h2) / den, bw = (d11 * h2 - d12 * h1) / den, bu = 1.0 - bv - bw;
   double mn = fmin(bu, fmin(bv, bw));
-  if (mn < -ORC_EPS) return 0; /* clearly outside */
-  int t_in = (t > -ORC_EPS * (1.0 + tf)) && (t <= tf * (1.0 + ORC_EPS));
-  if (mn <= ORC_EPS && t_in) f |= ORC_FLAG_EDGE;
-  if (fabs(t - tf) <= ORC_EPS * fmax(1.0, tf)) f |= ORC_FLAG_ENDPOINT;
+  /* conditioning: t = (N.C)/(N.D) and the barycentrics lose a factor 1/|cos| of the f32 precision
+   * when the ray runs nearly along the face, so the margins widen with it: 1e-5 down to
+   * |cos| = 0.05, 5e-7/|cos| below (found by the Moeller-Trumbore A/B count: a ray at
+   * |cos| = 2.7e-4 whose t differed from tfar by 9e-6 relative was decided differently by the two
+   * f32 predicates while outside the fixed 1e-5 margin) */
+  double eps = ORC_EPS * fmax(1.0, 0.05 / fabs(cosang));
+  if (mn < -eps) return 0; /* clearly outside */
+  int t_in = (t > -eps * (1.0 + tf)) && (t <= tf * (1.0 + eps));
+  if (mn <= eps && t_in) f |= ORC_FLAG_EDGE;
+  if (fabs(t - tf) <= eps * fmax(1.0, tf)) f |= ORC_FLAG_ENDPOINT;
   return f;
 }
 
@@ -544,6 +550,57 @@ orc_vis *orc_visibility_graph(const float *xyz, uint64_t nv, const uint32_t *tri
   finish_visible(r, C);
   free(T);
   return r;
+}
+
+/* ---- A/B counter against Embree's DEFAULT triangle intersector -------------------------------------
+ * The reference builds a default (non-robust) scene, for which Embree 3 tests triangles with its
+ * Moeller-Trumbore intersector, not the watertight Pluecker form used above.  Embree 3.8.0 is not
+ * vendored, so this is a restatement of the published algorithm (embree3 kernels/geometry
+ * triangle_intersector_moeller.h, from memory — UNPINNED like everything at that boundary): with the
+ * stored v0, e1 = v0 - v1, e2 = v2 - v0, Ng = e2 x e1,
+ *     C = v0 - org, R = C x dir, den = Ng . dir, U = (R . e2) ^ sign(den), V = (R . e1) ^ sign(den),
+ *     hit  <=>  den != 0  and  U >= 0  and  V >= 0  and  U + V <= |den|
+ *               and  |den| * tnear < T <= |den| * tfar   with  T = (Ng . C) ^ sign(den), tnear = 0,
+ * all in f32, dot products as Embree's fused madd chains.  It exists to COUNT the rays on which the two
+ * predicates disagree and to check that every such ray carries a flag (tests/test_oracle_visibility.py). */
+static float dot3m(const float *a, const float *b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
+int orc_ray_triangle_mt(const orc_ray *r, const float *v0, const float *v1, const float *v2) {
+  float e1[3], e2[3], Ng[3], Cv[3], R[3];
+  for (int k = 0; k < 3; ++k) {
+    e1[k] = v0[k] - v1[k];
+    e2[k] = v2[k] - v0[k];
+    Cv[k] = v0[k] - r->org[k];
+  }
+  cross3f(e2, e1, Ng);
+  cross3f(Cv, r->dir, R);
+  const float den = dot3m(Ng, r->dir);
+  const float ad = fabsf(den);
+  const float sg = den < 0.0f ? -1.0f : 1.0f; /* xor with the sign bit of den */
+  const float U = dot3m(R, e2) * sg, V = dot3m(R, e1) * sg;
+  if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && U + V <= ad)) return 0;
+  const float T = dot3m(Ng, Cv) * sg;
+  return (ad * 0.0f < T && T <= ad * r->tfar) ? 1 : 0;
+}
+
+/* occluded[] (one byte per candidate of v, same order) under the Moeller-Trumbore restatement */
+void orc_occluded_mt(const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt, const double *cams,
+                     uint64_t C, const double *pts, const uint64_t *cand_offsets, const uint64_t *cand_point,
+                     int endpoint_guard_rel, uint8_t *occluded) {
+  uint64_t ntri = 0;
+  tri9 *T = gather_tris(xyz, nv, tri, nt, &ntri);
+  for (uint64_t c = 0; c < C; ++c) {
+    double center[3];
+    orc_center(cams + ORC_CAM_STRIDE * c, center);
+    for (uint64_t k = cand_offsets[c]; k < cand_offsets[c + 1]; ++k) {
+      orc_ray ray;
+      orc_make_ray(center, pts + 3 * cand_point[k], &ray);
+      if (endpoint_guard_rel) ray.tfar = ray.tfar * (1.0f - 3.814697265625e-06f);
+      uint8_t occ = 0;
+      for (uint64_t t = 0; t < ntri && !occ; ++t) occ = (uint8_t)orc_ray_triangle_mt(&ray, T[t].v, T[t].v + 3, T[t].v + 6);
+      occluded[k] = occ;
+    }
+  }
+  free(T);
 }
 
 void orc_vis_free(orc_vis *v) {

@@ -92,6 +92,13 @@ orc_vis *orc_visibility_graph(const float *xyz, uint64_t nv, const uint32_t *tri
                               double max_dist, int endpoint_guard_rel, int want_flags);
 void orc_vis_free(orc_vis *v);
 
+/* A/B counter: Embree 3's default Moeller-Trumbore triangle test, restated (unpinned), and the occluded
+ * verdict of every candidate (cand_offsets / cand_point of an orc_vis) under it, one byte each */
+int orc_ray_triangle_mt(const orc_ray *ray, const float *v0, const float *v1, const float *v2);
+void orc_occluded_mt(const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt, const double *cams,
+                     uint64_t C, const double *pts, const uint64_t *cand_offsets, const uint64_t *cand_point,
+                     int endpoint_guard_rel, uint8_t *occluded);
+
 /* ---- multithreaded CPU reference arm: same predicates, BVH-accelerated any-hit,
  *      OpenMP over cameras (the rayon par_iter of src/generate.rs:435).  Returns
  *      visible CSR only (cand_* are NULL).  n_threads<=0: all cores. ---- */

@@ -217,6 +217,21 @@ def visibility_graph(xyz, tri, cams, pts, max_dist, endpoint_guard_rel=False, wa
     return Vis(r)
 
 
+def occluded_mt(xyz, tri, cams, pts, vis, endpoint_guard_rel=False):
+    """occluded verdict of every candidate of `vis` under the restatement of Embree's default
+    Moeller-Trumbore intersector (A/B counter against the watertight predicate; unpinned)."""
+    xyz, tri = _mesh(xyz, tri)
+    cams, pts = _d(cams).reshape(-1), _d(pts).reshape(-1)
+    off = np.ascontiguousarray(vis.cand_offsets, dtype=np.uint64)
+    cp = np.ascontiguousarray(vis.cand_point, dtype=np.uint64)
+    out = np.zeros(len(cp), dtype=np.uint8)
+    lib().orc_occluded_mt(
+        _p(xyz, C.c_float), _u64(xyz.size // 3), _p(tri, C.c_uint32), _u64(tri.size // 3), _p(cams),
+        _u64(cams.size // CAM), _p(pts), _p(off, C.c_uint64), _p(cp, C.c_uint64), C.c_int(int(endpoint_guard_rel)),
+        _p(out, C.c_uint8))
+    return out
+
+
 def ref_visibility_graph(xyz, tri, cams, pts, max_dist, endpoint_guard_rel=False, n_threads=0):
     """Multithreaded CPU arm (OpenMP over cameras + CPU BVH).  Returns (Vis, threads_used)."""
     xyz, tri = _mesh(xyz, tri)

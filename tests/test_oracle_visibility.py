@@ -151,3 +151,33 @@ def test_golden_reference_meshes(orc, name):
     assert np.array_equal(orc.generate_world_points_uniform(g["xyz"], g["tri"], g["cams"], len(g["pts"]), md, seed), g["pts"])
     # every world point lies ON a triangle, so every ray is an end-point case (SURVEY finding 3)
     assert g["flag_counts"][2] >= 0.99 * len(g["cand_idx"])
+
+
+def test_moeller_trumbore_ab_count(orc, capsys):
+    """A/B against a restatement of Embree's DEFAULT (non-watertight Moeller-Trumbore) triangle test, the
+    intersector the reference's scene actually uses: every cast ray on which it and the oracle's watertight
+    predicate disagree must be one the flagged-epsilon protocol already reports (edge / grazing / end point);
+    the counts go into DESIGN.md.  Both sides are restatements — parity with the Embree binary stays unpinned."""
+    cases = []
+    cams, pts = orc.grid_cameras(10, 4), orc.grid_points(10, 4)
+    xyz, tri = orc.city_mesh(4)
+    cases.append(("cfg2 lattice", xyz, tri, cams, pts, 10.0))
+    for name in ("cfg1_test_scene.npz", "box_obj.npz"):
+        g = np.load(os.path.join(GOLDEN, name))
+        cases.append((name, g["xyz"], g["tri"], g["cams"], g["pts"], float(g["max_dist"])))
+    rng = np.random.default_rng(17)
+    xyz, tri = procedural_scene(2)
+    cases.append(("procedural", xyz, tri, random_cameras(rng, 60), points_on_mesh(rng, xyz, tri, 3000), 30.0))
+    for name, xyz, tri, cams, pts, md in cases:
+        v = orc.visibility_graph(xyz, tri, cams, pts, md, want_flags=True)
+        mt = orc.occluded_mt(xyz, tri, cams, pts, v)
+        differ = mt != v.cand_occluded
+        ray_flags = v.cand_flags & 7          # edge | graze | end point
+        unflagged = int(np.count_nonzero(differ & (ray_flags == 0)))
+        with capsys.disabled():
+            print(f"\n  MT A/B {name}: {v.n_candidates} rays, {int(differ.sum())} disagree "
+                  f"({int(np.count_nonzero(differ & ((ray_flags & 4) != 0)))} end point, "
+                  f"{int(np.count_nonzero(differ & ((ray_flags & 1) != 0)))} edge, "
+                  f"{int(np.count_nonzero(differ & ((ray_flags & 2) != 0)))} grazing), {unflagged} unflagged")
+        assert unflagged == 0, f"{name}: the two predicates disagree on {unflagged} rays that carry no flag"
+        assert v.n_candidates > 0
