@@ -259,6 +259,45 @@ def test_arbitrary_orientations_and_cell_trimming(c2b, ctx, orc, seed):
                               f"orient{seed}/{mode}/{md}")
 
 
+@pytest.mark.parametrize("offset", [0.0, 2.0e4])
+def test_image_side_planes_never_lose_a_candidate(c2b, ctx, orc, offset):
+    """k1 = k2 = 0 cameras (the BASELINE intrinsics: the plan trims rows by the four side planes of the image
+    and by the ball) with fully random rotations and focal lengths that are small, large, negative and zero,
+    points placed ON the image border |u| = 1 / |v| = 1 and on the max_dist sphere, near the origin and 20 km
+    away from it (the slack of the trimming must scale with the magnitudes): grid schedule = oracle"""
+    rng = np.random.default_rng(77)
+    focals = [1.0, 0.3, 2.5, -1.2, 0.0, 1.0, 7.0, 1e-3]
+    cams = np.empty((64, 15))
+    for i in range(len(cams)):
+        R = orc.from_vec(np.concatenate([rng.normal(size=3) * 2.0, np.zeros(3), [1.0, 0.0, 0.0]]))[:9]
+        cams[i] = orc.from_position_direction(offset + rng.uniform(-12, 12, 3) * np.array([1, 0.4, 1]), R)
+        cams[i, 12:15] = (focals[i % len(focals)], 0.0, 0.0)
+    pts = [offset + rng.uniform(-25, 25, (5000, 3)) * np.array([1, 0.5, 1])]
+    md = 13.0
+    for c in cams[:24]:                                   # points constructed on the frustum's faces and the sphere
+        f = c[12]
+        cen = orc.center(c)
+        for _ in range(12):
+            z = -rng.uniform(0.5, 12.0)
+            s = rng.choice([-1.0, 1.0])
+            lim = abs(z / f) if f != 0.0 else 5.0          # |u| = 1  <=>  |x| = |z / f|
+            x, y = (s * lim, rng.uniform(-1, 1) * lim) if rng.uniform() < 0.5 else (rng.uniform(-1, 1) * lim, s * lim)
+            pts.append(orc.to_world(c, np.array([x, y, z]))[None])
+            d = rng.normal(size=3)
+            pts.append((cen + d / np.linalg.norm(d) * md * rng.choice([1.0, 1.0 - 1e-15, 1.0 + 1e-15]))[None])
+    pts = np.concatenate(pts)
+    ref = orc.visibility_graph(np.zeros((0, 3)), np.zeros((0, 3)), cams, pts, md)
+    assert ref.n_obs > 2000
+    empty = c2b.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), ctx=ctx)
+    for mode in MODES:
+        g = c2b.visibility_graph(empty, cams, pts, md, cull_mode=mode, ctx=ctx)
+        assert_same_graph(g, ref, f"side planes/{mode}/{offset}")
+    # every candidate was among the evaluated pairs (the points built on the image border of the f = 1e-3
+    # cameras lie kilometres out, so the grid is coarse here and the rows hold nearly all C x P pairs)
+    g = c2b.visibility_graph(empty, cams, pts, md, ctx=ctx)
+    assert ref.n_candidates <= g.stats["pairs_evaluated"] <= len(cams) * len(pts)
+
+
 def test_long_segments_use_the_radix_fallback(c2b, ctx, orc):
     """a camera that sees more than 4096 points exceeds the shared-memory segment sort"""
     rng = np.random.default_rng(77)
