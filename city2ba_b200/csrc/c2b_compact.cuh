@@ -80,16 +80,6 @@ __global__ void __launch_bounds__(256) k_probe_dfma(double *__restrict__ sink, i
 }
 
 // ---- helpers shared with the grid schedule (c2b_fused.cuh) ----------------------------------------
-__global__ void k_max_u32(const uint32_t *__restrict__ v, uint64_t n, uint32_t *__restrict__ out) {
-  uint32_t m = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (uint64_t)gridDim.x * blockDim.x)
-    m = max(m, v[i]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
-}
-
 // (u, v) of an observation, recomputed exactly as the cull kernel computed it
 __device__ __forceinline__ double2 observe(const double *cam, double x, double y, double z) {
   V3 pc = project_world(cam, V3{x, y, z});
@@ -112,10 +102,6 @@ __global__ void k_write_sorted(const uint64_t *keys, uint64_t n, int pbits, cons
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&cams[15 * cam + k]);
   out_uv[i] = observe(c, p_aos[3 * pt], p_aos[3 * pt + 1], p_aos[3 * pt + 2]);
   out_idx[i] = (uint32_t)pt;
-}
-__global__ void k_widen_offsets(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i];
 }
 
 // ---- analytic occlusion of `city2ba synthetic` ------------------------------------------------------

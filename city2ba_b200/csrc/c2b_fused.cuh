@@ -312,10 +312,6 @@ __global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
 // ---- the fused pass ---------------------------------------------------------------------------------
 constexpr int FU_WARPS = 8;
 constexpr int FU_STAGE = 64;
-#ifndef C2B_STAGE_COORDS
-#define C2B_STAGE_COORDS 0  // 1: survivors' coordinates staged in shared memory (48 KB/CTA, measured 3.11 ms at
-                            // cfg4); 0: re-read through L1 at ray set-up (36 KB/CTA, 3.07 ms)
-#endif
 
 enum { FU_OCC_MESH = 0, FU_OCC_NONE = 1, FU_OCC_ANALYTIC = 2 };
 
@@ -640,19 +636,14 @@ __device__ __forceinline__ int packet_bvh_hit(const FusedArgs &a, const Ray &ray
 template <int OCC, bool COUNT, int MIN_CTAS, bool WALK>
 __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
   __shared__ double s_cam[FU_WARPS][16];
-  // survivors of the cull wait here for their packet: a ring of FU_STAGE entries per warp holding the
-  // grid position and the coordinates just read (so that the ray set-up needs no second trip to global memory)
+  // survivors of the cull wait here for their packet: a ring of FU_STAGE grid positions per warp.  (Staging
+  // the coordinates as well, so that the ray set-up needs no second trip through L1, was measured: 48 KB of
+  // shared memory per CTA instead of 36 shrink L1, 3.11 ms against 3.07 ms at cfg4.)
   __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
-#if C2B_STAGE_COORDS
-  __shared__ double s_px[FU_WARPS][FU_STAGE], s_py[FU_WARPS][FU_STAGE], s_pz[FU_WARPS][FU_STAGE];
-#endif
   __shared__ float4 s_rec[FU_WARPS][4 * FU_HOIST];  // hoisted: 4 planes x FU_HOIST; chunked: 32 x 3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *c = s_cam[warp];
   uint32_t *stage = s_stage[warp];
-#if C2B_STAGE_COORDS
-  double *stx = s_px[warp], *sty = s_py[warp], *stz = s_pz[warp];
-#endif
   unsigned long long found_total = 0;
   unsigned n_vis_nodes = 0, n_tri = 0;
   const double cell_h = ddiv(1.0, a.g.inv_h);
@@ -707,11 +698,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
         const int e = (head + lane) & (FU_STAGE - 1);
         const uint32_t i = stage[e];
         pt = a.gidx[i];
-#if C2B_STAGE_COORDS
-        p = V3{stx[e], sty[e], stz[e]};
-#else
         p = V3{a.gx[i], a.gy[i], a.gz[i]};
-#endif
         if (OCC == FU_OCC_MESH) ray = make_ray(cen, p, a.endpoint_guard_rel != 0);
       }
       bool occ = false;
@@ -792,11 +779,6 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
           if (pass) {
             const int e = (head + qn + __popc(m & ((1u << lane) - 1u))) & (FU_STAGE - 1);
             stage[e] = i;
-#if C2B_STAGE_COORDS
-            stx[e] = pcur.x;
-            sty[e] = pcur.y;
-            stz[e] = pcur.z;
-#endif
           }
           qn += __popc(m);
           __syncwarp();
