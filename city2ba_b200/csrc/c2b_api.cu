@@ -137,6 +137,23 @@ int c2b_init(int device, c2b_ctx **out) {
     C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
     C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
   }
+  // NUMA node of the device (sysfs), for the pinned staging / result buffers (see PinBuf)
+  {
+    int node = -1;
+    const char *off = getenv("C2B_NUMA_LOCAL");
+    char bus[32] = {0};
+    if (!(off && atoi(off) == 0) && cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
+      for (char *c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+      const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+      if (FILE *f = fopen(path.c_str(), "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+      }
+    }
+    (void)cudaGetLastError();
+    ctx->numa_node = node;
+    for (PinBuf *b : {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small}) b->node = node;
+  }
   extras().push_back({ctx, new CtxExtra()});
   *out = ctx;
   return C2B_OK;
@@ -903,6 +920,7 @@ int grow_pinned(c2b_ctx *ctx, PinBuf &b, size_t need, size_t used) {
   if (need <= b.cap) return C2B_OK;
   C2B_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   PinBuf nb;
+  nb.node = b.node;
   C2B_TRY(nb.ensure(need + need / 2));
   if (used) memcpy(nb.p, b.p, used);
   b.release();

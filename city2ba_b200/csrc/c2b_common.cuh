@@ -8,6 +8,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#if defined(__linux__)
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
 
 #include "../../include/city2ba_cuda.h"
 
@@ -94,9 +98,33 @@ struct DevBuf {
 };
 
 // grow-only pinned host buffer
+// Pinned host buffers are allocated on the NUMA node the GPU hangs off (c2b_init reads it from sysfs):
+// with one process per GPU on a two-socket host, result slabs that land on the other socket cross the
+// inter-socket link on their way out of every GPU at once.  Done by setting the calling thread's memory
+// policy to MPOL_PREFERRED(node) around the allocation only; C2B_NUMA_LOCAL=0 switches it off.
+struct NumaPreferred {
+  bool active = false;
+  explicit NumaPreferred(int node) {
+#if defined(__linux__)
+    if (node < 0 || node >= 1024) return;
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    active = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1025ul) == 0;
+#else
+    (void)node;
+#endif
+  }
+  ~NumaPreferred() {
+#if defined(__linux__)
+    if (active) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+  }
+};
+
 struct PinBuf {
   void *p = nullptr;
   size_t cap = 0;
+  int node = -1;  // NUMA node of the GPU these buffers feed (-1: unknown / off)
   int ensure(size_t bytes) {
     if (bytes <= cap) return C2B_OK;
     if (p) {
@@ -105,6 +133,7 @@ struct PinBuf {
       cap = 0;
     }
     size_t want = bytes + bytes / 4 + 256;
+    NumaPreferred local(node);
     cudaError_t e = cudaMallocHost(&p, want);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -185,6 +214,7 @@ struct c2b_ctx {
   c2b::DevBuf tri_list, tri_count;  // per-camera leaf lists for list-driven traversal
   // fused grid schedule: per-camera plan (row points -> scratch slice), visible counts, CSR offsets
   c2b::DevBuf ev_off, vis_count, seg_off, scratch_idx, plan_rows, plan_row_count;
+  int numa_node = -1;  // of the device, from sysfs (-1: unknown)
 
   float noise_ms[3] = {0, 0, 0};  // last noise call: upload, statistics + kernels, download
 
