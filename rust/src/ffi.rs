@@ -22,6 +22,14 @@ pub struct c2b_obs {
     pub ms_traverse: c_float, pub ms_compact: c_float, pub ms_d2h: c_float, pub ms_total: c_float,
 }
 
+// Embree's RTCRay layout (48 bytes): what embree_rs::Ray wraps (src/generate.rs:253-262, :457-464)
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct c2b_ray48 {
+    pub org_x: c_float, pub org_y: c_float, pub org_z: c_float, pub tnear: c_float,
+    pub dir_x: c_float, pub dir_y: c_float, pub dir_z: c_float, pub time: c_float,
+    pub tfar: c_float, pub mask: u32, pub id: u32, pub flags: u32,
+}
+
 extern "C" {
     pub fn c2b_init(device: c_int, out: *mut *mut c2b_ctx) -> c_int;
     pub fn c2b_shutdown(ctx: *mut c2b_ctx);
@@ -32,6 +40,14 @@ extern "C" {
     pub fn c2b_scene_destroy(s: *mut c2b_scene);
     pub fn c2b_intersect1(ctx: *mut c2b_ctx, s: *const c2b_scene, org: *const c_float,
                           dir: *const c_float, hit: *mut c_int, tfar: *mut c_float) -> c_int;
+    // closest hit of a whole batch (generate_cameras_poisson's downward rays in one launch): flags = 1 and
+    // tfar = distance on a hit; any-hit batch (occluded_stream_aos): tfar = -inf on a hit
+    pub fn c2b_intersect(ctx: *mut c2b_ctx, s: *const c2b_scene, rays: *mut c2b_ray48, n: u64) -> c_int;
+    pub fn c2b_occluded(ctx: *mut c2b_ctx, s: *const c2b_scene, rays: *mut c2b_ray48, n: u64) -> c_int;
+    pub fn c2b_generate_world_points_uniform(ctx: *mut c2b_ctx, xyz: *const c_float, nv: u64, tri: *const u32,
+                                             nt: u64, cams: *const c_double, c: u64, num_points: u64,
+                                             max_dist: c_double, seed: u64, pts_out: *mut c_double,
+                                             n_out: *mut u64) -> c_int;
     pub fn c2b_vis_options_default(opt: *mut c2b_vis_options);
     pub fn c2b_visibility_graph(ctx: *mut c2b_ctx, s: *const c2b_scene, cams: *const c_double,
                                 c: u64, pts: *const c_double, p: u64, max_dist: c_double,
