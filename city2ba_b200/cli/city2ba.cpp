@@ -120,10 +120,12 @@ int run_synthetic(int argc, char **argv) {
                 {"seed", "0"}},
                {});
   if (a.positional.size() != 1) throw UsageError("The following required arguments were not provided:\n    <OUTPUT>");
+  // every value is parsed (usage errors) before the GPU is touched
+  const size_t cpb = a.usize("cameras-per-block"), ppb = a.usize("points-per-block"), blocks = a.usize("blocks");
+  const double length = a.f64("block-length"), inset = a.f64("block-inset"), cam_h = a.f64("camera-height"),
+               pt_h = a.f64("point-height"), max_dist = a.f64("max-dist");
   const Context ctx((int)a.usize("device"));
-  const BAProblem ba = synthetic::synthetic_grid(ctx, a.usize("cameras-per-block"), a.usize("points-per-block"),
-                                                 a.usize("blocks"), a.f64("block-length"), a.f64("block-inset"),
-                                                 a.f64("camera-height"), a.f64("point-height"), a.f64("max-dist"), true);
+  const BAProblem ba = synthetic::synthetic_grid(ctx, cpb, ppb, blocks, length, inset, cam_h, pt_h, max_dist, true);
   std::cout << ba.to_string() << "\n";
   ba.write(a.positional[0]);
   return 0;
@@ -136,10 +138,11 @@ int run_synthetic_line(int argc, char **argv) {
                 {"point-offset", "1"}, {"length", "20"}, {"device", "0"}, {"seed", "0"}},
                {});
   if (a.positional.size() != 1) throw UsageError("The following required arguments were not provided:\n    <OUTPUT>");
+  const size_t n_cams = a.usize("cameras"), n_pts = a.usize("points");
+  const double length = a.f64("length"), offset = a.f64("point-offset"), cam_h = a.f64("camera-height"),
+               pt_h = a.f64("point-height"), max_dist = a.f64("max-dist");
   const Context ctx((int)a.usize("device"));
-  const BAProblem ba = synthetic::synthetic_line(ctx, a.usize("cameras"), a.usize("points"), a.f64("length"),
-                                                 a.f64("point-offset"), a.f64("camera-height"), a.f64("point-height"),
-                                                 a.f64("max-dist"), true);
+  const BAProblem ba = synthetic::synthetic_line(ctx, n_cams, n_pts, length, offset, cam_h, pt_h, max_dist, true);
   std::cout << ba.to_string() << "\n";
   ba.write(a.positional[0]);
   return 0;
@@ -154,9 +157,14 @@ int run_noise(int argc, char **argv) {
                 {"sin-frequency", "1.0"}, {"device", "0"}, {"seed", "0"}},
                {"fixed-drift"});
   if (a.positional.size() != 2) throw UsageError("The following required arguments were not provided:\n    <FILE> <OUT>");
-  const Context ctx((int)a.usize("device"));
+  for (const char *k : {"rotation-std", "translation-std", "point-std", "observation-std", "drift-std", "drift-strength",
+                        "drift-angle", "mismatch-chance", "drop-features", "split-landmarks", "join-landmarks",
+                        "sin-strength", "sin-frequency"})
+    (void)a.f64(k);  // usage errors first
+  const int device = (int)a.usize("device");
   const uint64_t seed = seed_of(a);
-  BAProblem bal = BAProblem::from_file(a.positional[0]);
+  BAProblem bal = BAProblem::from_file(a.positional[0]);  // src/bin/city2ba.rs:281: a missing file fails before anything else
+  const Context ctx(device);
   std::cout << "Initial error: " << sci2(bal.total_reprojection_error(1.)) << " (L1) "
             << sci2(bal.total_reprojection_error(2.)) << " (L2)\n";
   if (a.f64("drop-features") < 1.0) bal = noise::drop_features(bal, a.f64("drop-features"), seed + 1).cull();
@@ -194,6 +202,11 @@ int run_generate(int argc, char **argv) {
   if (a.given.count("path") && a.given.count("ground"))
     throw UsageError("The argument '--path <path>' cannot be used with '--ground <ground>'");
   const uint64_t seed = seed_of(a);
+  const size_t num_cameras = a.usize("cameras"), num_points = a.usize("points");
+  const double max_dist = a.f64("max-dist"), ground = a.f64("ground"), height = a.f64("height"),
+               step_size = a.f64("step-size");
+  const Vector3 intrinsics_start = a.vec3("intrinsics-start"), intrinsics_end = a.vec3("intrinsics-end");
+  const int device = (int)a.usize("device");
   std::vector<tobj::Model> models = tobj::load_obj(a.positional[0]);
 
   std::optional<tobj::Model> model_path;
@@ -214,28 +227,28 @@ int run_generate(int argc, char **argv) {
   }
   if (a.flag("move-to-origin")) models = generate::move_to_origin(std::move(models));
 
-  const Context ctx((int)a.usize("device"));
+  const Context ctx(device);
   const Scene cscene = generate::commit_scene(ctx, models);
 
   std::vector<SnavelyCamera> cameras;
   if (model_path) {
-    if (a.f64("step-size") <= 0.0)
-      cameras = generate::generate_cameras_path(cscene, *model_path, a.usize("cameras"), seed + 1);
+    if (step_size <= 0.0)
+      cameras = generate::generate_cameras_path(cscene, *model_path, num_cameras, seed + 1);
     else
-      cameras = generate::generate_cameras_path_step(cscene, *model_path, a.usize("cameras"), a.f64("step-size"), &std::cout);
+      cameras = generate::generate_cameras_path_step(cscene, *model_path, num_cameras, step_size, &std::cout);
   } else {
-    cameras = generate::generate_cameras_poisson(cscene, a.usize("cameras"), a.f64("height"), a.f64("ground"), seed + 1);
+    cameras = generate::generate_cameras_poisson(cscene, num_cameras, height, ground, seed + 1);
   }
   std::cout << "Generated " << cameras.size() << " cameras\n";
 
-  generate::modify_intrinsics(cameras, a.vec3("intrinsics-start"), a.vec3("intrinsics-end"), seed + 2);
+  generate::modify_intrinsics(cameras, intrinsics_start, intrinsics_end, seed + 2);
   std::cout << "Modified intrinsics\n";
 
   std::vector<Point3> points =
-      generate::generate_world_points_uniform(ctx, models, cameras, a.usize("points"), a.f64("max-dist"), seed + 3);
+      generate::generate_world_points_uniform(ctx, models, cameras, num_points, max_dist, seed + 3);
   std::cout << "Generated " << points.size() << " world points\n";
 
-  VisGraph vis_graph = generate::visibility_graph(cscene, cameras, points, a.f64("max-dist"), true);
+  VisGraph vis_graph = generate::visibility_graph(cscene, cameras, points, max_dist, true);
   size_t edges = 0;
   for (const auto &v : vis_graph) edges += v.size();
   std::cout << "Computed visibility graph with " << edges << " edges\n";

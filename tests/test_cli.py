@@ -49,6 +49,15 @@ def test_cli_is_built_and_reports_usage():
     assert r.returncode == 2 and "cannot be used with" in r.stderr
     r = run("generate", "/nonexistent/scene.obj", "/tmp/x.bal")
     assert r.returncode == 1 and "Could not open file" in r.stderr  # src/bin/city2ba.rs:481-485
+    # values are parsed, and input files opened, before the GPU is touched: the same failures with or without one
+    r = run("noise", "/nonexistent/in.bbal", "/tmp/x.bbal")
+    assert r.returncode == 1 and "IOError" in r.stderr               # BAProblem::from_file, src/bin/city2ba.rs:281
+    r = run("synthetic", "--blocks", "many", "/tmp/x.bal")
+    assert r.returncode == 2 and "Invalid value for '--blocks" in r.stderr
+    r = run("noise", "a.bbal", "b.bbal", "--drift-std=abc")
+    assert r.returncode == 2 and "invalid float literal" in r.stderr
+    r = run("generate", "a.obj", "b.bal", "--intrinsics-start", "1,2")  # parse_vec3 unwraps a missing component, :25-31
+    assert r.returncode == 101 and "panicked" in r.stderr
 
 
 def test_cli_has_no_cpu_fallback(tmp_path):
