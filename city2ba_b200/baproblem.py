@@ -92,6 +92,34 @@ def _mat_from_quat(q):
                      xz2 + sy2, yz2 - sx2, 1.0 - xx2 - yy2], dtype=np.float64)
 
 
+def _ulps_eq(a, b):
+    """approx::ulps_eq! with its defaults (epsilon = f64::EPSILON, max_ulps = 4), as cgmath 0.17 uses it"""
+    if abs(a - b) <= 2.220446049250313e-16:
+        return True
+    if math.copysign(1.0, a) != math.copysign(1.0, b):
+        return False
+    ia, ib = (int(np.float64(x).view(np.int64)) for x in (a, b))
+    return abs(ia - ib) <= 4
+
+
+def between_vectors(a, b):
+    """cgmath 0.17 Basis3::between_vectors (through Quaternion::between_vectors), used by the path cameras
+    (src/generate.rs:144,200): column-major 3x3 as 9 doubles"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    k_cos_theta = float(a @ b)
+    if _ulps_eq(k_cos_theta, 1.0):
+        return np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float64)
+    k = math.sqrt(float(a @ a) * float(b @ b))
+    if _ulps_eq(k_cos_theta / k, -1.0):
+        o = np.cross([1.0, 0.0, 0.0], a)
+        if _ulps_eq(float(o @ o), 0.0):
+            o = np.cross([0.0, 1.0, 0.0], a)
+        o = o / np.linalg.norm(o)
+        return _mat_from_quat(np.array([0.0, o[0], o[1], o[2]]))
+    q = np.concatenate([[k + k_cos_theta], np.cross(a, b)])
+    return _mat_from_quat(q / np.linalg.norm(q))
+
+
 def from_rodrigues(v):
     """src/baproblem.rs:78-90"""
     x = [float(t) for t in v]

@@ -273,3 +273,227 @@ def generate_world_points_uniform(xyz, tri, cameras, num_points, max_dist, seed=
         cams.shape[0], int(num_points), float(max_dist), seed, out.ctypes.data_as(C.POINTER(C.c_double)),
         C.byref(n)))
     return out[: n.value]
+
+
+# ---- OBJ ingest and camera generators (src/generate.rs:109-280, 484-544; src/bin/city2ba.rs:481-538) -------
+# Host side, like the reference's; the same procedures as include/city2ba.hpp (seeded where the reference
+# draws from thread_rng(), so parity with it is distributional).
+
+class Model:
+    """tobj::Model: name + per-model vertex array (only the vertices its elements use, in order of first
+    use) + flat index list (triangles; `l` records append index pairs)."""
+
+    def __init__(self, name, positions, indices):
+        self.name = name
+        self.positions = np.asarray(positions, np.float32).reshape(-1, 3)
+        self.indices = np.asarray(indices, np.uint32).reshape(-1)
+
+
+def load_obj(path) -> list:
+    """tobj 0.1.12's rules (src/bin/city2ba.rs:481): one Model per `o` / `g` that is followed by elements;
+    quads as (a,b,c),(a,c,d), larger polygons as a fan from their first vertex; `l` records keep two indices,
+    `p` records one; materials are not read."""
+    from .baproblem import IOError_
+    try:
+        fh = open(path)
+    except OSError as e:
+        raise IOError_(f'Could not open file "{path}"') from e
+    pos, n_vt, n_vn = [], 0, 0
+    models, faces, name = [], [], "unnamed_object"
+
+    def flush():
+        nonlocal faces
+        if not faces:
+            return
+        seen, positions, indices = {}, [], []
+
+        def add(k):
+            if k not in seen:
+                seen[k] = len(positions)
+                positions.append(pos[k[0]])
+            indices.append(seen[k])
+        for e in faces:
+            if len(e) <= 3:
+                order = range(len(e))
+            elif len(e) == 4:
+                order = (0, 1, 2, 0, 2, 3)
+            else:
+                order = [j for i in range(1, len(e) - 1) for j in (0, i, i + 1)]
+            for i in order:
+                add(e[i])
+        models.append(Model(name, positions, indices))
+        faces = []
+
+    with fh:
+        for lineno, line in enumerate(fh, 1):
+            t = line.split()
+            if not t or t[0].startswith("#"):
+                continue
+            if t[0] == "v":
+                pos.append(tuple(float(x) for x in t[1:4]))
+            elif t[0] == "vt":
+                n_vt += 1
+            elif t[0] == "vn":
+                n_vn += 1
+            elif t[0] in ("f", "l", "p"):
+                e = []
+                for tok in t[1:]:
+                    parts = (tok.split("/") + ["", ""])[:3]
+                    key = []
+                    for part, n in zip(parts, (len(pos), n_vt, n_vn)):
+                        i = int(part) if part else 0
+                        key.append(i - 1 if i > 0 else n + i if i < 0 else -1)
+                    if not 0 <= key[0] < len(pos):
+                        raise IOError_(f"Load error: face vertex index out of range ({path}:{lineno})")
+                    e.append(tuple(key))
+                if not e:
+                    raise IOError_(f"Load error: face parse error ({path}:{lineno})")
+                faces.append(e)
+            elif t[0] in ("o", "g"):
+                flush()
+                name = line.split(None, 1)[1].strip() if len(t) > 1 else "unnamed_object"
+    flush()
+    return models
+
+
+def concat_models(models):
+    """all models as one (xyz, tri) pair for Scene / the point sampler: each model's index list regrouped
+    into triples on its own (num_tri = indices.len() / 3, src/generate.rs:78) and offset"""
+    xyz, tri, base = [], [], 0
+    for m in models:
+        xyz.append(m.positions)
+        n = len(m.indices) // 3 * 3
+        tri.append(m.indices[:n].reshape(-1, 3) + np.uint32(base))
+        base += len(m.positions)
+    if not xyz:
+        return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)
+    return np.concatenate(xyz), np.concatenate(tri).astype(np.uint32)
+
+
+def move_to_origin(models):
+    """src/generate.rs:484-527"""
+    mn = np.min([m.positions.min(axis=0) for m in models if len(m.positions)], axis=0)
+    return [Model(m.name, m.positions - mn, m.indices) for m in models]
+
+
+def modify_intrinsics(cameras, intrinsic_start, intrinsic_end, seed=None):
+    """src/generate.rs:530-544: intrinsics uniform in [start, end); returns a new (C,15) array"""
+    cams = _cam_array(cameras).copy()
+    rng = np.random.default_rng(seed)
+    s, e = np.asarray(intrinsic_start, float), np.asarray(intrinsic_end, float)
+    cams[:, 12:15] = s + rng.uniform(size=(len(cams), 3)) * (e - s)
+    return cams
+
+
+def _path_segments(path: Model):
+    v = path.positions.astype(np.float64)
+    idx = path.indices[: len(path.indices) // 2 * 2].reshape(-1, 2)
+    return v[idx[:, 0]], v[idx[:, 1]]
+
+
+def _camera_looking_along(pos, direction):
+    from .baproblem import SnavelyCamera, between_vectors
+    d = direction / np.linalg.norm(direction)
+    return SnavelyCamera.from_position_direction(pos, between_vectors(d, np.array([0.0, 0.0, -1.0]))).to_record()
+
+
+def generate_cameras_path(scene, path: Model, num_cameras, seed=None):
+    """src/generate.rs:109-148: random positions along the path (segments weighted by length), looking along it"""
+    a, b = _path_segments(path)
+    length = np.linalg.norm(b - a, axis=1)
+    if not length.sum() > 0:
+        raise AssertionError("called `Result::unwrap()` on an `Err` value: AllWeightsZero")
+    rng = np.random.default_rng(seed)
+    cams = np.empty((num_cameras, CAM_STRIDE))
+    for k, i in enumerate(rng.choice(len(a), size=num_cameras, p=length / length.sum())):
+        cams[k] = _camera_looking_along(a[i] + rng.uniform() * (b[i] - a[i]), b[i] - a[i])
+    return cams
+
+
+def generate_cameras_path_step(scene, path: Model, num_cameras, step_size):
+    """src/generate.rs:152-213: fixed steps from the start of the path"""
+    a, b = _path_segments(path)
+    length = np.linalg.norm(b - a, axis=1)
+    total = float(length.sum())
+    assert num_cameras * step_size <= total, (
+        f"Length of path {total} is less than the number of cameras ({num_cameras}) times the step size "
+        f"({step_size}) {num_cameras * step_size}")
+    seg, dist = 0, 0.0
+    cams = np.empty((num_cameras, CAM_STRIDE))
+    for k in range(num_cameras):
+        d = b[seg] - a[seg]                       # IndexError = the reference's out-of-bounds panic
+        cams[k] = _camera_looking_along(a[seg] + dist / length[seg] * d, d)
+        dist += step_size
+        while dist >= length[seg]:
+            dist -= length[seg]
+            seg += 1
+            length[seg]                           # the reference indexes the next segment here
+    return cams
+
+
+def _poisson_disk(samples, rng):
+    """Bridson dart throwing in the unit square at the hexagonal-packing radius for `samples` discs (the
+    reference's `poisson` crate, Ebeida's sampler at relative radius 1, is not vendored)"""
+    if samples == 0:
+        return np.zeros((0, 2))
+    r = 2.0 * np.sqrt(0.9068996821171089 / (samples * np.pi))
+    cell = r / np.sqrt(2.0)
+    n = max(1, int(np.ceil(1.0 / cell)))
+    grid = -np.ones((n, n), np.int64)
+    out, active = [], []
+
+    def cell_of(x):
+        return min(n - 1, int(x / cell))
+
+    def fits(x, y):
+        cx, cy = cell_of(x), cell_of(y)
+        for j in range(max(0, cy - 2), min(n - 1, cy + 2) + 1):
+            for i in range(max(0, cx - 2), min(n - 1, cx + 2) + 1):
+                k = grid[j, i]
+                if k >= 0 and (out[k][0] - x) ** 2 + (out[k][1] - y) ** 2 < r * r:
+                    return False
+        return True
+
+    def push(x, y):
+        grid[cell_of(y), cell_of(x)] = len(out)
+        active.append(len(out))
+        out.append((x, y))
+
+    push(rng.uniform(), rng.uniform())
+    while active:
+        a = int(rng.integers(len(active)))
+        bx, by = out[active[a]]
+        for _ in range(30):
+            ang, rad = rng.uniform(0.0, 2.0 * np.pi), r * np.sqrt(rng.uniform(1.0, 4.0))
+            x, y = bx + rad * np.cos(ang), by + rad * np.sin(ang)
+            if 0.0 <= x < 1.0 and 0.0 <= y < 1.0 and fits(x, y):
+                push(x, y)
+                break
+        else:
+            active[a] = active[-1]
+            active.pop()
+    return np.array(out)
+
+
+def generate_cameras_poisson(scene: Scene, num_points, height, ground, seed=None):
+    """src/generate.rs:217-280: Poisson-disk positions over the scene's (x, z) bounds, dropped onto the tallest
+    surface below them (ALL downward closest-hit rays in one GPU batch), raised by `height`, kept if
+    pt[2] < lower_y + ground (z against y, as the reference writes it, :264), random yaw about y"""
+    from .baproblem import SnavelyCamera, from_angle_y
+    rng = np.random.default_rng(seed)
+    smp = _poisson_disk(num_points * 2, rng)
+    lo, hi = scene.bounds()
+    start = np.array([float(hi[0]), float(hi[1]) + 0.1, float(hi[2])])
+    delta = np.array([float(hi[0] - lo[0]), 0.0, float(hi[2] - lo[2])])
+    origins = start - delta * np.stack([smp[:, 0], np.zeros(len(smp)), smp[:, 1]], axis=1)
+    if not len(origins):
+        return np.zeros((0, CAM_STRIDE))
+    hit, t = scene.intersect(origins, np.tile(np.array([0.0, -1.0, 0.0], np.float32), (len(origins), 1)))
+    cams = []
+    for o, h, tt in zip(origins, hit, t):
+        if not h:
+            continue
+        pt = o + np.array([0.0, -1.0, 0.0]) * float(tt) + np.array([0.0, height, 0.0])
+        if pt[2] < float(lo[1]) + ground:
+            cams.append(SnavelyCamera.from_position_direction(pt, from_angle_y(rng.uniform(0.0, 2.0 * np.pi))).to_record())
+    return np.array(cams).reshape(-1, CAM_STRIDE)

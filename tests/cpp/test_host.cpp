@@ -5,6 +5,7 @@
 // plus BAL text / binary round trips (src/baproblem.rs:580-785).
 //   test_host cpu            camera math, BAL I/O and cull on hand-made data (no GPU)
 //   test_host gpu <out.bbal> everything; writes the culled synthetic grid for a cross-check in pytest
+//   test_host obj <file.obj> dumps what tobj::load_obj read (cross-check against the Python loader)
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -388,8 +389,22 @@ static void generate_cameras(const Context &ctx, const std::string &tmp) {
   CHECK(ba.total_reprojection_error(1.0) < 1e-9);
 }
 
+// test_host obj <file.obj>: one line per model (name, vertices, indices, checksums) for a cross-check against
+// the Python mirror's loader on the reference's own OBJ fixtures (tests/test_host_mirror.py)
+static int dump_obj(const char *path) {
+  for (const auto &m : tobj::load_obj(path)) {
+    double ps = 0.0;
+    unsigned long long is = 0;
+    for (size_t i = 0; i < m.mesh.positions.size(); ++i) ps += (double)m.mesh.positions[i] * (double)(1 + i % 7);
+    for (size_t i = 0; i < m.mesh.indices.size(); ++i) is += (unsigned long long)m.mesh.indices[i] * (1 + i % 5);
+    std::printf("%s|%zu|%zu|%.9g|%llu\n", m.name.c_str(), m.mesh.positions.size() / 3, m.mesh.indices.size(), ps, is);
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
+  if (mode == "obj" && argc > 2) return dump_obj(argv[2]);
   const char *tmp = std::getenv("TMPDIR");
   rodrigues_idempotent();
   test_project_world();

@@ -77,3 +77,43 @@ def test_points_error_paths(c2b, ctx):
     far[:, 9:12] += 1e6                              # cameras nowhere near the mesh
     with pytest.raises(c2b.C2BError, match="Failed to generate enough points"):
         generate_world_points_uniform(xyz, tri, far, 100, 1.0, seed=1, ctx=ctx)
+
+
+def test_camera_generators_python_mirror(c2b, ctx, tmp_path):
+    """src/generate.rs:109-280 through the Python mirror on the small OBJ scene (the C++ mirror's counterpart is
+    tests/cpp/test_host.cpp::generate_cameras): path cameras sit on the poly-line and look along it, path-step
+    cameras are evenly spaced, Poisson cameras stand `height` above the tallest surface below them"""
+    from city2ba_b200 import generate
+    from test_host_mirror import _write_obj
+    obj = str(tmp_path / "scene.obj")
+    _write_obj(obj)
+    models = generate.load_obj(obj)
+    path, models = models[3], models[:3]
+    scene = c2b.Scene(*generate.concat_models(models), ctx=ctx)
+    assert scene.num_triangles == 2 + 12 + 3
+    cams = generate.generate_cameras_path(scene, path, 40, seed=3)
+    assert cams.shape == (40, 15)
+    for rec in cams:
+        cam = c2b.SnavelyCamera(record=rec)
+        p = cam.center()
+        assert abs(p[1] - 0.5) < 1e-12 and abs(p[2] - 3.0) < 1e-12 and -3.0 - 1e-12 <= p[0] <= 2.0 + 1e-12
+        ahead = cam.project_world(p + np.array([1.0, 0.0, 0.0]))
+        assert np.allclose(ahead, [0.0, 0.0, -1.0], atol=1e-9)          # +x along the path is straight ahead (-z)
+    stepped = generate.generate_cameras_path_step(scene, path, 20, 0.2)
+    xs = [c2b.SnavelyCamera(record=r).center()[0] for r in stepped]
+    assert np.allclose(xs, -3.0 + 0.2 * np.arange(20), atol=1e-9)
+    with pytest.raises(AssertionError):
+        generate.generate_cameras_path_step(scene, path, 100, 0.2)        # 20 > 5: the reference's assert!
+    poisson = generate.generate_cameras_poisson(scene, 100, 1.0, 10.0, seed=21)
+    assert 30 < len(poisson) <= 200
+    on_roof = 0
+    for rec in poisson:
+        p = c2b.SnavelyCamera(record=rec).center()
+        over_cube = abs(p[0]) < 1.0 and abs(p[2]) < 1.0
+        on_roof += over_cube
+        if over_cube or abs(p[0]) > 1.6 or abs(p[2]) > 1.1:
+            assert abs(p[1] - (3.0 if over_cube else 1.0)) < 1e-5
+    assert on_roof > 0
+    assert all(c2b.SnavelyCamera(record=r).center()[2] < 0.0 for r in generate.generate_cameras_poisson(scene, 100, 1.0, 0.0, seed=22))
+    with_intr = generate.modify_intrinsics(poisson, (1.0, -0.1, 0.0), (2.0, 0.1, 0.0), seed=1)
+    assert ((with_intr[:, 12] >= 1.0) & (with_intr[:, 12] < 2.0)).all() and (with_intr[:, 14] == 0.0).all()

@@ -73,3 +73,83 @@ def test_text_format_never_uses_exponent(c2b, tmp_path):
     ba.write(tmp_path / "x.bal")
     txt = open(tmp_path / "x.bal").read()
     assert "e" not in txt.lower() and "0.0000001" in txt and "0.30000000000000004" in txt
+
+
+def _write_obj(path):
+    """quads, a pentagon, relative indices, v/vt/vn forms and a poly-line object (the shape of the reference's
+    tests/box.obj); the same text tests/cpp/test_host.cpp writes"""
+    lines = ["# test scene", "mtllib none.mtl", "o Plane", "v -4 0 -4", "v 4 0 -4", "v 4 0 4", "v -4 0 4", "vn 0 1 0",
+             "usemtl None", "s off", "f 1//1 2//1 3//1 4//1", "o Cube"]
+    for k in range(8):
+        lines.append(f"v {1 if k & 1 else -1} {2 if k & 2 else 0} {1 if k & 4 else -1}")
+    lines += ["f 5 6 8 7", "f 9 11 12 10", "f 5 9 10 6", "f 7 8 12 11", "f 5 7 11 9", "f -7 -5 -1 -3",
+              "o Roof", "v -1 2 -1", "v 1 2 -1", "v 1.5 2 0", "v 1 2 1", "v -1 2 1", "f 13 14 15 16 17", "o Curve"]
+    lines += [f"v {-3.0 + k} 0.5 3" for k in range(6)] + [f"l {18 + k} {19 + k}" for k in range(5)]
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+def _dump(models):
+    out = []
+    for m in models:
+        p = m.positions.reshape(-1).astype(np.float64)
+        ps = float((p * (1 + np.arange(len(p)) % 7)).sum())
+        s = int((m.indices.astype(np.uint64) * (1 + np.arange(len(m.indices), dtype=np.uint64) % 5)).sum())
+        out.append((m.name, len(m.positions), len(m.indices), ps, s))
+    return out
+
+
+def test_obj_loader_python_equals_cpp(c2b, tmp_path):
+    """the two host mirrors read OBJ files identically (tobj 0.1.12's rules): the hand-written scene everywhere,
+    the reference's own fixtures where /root/reference exists (build container only)"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from city2ba_b200 import generate
+    exe = str(tmp_path / "test_host")
+    so_dir = os.path.join(ROOT, "city2ba_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_host.cpp"), "-o", exe, "-L", so_dir,
+                           "-lcity2ba_cuda", f"-Wl,-rpath,{so_dir}"])
+    mine = str(tmp_path / "scene.obj")
+    _write_obj(mine)
+    files = [mine] + [f for f in ("/root/reference/tests/box.obj", "/root/reference/test_scene.obj") if os.path.exists(f)]
+    for f in files:
+        cpp = []
+        for line in subprocess.check_output([exe, "obj", f], text=True).splitlines():
+            name, nv, ni, ps, s = line.split("|")
+            cpp.append((name, int(nv), int(ni), float(ps), int(s)))
+        py = _dump(generate.load_obj(f))
+        assert [(a[0], a[1], a[2], a[4]) for a in py] == [(a[0], a[1], a[2], a[4]) for a in cpp], f
+        assert np.allclose([a[3] for a in py], [a[3] for a in cpp], rtol=1e-8), f
+    models = generate.load_obj(mine)
+    assert [m.name for m in models] == ["Plane", "Cube", "Roof", "Curve"]
+    assert list(models[2].indices) == [0, 1, 2, 0, 2, 3, 0, 3, 4]               # fan
+    assert list(models[3].indices) == [0, 1, 1, 2, 2, 3, 3, 4, 4, 5]            # `l` records: index pairs
+    xyz, tri = generate.concat_models(models)
+    assert xyz.shape == (23, 3) and tri.shape == (20, 3)
+    assert generate.move_to_origin(models)[1].positions.min() >= 0.0
+    import pytest
+    with pytest.raises(c2b.baproblem.IOError_):
+        generate.load_obj(str(tmp_path / "missing.obj"))
+
+
+def test_graph_noise_python_mirror(c2b, orc):
+    """src/noise.rs:180-378 through the Python mirror: the reference's library properties (tests/main.rs:155-190)
+    on a problem whose projections are exact"""
+    from city2ba_b200 import noise
+    ba = _problem(orc, c2b).cull()
+    e0 = ba.total_reprojection_error(2.0)
+    n_obs = ba.vis_graph.num_observations
+    mis = noise.add_incorrect_correspondences(ba, 0.01, seed=4)
+    assert mis.vis_graph.num_observations == n_obs and mis.total_reprojection_error(2.0) > e0
+    assert np.array_equal(np.sort(mis.vis_graph.point_idx), np.sort(ba.vis_graph.point_idx))
+    dropped = noise.drop_features(ba, 0.1, seed=5)
+    assert np.array_equal(dropped.vis_graph.counts(), (ba.vis_graph.counts() * 0.1).astype(np.int64))
+    assert dropped.total_reprojection_error(2.0) >= e0 - 1e-9
+    split = noise.split_landmarks(ba, 0.1, seed=6)
+    assert split.num_points() == ba.num_points() + int(0.1 * ba.num_points())
+    assert split.total_reprojection_error(2.0) >= e0 - 1e-9 and abs(split.total_reprojection_error(2.0) - e0) < 1e-9
+    assert (split.vis_graph.point_idx >= ba.num_points()).sum() > 0
+    joined = noise.join_landmarks(ba, 0.01, seed=7)
+    changed = joined.vis_graph.point_idx != ba.vis_graph.point_idx
+    assert 0 < changed.sum() <= int(0.01 * ba.num_points()) and joined.total_reprojection_error(2.0) > e0
