@@ -14,6 +14,16 @@ from conftest import ROOT
 CLI = os.path.join(ROOT, "city2ba_b200", "bin", "city2ba")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _cli_binary():
+    """built by __graft_entry__.build(); rebuilt here (g++ only) if it is missing or older than its sources"""
+    import sys
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    assert os.path.exists(entry.SO), "libcity2ba_cuda.so is missing: run __graft_entry__.build()"
+    entry.build_cli()
+
+
 def run(*args):
     return subprocess.run([CLI, *map(str, args)], capture_output=True, text=True, timeout=600)
 
