@@ -133,6 +133,9 @@ int c2b_init(int device, c2b_ctx **out) {
   C2B_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (int i = 0; i < EV_COUNT; ++i) C2B_CUDA(cudaEventCreate(&ctx->ev[i]));
   C2B_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  C2B_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
     C2B_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -164,6 +167,7 @@ void c2b_shutdown(c2b_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   DevBuf *bufs[] = {&ctx->cams, &ctx->cam_center, &ctx->pts, &ctx->stage, &ctx->cell_of_pt,
                     &ctx->cell_start, &ctx->cell_cursor, &ctx->grid_x, &ctx->grid_y, &ctx->grid_z,
                     &ctx->grid_idx, &ctx->pool_key, &ctx->pool_uv, &ctx->cam_count, &ctx->counters,
@@ -183,6 +187,9 @@ void c2b_shutdown(c2b_ctx *ctx) {
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   auto &v = extras();
   for (size_t i = 0; i < v.size(); ++i)
@@ -540,10 +547,10 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   uint32_t *d_max = ctx->counters.as<uint32_t>() + 13;    // bytes 52..55
   unsigned long long h_cnt[8];
 
-  // plan: row points per camera -> scratch slices
-  k_cam_plan<<<blocks_for(C + 1, 128), 128, 0, st>>>(fa);
-  C2B_KERNEL_CHECK();
-  C2B_TRY(exclusive_scan_u32(st, fa.ev_count, fa.ev_count, slots + 1, nullptr, ctx->scan_tmp));
+  // Per-camera leaf lists (cameras + BVH only) and the plan (cameras + point grid only) are independent and
+  // each too small to fill the GPU (one thread or warp per camera, latency-bound): the lists run on a
+  // second stream beside the plan and its scan, and the main stream joins before the counters are read.
+  cudaStream_t ax = ctx->aux_stream;
   if (mesh) {
     uint32_t trilist_cap = 128;
     if (const char *e = getenv("C2B_TRILIST_CAP")) trilist_cap = (uint32_t)std::max(1, atoi(e));
@@ -562,16 +569,24 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     fa.packet_bvh = getenv("C2B_NO_PACKET_BVH") == nullptr;
     if (const char *e = getenv("C2B_HOIST_MAX")) fa.hoist_max = (uint32_t)std::min(std::max(0, atoi(e)), FU_HOIST);
     const bool tl_warp = getenv("C2B_TRILIST_WARP") ? atoi(getenv("C2B_TRILIST_WARP")) != 0 : C < 32768;  // env: test hook
+    C2B_CUDA(cudaEventRecord(ctx->ev_fork, st));  // after the counter reset and the camera upload
+    C2B_CUDA(cudaStreamWaitEvent(ax, ctx->ev_fork, 0));
     if (tl_warp)
-      k_cam_trilist_warp<<<blocks_for(C, TL_WARPS), TL_WARPS * 32, 0, st>>>(
+      k_cam_trilist_warp<<<blocks_for(C, TL_WARPS), TL_WARPS * 32, 0, ax>>>(
           fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax, fa.scene_absmax, trilist_cap,
           ctx->tri_list.as<uint32_t>(), ctx->tri_count.as<uint32_t>(), fa.counters + 0);
     else
-      k_cam_trilist<<<blocks_for(C, 128), 128, 0, st>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
+      k_cam_trilist<<<blocks_for(C, 128), 128, 0, ax>>>(fa.nodes, fa.n_nodes, fa.cen_x, fa.cen_y, fa.cen_z, C, rmax,
                                                        fa.scene_absmax, trilist_cap, ctx->tri_list.as<uint32_t>(),
                                                        ctx->tri_count.as<uint32_t>(), fa.counters + 0);
     C2B_KERNEL_CHECK();
+    C2B_CUDA(cudaEventRecord(ctx->ev_join, ax));
   }
+  // plan: row points per camera -> scratch slices
+  k_cam_plan<<<blocks_for(C + 1, 128), 128, 0, st>>>(fa);
+  C2B_KERNEL_CHECK();
+  C2B_TRY(exclusive_scan_u32(st, fa.ev_count, fa.ev_count, slots + 1, nullptr, ctx->scan_tmp));
+  if (mesh) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
   C2B_TRY(read_counters(ctx, h_cnt));
   pairs_eval = h_cnt[1];
   const bool any_overflow = h_cnt[0] != 0;  // cameras whose leaf list exceeded the cap

@@ -209,6 +209,8 @@ struct c2b_ctx {
   int out_sel = 0;
   uint64_t out_C = 0, out_O = 0;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;  // leaf lists beside the plan (visibility_grid_fused)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_ready[2] = {}, ev_copied[2] = {};
   c2b::DevBuf misc;  // small scratch (reductions)
   c2b::DevBuf tri_list, tri_count;  // per-camera leaf lists for list-driven traversal
