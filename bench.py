@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py — camera x point visibility tests/s on a synthetic city grid (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg4|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg4|cfg5]
                     [--cull-mode grid|exhaustive] [--impl reference]
 
-One "step" = one pass of the hot path (c2b_visibility_graph: cull -> sort -> BVH traversal ->
-compaction) over the whole workload; cameras are sharded across ranks (contiguous ranges, the
-mesh, BVH and points replicated), so total work is fixed as N grows ("strong" scaling on the
-named configuration).  Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path (c2b_visibility_graph: point grid -> plan -> fused cull + occlusion ->
+sort + write) over the whole workload; cameras are sharded across GPUs (contiguous ranges, the mesh, BVH and
+points replicated), so total work is fixed as N grows ("strong" scaling on the named configuration).  Prints
+ONE JSON line on rank 0.
 
-  value : C*P / t with inputs resident in HBM, t = device time of the step (CUDA events on the
-          library's stream), max over ranks.
-  e2e   : the same metric through the host-buffer C-ABI call (pinned host inputs copied H2D and
-          the CSR result copied D2H inside the timed region, wall clock around the call).
-  --impl reference : the reference's algorithm on the box's host cores (the oracle's OpenMP +
-          CPU-BVH arm; the Rust/Embree reference cannot be built in this image), on a bounded
-          camera sample of the same workload.
+  value : C*P / t with inputs resident in HBM, t = device time of the step (CUDA events on the library's
+          stream), max over ranks.  The point grid is derived data (it depends on max_dist), so it is dropped
+          before every timed step and its build is inside t; `value_cached_grid` is the same with the grid
+          kept between calls.
+  e2e   : the same metric through the host-buffer C-ABI call, wall clock around the call: pinned host inputs
+          copied H2D and the CSR result copied D2H inside the timed region.  N = 1: c2b_visibility_graph.
+          N > 1: rank 0 drives all N GPUs through the library's own multi-GPU entry
+          (c2b_visibility_graph_multi: per-GPU point shards + NCCL all-gather, one NCCL all-gather of the
+          per-GPU counts, every GPU writes its slab into ONE pinned host CSR); the clock stops when that CSR
+          is complete.  `e2e_pageable`: the same with pageable (numpy) inputs; `e2e_cold`: first call on a
+          fresh ctx (every device and pinned buffer allocated inside the call).
+  parity: rows of an evenly spaced camera sample of the e2e result compared bit for bit with the oracle's CPU
+          arm (the cpu_baseline sample at N = 1); result_hash: order-sensitive 64-bit hash of the whole CSR,
+          independent of N, checked against tests/golden/result_hashes.json.
+  --impl reference : the reference's algorithm on the box's host cores (the oracle's OpenMP + CPU-BVH arm,
+          built -O3 -march=native on the box; the Rust/Embree reference cannot be built in this image), on a
+          bounded camera sample of the same workload.
 """
 from __future__ import annotations
 
@@ -45,6 +55,7 @@ WORKLOADS = {
 TESS_K = 11
 MAX_DIST = 10.0
 BLOCK_LENGTH, BLOCK_INSET, CAM_H, PT_H, BUILDING_H = 20.0, 1.0, 1.0, 1.0, 10.0
+HASHES = os.path.join(ROOT, "tests", "golden", "result_hashes.json")
 
 
 def measured_peaks():
@@ -116,17 +127,40 @@ class ClockSampler:
         return out
 
 
-def build_workload(name):
-    from city2ba_b200 import synthetic
+def city_mesh_tessellated(n, k):
+    # plain numpy (no library call): city2ba_b200.synthetic imports without mapping the CUDA library
+    from city2ba_b200.synthetic import city_mesh_tessellated as f
+    return f(n, k, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)
+
+
+def build_workload(name, gen="product"):
+    """(cameras, points, xyz, tri) of a BASELINE config.  gen = "product": the library's host generators
+    (c2b_grid_*); gen = "oracle": the oracle's own (the reference arm never maps the CUDA library; the two
+    are checked equal in tests/test_host_mirror.py)."""
     n, cpb, ppb = WORKLOADS[name]
-    cams = synthetic.grid_cameras(cpb, n, BLOCK_LENGTH, CAM_H)
+    if gen == "oracle":
+        from oracle import oracle as g
+        cams = g.grid_cameras(cpb, n, BLOCK_LENGTH, CAM_H)
+        lattice = lambda: g.grid_points(ppb, n, BLOCK_LENGTH, BLOCK_INSET, PT_H)  # noqa: E731
+        box_mesh = lambda: g.city_mesh(n, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)  # noqa: E731
+    else:
+        from city2ba_b200 import synthetic as g
+        cams = g.grid_cameras(cpb, n, BLOCK_LENGTH, CAM_H)
+        lattice = lambda: g.grid_points(ppb, n, BLOCK_LENGTH, BLOCK_INSET, PT_H)  # noqa: E731
+        box_mesh = lambda: g.city_mesh(n, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)  # noqa: E731
     if name.startswith("cfg5"):
-        xyz, tri = synthetic.city_mesh_tessellated(n, TESS_K, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)
-        pts = sample_points_on_walls(xyz, tri, int(synthetic.lib().c2b_grid_num_points(ppb, n)))
+        xyz, tri = city_mesh_tessellated(n, TESS_K)
+        pts = sample_points_on_walls(xyz, tri, 12 * ppb * n * (n + 1))
         return cams, pts, xyz, tri
-    pts = synthetic.grid_points(ppb, n, BLOCK_LENGTH, BLOCK_INSET, PT_H)
-    xyz, tri = synthetic.city_mesh(n, BLOCK_LENGTH, BLOCK_INSET, BUILDING_H)
+    pts = lattice()
+    xyz, tri = box_mesh()
     return cams, pts, xyz, tri
+
+
+def describe(name, C, P):
+    n = WORKLOADS[name][0]
+    return (f"{name}: synthetic {n}x{n}-block city{', walls tessellated' if name.startswith('cfg5') else ''}, "
+            f"{C} cameras x {P} points, max_dist {MAX_DIST}")
 
 
 def sample_points_on_walls(xyz, tri, n, seed=0xC17B2A):
@@ -150,41 +184,105 @@ def shard(C, rank, world):
     return (rank * C) // world, ((rank + 1) * C) // world
 
 
-def cpu_arm(cams, pts, xyz, tri, budget_s, threads=0):
+# ---- result hash: order-sensitive inside a camera, additive over cameras (so it does not depend on how
+# the cameras were split over GPUs) ------------------------------------------------------------------------
+_K = [np.uint64(k) for k in (0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB, 0xD6E8FEB86659FD93,
+                             0xA0761D6478BD642F, 0xE7037ED1A0B428DB)]
+
+
+def result_hash(offsets, idx, uv, cam0=0, chunk=8192) -> int:
+    """64-bit hash of a CSR slab whose first camera has global index cam0: per observation a mix of (point
+    index, u bits, v bits, position in the row); per camera the wrapped sum of those, mixed with the camera's
+    global index and its count; the wrapped sum over cameras."""
+    off = np.asarray(offsets, np.int64)
+    idx = np.asarray(idx)
+    uvb = np.ascontiguousarray(uv, np.float64).reshape(-1).view(np.uint64).reshape(-1, 2)
+    C = len(off) - 1
+    total = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for a in range(0, C, chunk):
+            b = min(C, a + chunk)
+            o0, o1 = int(off[a]), int(off[b])
+            n = (off[a + 1:b + 1] - off[a:b]).astype(np.uint64)
+            cam = (np.arange(a, b, dtype=np.uint64) + np.uint64(cam0))
+            s = np.zeros(b - a, np.uint64)
+            if o1 > o0:
+                pos = (np.arange(o0, o1, dtype=np.int64) - np.repeat(off[a:b], n.astype(np.int64))).astype(np.uint64)
+                h = (idx[o0:o1].astype(np.uint64) + np.uint64(1)) * _K[0]
+                h ^= uvb[o0:o1, 0] * _K[1]
+                h ^= uvb[o0:o1, 1] * _K[2]
+                h ^= (pos + np.uint64(1)) * _K[3]
+                h ^= h >> np.uint64(29)
+                h *= _K[4]
+                h ^= h >> np.uint64(32)
+                nz = n > 0
+                s[nz] = np.add.reduceat(h, (off[a:b][nz] - o0))
+            g = (s + n * _K[5]) * (np.uint64(2) * cam + np.uint64(1))
+            g ^= g >> np.uint64(31)
+            total = total + g.sum(dtype=np.uint64)
+    return int(total)
+
+
+def expected_hash(workload):
+    try:
+        return int(json.load(open(HASHES))[workload], 16)
+    except Exception:
+        return None
+
+
+def parity_against(sample_idx, vis, offsets, idx, uv):
+    """rows `sample_idx` of the CSR (offsets, idx, uv) against the oracle graph `vis` of those cameras"""
+    off = np.asarray(offsets, np.int64)
+    rn = np.diff(vis.offsets.astype(np.int64))
+    n = off[sample_idx + 1] - off[sample_idx]
+    bad = n != rn
+    uv2 = np.asarray(uv).reshape(-1, 2)
+    for k in np.nonzero(~bad)[0]:
+        a, b = off[sample_idx[k]], off[sample_idx[k] + 1]
+        ra, rb = int(vis.offsets[k]), int(vis.offsets[k + 1])
+        if not (np.array_equal(np.asarray(idx[a:b], np.uint64), vis.point_idx[ra:rb]) and np.array_equal(uv2[a:b], vis.uv[ra:rb])):
+            bad[k] = True
+    return {"cameras_checked": int(len(sample_idx)), "observations_checked": int(rn.sum()),
+            "mismatches": int(bad.sum()), "against": "oracle CPU arm (orc_ref_visibility_graph), bit for bit: "
+            "row lengths, point indices, (u, v)"}
+
+
+def cpu_arm(cams, pts, xyz, tri, budget_s, threads=0, fixed_n=None):
     """Times the oracle's multithreaded CPU arm on a bounded camera sample (every k-th camera).
-    Returns (tests_per_s, cores, sample description, obs_per_s)."""
+    Returns (tests_per_s, cores, sample description, obs_per_s, sample camera indices, sample graph)."""
     from oracle import oracle as orc
     C, P = len(cams), len(pts)
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if threads <= 0:
         threads = ncores  # explicit: torchrun exports OMP_NUM_THREADS=1, which would serialise the arm
-    n = min(C, max(ncores, 8))
+    n = min(C, fixed_n if fixed_n else max(ncores, 8))
     for _ in range(4):  # grow the sample until it fills about the budget
-        idx = np.linspace(0, C - 1, n).astype(np.int64)
+        idx = np.unique(np.linspace(0, C - 1, n).astype(np.int64))
         t0 = time.perf_counter()
         v, used = orc.ref_visibility_graph(xyz, tri, cams[idx], pts, MAX_DIST, n_threads=threads)
         dt = time.perf_counter() - t0
-        if dt >= 0.5 * budget_s or n >= C:
+        if fixed_n or dt >= 0.5 * budget_s or n >= C:
             break
         n = int(min(C, max(n + used, 0.9 * n * budget_s / max(dt, 1e-6))))
         n = max(used, (n // used) * used)
-    return n * P / dt, used, f"{n} of {C} cameras (evenly spaced) x all {P} points, {dt:.1f} s", v.n_obs / dt
+    return (len(idx) * P / dt, used, f"{len(idx)} of {C} cameras (evenly spaced) x all {P} points, {dt:.1f} s",
+            v.n_obs / dt, idx, v)
 
 
 def run_reference(args):
-    """--impl reference: the CPU arm, rank 0 only."""
+    """--impl reference: the CPU arm, rank 0 only.  Inputs from the oracle's own generators: this process
+    never maps libcity2ba_cuda.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    orc.build()
-    cams, pts, xyz, tri = build_workload(args.workload)
+    os.environ["C2B_ORACLE_NATIVE"] = "1"
+    cams, pts, xyz, tri = build_workload(args.workload, gen="oracle")
     C, P = len(cams), len(pts)
     budget = 8.0
     vals, obs = [], []
     cores, sample = 1, ""
     for s in range(args.warmup + args.steps):
-        v, cores, sample, o = cpu_arm(cams, pts, xyz, tri, budget)
+        v, cores, sample, o, _, _ = cpu_arm(cams, pts, xyz, tri, budget)
         if s >= args.warmup:
             vals.append(v)
             obs.append(o)
@@ -194,13 +292,11 @@ def run_reference(args):
         "unit": "tests/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * C * P / value, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: synthetic {WORKLOADS[args.workload][0]}x"
-                               f"{WORKLOADS[args.workload][0]}-block city{', walls tessellated' if args.workload.startswith('cfg5') else ''}, "
-                               f"{C} cameras x {P} points, max_dist {MAX_DIST}", "cameras": C, "points": P,
+        "config": {"workload": describe(args.workload, C, P), "cameras": C, "points": P,
                    "triangles": int(len(tri)), "note": "reference binary (Rust + Embree 3.8) cannot be "
                    "built here; this is the oracle's C restatement of its algorithm: OpenMP over "
-                   "cameras, brute-force point loop, CPU BVH any-hit; ms_per_step extrapolates the "
-                   "sample to the whole workload"},
+                   "cameras, brute-force point loop, CPU BVH any-hit, compiled -O3 -march=native on this box; "
+                   "ms_per_step extrapolates the sample to the whole workload"},
         "observations_per_s": float(np.mean(obs)),
         "cpu_baseline": {"value": value, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,15 +316,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exhaustive", action="store_true")
     ap.add_argument("--no-noise", action="store_true")
-    ap.add_argument("--replicate-points", action="store_true",
-                    help="N > 1: every rank uploads all points itself instead of 1/N + NCCL all-gather")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / cfg5 lines of the default run")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e_pageable / e2e_cold")
     args = ap.parse_args()
+    default_run = args.workload is None
     if args.workload is None:
         # the metric's target is quoted on the 64x64-block city (cfg4); it fits one GPU
         args.workload = "cfg4"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    os.environ["C2B_ORACLE_NATIVE"] = "1"  # the CPU arm below is built -O3 -march=native on this box
+
+    import ctypes as Ct
 
     import torch
     import torch.distributed as dist
@@ -243,21 +343,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not occupy a GPU
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = c2b.context(local)
     L = _lib.lib()
-
-    cams, pts, xyz, tri = build_workload(args.workload)
-    C, P = len(cams), len(pts)
-    c0, c1 = shard(C, rank, world)
-    my_cams = torch.from_numpy(np.ascontiguousarray(cams[c0:c1])).pin_memory()
-    pin_pts = torch.from_numpy(pts).pin_memory()
-    Cr = c1 - c0
-    scene = c2b.Scene(xyz, tri, ctx=ctx)
-    rp = ResidentProblem(ctx)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    K = args.steps
 
     def barrier():
         if world > 1:
@@ -268,89 +361,199 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ("value") -------------------------------------------------------
-    def resident_arm(mode, steps, warmup, count=False):
-        rp.upload_points_ptr(pin_pts.data_ptr(), P)
-        rp.upload_cameras_ptr(my_cams.data_ptr(), Cr)
-        torch.cuda.synchronize()
-        st = None
-        tot = {k: 0.0 for k in ("ms_total", "ms_prep", "ms_cull", "ms_sort", "ms_traverse", "ms_compact")}
-        for s in range(warmup + steps):
-            if s == warmup:
-                barrier()
-            flush_l2()
-            st = rp.run(scene, MAX_DIST, cull_mode=mode, count_traversal=count)
-            if s >= warmup:
-                for k in tot:
-                    tot[k] += st[k]
-        barrier()
-        return tot, st
+    def rmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
+    def rsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    STAGES = ("ms_total", "ms_prep", "ms_cull", "ms_sort", "ms_traverse", "ms_compact")
+
+    class Problem:
+        """one workload on this rank: pinned host copies, the scene, the resident problem"""
+
+        def __init__(self, name):
+            self.name = name
+            self.cams, self.pts, self.xyz, self.tri = build_workload(name)
+            self.C, self.P = len(self.cams), len(self.pts)
+            self.c0, self.c1 = shard(self.C, rank, world)
+            self.pin_cams = torch.from_numpy(np.ascontiguousarray(self.cams)).pin_memory()
+            self.pin_pts = torch.from_numpy(self.pts).pin_memory()
+            t0 = time.perf_counter()
+            self.scene = c2b.Scene(self.xyz, self.tri, ctx=ctx)
+            self.scene_build_ms = 1e3 * (time.perf_counter() - t0)
+            self.rp = ResidentProblem(ctx)
+            self.opt = _options(args.cull_mode, "mesh", False, False, BLOCK_LENGTH, BLOCK_INSET)
+
+        def upload(self):
+            self.rp.upload_points_ptr(self.pin_pts.data_ptr(), self.P)
+            self.rp.upload_cameras_ptr(self.pin_cams.data_ptr() + 120 * self.c0, self.c1 - self.c0)
+            torch.cuda.synchronize()
+
+        def resident(self, mode, steps, warmup, count=False, drop_grid=True):
+            """device-resident arm: (sum of stage ms over the timed steps, stats of the last step)"""
+            self.upload()
+            st = None
+            tot = {k: 0.0 for k in STAGES}
+            for s in range(warmup + steps):
+                if s == warmup:
+                    barrier()
+                flush_l2()
+                if drop_grid:
+                    _lib.check(L.c2b_drop_point_grid(ctx.handle))
+                st = self.rp.run(self.scene, MAX_DIST, cull_mode=mode, count_traversal=count)
+                if s >= warmup:
+                    for k in tot:
+                        tot[k] += st[k]
+            barrier()
+            return tot, st
+
+        def e2e_single(self, steps, warmup, cams_ptr, pts_ptr, the_ctx=None):
+            """host buffers -> c2b_visibility_graph -> host CSR on this rank's GPU; wall seconds over `steps`"""
+            h = (the_ctx or ctx).handle
+            out = _lib.Obs()
+            t = 0.0
+            for s in range(warmup + steps):
+                flush_l2()
+                t0 = time.perf_counter()
+                _lib.check(L.c2b_visibility_graph(h, self.scene.handle, cams_ptr, self.C, pts_ptr, self.P, MAX_DIST,
+                                                  Ct.byref(self.opt), Ct.byref(out)))
+                dt = time.perf_counter() - t0
+                if s >= warmup:
+                    t += dt
+            return t, out
+
+    prob = Problem(args.workload)
+    C, P = prob.C, prob.P
+
+    # ---- device-resident arm ("value") ----------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.c2b_kernel_launches()
-    tot, st = resident_arm(args.cull_mode, args.steps, args.warmup)
+    tot, st = prob.resident(args.cull_mode, K, args.warmup)
     launches = L.c2b_kernel_launches() - launches0
-    launches_per_step = launches // (args.steps + args.warmup)
+    launches_per_step = launches // (K + args.warmup)
     t_dev = tot["ms_total"] / 1e3
+    tot_cached, _ = prob.resident(args.cull_mode, K, 1, drop_grid=False)
 
-    # ---- end-to-end arm: host buffers -> C-ABI call -> host CSR ------------------------------------
-    opt = _options(args.cull_mode, "mesh", False, False, BLOCK_LENGTH, BLOCK_INSET)
-    import ctypes as Ct
-    out = _lib.Obs()
-    e2e_t = 0.0
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    mine = torch.zeros(1, dtype=torch.int64, device=dev)
-    # N > 1: every rank uploads 1/N of the points over its own PCIe link and the shards are
-    # all-gathered over NVLink (NCCL) instead of N full uploads — the path's point exchange.
-    # (world == 1: the plain host-pointer call.)
-    shard_pts = world > 1 and not args.replicate_points
-    if shard_pts:
-        per = -(-P // world)
-        lo_p, hi_p = min(P, rank * per), min(P, (rank + 1) * per)
-        pin_shard = torch.zeros(per * 3, dtype=torch.float64).pin_memory()
-        pin_shard[:(hi_p - lo_p) * 3] = torch.from_numpy(pts[lo_p:hi_p].reshape(-1))
-        d_shard = torch.empty(per * 3, dtype=torch.float64, device=dev)
-        d_full = torch.empty(world * per * 3, dtype=torch.float64, device=dev)
-    h2d_pts = 0
-    for s in range(args.warmup + args.steps):
-        if s == args.warmup:
-            barrier()
-        flush_l2()
-        t0 = time.perf_counter()
-        if shard_pts:
-            d_shard.copy_(pin_shard, non_blocking=True)
-            dist.all_gather_into_tensor(d_full, d_shard)
-            torch.cuda.synchronize()
-            _lib.check(L.c2b_upload_points_device(ctx.handle, d_full.data_ptr(), P))
-            h2d_pts = per * 24
-            _lib.check(L.c2b_visibility_graph(ctx.handle, scene.handle, my_cams.data_ptr(), Cr,
-                                              None, P, MAX_DIST, Ct.byref(opt), Ct.byref(out)))
-        else:
-            _lib.check(L.c2b_visibility_graph(ctx.handle, scene.handle, my_cams.data_ptr(), Cr,
-                                              pin_pts.data_ptr(), P, MAX_DIST, Ct.byref(opt), Ct.byref(out)))
-        if world > 1:
-            # per-rank observation counts -> global CSR offsets
-            mine[0] = int(out.n_obs)
-            dist.all_gather_into_tensor(counts, mine)
-            counts_host = counts.cpu()
-        dt = time.perf_counter() - t0
-        if s >= args.warmup:
-            e2e_t += dt
-    barrier()
+    # ---- end-to-end arm: host buffers -> C-ABI call -> ONE host CSR ------------------------------------------
+    mctx = mscene = None
+    multi_stats = None
+    if world == 1:
+        e2e_t, out = prob.e2e_single(K, args.warmup, prob.pin_cams.data_ptr(), prob.pin_pts.data_ptr())
+    else:
+        out = _lib.Obs()
+        e2e_t = 0.0
+        barrier()
+        if rank == 0:
+            # the library's multi-GPU entry: this process drives all `world` GPUs (the other ranks wait at the
+            # barrier below with their GPUs idle)
+            mctx = c2b.MultiContext(world)
+            mscene = c2b.MultiScene(prob.xyz, prob.tri, mctx)
+            ms = _lib.MultiStats()
+            for s in range(args.warmup + K):
+                flush_l2()
+                t0 = time.perf_counter()
+                _lib.check(L.c2b_visibility_graph_multi(mctx.handle, mscene.handle, prob.pin_cams.data_ptr(), C,
+                                                        prob.pin_pts.data_ptr(), P, MAX_DIST, Ct.byref(prob.opt),
+                                                        Ct.byref(out), Ct.byref(ms)))
+                dt = time.perf_counter() - t0
+                if s >= args.warmup:
+                    e2e_t += dt
+            multi_stats = {k: [round(float(getattr(ms, k)[g]), 4) for g in range(world)]
+                           for k in ("ms_points", "ms_compute", "ms_exchange", "ms_d2h")}
+            multi_stats["n_obs"] = [int(ms.n_obs[g]) for g in range(world)]
+            multi_stats["ms_wall_last_step"] = float(ms.ms_wall)
+        # a CPU barrier: an NCCL one would park a spinning kernel on GPUs 1..N-1 while rank 0 is timing them
+        dist.barrier(group=cpu_group)
     clocks = sampler.stop() if sampler else None
-    h2d, d2h = int(out.h2d_bytes) + h2d_pts, int(out.d2h_bytes)
-    n_obs_local = int(out.n_obs)
+
+    csr = None
+    res_hash = None
+    if rank == 0:
+        O = int(out.n_obs)
+        csr = (np.ctypeslib.as_array(out.offsets, shape=(C + 1,)).copy(),
+               np.ctypeslib.as_array(out.point_idx, shape=(max(O, 1),))[:O].copy(),
+               np.ctypeslib.as_array(out.uv, shape=(max(2 * O, 1),))[:2 * O].copy())
+        res_hash = result_hash(*csr)
+    h2d, d2h = int(out.h2d_bytes), int(out.d2h_bytes)
+    n_obs_e2e = int(out.n_obs)
     e2e_stage = {k: float(getattr(out, k)) for k in ("ms_h2d", "ms_prep", "ms_cull", "ms_sort", "ms_traverse", "ms_compact", "ms_d2h")}
+
+    # ---- e2e with pageable inputs, and the first call on a fresh ctx (rank 0) ---------------------------------
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        pg_cams, pg_pts = np.array(prob.cams, copy=True), np.array(prob.pts, copy=True)  # plain numpy = pageable
+        steps_pg = max(3, K // 2)
+        if world == 1:
+            t_pg, o2 = prob.e2e_single(steps_pg, 1, pg_cams.ctypes.data, pg_pts.ctypes.data)
+            ms_h2d_pg = float(o2.ms_h2d)
+            ctx.tune("stage_threads", 0)
+            t_drv, o3 = prob.e2e_single(steps_pg, 1, pg_cams.ctypes.data, pg_pts.ctypes.data)
+            ctx.tune("reset", 0)
+            ms_h2d_drv = float(o3.ms_h2d)
+        else:
+            o2 = _lib.Obs()
+            def multi_pageable(n):
+                t = 0.0
+                for s in range(1 + n):
+                    flush_l2()
+                    t0 = time.perf_counter()
+                    _lib.check(L.c2b_visibility_graph_multi(mctx.handle, mscene.handle, pg_cams.ctypes.data, C,
+                                                            pg_pts.ctypes.data, P, MAX_DIST, Ct.byref(prob.opt),
+                                                            Ct.byref(o2), None))
+                    if s >= 1:
+                        t += time.perf_counter() - t0
+                return t
+            t_pg = multi_pageable(steps_pg)
+            ms_h2d_pg = float(o2.ms_h2d)
+            mctx.tune("stage_threads", 0)
+            t_drv = multi_pageable(steps_pg)
+            mctx.tune("reset", 0)
+            ms_h2d_drv = float(o2.ms_h2d)
+        extras["e2e_pageable"] = {
+            "value": C * P * steps_pg / t_pg, "unit": "tests/s", "ms_per_step": 1e3 * t_pg / steps_pg, "steps": steps_pg,
+            "ms_h2d": ms_h2d_pg,
+            "driver_staged": {"ms_per_step": 1e3 * t_drv / steps_pg, "ms_h2d": ms_h2d_drv,
+                              "note": "stage_threads = 0: cudaMemcpyAsync straight from the pageable arrays"},
+            "note": "caller arrays are plain numpy (pageable), what a Rust Vec's as_ptr() is; the library stages "
+                    "them through its pinned ring with 4 host threads; results land in the library's pinned CSR"}
+        if world == 1:
+            cold = _lib.Context(local)
+            t0 = time.perf_counter()
+            cold_scene = c2b.Scene(prob.xyz, prob.tri, ctx=cold)
+            t_scene = time.perf_counter() - t0
+            o4 = _lib.Obs()
+            t0 = time.perf_counter()
+            _lib.check(L.c2b_visibility_graph(cold.handle, cold_scene.handle, pg_cams.ctypes.data, C, pg_pts.ctypes.data, P,
+                                              MAX_DIST, Ct.byref(prob.opt), Ct.byref(o4)))
+            t_cold = time.perf_counter() - t0
+            extras["e2e_cold"] = {
+                "value": C * P / t_cold, "unit": "tests/s", "ms": 1e3 * t_cold, "scene_build_ms": 1e3 * t_scene,
+                "note": "first call on a fresh c2b_ctx with pageable inputs: every device buffer and the pinned "
+                        "result arrays are allocated inside the call (the CUDA primary context already exists)"}
+            cold_scene.close()
+            cold.close()
+    if mctx is not None:
+        mscene.close()
+        mctx.close()
 
     # ---- noise pass on the generated problem (config 2 / 5: drift + Gaussian noise), rank 0 only ------
     noise = None
     if not args.no_noise and rank == 0:
-        O = int(out.n_obs)
+        O = n_obs_e2e
         pd_ = Ct.POINTER(Ct.c_double)
         # pinned host arrays (what a host program that cares about transfer time would hand over)
-        t_uv = torch.from_numpy(np.ctypeslib.as_array(out.uv, shape=(2 * O,)).copy() if O else np.zeros(0)).pin_memory()
-        t_cam = torch.from_numpy(np.ascontiguousarray(cams[c0:c1]).copy()).pin_memory()
-        t_pts = torch.from_numpy(pts.copy()).pin_memory()
+        t_uv = torch.from_numpy(csr[2].copy() if O else np.zeros(0)).pin_memory()
+        t_cam = torch.from_numpy(np.ascontiguousarray(prob.cams).copy()).pin_memory()
+        t_pts = torch.from_numpy(prob.pts.copy()).pin_memory()
         uv, ncam, npts = t_uv.numpy(), t_cam.numpy(), t_pts.numpy()
         ms3 = (Ct.c_float * 3)()
         noise = {}
@@ -377,35 +580,21 @@ def main():
                                    "ms_kernels = statistics reductions + elementwise kernels (CUDA events)"}
 
     # ---- traversal counters (one untimed instrumented run) and the exhaustive arm ------------------
-    _, stc = resident_arm(args.cull_mode, 1, 0, count=True)
+    _, stc = prob.resident(args.cull_mode, 1, 0, count=True)
     ex = None
     if not args.no_exhaustive and args.cull_mode == "grid":
         ex_steps = 2 if C * P > 2e11 else 5
-        ex_tot, ex_st = resident_arm("exhaustive", ex_steps, 1)
+        ex_tot, ex_st = prob.resident("exhaustive", ex_steps, 1)
         ex = (ex_tot, ex_st, ex_steps)
 
     # ---- reduce over ranks (max time, summed work) -----------------------------------------------------
-    def rmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def rsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     t_dev_max = rmax(t_dev)
+    t_cached_max = rmax(tot_cached["ms_total"] / 1e3)
     e2e_max = rmax(e2e_t)
-    n_obs = rsum(float(n_obs_local))
+    n_obs = rsum(float(st["n_obs"]))
     n_cand = rsum(float(st["n_candidates"]))
     pairs_eval = rsum(float(st["pairs_evaluated"]))
-    h2d_all, d2h_all = rsum(float(h2d)), rsum(float(d2h))
-    stage_ms = {k: rmax(tot[k] / args.steps) for k in tot}
+    stage_ms = {k: rmax(tot[k] / K) for k in tot}
     nodes = rsum(float(stc["nodes_visited"]))
     tris_t = rsum(float(stc["tris_tested"]))
     if ex is not None:
@@ -417,8 +606,24 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- parity of the e2e result against the oracle's CPU arm (and the CPU baseline at N = 1) ----------------
+    cpu_line = None
+    parity = None
+    if not args.no_cpu_baseline:
+        if world == 1:
+            v, cores, sample, _, sidx, svis = cpu_arm(prob.cams, prob.pts, prob.xyz, prob.tri, 12.0)
+            cpu_line = {"value": v, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample,
+                        "build": "-O3 -march=native -fopenmp, on this box"}
+        else:
+            _, _, _, _, sidx, svis = cpu_arm(prob.cams, prob.pts, prob.xyz, prob.tri, 0.0, fixed_n=8 * world)
+        parity = parity_against(sidx, svis, *csr)
+    exp = expected_hash(args.workload)
+    hash_line = {"value": f"0x{res_hash:016x}", "expected": f"0x{exp:016x}" if exp is not None else None,
+                 "ok": (res_hash == exp) if exp is not None else None, "observations": n_obs_e2e,
+                 "note": "order-sensitive hash of the ONE host CSR the e2e call returned; additive over cameras, so "
+                         "the same at every N; expected = tests/golden/result_hashes.json (the N = 1 result)"}
+
     peak, peak_kind = measured_peaks()
-    K = args.steps
     value = C * P * K / t_dev_max
     e2e_value = C * P * K / e2e_max
     # algorithmic bytes per stage (DESIGN.md "roofline bookkeeping"), whole job, per step
@@ -440,15 +645,18 @@ def main():
         b_trav = 56.0 * n_cand + 32.0 * nodes + 48.0 * tris_t + 4.0 * n_words
         b_sort = 24.0 * n_cand * max(1, -(-(int(np.ceil(np.log2(max(C // world, 2)))) + int(np.ceil(np.log2(P)))) // 8))
         b_comp = 12.0 * n_cand + 8.0 * n_words + 24.0 * n_obs * 2 + 8.0 * (C + 1)
+    b_prep = 24.0 * P * 2 + 28.0 * P + 8.0 * P  # grid build: SoA points read twice (count, fill), grid copy written, cell ids
     stages = {
+        "prep": (b_prep * world, stage_ms["ms_prep"]),
         "cull": (b_cull, stage_ms["ms_cull"]), "sort": (b_sort, stage_ms["ms_sort"]),
         "traverse": (b_trav, stage_ms["ms_traverse"]), "compact": (b_comp, stage_ms["ms_compact"]),
     }
     dom = max(stages, key=lambda k: stages[k][1])
     ach = stages[dom][0] / (stages[dom][1] * 1e-3) / 1e9 if stages[dom][1] > 0 else 0.0
-    kernel_of = ({"cull": "k_cam_plan + k_cam_trilist", "traverse": "k_visibility_fused (cull + ray build + occlusion)",
+    kernel_of = ({"prep": "k_grid_count + k_grid_fill", "cull": "k_cam_plan + k_cam_trilist",
+                  "traverse": "k_visibility_fused (cull + ray build + occlusion)",
                   "compact": "k_sort_write", "sort": "-"} if args.cull_mode == "grid" else
-                 {"cull": "k_cull_exhaustive", "sort": "k_rs_scatter (radix sort)", "traverse": "k_traverse",
+                 {"prep": "-", "cull": "k_cull_exhaustive", "sort": "k_rs_scatter (radix sort)", "traverse": "k_traverse",
                   "compact": "k_compact_write"})
     traffic, traffic_src = ncu_traffic(dom, args.workload, args.cull_mode)
     line = {
@@ -457,21 +665,24 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: synthetic {WORKLOADS[args.workload][0]}x"
-                        f"{WORKLOADS[args.workload][0]}-block city{', walls tessellated' if args.workload.startswith('cfg5') else ''}, "
-                        f"{C} cameras x {P} points, max_dist {MAX_DIST}",
-            "cameras": C, "points": P, "triangles": int(len(tri)), "bvh_nodes": scene.num_nodes,
+            "workload": describe(args.workload, C, P),
+            "cameras": C, "points": P, "triangles": int(len(prob.tri)), "bvh_nodes": prob.scene.num_nodes,
             "cull_mode": args.cull_mode, "parallelism": f"camera ranges over {world} GPU(s), mesh/BVH/points replicated"
-                           + ("; e2e: points uploaded 1/N per rank + NCCL all-gather" if shard_pts else ""),
+                           + ("; e2e: one process (rank 0) drives all GPUs through c2b_visibility_graph_multi: "
+                              "points uploaded 1/N per GPU + ncclAllGather, one ncclAllGather of counts, one host CSR" if world > 1 else ""),
             "l2": "256 MB buffer written between timed steps (L2 flush)",
+            "grid": "point grid dropped before every timed step: its build is inside value",
             "candidates": int(n_cand), "observations": int(n_obs),
             "pairs_evaluated_per_step": int(pairs_eval),
         },
+        "value_cached_grid": {"value": C * P * K / t_cached_max, "ms_per_step": 1e3 * t_cached_max / K,
+                              "note": "point grid kept between calls (same points, same max_dist)"},
         "observations_per_s": n_obs * K / t_dev_max,
         "evaluated_pairs_per_s": pairs_eval * K / t_dev_max,
-        "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": int(h2d_all),
-                "d2h_bytes_per_step": int(d2h_all), "ms_per_step": 1e3 * e2e_max / K,
-                "observations_per_s": n_obs * K / e2e_max, "stage_ms_last_step_rank0": e2e_stage},
+        "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_max / K,
+                "observations_per_s": n_obs_e2e * K / e2e_max, "stage_ms_last_step": e2e_stage,
+                "inputs": "pinned host arrays", "entry": "c2b_visibility_graph" if world == 1 else "c2b_visibility_graph_multi"},
         "gpu_launches": int(launches_per_step * K),
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
         "roofline": {
@@ -488,7 +699,13 @@ def main():
                 24.0 * pairs_eval + 120.0 * C + 64.0 * nodes + 48.0 * tris_t + 24.0 * n_obs + 8.0 * (C + 1)),
         },
         "clocks": clocks,
+        "result_hash": hash_line,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if multi_stats is not None:
+        line["e2e"]["per_gpu_last_step"] = multi_stats
+    line.update(extras)
     if noise is not None:
         line["noise"] = noise
     if ex is not None:
@@ -497,17 +714,38 @@ def main():
                               "note": "every camera x point pair tested on the GPU (the reference's loop)"}
         # secondary bound: the exhaustive cull's hot loop issues 7 FP64-pipe instructions per
         # pair (3 DADD + DMUL + 2 DFMA + DSETP); the probe is a loop of independent DFMAs on the same device
-        import ctypes as _C
-        rate = _C.c_double(0.0)
-        if _lib.lib().c2b_probe_fp64(ctx.handle, _C.byref(rate)) == 0 and rate.value > 0 and ex_cull > 0:
+        rate = Ct.c_double(0.0)
+        if L.c2b_probe_fp64(ctx.handle, Ct.byref(rate)) == 0 and rate.value > 0 and ex_cull > 0:
             per_rank_pairs = C * P / world
             line["exhaustive"]["fp64_probe_dfma_per_s"] = rate.value
             line["exhaustive"]["fp64_pipe_frac"] = 7.0 * per_rank_pairs / (ex_cull * 1e-3) / rate.value
-    if not args.no_cpu_baseline and world == 1:
-        from oracle import oracle as orc
-        orc.build()
-        v, cores, sample, _ = cpu_arm(cams, pts, xyz, tri, 12.0)
-        line["cpu_baseline"] = {"value": v, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample}
+    if cpu_line is not None:
+        line["cpu_baseline"] = cpu_line
+
+    # ---- the other single-GPU configurations, briefly (default run at N = 1 only) ------------------------------
+    if default_run and world == 1 and not args.no_secondary:
+        sec = {}
+        prob.scene.close()
+        del prob
+        for name in ("cfg3", "cfg5"):
+            p2 = Problem(name)
+            t2, s2 = p2.resident(args.cull_mode, 5, 2)
+            te, o5 = p2.e2e_single(5, 2, p2.pin_cams.data_ptr(), p2.pin_pts.data_ptr())
+            O5 = int(o5.n_obs)
+            h5 = result_hash(np.ctypeslib.as_array(o5.offsets, shape=(p2.C + 1,)),
+                             np.ctypeslib.as_array(o5.point_idx, shape=(max(O5, 1),))[:O5],
+                             np.ctypeslib.as_array(o5.uv, shape=(max(2 * O5, 1),))[:2 * O5])
+            e5 = expected_hash(name)
+            sec[name] = {"workload": describe(name, p2.C, p2.P), "triangles": int(len(p2.tri)),
+                         "scene_build_ms": p2.scene_build_ms,
+                         "ms_per_step": t2["ms_total"] / 5, "value": p2.C * p2.P * 5 / (t2["ms_total"] / 1e3),
+                         "stage_ms": {k: round(t2[k] / 5, 4) for k in STAGES},
+                         "e2e_ms_per_step": 1e3 * te / 5, "e2e_value": p2.C * p2.P * 5 / te,
+                         "observations": O5, "result_hash": f"0x{h5:016x}",
+                         "result_hash_ok": (h5 == e5) if e5 is not None else None}
+            p2.scene.close()
+            del p2
+        line["secondary"] = sec
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -64,6 +64,20 @@ class Ray48(C.Structure):
     ]
 
 
+MAX_GPUS = 16
+
+
+class MultiStats(C.Structure):
+    _fields_ = [
+        ("n_gpus", C.c_int),
+        ("cam_begin", C.c_uint64 * MAX_GPUS), ("cam_end", C.c_uint64 * MAX_GPUS),
+        ("n_obs", C.c_uint64 * MAX_GPUS), ("obs_base", C.c_uint64 * MAX_GPUS),
+        ("ms_points", C.c_float * MAX_GPUS), ("ms_compute", C.c_float * MAX_GPUS),
+        ("ms_exchange", C.c_float * MAX_GPUS), ("ms_d2h", C.c_float * MAX_GPUS),
+        ("ms_wall", C.c_float),
+    ]
+
+
 CULL_GRID, CULL_EXHAUSTIVE = 0, 1
 OCC_MESH, OCC_NONE, OCC_ANALYTIC = 0, 1, 2
 
@@ -72,7 +86,10 @@ EXPORTS = [
     "c2b_init", "c2b_shutdown", "c2b_last_error", "c2b_abi_version", "c2b_kernel_launches", "c2b_probe_fp64",
     "c2b_scene_create", "c2b_scene_bounds", "c2b_scene_num_triangles", "c2b_scene_num_nodes",
     "c2b_scene_destroy", "c2b_occluded", "c2b_intersect", "c2b_intersect1", "c2b_vis_options_default",
-    "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_points_device", "c2b_upload_cameras",
+    "c2b_visibility_graph", "c2b_obs_free", "c2b_upload_points", "c2b_upload_points_device", "c2b_upload_cameras", "c2b_drop_point_grid",
+    "c2b_tune", "c2b_points_device_buffer", "c2b_points_commit", "c2b_download_obs_into",
+    "c2b_init_multi", "c2b_shutdown_multi", "c2b_multi_num_gpus", "c2b_multi_ctx", "c2b_scene_create_multi",
+    "c2b_scene_destroy_multi", "c2b_multi_scene_get", "c2b_visibility_graph_multi",
     "c2b_visibility_graph_resident", "c2b_download_obs", "c2b_reprojection_error_resident",
     "c2b_add_drift", "c2b_add_drift_normalized", "c2b_add_noise", "c2b_add_sin_noise", "c2b_noise_timing",
     "c2b_mean_std", "c2b_generate_world_points_uniform",
@@ -122,6 +139,24 @@ def lib():
     L.c2b_upload_points.argtypes = [vp, vp, u64]
     L.c2b_upload_points_device.argtypes = [vp, vp, u64]
     L.c2b_upload_cameras.argtypes = [vp, vp, u64]
+    L.c2b_drop_point_grid.argtypes = [vp]
+    L.c2b_tune.argtypes = [vp, C.c_char_p, dbl]
+    L.c2b_points_device_buffer.argtypes = [vp, u64, C.POINTER(vp)]
+    L.c2b_points_commit.argtypes = [vp, u64]
+    L.c2b_download_obs_into.argtypes = [vp, u64, vp, vp, vp, i32, pf]
+    L.c2b_init_multi.argtypes = [i32, C.POINTER(i32), C.POINTER(vp)]
+    L.c2b_shutdown_multi.argtypes = [vp]
+    L.c2b_shutdown_multi.restype = None
+    L.c2b_multi_num_gpus.argtypes = [vp]
+    L.c2b_multi_ctx.argtypes = [vp, i32]
+    L.c2b_multi_ctx.restype = vp
+    L.c2b_scene_create_multi.argtypes = [vp, pf, u64, pu32, u64, C.POINTER(vp)]
+    L.c2b_scene_destroy_multi.argtypes = [vp]
+    L.c2b_multi_scene_get.argtypes = [vp, i32]
+    L.c2b_multi_scene_get.restype = vp
+    L.c2b_scene_destroy_multi.restype = None
+    L.c2b_visibility_graph_multi.argtypes = [vp, vp, vp, u64, vp, u64, dbl, C.POINTER(VisOptions), C.POINTER(Obs),
+                                             C.POINTER(MultiStats)]
     L.c2b_visibility_graph_resident.argtypes = [vp, vp, dbl, C.POINTER(VisOptions), C.POINTER(Obs)]
     L.c2b_download_obs.argtypes = [vp, C.POINTER(Obs)]
     L.c2b_reprojection_error_resident.argtypes = [vp, dbl, pd]
@@ -174,9 +209,42 @@ class Context:
     def handle(self):
         return self._h
 
+    def tune(self, name: str, value: float):
+        """measurement / test hook (include/city2ba_cuda.h: c2b_tune); name "reset" restores the defaults"""
+        check(lib().c2b_tune(self._h, name.encode(), float(value)))
+
     def close(self):
         if self._h:
             lib().c2b_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """c2b_multi: one process driving n GPUs of one box (camera ranges, one NCCL communicator)."""
+
+    def __init__(self, n_gpus: int, devices=None):
+        self._h = C.c_void_p()
+        dev = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        check(lib().c2b_init_multi(int(n_gpus), dev, C.byref(self._h)))
+        self.n_gpus = int(n_gpus)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def tune(self, name: str, value: float):
+        for g in range(self.n_gpus):
+            check(lib().c2b_tune(lib().c2b_multi_ctx(self._h, g), name.encode(), float(value)))
+
+    def close(self):
+        if self._h:
+            lib().c2b_shutdown_multi(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -495,8 +495,17 @@ class BAProblem:
         """src/baproblem.rs:580-628 (any whitespace separates tokens)."""
         tok = open(path).read().split()
         try:
-            nc, npt, no = int(tok[0]), int(tok[1]), int(tok[2])
-            o = np.array(tok[3:3 + 4 * no], dtype=np.float64).reshape(no, 4)
+            def digits(t):  # nom's digit1: an index is digits only ("-1", "1.5", "1e3" are parse errors)
+                if not t.isdigit():
+                    raise ValueError(f"not an unsigned integer: {t!r}")
+                return int(t)
+            nc, npt, no = digits(tok[0]), digits(tok[1]), digits(tok[2])
+            if 4 * no + 9 * nc + 3 * npt > len(tok) - 3:
+                raise ValueError("header counts exceed the file")
+            ci = [digits(t) for t in tok[3:3 + 4 * no:4]]
+            pi = [digits(t) for t in tok[4:3 + 4 * no:4]]
+            ou = np.array(tok[5:3 + 4 * no:4], dtype=np.float64)
+            ov = np.array(tok[6:3 + 4 * no:4], dtype=np.float64)
             base = 3 + 4 * no
             cams9 = np.array(tok[base:base + 9 * nc], dtype=np.float64).reshape(nc, 9)
             base += 9 * nc
@@ -504,7 +513,7 @@ class BAProblem:
         except (ValueError, IndexError) as e:
             raise ParseError(str(e)) from e
         cams = np.stack([SnavelyCamera.from_vec(v).rec for v in cams9]) if nc else np.zeros((0, CAM_STRIDE))
-        return cls.new(cams, pts, [(int(r[0]), int(r[1]), r[2], r[3]) for r in o])
+        return cls.new(cams, pts, list(zip(ci, pi, ou.tolist(), ov.tolist())))
 
     @classmethod
     def from_file(cls, path):

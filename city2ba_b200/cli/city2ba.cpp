@@ -6,8 +6,11 @@
 //   noise           :188-262, :280-357
 // (`ply`, :360-445, is a visualisation dump and is not provided.)  The reference draws every random
 // number from an unseedable thread_rng(); here `--seed N` (default: from the clock) makes a run
-// repeatable.  `--device N` picks the GPU.  There is no CPU fallback: without an sm_100 GPU every
-// sub-command fails in c2b_init.
+// repeatable.  `--device N` picks the GPU, `--gpus N` (generate, synthetic, synthetic-line) shares the
+// visibility graph's cameras between GPUs device .. device+N-1 (c2b_visibility_graph_multi; same output),
+// `synthetic --occlusion mesh [--building-height H]` casts rays at the city-block box mesh instead of the
+// reference's analytic 2-D wall test.  There is no CPU fallback: without an sm_100 GPU every sub-command
+// fails in c2b_init.
 //
 // Exit status mirrors a Rust binary whose main returns Result<(), city2ba::Error>: 0, 1 with
 // `Error: ...` on stderr for an Err, 101 with a panic line for a failed precondition (assert!/panic!/
@@ -101,6 +104,13 @@ uint64_t seed_of(const Args &a) {
   return (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count() * 0x9E3779B97F4A7C15ull;
 }
 
+// --gpus N (not in the reference): GPUs device .. device+N-1 of this box share the visibility graph's cameras
+int gpus_of(const Args &a) {
+  const size_t n = a.usize("gpus");
+  if (n < 1 || n > C2B_MAX_GPUS) throw UsageError("Invalid value for '--gpus <gpus>': expected 1.." + std::to_string(C2B_MAX_GPUS));
+  return (int)n;
+}
+
 // Rust's `{:.2e}`: two decimals, bare exponent (1.23e4, 5.00e-3, 0.00e0)
 std::string sci2(double x) {
   if (std::isnan(x)) return "NaN";
@@ -117,15 +127,20 @@ int run_synthetic(int argc, char **argv) {
   const Args a(argc, argv, 2,
                {{"cameras-per-block", "10"}, {"points-per-block", "10"}, {"max-dist", "10"}, {"camera-height", "1"},
                 {"point-height", "1"}, {"block-inset", "1"}, {"block-length", "20"}, {"blocks", "5"}, {"device", "0"},
-                {"seed", "0"}},
+                {"seed", "0"}, {"gpus", "1"}, {"occlusion", "analytic"}, {"building-height", "10"}},
                {});
   if (a.positional.size() != 1) throw UsageError("The following required arguments were not provided:\n    <OUTPUT>");
   // every value is parsed (usage errors) before the GPU is touched
   const size_t cpb = a.usize("cameras-per-block"), ppb = a.usize("points-per-block"), blocks = a.usize("blocks");
   const double length = a.f64("block-length"), inset = a.f64("block-inset"), cam_h = a.f64("camera-height"),
                pt_h = a.f64("point-height"), max_dist = a.f64("max-dist");
-  const Context ctx((int)a.usize("device"));
-  const BAProblem ba = synthetic::synthetic_grid(ctx, cpb, ppb, blocks, length, inset, cam_h, pt_h, max_dist, true);
+  const std::string occ = a.values.at("occlusion");
+  if (occ != "analytic" && occ != "mesh")
+    throw UsageError("Invalid value for '--occlusion <occlusion>': '" + occ + "' (expected analytic or mesh)");
+  const double building_h = a.f64("building-height");
+  const Context ctx((int)a.usize("device"), gpus_of(a));
+  const BAProblem ba = synthetic::synthetic_grid(ctx, cpb, ppb, blocks, length, inset, cam_h, pt_h, max_dist, true,
+                                                 occ == "mesh", building_h);
   std::cout << ba.to_string() << "\n";
   ba.write(a.positional[0]);
   return 0;
@@ -135,13 +150,13 @@ int run_synthetic(int argc, char **argv) {
 int run_synthetic_line(int argc, char **argv) {
   const Args a(argc, argv, 2,
                {{"cameras", "10"}, {"points", "10"}, {"max-dist", "10"}, {"camera-height", "1"}, {"point-height", "1"},
-                {"point-offset", "1"}, {"length", "20"}, {"device", "0"}, {"seed", "0"}},
+                {"point-offset", "1"}, {"length", "20"}, {"device", "0"}, {"seed", "0"}, {"gpus", "1"}},
                {});
   if (a.positional.size() != 1) throw UsageError("The following required arguments were not provided:\n    <OUTPUT>");
   const size_t n_cams = a.usize("cameras"), n_pts = a.usize("points");
   const double length = a.f64("length"), offset = a.f64("point-offset"), cam_h = a.f64("camera-height"),
                pt_h = a.f64("point-height"), max_dist = a.f64("max-dist");
-  const Context ctx((int)a.usize("device"));
+  const Context ctx((int)a.usize("device"), gpus_of(a));
   const BAProblem ba = synthetic::synthetic_line(ctx, n_cams, n_pts, length, offset, cam_h, pt_h, max_dist, true);
   std::cout << ba.to_string() << "\n";
   ba.write(a.positional[0]);
@@ -196,7 +211,7 @@ int run_generate(int argc, char **argv) {
   const Args a(argc, argv, 2,
                {{"cameras", "100"}, {"intrinsics-start", "1,0,0"}, {"intrinsics-end", "1,0,0"}, {"points", "1000"},
                 {"max-dist", "100"}, {"ground", "0"}, {"height", "1"}, {"path", ""}, {"step-size", "0"}, {"device", "0"},
-                {"seed", "0"}},
+                {"seed", "0"}, {"gpus", "1"}},
                {"no-lcc", "move-to-origin"});
   if (a.positional.size() != 2) throw UsageError("The following required arguments were not provided:\n    <FILE> <OUT>");
   if (a.given.count("path") && a.given.count("ground"))
@@ -206,7 +221,7 @@ int run_generate(int argc, char **argv) {
   const double max_dist = a.f64("max-dist"), ground = a.f64("ground"), height = a.f64("height"),
                step_size = a.f64("step-size");
   const Vector3 intrinsics_start = a.vec3("intrinsics-start"), intrinsics_end = a.vec3("intrinsics-end");
-  const int device = (int)a.usize("device");
+  const int device = (int)a.usize("device"), gpus = gpus_of(a);
   std::vector<tobj::Model> models = tobj::load_obj(a.positional[0]);
 
   std::optional<tobj::Model> model_path;
@@ -227,7 +242,7 @@ int run_generate(int argc, char **argv) {
   }
   if (a.flag("move-to-origin")) models = generate::move_to_origin(std::move(models));
 
-  const Context ctx(device);
+  const Context ctx(device, gpus);
   const Scene cscene = generate::commit_scene(ctx, models);
 
   std::vector<SnavelyCamera> cameras;
@@ -299,5 +314,11 @@ int main(int argc, char **argv) {
   } catch (const std::logic_error &e) {
     std::cerr << "thread 'main' panicked at '" << e.what() << "'\n";
     return 101;
+  } catch (const std::bad_alloc &) {
+    std::cerr << "Error: IOError(\"out of memory\")\n";
+    return 1;
+  } catch (const std::exception &e) {
+    std::cerr << "Error: IOError(\"" << e.what() << "\")\n";
+    return 1;
   }
 }

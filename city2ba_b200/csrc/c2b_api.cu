@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "c2b_bvh.cuh"
@@ -12,6 +14,7 @@
 #include "c2b_compact.cuh"
 #include "c2b_cull.cuh"
 #include "c2b_fused.cuh"
+#include "c2b_internal.h"
 #include "c2b_math.cuh"
 #include "c2b_noise.cuh"
 #include "c2b_sample.cuh"
@@ -73,7 +76,24 @@ struct GridCache {
   uint64_t n_cells = 0;
 };
 
+// Measurement / test hooks (include/city2ba_cuda.h, c2b_tune).  Defaults are the product's behaviour; the
+// environment variables of the same names in upper case with a C2B_ prefix are read ONCE, in c2b_init.
+struct Tunables {
+  int parts_log2 = -1;             // tickets per camera = 2^k; -1 = automatic
+  int trilist_cap = 128;           // entries of a camera's leaf list before it counts as overflowed
+  uint64_t max_pairs = 0xffffffffull;  // 32-bit scratch offsets: pairs inside max_dist per resident pass
+  int hoist_max = 64;              // leaf lists up to this length get per-camera triangle records (<= FU_HOIST)
+  int packet_bvh = 1;              // list overflow: 1 = lane = node packet traversal, 0 = per-ray stackless walk
+  int trilist_warp = -1;           // leaf lists by one warp per camera (1) / one thread (0); -1 = by camera count
+  int batches = 0;                 // camera batches of the host-buffer call; 0 = automatic
+  int fu_occ3 = 0;                 // fused kernel at 3 CTAs/SM (80 registers) instead of 4 (64)
+  double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
+  int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
+                                   // driver copy from pageable memory itself
+};
+
 struct CtxExtra {
+  Tunables tun;
   GridCache grid;
   uint64_t points_version = 0;
   double pts_bounds[6] = {0, 0, 0, 0, 0, 0};
@@ -92,6 +112,22 @@ static CtxExtra *extra_of(c2b_ctx *ctx) {
   for (auto &e : extras())
     if (e.first == ctx) return e.second;
   return nullptr;
+}
+
+static bool tune(Tunables &t, const char *name, double v) {
+  const std::string n(name);
+  if (n == "parts_log2") t.parts_log2 = v < 0 ? -1 : std::min((int)v, 2);
+  else if (n == "trilist_cap") t.trilist_cap = std::max(1, (int)v);
+  else if (n == "max_pairs") t.max_pairs = std::min<uint64_t>(0xffffffffull, v < 0 ? 0 : (uint64_t)v);
+  else if (n == "hoist_max") t.hoist_max = std::min(std::max(0, (int)v), 64);
+  else if (n == "packet_bvh") t.packet_bvh = v != 0;
+  else if (n == "trilist_warp") t.trilist_warp = v < 0 ? -1 : (v != 0);
+  else if (n == "batches") t.batches = std::max(0, (int)v);
+  else if (n == "fu_occ3") t.fu_occ3 = v != 0;
+  else if (n == "grid_cell_factor") t.grid_cell_factor = v > 0 ? v : 0.25;
+  else if (n == "stage_threads") t.stage_threads = std::min(std::max(0, (int)v), 16);
+  else return false;
+  return true;
 }
 
 static float scene_abs_max(const c2b_scene *scene) {
@@ -157,8 +193,28 @@ int c2b_init(int device, c2b_ctx **out) {
     ctx->numa_node = node;
     for (PinBuf *b : {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small}) b->node = node;
   }
-  extras().push_back({ctx, new CtxExtra()});
+  CtxExtra *x = new CtxExtra();
+  {
+    struct { const char *env, *name; } hooks[] = {
+        {"C2B_PARTS_LOG2", "parts_log2"}, {"C2B_TRILIST_CAP", "trilist_cap"}, {"C2B_MAX_PAIRS", "max_pairs"},
+        {"C2B_HOIST_MAX", "hoist_max"}, {"C2B_PACKET_BVH", "packet_bvh"}, {"C2B_TRILIST_WARP", "trilist_warp"},
+        {"C2B_BATCHES", "batches"}, {"C2B_FU_OCC3", "fu_occ3"}, {"C2B_GRID_CELL_FACTOR", "grid_cell_factor"},
+        {"C2B_STAGE_THREADS", "stage_threads"}};
+    for (auto &h : hooks)
+      if (const char *e = getenv(h.env)) (void)tune(x->tun, h.name, atof(e));
+  }
+  extras().push_back({ctx, x});
   *out = ctx;
+  return C2B_OK;
+}
+
+int c2b_tune(c2b_ctx *ctx, const char *name, double value) {
+  if (!ctx || !name) return set_error(C2B_ERR_INVALID, "c2b_tune: null argument");
+  if (!strcmp(name, "reset")) {
+    extra_of(ctx)->tun = Tunables();
+    return C2B_OK;
+  }
+  if (!tune(extra_of(ctx)->tun, name, value)) return set_error(C2B_ERR_INVALID, "c2b_tune: unknown hook '%s'", name);
   return C2B_OK;
 }
 
@@ -320,8 +376,87 @@ void c2b_vis_options_default(c2b_vis_options *opt) {
   opt->block_inset = 1.0;
 }
 
-static int upload_points_impl(c2b_ctx *ctx, const double *pts, uint64_t P, cudaMemcpyKind kind) {
-  if (!ctx || (P && !pts)) return set_error(C2B_ERR_INVALID, "c2b_upload_points: null argument");
+// Host -> device copy of a caller's array on ctx->stream.  A pinned (or registered) source goes to the copy
+// engine as it is.  A PAGEABLE one — what `points.as_ptr()` of a Rust Vec or a numpy array is — would be
+// staged by the driver through its own bounce buffer on one thread; instead `stage_threads` host threads
+// copy 4 MB chunks into the ctx's pinned ring (two slots per thread) and queue each chunk's DMA as soon as
+// it is staged, so the host-side memcpy runs at several cores' bandwidth and overlaps the PCIe transfer.
+int copy_in(c2b_ctx *ctx, void *d, const void *h, size_t bytes, cudaMemcpyKind kind) {
+  cudaStream_t st = ctx->stream;
+  if (bytes == 0) return C2B_OK;
+  const int T = extra_of(ctx)->tun.stage_threads;
+  constexpr size_t CH = 4u << 20;
+  bool pageable = false;
+  if (kind == cudaMemcpyHostToDevice && T > 0 && bytes >= 4 * CH) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) == cudaSuccess)
+      pageable = at.type == cudaMemoryTypeUnregistered;
+    else
+      (void)cudaGetLastError();
+  }
+  if (!pageable) {
+    C2B_CUDA(cudaMemcpyAsync(d, h, bytes, kind, st));
+    return C2B_OK;
+  }
+  const size_t n_chunks = (bytes + CH - 1) / CH;
+  const int nt = (int)std::min<size_t>((size_t)T, n_chunks);
+  C2B_TRY(ctx->pin_in.ensure((size_t)nt * 2 * CH));
+  // the ring may still feed the previous call's DMA
+  C2B_CUDA(cudaStreamSynchronize(st));
+  std::vector<cudaError_t> err((size_t)nt, cudaSuccess);
+  std::vector<std::thread> workers;
+  const int device = ctx->device;
+  char *ring = ctx->pin_in.as<char>();
+  for (int t = 0; t < nt; ++t)
+    workers.emplace_back([=, &err]() {
+      cudaError_t e = cudaSetDevice(device);
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+      size_t turn = 0;
+      for (size_t c = (size_t)t; c < n_chunks && e == cudaSuccess; c += (size_t)nt, ++turn) {
+        const int slot = (int)(turn & 1);
+        char *pin = ring + ((size_t)t * 2 + slot) * CH;
+        const size_t off = c * CH, n = std::min(CH, bytes - off);
+        if (turn >= 2) e = cudaEventSynchronize(ev[slot]);  // the slot's previous DMA has drained
+        if (e != cudaSuccess) break;
+        memcpy(pin, static_cast<const char *>(h) + off, n);
+        e = cudaMemcpyAsync(static_cast<char *>(d) + off, pin, n, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[slot], st);
+      }
+      for (int k = 0; k < 2; ++k)
+        if (ev[k]) {
+          if (e == cudaSuccess) e = cudaEventSynchronize(ev[k]);
+          cudaEventDestroy(ev[k]);
+        }
+      err[(size_t)t] = e;
+    });
+  for (auto &w : workers) w.join();
+  for (cudaError_t e : err)
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return set_error(C2B_ERR_CUDA, "staged host-to-device copy failed: %s", cudaGetErrorString(e));
+    }
+  return C2B_OK;
+}
+
+int c2b_internal_copy_in(c2b_ctx *ctx, void *d, const void *h, size_t bytes) {
+  return copy_in(ctx, d, h, bytes, cudaMemcpyHostToDevice);
+}
+
+// The AoS point array of the ctx, with room for `capacity` points, for callers that fill it on the device
+// themselves (an NCCL all-gather of per-GPU shards, c2b_multi.cu); followed by c2b_points_commit.
+int c2b_points_device_buffer(c2b_ctx *ctx, uint64_t capacity, double **d_out) {
+  if (!ctx || !d_out) return set_error(C2B_ERR_INVALID, "c2b_points_device_buffer: null argument");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  C2B_TRY(ctx->pts_aos.ensure(std::max<uint64_t>(capacity, 1) * 24));
+  *d_out = ctx->pts_aos.as<double>();
+  return C2B_OK;
+}
+
+// pts_aos[0, P) is (being) written on ctx->stream: derive the SoA copy and the coordinate bounds
+int c2b_points_commit(c2b_ctx *ctx, uint64_t P) {
+  if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_points_commit: null ctx");
+  if (P * 24 > ctx->pts_aos.cap) return set_error(C2B_ERR_INVALID, "c2b_points_commit: %llu points exceed the buffer", (unsigned long long)P);
   if (P >= 0xffffffffull) return set_error(C2B_ERR_INVALID, "too many points (%llu)", (unsigned long long)P);
   CtxExtra *x = extra_of(ctx);
   C2B_CUDA(cudaSetDevice(ctx->device));
@@ -331,9 +466,7 @@ static int upload_points_impl(c2b_ctx *ctx, const double *pts, uint64_t P, cudaM
   x->have_points = true;
   x->have_result = false;
   if (P == 0) return C2B_OK;
-  C2B_TRY(ctx->pts_aos.ensure(P * 24));
   C2B_TRY(ctx->pts.ensure(P * 24));
-  C2B_CUDA(cudaMemcpyAsync(ctx->pts_aos.p, pts, P * 24, kind, ctx->stream));
   double *px = ctx->pts.as<double>(), *py = px + P, *pz = py + P;
   k_aos_to_soa3<<<blocks_for(P, 256), 256, 0, ctx->stream>>>(ctx->pts_aos.as<double>(), P, px, py, pz);
   C2B_KERNEL_CHECK();
@@ -349,12 +482,27 @@ static int upload_points_impl(c2b_ctx *ctx, const double *pts, uint64_t P, cudaM
   return C2B_OK;
 }
 
+static int upload_points_impl(c2b_ctx *ctx, const double *pts, uint64_t P, cudaMemcpyKind kind) {
+  if (!ctx || (P && !pts)) return set_error(C2B_ERR_INVALID, "c2b_upload_points: null argument");
+  if (P >= 0xffffffffull) return set_error(C2B_ERR_INVALID, "too many points (%llu)", (unsigned long long)P);
+  double *d = nullptr;
+  C2B_TRY(c2b_points_device_buffer(ctx, P, &d));
+  if (P) C2B_TRY(copy_in(ctx, d, pts, P * 24, kind));
+  return c2b_points_commit(ctx, P);
+}
+
 int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P) {
   return upload_points_impl(ctx, pts, P, cudaMemcpyHostToDevice);
 }
 
 int c2b_upload_points_device(c2b_ctx *ctx, const double *d_pts, uint64_t P) {
   return upload_points_impl(ctx, d_pts, P, cudaMemcpyDeviceToDevice);
+}
+
+int c2b_drop_point_grid(c2b_ctx *ctx) {
+  if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_drop_point_grid: null ctx");
+  extra_of(ctx)->grid.valid = false;
+  return C2B_OK;
 }
 
 int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C) {
@@ -391,11 +539,7 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   const uint64_t P = ctx->P;
   C2B_CUDA(cudaStreamSynchronize(st));  // pts_bounds has landed
   GridDesc g;
-  double h = max_dist * 0.25;
-  if (const char *e = getenv("C2B_GRID_CELL_FACTOR")) {
-    double f = atof(e);
-    if (f > 0.0) h = max_dist * f;
-  }
+  double h = max_dist * x->tun.grid_cell_factor;
   double ext[3];
   for (int k = 0; k < 3; ++k) {
     g.min_c[k] = x->pts_bounds[k];
@@ -507,7 +651,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     const uint64_t warps = (uint64_t)ctx->sm_count * 4 * FU_WARPS;
     if (2 * C <= warps) parts_log2 = 1;
     if (4 * C <= warps) parts_log2 = 2;
-    if (const char *e = getenv("C2B_PARTS_LOG2")) parts_log2 = std::min(std::max(0, atoi(e)), 2);  // test hook
+    if (x->tun.parts_log2 >= 0) parts_log2 = x->tun.parts_log2;  // test hook
   }
   const uint64_t slots = C << parts_log2;
   C2B_TRY(ctx->ev_off.ensure((slots + 1) * 4));
@@ -552,8 +696,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   // second stream beside the plan and its scan, and the main stream joins before the counters are read.
   cudaStream_t ax = ctx->aux_stream;
   if (mesh) {
-    uint32_t trilist_cap = 128;
-    if (const char *e = getenv("C2B_TRILIST_CAP")) trilist_cap = (uint32_t)std::max(1, atoi(e));
+    const uint32_t trilist_cap = (uint32_t)x->tun.trilist_cap;
     C2B_TRY(ctx->tri_list.ensure((size_t)C * trilist_cap * 4));
     C2B_TRY(ctx->tri_count.ensure(C * 4));
     float rmax = (float)max_dist;
@@ -565,10 +708,9 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     fa.tri_list = ctx->tri_list.as<uint32_t>();
     fa.tri_count = ctx->tri_count.as<uint32_t>();
     fa.tri_cap = trilist_cap;
-    fa.hoist_max = FU_HOIST;
-    fa.packet_bvh = getenv("C2B_NO_PACKET_BVH") == nullptr;
-    if (const char *e = getenv("C2B_HOIST_MAX")) fa.hoist_max = (uint32_t)std::min(std::max(0, atoi(e)), FU_HOIST);
-    const bool tl_warp = getenv("C2B_TRILIST_WARP") ? atoi(getenv("C2B_TRILIST_WARP")) != 0 : C < 32768;  // env: test hook
+    fa.hoist_max = (uint32_t)std::min(x->tun.hoist_max, FU_HOIST);
+    fa.packet_bvh = x->tun.packet_bvh;
+    const bool tl_warp = x->tun.trilist_warp >= 0 ? x->tun.trilist_warp != 0 : C < 32768;
     C2B_CUDA(cudaEventRecord(ctx->ev_fork, st));  // after the counter reset and the camera upload
     C2B_CUDA(cudaStreamWaitEvent(ax, ctx->ev_fork, 0));
     if (tl_warp)
@@ -590,8 +732,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_TRY(read_counters(ctx, h_cnt));
   pairs_eval = h_cnt[1];
   const bool any_overflow = h_cnt[0] != 0;  // cameras whose leaf list exceeded the cap
-  uint64_t max_pairs = 0xffffffffull;  // 32-bit scratch offsets
-  if (const char *e = getenv("C2B_MAX_PAIRS")) max_pairs = std::min<uint64_t>(max_pairs, (uint64_t)atoll(e));  // test hook
+  const uint64_t max_pairs = x->tun.max_pairs;  // 32-bit scratch offsets (lower: test hook)
   if (pairs_eval >= max_pairs)
     return set_error(ERR_TOO_LARGE, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
   C2B_TRY(ctx->scratch_idx.ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
@@ -607,7 +748,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     const bool cnt = opt.count_traversal != 0;
     // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3).  Measured at cfg4: 2.68 ms; 3 CTAs/SM 2.69 ms; 5 CTAs/SM at
     // 48 registers 2.74 ms
-    static const bool occ4 = getenv("C2B_FU_OCC3") == nullptr;
+    const bool occ4 = !x->tun.fu_occ3;
     if (mesh) {
       if (cnt)
         k_visibility_fused<FU_OCC_MESH, true, 3, true><<<nb, nt, 0, st>>>(fa);
@@ -929,6 +1070,44 @@ __global__ void k_add_u64(uint64_t *v, uint64_t n, uint64_t add) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] += add;
 }
+}  // namespace
+
+int c2b_download_obs_into(c2b_ctx *ctx, uint64_t obs_base, uint64_t *offsets_dst, uint32_t *idx_dst, double *uv_dst,
+                          int with_end, float *ms_d2h) {
+  if (!ctx || !offsets_dst) return set_error(C2B_ERR_INVALID, "c2b_download_obs_into: null argument");
+  CtxExtra *x = extra_of(ctx);
+  if (!x->have_result) return set_error(C2B_ERR_INVALID, "no resident result to download");
+  const uint64_t C = ctx->out_C, O = ctx->out_O;
+  if (O && (!idx_dst || !uv_dst)) return set_error(C2B_ERR_INVALID, "c2b_download_obs_into: null result array");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int sel = ctx->out_sel;
+  if (obs_base) {
+    k_add_u64<<<blocks_for(C + 1, 256), 256, 0, st>>>(ctx->out_offsets[sel].as<uint64_t>(), C + 1, obs_base);
+    C2B_KERNEL_CHECK();
+  }
+  cudaEvent_t e0 = ctx->ev[EV_COMPACT], e1 = ctx->ev[EV_D2H];
+  C2B_CUDA(cudaEventRecord(e0, st));
+  C2B_CUDA(cudaMemcpyAsync(offsets_dst, ctx->out_offsets[sel].p, (C + (with_end ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st));
+  if (O) {
+    C2B_CUDA(cudaMemcpyAsync(idx_dst, ctx->out_idx[sel].p, O * 4, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaMemcpyAsync(uv_dst, ctx->out_uv[sel].p, O * 16, cudaMemcpyDeviceToHost, st));
+  }
+  C2B_CUDA(cudaEventRecord(e1, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  if (obs_base) {  // leave the resident CSR as it was (a second download must not rebase twice)
+    k_add_u64<<<blocks_for(C + 1, 256), 256, 0, st>>>(ctx->out_offsets[sel].as<uint64_t>(), C + 1, (uint64_t)0 - obs_base);
+    C2B_KERNEL_CHECK();
+  }
+  if (ms_d2h) {
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    *ms_d2h = t;
+  }
+  return C2B_OK;
+}
+
+namespace {
 
 // grow a pinned result buffer while copies into it may be in flight: drain, allocate, carry over
 int grow_pinned(c2b_ctx *ctx, PinBuf &b, size_t need, size_t used) {
@@ -962,8 +1141,8 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   // early as possible: the first batches are small (1/32, 1/32, 1/16, 1/8 of the cameras), the rest 1/8.
   std::vector<uint64_t> bounds;  // batch b = cameras [bounds[b], bounds[b+1])
   bounds.push_back(0);
-  if (const char *e = getenv("C2B_BATCHES")) {
-    const uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)atoll(e)));
+  if (x->tun.batches > 0) {
+    const uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)x->tun.batches));
     for (uint64_t b = 1; b <= nb; ++b) bounds.push_back((b * C) / nb);
   } else if (C >= 16384) {
     for (uint64_t f : {1, 2, 4, 8, 12, 16, 20, 24, 28, 32}) bounds.push_back((f * C) / 32);

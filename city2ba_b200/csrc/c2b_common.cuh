@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -49,8 +50,8 @@ inline int set_error(int code, const char *fmt, ...) {
 
 // every kernel launch in the library is followed by this macro: it also counts launches
 // (c2b_kernel_launches, used by bench.py's gpu_launches)
-inline uint64_t &launch_counter() {
-  static uint64_t n = 0;
+inline std::atomic<uint64_t> &launch_counter() {
+  static std::atomic<uint64_t> n{0};
   return n;
 }
 #define C2B_KERNEL_CHECK()           \
@@ -134,11 +135,12 @@ struct PinBuf {
     }
     size_t want = bytes + bytes / 4 + 256;
     NumaPreferred local(node);
-    cudaError_t e = cudaMallocHost(&p, want);
+    // portable: every device of the process may DMA into it (the one host CSR of c2b_visibility_graph_multi)
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       p = nullptr;
-      return set_error(C2B_ERR_OOM, "cudaMallocHost(%zu bytes) failed: %s", want,
+      return set_error(C2B_ERR_OOM, "cudaHostAlloc(%zu bytes) failed: %s", want,
                        cudaGetErrorString(e));
     }
     cap = want;

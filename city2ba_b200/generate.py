@@ -203,6 +203,56 @@ def visibility_graph(scene, cameras, points, max_dist, verbose=False, *, cull_mo
     return VisGraph(offsets, idx, uv, st)
 
 
+class MultiScene:
+    """The triangle scene replicated on every GPU of a MultiContext (c2b_scene_create_multi)."""
+
+    def __init__(self, xyz, tri, mctx: _lib.MultiContext):
+        self.mctx = mctx
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        tri = np.ascontiguousarray(tri, dtype=np.uint32).reshape(-1, 3)
+        self._h = C.c_void_p()
+        check(lib().c2b_scene_create_multi(
+            mctx.handle, xyz.ctypes.data_as(C.POINTER(C.c_float)), xyz.shape[0],
+            tri.ctypes.data_as(C.POINTER(C.c_uint32)), tri.shape[0], C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().c2b_scene_destroy_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def visibility_graph_multi(mctx, scene, cameras, points, max_dist, *, cull_mode="grid", occlusion="mesh",
+                           endpoint_guard_rel=False, block_length=20.0, block_inset=1.0) -> VisGraph:
+    """visibility_graph over the GPUs of `mctx` (camera ranges; c2b_visibility_graph_multi): ONE host CSR,
+    identical to the single-GPU result.  stats["multi"] holds the per-GPU ranges, counts and stage times."""
+    cams, pts = _cam_array(cameras), _pts_array(points)
+    opt = _options(cull_mode, occlusion, endpoint_guard_rel, False, block_length, block_inset)
+    out, ms = Obs(), _lib.MultiStats()
+    check(lib().c2b_visibility_graph_multi(
+        mctx.handle, scene.handle if scene is not None else None, cams.ctypes.data, cams.shape[0],
+        pts.ctypes.data, pts.shape[0], float(max_dist), C.byref(opt), C.byref(out), C.byref(ms)))
+    Cn, O = int(out.n_cameras), int(out.n_obs)
+    offsets = np.ctypeslib.as_array(out.offsets, shape=(Cn + 1,)).copy()
+    idx = np.ctypeslib.as_array(out.point_idx, shape=(O,)).copy() if O else np.zeros(0, np.uint32)
+    uv = np.ctypeslib.as_array(out.uv, shape=(2 * O,)).copy() if O else np.zeros(0)
+    st = _stats(out)
+    G = ms.n_gpus
+    st["multi"] = {k: [getattr(ms, k)[g] for g in range(G)] for k in
+                   ("cam_begin", "cam_end", "n_obs", "obs_base", "ms_points", "ms_compute", "ms_exchange", "ms_d2h")}
+    st["multi"]["ms_wall"] = ms.ms_wall
+    return VisGraph(offsets, idx, uv, st)
+
+
 class ResidentProblem:
     """Keeps cameras / points / result in HBM between calls (the three-call form of the ABI)."""
 

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <array>
 #include <charconv>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -306,16 +307,36 @@ struct SnavelyCamera {
 };
 
 // ---- GPU context and scene (where embree_rs::Device / CommittedScene stood) ------------------------
+// n_gpus > 1: GPUs device .. device + n_gpus - 1 of this box behind one c2b_multi (one process, camera ranges,
+// one NCCL communicator); visibility_graph then runs on all of them and returns the same graph, everything
+// else (noise, ray queries, point sampling) runs on the first.
 class Context {
  public:
-  explicit Context(int device = 0) { detail::check(c2b_init(device, &h_)); }
-  ~Context() { c2b_shutdown(h_); }
+  explicit Context(int device = 0, int n_gpus = 1) {
+    if (n_gpus > 1) {
+      std::vector<int> dev((size_t)n_gpus);
+      for (int g = 0; g < n_gpus; ++g) dev[(size_t)g] = device + g;
+      detail::check(c2b_init_multi(n_gpus, dev.data(), &m_));
+      h_ = c2b_multi_ctx(m_, 0);
+    } else {
+      detail::check(c2b_init(device, &h_));
+    }
+  }
+  ~Context() {
+    if (m_)
+      c2b_shutdown_multi(m_);
+    else
+      c2b_shutdown(h_);
+  }
   Context(const Context &) = delete;
   Context &operator=(const Context &) = delete;
   c2b_ctx *handle() const { return h_; }
+  c2b_multi *multi() const { return m_; }
+  int num_gpus() const { return m_ ? c2b_multi_num_gpus(m_) : 1; }
 
  private:
   c2b_ctx *h_ = nullptr;
+  c2b_multi *m_ = nullptr;
 };
 
 class Scene {
@@ -323,9 +344,20 @@ class Scene {
   // Scene::new + model_to_geometry per model + attach + commit (src/bin/city2ba.rs:515-521);
   // xyz: 3 floats per vertex, tri: 3 indices per triple, all models concatenated
   Scene(const Context &ctx, const std::vector<float> &xyz, const std::vector<uint32_t> &tri) : ctx_(&ctx) {
-    detail::check(c2b_scene_create(ctx.handle(), xyz.data(), xyz.size() / 3, tri.data(), tri.size() / 3, &h_));
+    if (ctx.multi()) {  // the BVH on every GPU; ray queries go to the first copy
+      detail::check(c2b_scene_create_multi(ctx.multi(), xyz.data(), xyz.size() / 3, tri.data(), tri.size() / 3, &ms_));
+      h_ = c2b_multi_scene_get(ms_, 0);
+    } else {
+      detail::check(c2b_scene_create(ctx.handle(), xyz.data(), xyz.size() / 3, tri.data(), tri.size() / 3, &h_));
+    }
   }
-  ~Scene() { c2b_scene_destroy(h_); }
+  ~Scene() {
+    if (ms_)
+      c2b_scene_destroy_multi(ms_);
+    else
+      c2b_scene_destroy(h_);
+  }
+  c2b_multi_scene *multi_handle() const { return ms_; }
   Scene(const Scene &) = delete;
   Scene &operator=(const Scene &) = delete;
   const Context &context() const { return *ctx_; }
@@ -352,6 +384,7 @@ class Scene {
  private:
   const Context *ctx_;
   c2b_scene *h_ = nullptr;
+  c2b_multi_scene *ms_ = nullptr;
 };
 
 namespace detail {
@@ -380,8 +413,13 @@ inline VisGraph run_visibility(const Context &ctx, const Scene *scene, const std
   opt.block_inset = block_inset;
   c2b_obs out;
   std::memset(&out, 0, sizeof out);
-  check(c2b_visibility_graph(ctx.handle(), scene ? scene->handle() : nullptr, cams.data(), cameras.size(),
-                             points.empty() ? nullptr : points[0].data(), points.size(), max_dist, &opt, &out));
+  if (ctx.multi())
+    check(c2b_visibility_graph_multi(ctx.multi(), scene ? scene->multi_handle() : nullptr, cams.data(), cameras.size(),
+                                     points.empty() ? nullptr : points[0].data(), points.size(), max_dist, &opt, &out,
+                                     nullptr));
+  else
+    check(c2b_visibility_graph(ctx.handle(), scene ? scene->handle() : nullptr, cams.data(), cameras.size(),
+                               points.empty() ? nullptr : points[0].data(), points.size(), max_dist, &opt, &out));
   VisGraph g = unpack(out);
   c2b_obs_free(ctx.handle(), &out);
   return g;
@@ -988,13 +1026,29 @@ struct BAProblem {
     if (ext == "bal") {
       std::ifstream f(path);
       if (!f) throw Error(Error::IOError, "cannot open " + path);
+      // file size bounds every count (a camera takes >= 18 bytes, a point >= 6, an observation >= 8): a
+      // malformed header is a ParseError (src/baproblem.rs:580-628 fails in nom), never a huge allocation
+      f.seekg(0, std::ios::end);
+      const uint64_t fsize = (uint64_t)f.tellg();
+      f.seekg(0);
+      // nom's digit1 takes digits only: a sign ("-1" would wrap in operator>>) is a parse error
+      auto getu = [&](size_t &out) {
+        f >> std::ws;
+        const int ch = f.peek();
+        if (ch < '0' || ch > '9') return false;
+        if (!(f >> out)) return false;
+        const int next = f.peek();  // "1.5" or "1e3" is not an index
+        return next == std::char_traits<char>::eof() || std::isspace(next);
+      };
       size_t nc, np, no;
-      if (!(f >> nc >> np >> no)) throw Error(Error::ParseError, "bad BAL header");
+      if (!(getu(nc) && getu(np) && getu(no))) throw Error(Error::ParseError, "bad BAL header");
+      if (nc > fsize / 18 || np > fsize / 6 || no > fsize / 8)
+        throw Error(Error::ParseError, "BAL header counts exceed the file size");
       ba.vis_graph.assign(nc, {});
       for (size_t i = 0; i < no; ++i) {
         size_t c, p;
         double u, v;
-        if (!(f >> c >> p >> u >> v)) throw Error(Error::ParseError, "bad observation line");
+        if (!(getu(c) && getu(p) && (f >> u >> v))) throw Error(Error::ParseError, "bad observation line");
         detail::require(c < nc && p < np, "observation index out of range");
         ba.vis_graph[c].push_back({p, {u, v}});
       }
@@ -1026,11 +1080,18 @@ struct BAProblem {
         std::memcpy(&d, &v, 8);
         return d;
       };
+      f.seekg(0, std::ios::end);
+      const uint64_t fsize = (uint64_t)f.tellg();
+      f.seekg(0);
       const uint64_t nc = get64(), np = get64(), no = get64();
+      // 8 + 72 bytes per camera, 24 per point, 24 per observation (src/baproblem.rs:736-764)
+      if (nc > fsize / 80 || np > fsize / 24 || no > fsize / 24)
+        throw Error(Error::ParseError, "binary BAL header counts exceed the file size");
       size_t seen = 0;
       ba.vis_graph.assign(nc, {});
       for (uint64_t c = 0; c < nc; ++c) {
         const uint64_t n = get64();
+        if (n > no - seen) throw Error(Error::ParseError, "observation count does not match the header");
         for (uint64_t i = 0; i < n; ++i) {
           const uint64_t p = get64();
           const double u = getf(), v = getf();
@@ -1053,8 +1114,7 @@ struct BAProblem {
     } else {
       throw Error(Error::IOError, "unknown file extension: " + path);
     }
-    if (ba.cameras.empty() || ba.points.empty()) throw Error(Error::EmptyProblem, "Bundle adjustment problem is empty");
-    return ba;
+    return ba;  // possibly empty, like the reference's from_file; EmptyProblem is run_generate's (src/bin/city2ba.rs:550-554)
   }
   // impl Display, src/baproblem.rs:788-801
   std::string to_string() const {
@@ -1066,10 +1126,13 @@ struct BAProblem {
 };
 
 namespace synthetic {
-// src/synthetic.rs:163-300.  Occlusion by the analytic 2-D wall test of the reference (src/synthetic.rs:52-124).
+// src/synthetic.rs:163-300.  Occlusion by the analytic 2-D wall test of the reference (src/synthetic.rs:52-124),
+// or — mesh_occlusion, the north star's configuration, not in the reference — by rays against one box of
+// height building_height per city block (c2b_city_mesh).
 inline BAProblem synthetic_grid(const Context &ctx, size_t num_cameras_per_block, size_t num_points_per_block,
                                 size_t num_blocks, double block_length, double block_inset, double camera_height,
-                                double point_height, double max_dist, bool /*verbose*/) {
+                                double point_height, double max_dist, bool /*verbose*/, bool mesh_occlusion = false,
+                                double building_height = 10.0) {
   detail::require(block_inset * 2.0 < block_length,
                   "Block inset must be less than half the block length, to not violate physical constraints.");
   std::vector<SnavelyCamera> cams(c2b_grid_num_cameras(num_cameras_per_block, num_blocks));
@@ -1079,7 +1142,16 @@ inline BAProblem synthetic_grid(const Context &ctx, size_t num_cameras_per_block
                                  cams.empty() ? nullptr : cams[0].rec));
   detail::check(c2b_grid_points(num_points_per_block, num_blocks, block_length, block_inset, point_height,
                                 pts.empty() ? nullptr : pts[0].data()));
-  VisGraph g = detail::run_visibility(ctx, nullptr, cams, pts, max_dist, C2B_OCC_ANALYTIC, block_length, block_inset);
+  VisGraph g;
+  if (mesh_occlusion) {
+    std::vector<float> xyz(3 * 8 * num_blocks * num_blocks);
+    std::vector<uint32_t> tri(3 * 12 * num_blocks * num_blocks);
+    detail::check(c2b_city_mesh(num_blocks, block_length, block_inset, building_height, xyz.data(), tri.data()));
+    const Scene scene(ctx, xyz, tri);
+    g = detail::run_visibility(ctx, &scene, cams, pts, max_dist, C2B_OCC_MESH, block_length, block_inset);
+  } else {
+    g = detail::run_visibility(ctx, nullptr, cams, pts, max_dist, C2B_OCC_ANALYTIC, block_length, block_inset);
+  }
   return BAProblem::from_visibility(std::move(cams), std::move(pts), std::move(g)).cull();
 }
 
@@ -1127,6 +1199,8 @@ struct Flat {
 // src/noise.rs:68-116
 inline BAProblem add_drift(const Context &ctx, const BAProblem &ba, double strength, double angle_strength, double std_,
                            const Vector3 &dir, uint64_t seed) {
+  // the reference's nearest-to-origin fold1(..).unwrap() (src/noise.rs:75-87) panics on an empty problem
+  detail::require(ba.num_cameras() + ba.num_points() > 0, "called `Option::unwrap()` on a `None` value");
   detail_n::Flat f(ba);
   detail::check(c2b_add_drift(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(), strength,
                               angle_strength, std_, dir.data(), seed));
@@ -1135,6 +1209,7 @@ inline BAProblem add_drift(const Context &ctx, const BAProblem &ba, double stren
 // src/noise.rs:47-56
 inline BAProblem add_drift_normalized(const Context &ctx, const BAProblem &ba, double strength, double angle_strength,
                                       double std_, uint64_t seed) {
+  detail::require(ba.num_cameras() + ba.num_points() > 0, "called `Option::unwrap()` on a `None` value");
   detail_n::Flat f(ba);
   detail::check(c2b_add_drift_normalized(ctx.handle(), f.cams.data(), ba.num_cameras(), f.pts.data(), ba.num_points(),
                                          strength, angle_strength, std_, seed));

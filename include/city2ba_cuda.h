@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define C2B_ABI_VERSION 2
+#define C2B_ABI_VERSION 3
 
 typedef enum {
   C2B_OK = 0,
@@ -30,7 +30,8 @@ typedef enum {
   C2B_ERR_NO_DEVICE = -2, /* no usable CUDA device                                        */
   C2B_ERR_CUDA = -3,      /* a CUDA runtime call or kernel failed; message has the detail */
   C2B_ERR_OOM = -4,       /* device or pinned-host allocation failed                      */
-  C2B_ERR_EMPTY = -5      /* empty problem (reference: Error::EmptyProblem, src/baproblem.rs:36) */
+  C2B_ERR_EMPTY = -5,     /* empty problem (reference: Error::EmptyProblem, src/baproblem.rs:36) */
+  C2B_ERR_NCCL = -6       /* libnccl.so.2 could not be loaded, or an NCCL call failed (multi-GPU entries only) */
 } c2b_status;
 
 typedef struct c2b_ctx c2b_ctx;
@@ -49,6 +50,21 @@ const char *c2b_last_error(void);
 int c2b_abi_version(void);
 /* number of CUDA kernels this library has launched in this process so far */
 uint64_t c2b_kernel_launches(void);
+/* Measurement / test hooks.  Defaults are the product's behaviour; each hook is also read ONCE from the
+ * environment in c2b_init (upper case, C2B_ prefix: C2B_BATCHES=1 ...).  name = "reset" restores the defaults.
+ *   parts_log2 (-1 auto | 0..2)  tickets per camera in the fused kernel = 2^k
+ *   trilist_cap (128)            leaf-list entries per camera before the camera traverses the BVH instead
+ *   max_pairs (2^32-1)           pairs inside max_dist one resident pass may hold (lower: forces range splits)
+ *   hoist_max (64)               leaf lists up to this length get per-camera triangle records
+ *   packet_bvh (1)               list overflow: 1 lane = node packet traversal, 0 per-ray stackless walk
+ *   trilist_warp (-1 auto|0|1)   leaf lists built by one warp / one thread per camera
+ *   batches (0 auto)             camera batches of the host-buffer call
+ *   fu_occ3 (0)                  fused kernel at 3 CTAs/SM
+ *   grid_cell_factor (0.25)      point-grid cell side / max_dist
+ *   stage_threads (4)            host threads staging a PAGEABLE input array through the pinned ring (0: leave
+ *                                the pageable copy to the driver)
+ * Unknown names are C2B_ERR_INVALID. */
+int c2b_tune(c2b_ctx *ctx, const char *name, double value);
 /* measurement aid: sustained rate of independent f64 FMAs on this device, in DFMA/s
  * (one fused multiply-add per thread counted as one).  The secondary bound of the exhaustive cull, whose
  * hot loop is FP64-issue-bound; not part of the reference's surface. */
@@ -149,10 +165,67 @@ int c2b_upload_points(c2b_ctx *ctx, const double *pts, uint64_t P);
  * rank uploaded 1/N of the points over its own PCIe link); the caller's stream must have finished
  * writing d_pts.  The data is copied; d_pts may be reused afterwards. */
 int c2b_upload_points_device(c2b_ctx *ctx, const double *d_pts, uint64_t P);
+/* zero-copy variant: the ctx's own device array of xyz records (room for `capacity` points) for a caller
+ * that fills it on the device — c2b_visibility_graph_multi all-gathers the per-GPU shards straight into it —
+ * then c2b_points_commit(P) once the writes are ordered before the ctx's work (same stream or synchronised). */
+int c2b_points_device_buffer(c2b_ctx *ctx, uint64_t capacity, double **d_out);
+int c2b_points_commit(c2b_ctx *ctx, uint64_t P);
 int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C);
+/* The point grid (cells of side max_dist/4) is derived data that the ctx keeps between calls on the same
+ * points and max_dist.  This forgets it, so that the next resident pass pays the build again (ms_prep):
+ * what a one-shot `visibility_graph` call costs; bench.py's `value` is measured this way. */
+int c2b_drop_point_grid(c2b_ctx *ctx);
 int c2b_visibility_graph_resident(c2b_ctx *ctx, const c2b_scene *scene, double max_dist,
                                   const c2b_vis_options *opt, c2b_obs *stats_out);
 int c2b_download_obs(c2b_ctx *ctx, c2b_obs *out);
+/* the resident CSR into CALLER-owned arrays (pinned for full PCIe rate; pageable works): offsets_dst receives
+ * n_cameras entries (+ the closing one if with_end), each increased by obs_base — the slot of a camera range
+ * inside a larger CSR; idx_dst / uv_dst receive n_obs entries.  ms_d2h (optional): device time of the copies. */
+int c2b_download_obs_into(c2b_ctx *ctx, uint64_t obs_base, uint64_t *offsets_dst, uint32_t *idx_dst,
+                          double *uv_dst, int with_end, float *ms_d2h);
+
+/* ---- the same path on several GPUs of one box -------------------------------------------
+ * replaces the rayon par_iter over cameras (src/generate.rs:434-441) and its order-preserving collect
+ * (:479-481).  ONE process drives n_gpus devices: one c2b_ctx + stream set + host thread per device and one
+ * NCCL communicator (ncclCommInitAll; libnccl.so.2 is loaded with dlopen the first time, so single-GPU users
+ * need no NCCL).  Mesh / BVH and points are replicated, GPU g owns the contiguous camera range
+ * [floor(g C / G), floor((g+1) C / G)).  Data exchanged over NVLink: (1) every GPU uploads 1/G of the point
+ * array over its own PCIe link and the shards are all-gathered (ncclAllGather) into each GPU's point array;
+ * (2) ONE ncclAllGather of the per-GPU observation counts, from which every GPU rebases its CSR offsets on
+ * the device and learns where its slab starts; every GPU then copies its slab into the SAME pinned host CSR
+ * at that offset.  The result is identical to c2b_visibility_graph's, bit for bit. */
+typedef struct c2b_multi c2b_multi;
+typedef struct c2b_multi_scene c2b_multi_scene;
+#define C2B_MAX_GPUS 16
+/* devices == NULL: ordinals 0 .. n_gpus-1 */
+int c2b_init_multi(int n_gpus, const int *devices, c2b_multi **out);
+void c2b_shutdown_multi(c2b_multi *m);
+int c2b_multi_num_gpus(const c2b_multi *m);
+/* the per-GPU context (valid until c2b_shutdown_multi), e.g. for c2b_tune or the single-GPU entries */
+c2b_ctx *c2b_multi_ctx(c2b_multi *m, int g);
+/* the BVH is built on every GPU (the build is deterministic: identical copies) */
+int c2b_scene_create_multi(c2b_multi *m, const float *xyz, uint64_t nv, const uint32_t *tri, uint64_t nt,
+                           c2b_multi_scene **out);
+void c2b_scene_destroy_multi(c2b_multi_scene *scene);
+/* GPU g's copy (owned by the multi scene), e.g. for c2b_intersect on c2b_multi_ctx(m, g) */
+c2b_scene *c2b_multi_scene_get(const c2b_multi_scene *scene, int g);
+typedef struct {
+  int n_gpus;
+  uint64_t cam_begin[C2B_MAX_GPUS], cam_end[C2B_MAX_GPUS]; /* camera range of GPU g                     */
+  uint64_t n_obs[C2B_MAX_GPUS];                            /* its observation count = slab length         */
+  uint64_t obs_base[C2B_MAX_GPUS];                         /* its slab's start in the host CSR (from the
+                                                              all-gathered counts, computed on the device) */
+  float ms_points[C2B_MAX_GPUS];  /* shard H2D + point all-gather + SoA / bounds                          */
+  float ms_compute[C2B_MAX_GPUS]; /* resident pass (grid build, plan, fused kernel, sort + write)         */
+  float ms_exchange[C2B_MAX_GPUS];/* count all-gather + offset rebase                                     */
+  float ms_d2h[C2B_MAX_GPUS];     /* slab -> host CSR                                                     */
+  float ms_wall;                  /* host wall clock of the whole call                                    */
+} c2b_multi_stats;
+/* out: the ONE host CSR (pinned, owned by `m`, valid until the next call or c2b_shutdown_multi); the stage
+ * timers of `out` are the maxima over GPUs.  stats may be NULL. */
+int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const double *cams, uint64_t C,
+                               const double *pts, uint64_t P, double max_dist, const c2b_vis_options *opt,
+                               c2b_obs *out, c2b_multi_stats *stats);
 
 /* total_reprojection_error (src/baproblem.rs:265-279) of the resident problem, norm 1 or 2 fast
  * paths, anything else through pow(). */

@@ -49,11 +49,42 @@ class _Vis(C.Structure):
 _lib = None
 
 
+def _cpu_id() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                import hashlib
+                return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build_native() -> str:
+    """-O3 -march=native build of the same sources for the TIMED CPU arm, made on the machine that runs it
+    (rebuilt when it was made on a CPU with other ISA flags: the repo snapshot travels between machines)."""
+    so, tag = os.path.join(_HERE, "liboracle_native.so"), os.path.join(_HERE, "liboracle_native.cpu")
+    srcs = [os.path.join(_HERE, f) for f in ("cpu_ref.c", "c2b_oracle.c", "c2b_oracle.h")]
+    cpu = _cpu_id()
+    fresh = (os.path.exists(so) and os.path.exists(tag) and open(tag).read() == cpu
+             and all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs))
+    if not fresh:
+        if os.path.exists(so):
+            os.unlink(so)
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native"])
+        open(tag, "w").write(cpu)
+    return so
+
+
 def lib():
+    """C2B_ORACLE_NATIVE=1 (set by bench.py for its CPU arms) selects the -march=native build."""
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(_SO)
+        if os.environ.get("C2B_ORACLE_NATIVE") == "1":
+            _lib = C.CDLL(build_native())
+        else:
+            build()
+            _lib = C.CDLL(_SO)
         _lib.orc_visibility_graph.restype = C.POINTER(_Vis)
         _lib.orc_ref_visibility_graph.restype = C.POINTER(_Vis)
         _lib.orc_synthetic_visibility.restype = C.POINTER(_Vis)

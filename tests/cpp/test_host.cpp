@@ -402,6 +402,42 @@ static int dump_obj(const char *path) {
   return 0;
 }
 
+// malformed / hostile BAL files are ParseErrors (the reference fails in nom / read_exact), never an allocation
+// sized by an unvalidated header; empty files parse to empty problems (src/baproblem.rs:580-706)
+static void malformed_files(const std::string &tmp) {
+  auto write = [&](const std::string &name, const std::string &bytes) {
+    const std::string path = tmp + "/" + name;
+    FILE *f = std::fopen(path.c_str(), "wb");
+    std::fwrite(bytes.data(), 1, bytes.size(), f);
+    std::fclose(f);
+    return path;
+  };
+  auto kind_of = [&](const std::string &path) {
+    try {
+      (void)BAProblem::from_file(path);
+    } catch (const Error &e) {
+      return (int)e.kind;
+    } catch (...) {
+      return 99;
+    }
+    return -1;
+  };
+  CHECK(kind_of(write("neg.bal", "-1 2 3\n")) == Error::ParseError);
+  CHECK(kind_of(write("huge.bal", "99999999999999 1 1\n0 0 0.5 0.5\n")) == Error::ParseError);
+  CHECK(kind_of(write("negobs.bal", "1 1 1\n-1 0 0.5 0.5\n")) == Error::ParseError);
+  CHECK(kind_of(write("float_index.bal", "1 1 1\n0 1.5 0.5 0.5\n")) == Error::ParseError);
+  std::string huge(24, '\xff');  // nc = np = no = 2^64 - 1
+  CHECK(kind_of(write("huge.bbal", huge)) == Error::ParseError);
+  std::string liar(24, '\0');  // 1 camera, 1 point, 1 observation, then a camera that claims 2^56 observations
+  liar[7] = liar[15] = liar[23] = 1;
+  liar += std::string("\x01", 1) + std::string(7, '\0');
+  liar += std::string(200, '\0');
+  CHECK(kind_of(write("liar.bbal", liar)) == Error::ParseError);
+  CHECK(kind_of(write("empty.bal", "0 0 0\n")) == -1);  // an empty problem is not an error of from_file
+  CHECK(kind_of(write("empty.bbal", std::string(24, '\0'))) == -1);
+  CHECK(kind_of(tmp + "/does_not_exist.bal") == Error::IOError);
+}
+
 int main(int argc, char **argv) {
   const std::string mode = argc > 1 ? argv[1] : "cpu";
   if (mode == "obj" && argc > 2) return dump_obj(argv[2]);
@@ -413,6 +449,7 @@ int main(int argc, char **argv) {
   graph_and_io(tmp ? tmp : "/tmp");
   obj_and_cameras(tmp ? tmp : "/tmp");
   graph_noise();
+  malformed_files(tmp ? tmp : "/tmp");
   if (mode == "gpu") {
     try {
       const Context ctx(0);

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported(c2b):
 
 def test_abi_version_and_defaults(c2b):
     L = c2b._lib.lib()
-    assert L.c2b_abi_version() == 2
+    assert L.c2b_abi_version() == 3
     o = c2b._lib.VisOptions()
     L.c2b_vis_options_default(ctypes.byref(o))
     assert (o.cull_mode, o.occlusion, o.endpoint_guard_rel, o.count_traversal) == (0, 0, 0, 0)

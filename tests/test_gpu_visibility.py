@@ -331,34 +331,40 @@ def test_dense_mesh_overflows_triangle_lists(c2b, ctx, orc):
         assert_same_graph(c2b.visibility_graph(scene, cams, pts, 12.0, cull_mode=mode, ctx=ctx), ref, f"dense/{mode}")
 
 
-def test_list_modes_agree(c2b, ctx, orc, cfg2, monkeypatch):
+def test_list_modes_agree(c2b, ctx, orc, cfg2):
     """the four ways a packet finds its triangles — per-camera records in shared memory (leaf list
-    <= 64), per-packet records (<= 128, forced here with C2B_HOIST_MAX=0), the lane = node packet
-    traversal of the BVH (list overflow, forced with C2B_TRILIST_CAP=1) and the per-ray stackless
-    walk (C2B_NO_PACKET_BVH) — give the same graph"""
+    <= 64), per-packet records (<= 128, forced here with the hook hoist_max = 0), the lane = node packet
+    traversal of the BVH (list overflow, forced with trilist_cap = 1) and the per-ray stackless
+    walk (packet_bvh = 0) — give the same graph"""
     cams, pts, xyz, tri = cfg2
     scene = c2b.Scene(xyz, tri, ctx=ctx)
     ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "hoisted")
-    for form in ("0", "1"):      # leaf lists built by one thread per camera / one warp per camera (lane = node)
-        monkeypatch.setenv("C2B_TRILIST_WARP", form)
-        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, f"trilist form {form}")
-    monkeypatch.delenv("C2B_TRILIST_WARP")
-    monkeypatch.setenv("C2B_HOIST_MAX", "0")
-    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-packet records")
-    monkeypatch.setenv("C2B_TRILIST_CAP", "1")
-    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "packet bvh")
-    monkeypatch.setenv("C2B_NO_PACKET_BVH", "1")
-    assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-ray walk")
+    try:
+        for form in (0, 1):      # leaf lists built by one thread per camera / one warp per camera (lane = node)
+            ctx.tune("trilist_warp", form)
+            assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, f"trilist form {form}")
+        ctx.tune("trilist_warp", -1)
+        ctx.tune("hoist_max", 0)
+        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-packet records")
+        ctx.tune("trilist_cap", 1)
+        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "packet bvh")
+        ctx.tune("packet_bvh", 0)
+        assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), ref, "per-ray walk")
+        with pytest.raises(c2b.C2BError, match="unknown hook"):
+            ctx.tune("no_such_hook", 1)
+    finally:
+        ctx.tune("reset", 0)
 
 
 @pytest.mark.parametrize("parts_log2", ["0", "1", "2"])
-def test_camera_tickets_agree(c2b, ctx, orc, cfg2, monkeypatch, parts_log2):
+def test_camera_tickets_agree(c2b, ctx, orc, cfg2, parts_log2, request):
     """a camera's rows dealt to 1, 2 or 4 tickets (own scratch slice and visible count each, stitched
     back together by the sort/write pass) give the same graph — mesh, analytic and no occlusion, and the
     block-sort / global-sort fallbacks of cameras that see more than 1,024 / 4,096 points"""
     cams, pts, xyz, tri = cfg2
-    monkeypatch.setenv("C2B_PARTS_LOG2", parts_log2)
+    ctx.tune("parts_log2", int(parts_log2))
+    request.addfinalizer(lambda: ctx.tune("reset", 0))
     scene = c2b.Scene(xyz, tri, ctx=ctx)
     assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx), orc.visibility_graph(xyz, tri, cams, pts, 10.0),
                       f"mesh/{parts_log2}")
@@ -528,15 +534,16 @@ def test_reference_meshes_golden(c2b, ctx, name, mode):
     assert np.array_equal(generate_world_points_uniform(g["xyz"], g["tri"], g["cams"], len(g["pts"]), md, seed=seed, ctx=ctx), g["pts"])
 
 
-def test_oversized_batches_are_split(c2b, ctx, orc, cfg2, monkeypatch):
+def test_oversized_batches_are_split(c2b, ctx, orc, cfg2, request):
     """a camera batch whose row points exceed the 32-bit scratch offsets is halved and retried
-    (C2B_MAX_PAIRS lowers the limit so that the path runs at test size); the graph is unchanged"""
+    (the hook max_pairs lowers the limit so that the path runs at test size); the graph is unchanged"""
+    request.addfinalizer(lambda: ctx.tune("reset", 0))
     cams, pts, xyz, tri = cfg2
     scene = c2b.Scene(xyz, tri, ctx=ctx)
     ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
-    monkeypatch.setenv("C2B_MAX_PAIRS", "20000")          # 800 cameras x ~90 row points: several splits
+    ctx.tune("max_pairs", 20000)                          # 800 cameras x ~90 row points: several splits
     g = c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx)
     assert_same_graph(g, ref, "split batches")
-    monkeypatch.setenv("C2B_MAX_PAIRS", "10")             # not even one camera fits: a clean error
+    ctx.tune("max_pairs", 10)                             # not even one camera fits: a clean error
     with pytest.raises(c2b.C2BError, match="shard the cameras"):
         c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx)
