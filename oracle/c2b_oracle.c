@@ -844,19 +844,105 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[3] = c3;
 }
 
-/* counter = (index lo, index hi, stream, slot), key = seed; Box-Muller in f64:
- * u1 = ((x>>11)+1)*2^-53 in (0,1], u2 = (y>>11)*2^-53 in [0,1) */
-void orc_normal_pair(uint64_t seed, uint32_t stream, uint64_t index, uint32_t slot, double *z) {
+/* ---- the noise draws -------------------------------------------------------------------------
+ * The reference draws a direction as a NORMALISED Gaussian pair / triple (unit_random, src/noise.rs:35-43;
+ * (nx, ny) / |(nx, ny)|, :159-163) and a magnitude as Normal(mean, std) (rand 0.6.5 Ziggurat), all from the
+ * unseedable thread_rng(): only distributions can be matched.  A normalised Gaussian pair IS a uniform
+ * direction on the circle, a normalised triple a uniform point on the sphere, so one Philox4x32-10 block
+ * per element supplies
+ *     circle   (cos, sin)(2 pi w / 2^32)                                  from one 32-bit word,
+ *     sphere   z = 1 - 2 (b + 1/2) / 2^32 (Archimedes), azimuth from a    from two words,
+ *     N(0,1)   Box-Muller: sqrt(-2 ln u1) cos(theta), u1 = (n40 + 1) 2^-40 in (0, 1], theta from 24 bits,
+ *                                                                         from two words,
+ * evaluated by table + short polynomial (cos / sin of k 2pi/256 and a degree-5/6 Taylor remainder; ln by
+ * 128 intervals of the mantissa and a degree-6 series) with every operation an explicit fma / mul / add in
+ * a fixed order.  The CUDA path (c2b_noise.cuh) performs the same operations on the same tables, so points
+ * and observations agree with this file bit for bit; the functions themselves are pinned against libm in
+ * tests/test_oracle_noise.py (<= 4e-16 absolute) and the distributions by moment / KS tests. */
+static double SC_TAB[256][2]; /* cos, sin of k * 2 pi / 256 */
+static double LN_TAB[128][2]; /* 1 / c_j, ln c_j with c_j = 1 + (2 j + 1) / 256 */
+static int noise_tabs_ready = 0;
+
+void orc_noise_tables(double *sc, double *ln) {
+  if (!noise_tabs_ready) {
+    for (int k = 0; k < 256; ++k) {
+      const double a = (double)k * (6.283185307179586 / 256.0);
+      SC_TAB[k][0] = cos(a);
+      SC_TAB[k][1] = sin(a);
+    }
+    for (int j = 0; j < 128; ++j) {
+      const double c = 1.0 + (double)(2 * j + 1) / 256.0;
+      LN_TAB[j][0] = 1.0 / c;
+      LN_TAB[j][1] = log(c);
+    }
+    noise_tabs_ready = 1;
+  }
+  if (sc) memcpy(sc, SC_TAB, sizeof SC_TAB);
+  if (ln) memcpy(ln, LN_TAB, sizeof LN_TAB);
+}
+
+/* (cos, sin) of 2 pi w / 2^32 */
+void orc_unit2(uint32_t w, double *c, double *s) {
+  if (!noise_tabs_ready) orc_noise_tables(NULL, NULL);
+  const uint32_t k = w >> 24;
+  const double d = (double)(w & 0xffffffu) * 1.4629180792671596e-09; /* 2 pi / 2^32 */
+  const double d2 = d * d;
+  double ps = fma(d2, 1.0 / 120.0, -1.0 / 6.0);
+  ps = fma(d2, ps, 1.0);
+  const double sd = d * ps;
+  double pc = fma(d2, -1.0 / 720.0, 1.0 / 24.0);
+  pc = fma(d2, pc, -0.5);
+  const double cd = fma(d2, pc, 1.0);
+  const double ca = SC_TAB[k][0], sa = SC_TAB[k][1];
+  *c = fma(ca, cd, -(sa * sd));
+  *s = fma(sa, cd, ca * sd);
+}
+
+/* -2 ln u, u = (n40 + 1) * 2^-40 in (0, 1]; never negative */
+double orc_neg2ln40(uint64_t n40) {
+  if (!noise_tabs_ready) orc_noise_tables(NULL, NULL);
+  const double u = (double)(n40 + 1) * 9.094947017729282e-13; /* 2^-40, exact */
+  uint64_t bits;
+  memcpy(&bits, &u, 8);
+  const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  const int j = (int)((bits >> 45) & 127);
+  const uint64_t mb = (bits & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+  double m;
+  memcpy(&m, &mb, 8);
+  const double r = fma(m, LN_TAB[j][0], -1.0);
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 1.0 / 3.0);
+  p = fma(r, p, -0.5);
+  p = fma(r, p, 1.0);
+  p = r * p;
+  const double ln = fma((double)e, 0.6931471805599453, LN_TAB[j][1]) + p;
+  return fmax(-2.0 * ln, 0.0);
+}
+
+/* N(0,1) from two words: u1 from a and the top byte of b (40 bits), the angle from b's other 24 bits */
+double orc_normal40(uint32_t a, uint32_t b) {
+  const uint64_t n40 = (uint64_t)a | ((uint64_t)(b >> 24) << 32);
+  double c, s;
+  orc_unit2(b << 8, &c, &s);
+  return sqrt(orc_neg2ln40(n40)) * c;
+}
+
+/* uniform point on the unit sphere from two words */
+void orc_sphere(uint32_t a, uint32_t b, double *o) {
+  double c, s;
+  orc_unit2(a, &c, &s);
+  const double z = 1.0 - ((double)b + 0.5) * 4.656612873077393e-10; /* 2^-31 */
+  const double q = sqrt(fmax(fma(-z, z, 1.0), 0.0));
+  o[0] = q * c;
+  o[1] = q * s;
+  o[2] = z;
+}
+
+static void noise_block(uint64_t seed, uint32_t stream, uint64_t index, uint32_t slot, uint32_t *o) {
   uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), stream, slot};
-  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   orc_philox4x32_10(ctr, key, o);
-  uint64_t x = (uint64_t)o[0] | ((uint64_t)o[1] << 32), y = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
-  double u1 = (double)((x >> 11) + 1) * 1.1102230246251565e-16;
-  double u2 = (double)(y >> 11) * 1.1102230246251565e-16;
-  double rr = sqrt(-2.0 * log(u1));
-  double th = 6.283185307179586 * u2;
-  z[0] = rr * cos(th);
-  z[1] = rr * sin(th);
 }
 
 enum { ST_DRIFT_CAM = 1, ST_DRIFT_PT = 2, ST_NOISE_CAM = 3, ST_NOISE_PT = 4, ST_NOISE_OBS = 5 };
@@ -913,7 +999,10 @@ void orc_add_drift(double *cams, uint64_t C, double *pts, uint64_t P, double str
     orc_center(cam, c);
     double d[3] = {c[0] - origin[0], c[1] - origin[1], c[2] - origin[2]};
     double distance = mag3(d);
-    orc_normal_pair(seed, ST_DRIFT_CAM, i, 0, z);
+    uint32_t o[4];
+    noise_block(seed, ST_DRIFT_CAM, i, 0, o);
+    z[0] = orc_normal40(o[0], o[1]); /* the angle's draw first (:104-107) */
+    z[1] = orc_normal40(o[2], o[3]);
     double v1 = 1.0 + std * z[0], v2 = 1.0 + std * z[1];
     double angle = (angle_strength * v1) * pow(distance, 1.2); /* :97, drawn first (:105) */
     for (int k = 0; k < 3; ++k) dl[k] = (((dir[k] * strength) * v2) * distance) * distance; /* :92 */
@@ -925,7 +1014,9 @@ void orc_add_drift(double *cams, uint64_t C, double *pts, uint64_t P, double str
     double *p = pts + 3 * i, z[2];
     double d[3] = {p[0] - origin[0], p[1] - origin[1], p[2] - origin[2]};
     double distance = mag3(d);
-    orc_normal_pair(seed, ST_DRIFT_PT, i, 0, z);
+    uint32_t o[4];
+    noise_block(seed, ST_DRIFT_PT, i, 0, o);
+    z[0] = orc_normal40(o[0], o[1]);
     double v = 1.0 + std * z[0];
     for (int k = 0; k < 3; ++k) p[k] = p[k] + (((dir[k] * strength) * v) * distance) * distance;
   }
@@ -941,12 +1032,9 @@ void orc_add_drift_normalized(double *cams, uint64_t C, double *pts, uint64_t P,
   orc_add_drift(cams, C, pts, P, strength * bal_std, angle_strength, std, dir, seed);
 }
 
-static void unit_from(double a, double b, double c, double *o) {
-  double v[3] = {a, b, c};
-  normalize3(v, o);
-}
-
-/* src/noise.rs:119-177 */
+/* src/noise.rs:119-177.  Draw order of the reference per camera: axis, angle, translation direction,
+ * magnitude (:140-141) = block 0 {sphere, N}, block 1 {sphere, N}; per point: direction, magnitude (:149) =
+ * one block {sphere, N}; per observation: direction (nx, ny), r (:159-163) = one block {circle, -, N}. */
 void orc_add_noise(double *cams, uint64_t C, double *pts, uint64_t P, double *uv, uint64_t O,
                    double translation_std, double rotation_std, double point_std,
                    double observations_std, uint64_t seed) {
@@ -954,38 +1042,36 @@ void orc_add_noise(double *cams, uint64_t C, double *pts, uint64_t P, double *uv
   orc_std(cams, C, pts, P, s);
   double bal_std = mag3(s);
   for (uint64_t i = 0; i < C; ++i) {
-    double *cam = cams + ORC_CAM_STRIDE * i, z0[2], z1[2], z2[2], z3[2], ax[3], tr[3], R[9], dl[3];
+    double *cam = cams + ORC_CAM_STRIDE * i, ax[3], tr[3], R[9], dl[3];
     double out[ORC_CAM_STRIDE];
-    orc_normal_pair(seed, ST_NOISE_CAM, i, 0, z0);
-    orc_normal_pair(seed, ST_NOISE_CAM, i, 1, z1);
-    orc_normal_pair(seed, ST_NOISE_CAM, i, 2, z2);
-    orc_normal_pair(seed, ST_NOISE_CAM, i, 3, z3);
-    unit_from(z0[0], z0[1], z1[0], ax);
-    double angle = 0.0 + rotation_std * z1[1];
-    unit_from(z2[0], z2[1], z3[0], tr);
-    double mag = 0.0 + translation_std * z3[1];
+    uint32_t o0[4], o1[4];
+    noise_block(seed, ST_NOISE_CAM, i, 0, o0);
+    noise_block(seed, ST_NOISE_CAM, i, 1, o1);
+    orc_sphere(o0[0], o0[1], ax);
+    double angle = 0.0 + rotation_std * orc_normal40(o0[2], o0[3]);
+    orc_sphere(o1[0], o1[1], tr);
+    double mag = 0.0 + translation_std * orc_normal40(o1[2], o1[3]);
     orc_from_axis_angle(ax, angle, R);
     for (int k = 0; k < 3; ++k) dl[k] = (tr[k] * bal_std) * mag;
     orc_transform(cam, R, dl, out);
     memcpy(cam, out, sizeof out);
   }
   for (uint64_t i = 0; i < P; ++i) {
-    double *p = pts + 3 * i, z0[2], z1[2], ax[3];
-    orc_normal_pair(seed, ST_NOISE_PT, i, 0, z0);
-    orc_normal_pair(seed, ST_NOISE_PT, i, 1, z1);
-    unit_from(z0[0], z0[1], z1[0], ax);
-    double mag = 0.0 + point_std * z1[1];
+    double *p = pts + 3 * i, ax[3];
+    uint32_t o[4];
+    noise_block(seed, ST_NOISE_PT, i, 0, o);
+    orc_sphere(o[0], o[1], ax);
+    double mag = 0.0 + point_std * orc_normal40(o[2], o[3]);
     for (int k = 0; k < 3; ++k) p[k] = p[k] + ax[k] * mag;
   }
   for (uint64_t i = 0; i < O; ++i) {
-    double z0[2], z1[2];
-    orc_normal_pair(seed, ST_NOISE_OBS, i, 0, z0);
-    orc_normal_pair(seed, ST_NOISE_OBS, i, 1, z1);
-    double nx = z0[0], ny = z0[1];
-    double m = sqrt(nx * nx + ny * ny);
-    double r = 0.0 + observations_std * z1[0];
-    uv[2 * i] = uv[2 * i] + nx / m * r;
-    uv[2 * i + 1] = uv[2 * i + 1] + ny / m * r;
+    uint32_t o[4];
+    double nx, ny;
+    noise_block(seed, ST_NOISE_OBS, i, 0, o);
+    orc_unit2(o[0], &nx, &ny);
+    double r = 0.0 + observations_std * orc_normal40(o[2], o[3]);
+    uv[2 * i] = uv[2 * i] + nx * r;
+    uv[2 * i + 1] = uv[2 * i + 1] + ny * r;
   }
 }
 
