@@ -545,9 +545,9 @@ def main():
         mscene.close()
         mctx.close()
 
-    # ---- noise pass on the generated problem (config 2 / 5: drift + Gaussian noise), rank 0 only ------
+    # ---- noise pass on the generated problem (config 2 / 5: drift + Gaussian noise), N = 1 only ------
     noise = None
-    if not args.no_noise and rank == 0:
+    if not args.no_noise and world == 1:
         O = n_obs_e2e
         pd_ = Ct.POINTER(Ct.c_double)
         # pinned host arrays (what a host program that cares about transfer time would hand over)
@@ -557,27 +557,42 @@ def main():
         uv, ncam, npts = t_uv.numpy(), t_cam.numpy(), t_pts.numpy()
         ms3 = (Ct.c_float * 3)()
         noise = {}
+        b_drift = 2 * (120 * C + 24 * P) + 3 * 24 * (C + P)
+        b_noise = 2 * (120 * C + 24 * P + 16 * O) + 2 * 24 * (C + P)
+        # (1) resident: generate -> noise without leaving HBM; ms_kernels = statistics reductions + elementwise
+        # kernels, CUDA events on the library's stream
+        prob.upload()
+        prob.rp.run(prob.scene, MAX_DIST, cull_mode=args.cull_mode)
         for name, call, nbytes in (
+            ("add_drift_normalized", lambda: L.c2b_add_drift_resident(ctx.handle, 0.001, 0.0, 0.0, None, 1), b_drift),
+            ("add_noise", lambda: L.c2b_add_noise_resident(ctx.handle, 0.0, 0.0001, 0.01, 0.001, 42), b_noise),
+        ):
+            kern = 1e9
+            for _ in range(4):
+                flush_l2()
+                _lib.check(call())
+                _lib.check(L.c2b_noise_timing(ctx.handle, ms3))
+                kern = min(kern, float(ms3[1]))
+            noise[name] = {"elements": C + P + (O if name == "add_noise" else 0), "ms_kernels_resident": kern,
+                           "algorithmic_bytes": nbytes, "kernel_GBps": nbytes / (kern * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": nbytes / (kern * 1e-3) / 1e9 / measured_peaks()[0]}
+        # (2) host arrays in and out through the reference-shaped entries
+        for name, call in (
             ("add_drift_normalized", lambda: L.c2b_add_drift_normalized(
-                ctx.handle, ncam.ctypes.data_as(pd_), len(ncam), npts.ctypes.data_as(pd_), len(npts),
-                0.001, 0.0, 0.0, 1), 2 * (120 * len(ncam) + 24 * len(npts)) + 3 * 24 * (len(ncam) + len(npts))),
+                ctx.handle, ncam.ctypes.data_as(pd_), len(ncam), npts.ctypes.data_as(pd_), len(npts), 0.001, 0.0, 0.0, 1)),
             ("add_noise", lambda: L.c2b_add_noise(
                 ctx.handle, ncam.ctypes.data_as(pd_), len(ncam), npts.ctypes.data_as(pd_), len(npts),
-                uv.ctypes.data_as(pd_), O, 0.0, 0.0001, 0.01, 0.001, 42),
-             2 * (120 * len(ncam) + 24 * len(npts) + 16 * O) + 2 * 24 * (len(ncam) + len(npts))),
+                uv.ctypes.data_as(pd_), O, 0.0, 0.0001, 0.01, 0.001, 42)),
         ):
-            best_wall, kern = 1e9, 0.0
+            best_wall = 1e9
             for _ in range(3):
                 t0 = time.perf_counter()
                 _lib.check(call())
                 best_wall = min(best_wall, time.perf_counter() - t0)
-                _lib.check(L.c2b_noise_timing(ctx.handle, ms3))
-                kern = float(ms3[1])
-            noise[name] = {"elements": len(ncam) + len(npts) + (O if name == "add_noise" else 0),
-                           "ms_host_to_host": 1e3 * best_wall, "ms_kernels": kern,
-                           "algorithmic_bytes": nbytes, "kernel_GBps": nbytes / (kern * 1e-3) / 1e9 if kern > 0 else None,
-                           "note": "pinned host arrays in and out (H2D + D2H inside ms_host_to_host); "
-                                   "ms_kernels = statistics reductions + elementwise kernels (CUDA events)"}
+            noise[name]["ms_host_to_host"] = 1e3 * best_wall
+            noise[name]["note"] = ("ms_kernels_resident: c2b_add_*_resident on the problem in HBM (statistics + elementwise "
+                                   "kernels, CUDA events); ms_host_to_host: pinned host arrays in and out, observations "
+                                   "streamed in chunks so that upload and download overlap")
 
     # ---- traversal counters (one untimed instrumented run) and the exhaustive arm ------------------
     _, stc = prob.resident(args.cull_mode, 1, 0, count=True)

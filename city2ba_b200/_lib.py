@@ -92,6 +92,7 @@ EXPORTS = [
     "c2b_scene_destroy_multi", "c2b_multi_scene_get", "c2b_visibility_graph_multi",
     "c2b_visibility_graph_resident", "c2b_download_obs", "c2b_reprojection_error_resident",
     "c2b_add_drift", "c2b_add_drift_normalized", "c2b_add_noise", "c2b_add_sin_noise", "c2b_noise_timing",
+    "c2b_add_drift_resident", "c2b_add_noise_resident", "c2b_add_sin_noise_resident", "c2b_download_problem",
     "c2b_mean_std", "c2b_generate_world_points_uniform",
     "c2b_grid_num_cameras", "c2b_grid_num_points", "c2b_grid_cameras", "c2b_grid_points",
     "c2b_line_cameras", "c2b_line_points", "c2b_city_mesh", "c2b_camera_center",
@@ -165,6 +166,10 @@ def lib():
     L.c2b_add_noise.argtypes = [vp, pd, u64, pd, u64, pd, u64, dbl, dbl, dbl, dbl, u64]
     L.c2b_add_sin_noise.argtypes = [vp, pd, u64, pd, u64, pd, pd, dbl, dbl]
     L.c2b_noise_timing.argtypes = [vp, pf]
+    L.c2b_add_drift_resident.argtypes = [vp, dbl, dbl, dbl, pd, u64]
+    L.c2b_add_noise_resident.argtypes = [vp, dbl, dbl, dbl, dbl, u64]
+    L.c2b_add_sin_noise_resident.argtypes = [vp, pd, pd, dbl, dbl]
+    L.c2b_download_problem.argtypes = [vp, pd, pd]
     L.c2b_mean_std.argtypes = [vp, pd, u64, pd, u64, pd, pd]
     L.c2b_probe_fp64.argtypes = [vp, pd]
     L.c2b_generate_world_points_uniform.argtypes = [vp, pf, u64, pu32, u64, pd, u64, u64, dbl, u64, pd,

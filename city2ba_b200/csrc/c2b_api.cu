@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -193,6 +194,13 @@ int c2b_init(int device, c2b_ctx **out) {
     ctx->numa_node = node;
     for (PinBuf *b : {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small}) b->node = node;
   }
+  {  // tables of the noise draws (c2b_noise.cuh), one copy per device
+    static double2 sc[256], ln[128];
+    static std::once_flag once;
+    std::call_once(once, [] { noise_tables_host(sc, ln); });
+    C2B_CUDA(cudaMemcpyToSymbol(g_sc_tab, sc, sizeof sc));
+    C2B_CUDA(cudaMemcpyToSymbol(g_ln_tab, ln, sizeof ln));
+  }
   CtxExtra *x = new CtxExtra();
   {
     struct { const char *env, *name; } hooks[] = {
@@ -232,7 +240,8 @@ void c2b_shutdown(c2b_ctx *ctx) {
                     &ctx->vis_words, &ctx->word_prefix, &ctx->out_offsets[0], &ctx->out_idx[0],
                     &ctx->out_uv[0], &ctx->out_offsets[1], &ctx->out_idx[1], &ctx->out_uv[1],
                     &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos, &ctx->ev_off,
-                    &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx, &ctx->plan_rows, &ctx->plan_row_count};
+                    &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx, &ctx->plan_rows, &ctx->plan_row_count,
+                    &ctx->nz_cams, &ctx->nz_centers, &ctx->nz_pts, &ctx->nz_uv, &ctx->nz_scratch};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
@@ -1287,15 +1296,13 @@ int c2b_reprojection_error_resident(c2b_ctx *ctx, double norm, double *out) {
 
 // ---- noise ----------------------------------------------------------------------------------------------
 namespace {
-struct NoiseBufs {
-  DevBuf cams, centers, pts, uv, scratch;
-  ~NoiseBufs() {
-    cams.release();
-    centers.release();
-    pts.release();
-    uv.release();
-    scratch.release();
-  }
+// the arrays a noise pass works on, all on the device
+struct NoiseView {
+  double *cams = nullptr;     // [15 C]
+  double *centers = nullptr;  // [3 C] SoA, up to date with cams
+  double *pts = nullptr;      // [3 P] xyz records
+  double2 *uv = nullptr;      // [O]
+  uint64_t C = 0, P = 0, O = 0;
 };
 
 // device time of the last noise call: [0] upload, [1] statistics + kernels, [2] download
@@ -1319,19 +1326,22 @@ struct NoiseTimer {
   }
 };
 
+inline unsigned nz_grid(c2b_ctx *ctx, uint64_t n) {
+  return (unsigned)std::min<uint64_t>(std::max<uint64_t>(blocks_for(n, NZ_THREADS), 1), (uint64_t)ctx->sm_count * 8);
+}
+
 // mean / std / nearest-origin of the chained sequence on the device.  scratch layout (doubles):
 // [0..2] mean, [3..5] sumsq, [6..8] origin, then partials.
-int device_stats(c2b_ctx *ctx, NoiseBufs &nb, uint64_t C, uint64_t P, double mean[3], double sd[3],
-                 bool want_origin) {
+int device_stats(c2b_ctx *ctx, const NoiseView &v, double mean[3], double sd[3], bool want_origin) {
   cudaStream_t st = ctx->stream;
-  const uint64_t n = C + P;
+  const uint64_t C = v.C, P = v.P, n = C + P;
   const double num = (double)n;
   int blocks = (int)std::min<uint64_t>(std::max<uint64_t>(blocks_for(n, ST_THREADS), 1), ST_BLOCKS);
-  C2B_TRY(nb.scratch.ensure((size_t)(16 + 8 * blocks) * 8));
-  double *s = nb.scratch.as<double>();
+  C2B_TRY(ctx->nz_scratch.ensure((size_t)(16 + 8 * blocks) * 8));
+  double *s = ctx->nz_scratch.as<double>();
   double *partial = s + 16;
-  const double *cx = nb.centers.as<double>();
-  const double *pts = nb.pts.as<double>();
+  const double *cx = v.centers;
+  const double *pts = v.pts;
   k_stats_partial<0><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num, V3{0, 0, 0}, partial);
   C2B_KERNEL_CHECK();
   k_stats_final<<<1, 32, 0, st>>>(partial, blocks, s);
@@ -1358,39 +1368,62 @@ int device_stats(c2b_ctx *ctx, NoiseBufs &nb, uint64_t C, uint64_t P, double mea
   return C2B_OK;
 }
 
-int noise_upload(c2b_ctx *ctx, NoiseBufs &nb, const double *cams, uint64_t C, const double *pts,
-                 uint64_t P, const double *uv, uint64_t O) {
+// host arrays -> the ctx's noise buffers (grow-only, kept between calls)
+int noise_upload(c2b_ctx *ctx, NoiseView &v, const double *cams, uint64_t C, const double *pts, uint64_t P) {
   cudaStream_t st = ctx->stream;
-  C2B_TRY(nb.cams.ensure(std::max<uint64_t>(C, 1) * 120));
-  C2B_TRY(nb.centers.ensure(std::max<uint64_t>(C, 1) * 24));
-  C2B_TRY(nb.pts.ensure(std::max<uint64_t>(P, 1) * 24));
+  C2B_TRY(ctx->nz_cams.ensure(std::max<uint64_t>(C, 1) * 120));
+  C2B_TRY(ctx->nz_centers.ensure(std::max<uint64_t>(C, 1) * 24));
+  C2B_TRY(ctx->nz_pts.ensure(std::max<uint64_t>(P, 1) * 24));
+  v.cams = ctx->nz_cams.as<double>();
+  v.centers = ctx->nz_centers.as<double>();
+  v.pts = ctx->nz_pts.as<double>();
+  v.C = C;
+  v.P = P;
   if (C) {
-    C2B_CUDA(cudaMemcpyAsync(nb.cams.p, cams, C * 120, cudaMemcpyHostToDevice, st));
-    double *cx = nb.centers.as<double>();
-    k_cam_prep<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, cx, cx + C, cx + 2 * C);
+    C2B_TRY(copy_in(ctx, v.cams, cams, C * 120, cudaMemcpyHostToDevice));
+    k_cam_prep<<<blocks_for(C, 128), 128, 0, st>>>(v.cams, C, v.centers, v.centers + C, v.centers + 2 * C);
     C2B_KERNEL_CHECK();
   }
-  if (P) C2B_CUDA(cudaMemcpyAsync(nb.pts.p, pts, P * 24, cudaMemcpyHostToDevice, st));
-  if (O) {
-    C2B_TRY(nb.uv.ensure(O * 16));
-    C2B_CUDA(cudaMemcpyAsync(nb.uv.p, uv, O * 16, cudaMemcpyHostToDevice, st));
-  }
+  if (P) C2B_TRY(copy_in(ctx, v.pts, pts, P * 24, cudaMemcpyHostToDevice));
   return C2B_OK;
 }
 
-int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double strength,
-               double angle_strength, double std_, const double *dir_in, bool normalized,
-               uint64_t seed) {
-  if (!ctx || (C && !cams) || (P && !pts)) return set_error(C2B_ERR_INVALID, "add_drift: null argument");
-  if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_drift: problem has no cameras and no points");
-  C2B_CUDA(cudaSetDevice(ctx->device));
+// the resident problem as a NoiseView (cameras + points of the last uploads, (u, v) of the last resident pass)
+int resident_view(c2b_ctx *ctx, NoiseView &v, const char *who) {
+  CtxExtra *x = extra_of(ctx);
+  if (!x->have_points || !x->have_cameras) return set_error(C2B_ERR_INVALID, "%s: upload cameras and points first", who);
+  v.cams = ctx->cams.as<double>();
+  v.centers = ctx->cam_center.as<double>();
+  v.pts = ctx->pts_aos.as<double>();
+  v.C = ctx->C;
+  v.P = ctx->P;
+  v.uv = x->have_result ? ctx->out_uv[ctx->out_sel].as<double2>() : nullptr;
+  v.O = x->have_result ? ctx->out_O : 0;
+  return C2B_OK;
+}
+
+// after a resident noise pass: camera centres and the SoA points / bounds / grid follow the new values
+int resident_refresh(c2b_ctx *ctx, bool cams_moved, bool pts_moved) {
+  if (cams_moved && ctx->C) {
+    double *cx = ctx->cam_center.as<double>();
+    k_cam_prep<<<blocks_for(ctx->C, 128), 128, 0, ctx->stream>>>(ctx->cams.as<double>(), ctx->C, cx, cx + ctx->C, cx + 2 * ctx->C);
+    C2B_KERNEL_CHECK();
+  }
+  if (pts_moved) {
+    CtxExtra *x = extra_of(ctx);
+    const bool had = x->have_result;
+    C2B_TRY(c2b_points_commit(ctx, ctx->P));
+    x->have_result = had;  // the CSR is still the graph of this problem
+  }
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
+  return C2B_OK;
+}
+
+int drift_kernels(c2b_ctx *ctx, const NoiseView &v, double strength, double angle_strength, double std_,
+                  const double *dir_in, bool normalized, uint64_t seed) {
   cudaStream_t st = ctx->stream;
-  NoiseBufs nb;
-  NoiseTimer tm(ctx);
-  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
-  tm.mark(1);
   double mean[3], sd[3];
-  C2B_TRY(device_stats(ctx, nb, C, P, mean, sd, true));
+  C2B_TRY(device_stats(ctx, v, mean, sd, true));
   V3 dir;
   if (normalized) {
     // add_drift_normalized, src/noise.rs:53-55
@@ -1402,22 +1435,90 @@ int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, 
   } else {
     dir = V3{dir_in[0], dir_in[1], dir_in[2]};
   }
-  const double *origin = nb.scratch.as<double>() + 6;
-  if (C) {
-    k_drift_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, origin, dir, strength,
-                                                     angle_strength, std_, seed);
+  const double *origin = ctx->nz_scratch.as<double>() + 6;
+  if (v.C) {
+    k_drift_cams<<<blocks_for(v.C, NZ_THREADS), NZ_THREADS, 0, st>>>(v.cams, v.C, origin, dir, strength, angle_strength, std_, seed);
     C2B_KERNEL_CHECK();
   }
-  if (P) {
-    k_drift_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, origin, dir, strength, std_, seed);
+  if (v.P) {
+    k_drift_pts<<<nz_grid(ctx, v.P), NZ_THREADS, 0, st>>>(v.pts, v.P, origin, dir, strength, std_, seed);
     C2B_KERNEL_CHECK();
   }
+  return C2B_OK;
+}
+
+int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double strength,
+               double angle_strength, double std_, const double *dir_in, bool normalized,
+               uint64_t seed) {
+  if (!ctx || (C && !cams) || (P && !pts)) return set_error(C2B_ERR_INVALID, "add_drift: null argument");
+  if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_drift: problem has no cameras and no points");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  NoiseView v;
+  NoiseTimer tm(ctx);
+  C2B_TRY(noise_upload(ctx, v, cams, C, pts, P));
+  tm.mark(1);
+  C2B_TRY(drift_kernels(ctx, v, strength, angle_strength, std_, dir_in, normalized, seed));
   tm.mark(2);
-  if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
-  if (P) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  if (C) C2B_CUDA(cudaMemcpyAsync(cams, v.cams, C * 120, cudaMemcpyDeviceToHost, st));
+  if (P) C2B_CUDA(cudaMemcpyAsync(pts, v.pts, P * 24, cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   C2B_CUDA(cudaStreamSynchronize(st));
   tm.finish();
+  return C2B_OK;
+}
+
+// cameras and points of add_noise (the observations are separate: the host entry streams them in chunks)
+int noise_kernels(c2b_ctx *ctx, const NoiseView &v, double translation_std, double rotation_std, double point_std,
+                  uint64_t seed) {
+  cudaStream_t st = ctx->stream;
+  double mean[3], sd[3];
+  C2B_TRY(device_stats(ctx, v, mean, sd, false));
+  double bal_std = std::sqrt((sd[0] * sd[0] + sd[1] * sd[1]) + sd[2] * sd[2]);
+  if (v.C) {
+    k_noise_cams<<<blocks_for(v.C, NZ_THREADS), NZ_THREADS, 0, st>>>(v.cams, v.C, bal_std, translation_std, rotation_std, seed);
+    C2B_KERNEL_CHECK();
+  }
+  // a zero standard deviation adds unit_random() * 0 (src/noise.rs:149,159-168): the array is unchanged, so its
+  // kernel — and in the host entry its round trip over PCIe — is skipped
+  if (v.P && point_std != 0.0) {
+    k_noise_pts<<<nz_grid(ctx, v.P), NZ_THREADS, 0, st>>>(v.pts, v.P, point_std, seed);
+    C2B_KERNEL_CHECK();
+  }
+  return C2B_OK;
+}
+
+int sin_kernels(c2b_ctx *ctx, const NoiseView &v, const double dir[3], const double noise_dir[3], double strength,
+                double frequency) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t C = v.C, P = v.P, n = C + P;
+  int blocks = (int)std::min<uint64_t>(std::max<uint64_t>(blocks_for(n, ST_THREADS), 1), ST_BLOCKS);
+  C2B_TRY(ctx->nz_scratch.ensure((size_t)(8 + 6 * blocks) * 8));
+  double *s = ctx->nz_scratch.as<double>();
+  const double *cx = v.centers;
+  k_extent_partial<<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, v.pts, P, s + 8);
+  C2B_KERNEL_CHECK();
+  k_extent_final<<<1, 32, 0, st>>>(s + 8, blocks, s);
+  C2B_KERNEL_CHECK();
+  double ext[6];
+  C2B_CUDA(cudaMemcpyAsync(ext, s, 48, cudaMemcpyDeviceToHost, st));
+  C2B_CUDA(cudaStreamSynchronize(st));
+  V3 dim{ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
+  // "Add epsilon to nonexistent dimensions" (src/noise.rs:395-396)
+  if (dim.x == 0.0) dim.x = 1e-8;
+  if (dim.y == 0.0) dim.y = 1e-8;
+  if (dim.z == 0.0) dim.z = 1e-8;
+  const double nm = std::sqrt((noise_dir[0] * noise_dir[0] + noise_dir[1] * noise_dir[1]) + noise_dir[2] * noise_dir[2]);
+  const double inv = 1.0 / nm;
+  const V3 nd{noise_dir[0] * inv, noise_dir[1] * inv, noise_dir[2] * inv}, d{dir[0], dir[1], dir[2]};
+  if (C) {
+    k_sin_cams<<<blocks_for(C, 128), 128, 0, st>>>(v.cams, C, dim, d, nd, strength, frequency);
+    C2B_KERNEL_CHECK();
+  }
+  if (P) {
+    k_sin_pts<<<blocks_for(P, 256), 256, 0, st>>>(v.pts, P, dim, d, nd, strength, frequency);
+    C2B_KERNEL_CHECK();
+  }
   return C2B_OK;
 }
 }  // namespace
@@ -1440,35 +1541,56 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
     return set_error(C2B_ERR_INVALID, "c2b_add_noise: null argument");
   if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_noise: problem has no cameras and no points");
   C2B_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  NoiseBufs nb;
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  NoiseView v;
   NoiseTimer tm(ctx);
-  // a zero standard deviation adds unit_random() * 0 (src/noise.rs:149,159-168): the array is unchanged, so
-  // its kernel — and for the observations the round trip over PCIe — is skipped
   if (observations_std == 0.0) O = 0;
-  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, uv, O));
-  tm.mark(1);
-  double mean[3], sd[3];
-  C2B_TRY(device_stats(ctx, nb, C, P, mean, sd, false));
-  double bal_std = std::sqrt((sd[0] * sd[0] + sd[1] * sd[1]) + sd[2] * sd[2]);
-  if (C) {
-    k_noise_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, bal_std, translation_std,
-                                                     rotation_std, seed);
-    C2B_KERNEL_CHECK();
-  }
-  const bool move_points = P && point_std != 0.0;
-  if (move_points) {
-    k_noise_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, point_std, seed);
-    C2B_KERNEL_CHECK();
-  }
+  // The observations (16 B each way, by far the largest array) stream through the GPU in chunks on the copy
+  // stream while cameras and points are handled on the main one: PCIe is full duplex, so chunk k's download
+  // overlaps chunk k+1's upload and the call costs about one direction of the transfer, not two.
+  cudaEvent_t obs_done = nullptr;
   if (O) {
-    k_noise_obs<<<blocks_for(O, 256), 256, 0, st>>>(nb.uv.as<double2>(), O, observations_std, seed);
-    C2B_KERNEL_CHECK();
+    const uint64_t chunk = std::max<uint64_t>(1u << 20, (O + 15) / 16);
+    C2B_TRY(ctx->nz_uv.ensure(std::min(O, 2 * chunk) * 16));
+    double2 *buf = ctx->nz_uv.as<double2>();
+    cudaEvent_t slot_free[2] = {nullptr, nullptr}, up[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) {
+      C2B_CUDA(cudaEventCreateWithFlags(&slot_free[k], cudaEventDisableTiming));
+      C2B_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
+    }
+    C2B_CUDA(cudaEventCreateWithFlags(&obs_done, cudaEventDisableTiming));
+    // uploads + kernels on the aux stream, downloads on the copy stream; two slots
+    cudaStream_t ax = ctx->aux_stream;
+    uint64_t k = 0;
+    for (uint64_t first = 0; first < O; first += chunk, ++k) {
+      const uint64_t n = std::min(chunk, O - first);
+      const int slot = (int)(k & 1);
+      double2 *d = buf + (uint64_t)slot * chunk;
+      if (k >= 2) C2B_CUDA(cudaStreamWaitEvent(ax, slot_free[slot], 0));
+      C2B_CUDA(cudaMemcpyAsync(d, uv + 2 * first, n * 16, cudaMemcpyHostToDevice, ax));
+      k_noise_obs<<<nz_grid(ctx, n), NZ_THREADS, 0, ax>>>(d, n, first, observations_std, seed);
+      C2B_KERNEL_CHECK();
+      C2B_CUDA(cudaEventRecord(up[slot], ax));
+      C2B_CUDA(cudaStreamWaitEvent(cs, up[slot], 0));
+      C2B_CUDA(cudaMemcpyAsync(uv + 2 * first, d, n * 16, cudaMemcpyDeviceToHost, cs));
+      C2B_CUDA(cudaEventRecord(slot_free[slot], cs));
+    }
+    C2B_CUDA(cudaEventRecord(obs_done, cs));
+    for (int q = 0; q < 2; ++q) {
+      cudaEventDestroy(slot_free[q]);
+      cudaEventDestroy(up[q]);
+    }
   }
+  C2B_TRY(noise_upload(ctx, v, cams, C, pts, P));
+  tm.mark(1);
+  C2B_TRY(noise_kernels(ctx, v, translation_std, rotation_std, point_std, seed));
   tm.mark(2);
-  if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
-  if (move_points) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
-  if (O) C2B_CUDA(cudaMemcpyAsync(uv, nb.uv.p, O * 16, cudaMemcpyDeviceToHost, st));
+  if (C) C2B_CUDA(cudaMemcpyAsync(cams, v.cams, C * 120, cudaMemcpyDeviceToHost, st));
+  if (P && point_std != 0.0) C2B_CUDA(cudaMemcpyAsync(pts, v.pts, P * 24, cudaMemcpyDeviceToHost, st));
+  if (obs_done) {
+    C2B_CUDA(cudaStreamWaitEvent(st, obs_done, 0));
+    cudaEventDestroy(obs_done);
+  }
   tm.mark(3);
   C2B_CUDA(cudaStreamSynchronize(st));
   tm.finish();
@@ -1482,44 +1604,85 @@ int c2b_add_sin_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint6
   if (C + P == 0) return set_error(C2B_ERR_EMPTY, "add_sin_noise: problem has no cameras and no points");
   C2B_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  NoiseBufs nb;
+  NoiseView v;
   NoiseTimer tm(ctx);
-  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
+  C2B_TRY(noise_upload(ctx, v, cams, C, pts, P));
   tm.mark(1);
-  const uint64_t n = C + P;
-  int blocks = (int)std::min<uint64_t>(std::max<uint64_t>(blocks_for(n, ST_THREADS), 1), ST_BLOCKS);
-  C2B_TRY(nb.scratch.ensure((size_t)(8 + 6 * blocks) * 8));
-  double *s = nb.scratch.as<double>();
-  const double *cx = nb.centers.as<double>();
-  k_extent_partial<<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, nb.pts.as<double>(), P, s + 8);
-  C2B_KERNEL_CHECK();
-  k_extent_final<<<1, 32, 0, st>>>(s + 8, blocks, s);
-  C2B_KERNEL_CHECK();
-  double ext[6];
-  C2B_CUDA(cudaMemcpyAsync(ext, s, 48, cudaMemcpyDeviceToHost, st));
-  C2B_CUDA(cudaStreamSynchronize(st));
-  V3 dim{ext[3] - ext[0], ext[4] - ext[1], ext[5] - ext[2]};
-  // "Add epsilon to nonexistent dimensions" (src/noise.rs:395-396)
-  if (dim.x == 0.0) dim.x = 1e-8;
-  if (dim.y == 0.0) dim.y = 1e-8;
-  if (dim.z == 0.0) dim.z = 1e-8;
-  const double nm = std::sqrt((noise_dir[0] * noise_dir[0] + noise_dir[1] * noise_dir[1]) + noise_dir[2] * noise_dir[2]);
-  const double inv = 1.0 / nm;
-  const V3 nd{noise_dir[0] * inv, noise_dir[1] * inv, noise_dir[2] * inv}, d{dir[0], dir[1], dir[2]};
-  if (C) {
-    k_sin_cams<<<blocks_for(C, 128), 128, 0, st>>>(nb.cams.as<double>(), C, dim, d, nd, strength, frequency);
-    C2B_KERNEL_CHECK();
-  }
-  if (P) {
-    k_sin_pts<<<blocks_for(P, 256), 256, 0, st>>>(nb.pts.as<double>(), P, dim, d, nd, strength, frequency);
-    C2B_KERNEL_CHECK();
-  }
+  C2B_TRY(sin_kernels(ctx, v, dir, noise_dir, strength, frequency));
   tm.mark(2);
-  if (C) C2B_CUDA(cudaMemcpyAsync(cams, nb.cams.p, C * 120, cudaMemcpyDeviceToHost, st));
-  if (P) C2B_CUDA(cudaMemcpyAsync(pts, nb.pts.p, P * 24, cudaMemcpyDeviceToHost, st));
+  if (C) C2B_CUDA(cudaMemcpyAsync(cams, v.cams, C * 120, cudaMemcpyDeviceToHost, st));
+  if (P) C2B_CUDA(cudaMemcpyAsync(pts, v.pts, P * 24, cudaMemcpyDeviceToHost, st));
   tm.mark(3);
   C2B_CUDA(cudaStreamSynchronize(st));
   tm.finish();
+  return C2B_OK;
+}
+
+// ---- the same passes on the RESIDENT problem: no PCIe traffic at all -------------------------------------
+int c2b_add_drift_resident(c2b_ctx *ctx, double strength, double angle_strength, double std_, const double *dir,
+                           uint64_t seed) {
+  if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_add_drift_resident: null ctx");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  NoiseView v;
+  C2B_TRY(resident_view(ctx, v, "c2b_add_drift_resident"));
+  if (v.C + v.P == 0) return set_error(C2B_ERR_EMPTY, "add_drift: problem has no cameras and no points");
+  NoiseTimer tm(ctx);
+  tm.mark(1);
+  C2B_TRY(drift_kernels(ctx, v, strength, angle_strength, std_, dir, dir == nullptr, seed));
+  tm.mark(2);
+  tm.mark(3);
+  C2B_TRY(resident_refresh(ctx, true, true));
+  tm.finish();
+  return C2B_OK;
+}
+
+int c2b_add_noise_resident(c2b_ctx *ctx, double translation_std, double rotation_std, double point_std,
+                           double observations_std, uint64_t seed) {
+  if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_add_noise_resident: null ctx");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  NoiseView v;
+  C2B_TRY(resident_view(ctx, v, "c2b_add_noise_resident"));
+  if (v.C + v.P == 0) return set_error(C2B_ERR_EMPTY, "add_noise: problem has no cameras and no points");
+  NoiseTimer tm(ctx);
+  tm.mark(1);
+  C2B_TRY(noise_kernels(ctx, v, translation_std, rotation_std, point_std, seed));
+  if (v.O && observations_std != 0.0) {
+    k_noise_obs<<<nz_grid(ctx, v.O), NZ_THREADS, 0, ctx->stream>>>(v.uv, v.O, 0, observations_std, seed);
+    C2B_KERNEL_CHECK();
+  }
+  tm.mark(2);
+  tm.mark(3);
+  C2B_TRY(resident_refresh(ctx, true, point_std != 0.0));
+  tm.finish();
+  return C2B_OK;
+}
+
+int c2b_add_sin_noise_resident(c2b_ctx *ctx, const double dir[3], const double noise_dir[3], double strength,
+                               double frequency) {
+  if (!ctx || !dir || !noise_dir) return set_error(C2B_ERR_INVALID, "c2b_add_sin_noise_resident: null argument");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  NoiseView v;
+  C2B_TRY(resident_view(ctx, v, "c2b_add_sin_noise_resident"));
+  if (v.C + v.P == 0) return set_error(C2B_ERR_EMPTY, "add_sin_noise: problem has no cameras and no points");
+  NoiseTimer tm(ctx);
+  tm.mark(1);
+  C2B_TRY(sin_kernels(ctx, v, dir, noise_dir, strength, frequency));
+  tm.mark(2);
+  tm.mark(3);
+  C2B_TRY(resident_refresh(ctx, true, true));
+  tm.finish();
+  return C2B_OK;
+}
+
+int c2b_download_problem(c2b_ctx *ctx, double *cams_out, double *pts_out) {
+  if (!ctx) return set_error(C2B_ERR_INVALID, "c2b_download_problem: null ctx");
+  NoiseView v;
+  C2B_TRY(resident_view(ctx, v, "c2b_download_problem"));
+  if ((v.C && !cams_out) || (v.P && !pts_out)) return set_error(C2B_ERR_INVALID, "c2b_download_problem: null output array");
+  C2B_CUDA(cudaSetDevice(ctx->device));
+  if (v.C) C2B_CUDA(cudaMemcpyAsync(cams_out, v.cams, v.C * 120, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v.P) C2B_CUDA(cudaMemcpyAsync(pts_out, v.pts, v.P * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
   return C2B_OK;
 }
 
@@ -1712,9 +1875,9 @@ int c2b_mean_std(c2b_ctx *ctx, const double *cams, uint64_t C, const double *pts
     return set_error(C2B_ERR_INVALID, "c2b_mean_std: null argument");
   if (C + P == 0) return set_error(C2B_ERR_EMPTY, "mean/std of an empty problem");
   C2B_CUDA(cudaSetDevice(ctx->device));
-  NoiseBufs nb;
-  C2B_TRY(noise_upload(ctx, nb, cams, C, pts, P, nullptr, 0));
-  return device_stats(ctx, nb, C, P, mean, sd, false);
+  NoiseView v;
+  C2B_TRY(noise_upload(ctx, v, cams, C, pts, P));
+  return device_stats(ctx, v, mean, sd, false);
 }
 
 }  // extern "C"

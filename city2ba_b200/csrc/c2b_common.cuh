@@ -220,6 +220,8 @@ struct c2b_ctx {
   c2b::DevBuf ev_off, vis_count, seg_off, scratch_idx, plan_rows, plan_row_count;
   int numa_node = -1;  // of the device, from sysfs (-1: unknown)
 
+  // noise passes on host arrays: grow-only device copies kept between calls
+  c2b::DevBuf nz_cams, nz_centers, nz_pts, nz_uv, nz_scratch;
   float noise_ms[3] = {0, 0, 0};  // last noise call: upload, statistics + kernels, download
 
   // host results

@@ -3,9 +3,20 @@
 // src/baproblem.rs:282-304, and the element nearest the world origin, src/noise.rs:75-87) as
 // deterministic two-stage tree reductions.
 //
-// Random stream: Philox4x32-10, key = seed, counter = (index lo, index hi, stream, slot); each
-// counter yields two N(0,1) draws by Box-Muller in f64 (u1 in (0,1], u2 in [0,1)).  Streams and
-// slots follow the reference's draw order (angle before translation, axis before magnitude).
+// Random stream: Philox4x32-10, key = seed, counter = (index lo, index hi, stream, slot); ONE block per
+// point / observation (two per camera).  The reference draws a direction as a normalised Gaussian pair or
+// triple (unit_random, src/noise.rs:35-43; (nx, ny) / |(nx, ny)|, :159-163) and a magnitude as Normal(m, s)
+// from the unseedable thread_rng(): only distributions can be matched, and a normalised Gaussian pair IS a
+// uniform direction on the circle, a triple a uniform point on the sphere.  So a block supplies
+//     circle  (cos, sin)(2 pi w / 2^32)                                one 32-bit word
+//     sphere  z = 1 - 2 (b + 1/2) / 2^32, azimuth from a               two words
+//     N(0,1)  Box-Muller, u1 = (n40 + 1) 2^-40, angle from 24 bits     two words
+// evaluated by table + short polynomial (cos / sin of k 2 pi / 256 with a Taylor remainder, ln by 128
+// mantissa intervals and a degree-6 series): ~55 FP64 instructions per observation where two Box-Muller
+// pairs through libm's log / sincos took ~160 (profiles/r01m_ncu_r01m_noise_obs.txt: FP64 pipe 47 %, 0.26 of
+// the HBM peak).  Every operation is an explicit fma / mul / add in a fixed order, so a CPU restatement
+// that performs the same ones on the same tables (filled on the host by c2b_init with libm) reproduces points
+// and observations bit for bit (the test suite's checker does); cameras (sin / cos / pow of libm inside) to a few ulp.
 #pragma once
 #include "c2b_common.cuh"
 #include "c2b_math.cuh"
@@ -34,20 +45,86 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[3] = c3;
 }
 
-__device__ __forceinline__ void normal_pair(uint64_t seed, uint32_t stream, uint64_t index,
-                                            uint32_t slot, double &z0, double &z1) {
-  uint32_t o[4];
-  philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, slot, (uint32_t)seed,
-                (uint32_t)(seed >> 32), o);
-  uint64_t x = (uint64_t)o[0] | ((uint64_t)o[1] << 32), y = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
-  double u1 = dmul((double)((x >> 11) + 1), 1.1102230246251565e-16);
-  double u2 = dmul((double)(y >> 11), 1.1102230246251565e-16);
-  double rr = dsqrt(dmul(-2.0, log(u1)));
-  double th = dmul(6.283185307179586, u2);
-  double s, c;
-  sincos(th, &s, &c);
-  z0 = dmul(rr, c);
-  z1 = dmul(rr, s);
+__device__ double2 g_sc_tab[256];  // (cos, sin)(k 2 pi / 256)
+__device__ double2 g_ln_tab[128];  // (1 / c_j, ln c_j), c_j = 1 + (2 j + 1) / 256
+
+// the host's copy of the tables (libm), uploaded to every device by c2b_init
+inline void noise_tables_host(double2 *sc, double2 *ln) {
+  for (int k = 0; k < 256; ++k) {
+    const double a = (double)k * (6.283185307179586 / 256.0);
+    sc[k] = make_double2(cos(a), sin(a));
+  }
+  for (int j = 0; j < 128; ++j) {
+    const double c = 1.0 + (double)(2 * j + 1) / 256.0;
+    ln[j] = make_double2(1.0 / c, log(c));
+  }
+}
+
+struct NoiseTabs {
+  double2 sc[256];
+  double2 ln[128];
+};
+
+// block-wide: the tables into shared memory (random indices: a table in constant memory would serialise)
+__device__ __forceinline__ void load_noise_tabs(NoiseTabs &t) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t.sc[i] = g_sc_tab[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) t.ln[i] = g_ln_tab[i];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void noise_block(uint64_t seed, uint32_t stream, uint64_t index, uint32_t slot, uint32_t *o) {
+  philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), stream, slot, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+}
+
+// (cos, sin) of 2 pi w / 2^32
+__device__ __forceinline__ void unit2(const NoiseTabs &t, uint32_t w, double &c, double &s) {
+  const uint32_t k = (w + 0x800000u) >> 24;  // nearest table angle; wraps to 0 at the top
+  const double d = __dmul_rn((double)(int32_t)(w - (k << 24)), 1.4629180792671596e-09);  // 2 pi / 2^32; |d| <= pi / 256
+  const double d2 = __dmul_rn(d, d);
+  double ps = __fma_rn(d2, 1.0 / 120.0, -1.0 / 6.0);
+  ps = __fma_rn(d2, ps, 1.0);
+  const double sd = __dmul_rn(d, ps);
+  double pc = __fma_rn(d2, -1.0 / 720.0, 1.0 / 24.0);
+  pc = __fma_rn(d2, pc, -0.5);
+  const double cd = __fma_rn(d2, pc, 1.0);
+  const double2 a = t.sc[k & 255u];
+  c = __fma_rn(a.x, cd, -__dmul_rn(a.y, sd));
+  s = __fma_rn(a.y, cd, __dmul_rn(a.x, sd));
+}
+
+// -2 ln u, u = (n40 + 1) 2^-40 in (0, 1]; never negative
+__device__ __forceinline__ double neg2ln40(const NoiseTabs &t, uint64_t n40) {
+  const double u = __dmul_rn(__ull2double_rn(n40 + 1ull), 9.094947017729282e-13);  // 2^-40, exact
+  const long long bits = __double_as_longlong(u);
+  const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  const double2 tj = t.ln[(int)((bits >> 45) & 127)];
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+  const double r = __fma_rn(m, tj.x, -1.0);
+  double p = __fma_rn(r, -1.0 / 6.0, 0.2);
+  p = __fma_rn(r, p, -0.25);
+  p = __fma_rn(r, p, 1.0 / 3.0);
+  p = __fma_rn(r, p, -0.5);
+  p = __fma_rn(r, p, 1.0);
+  p = __dmul_rn(r, p);
+  const double ln = __dadd_rn(__fma_rn((double)e, 0.6931471805599453, tj.y), p);
+  return fmax(__dmul_rn(-2.0, ln), 0.0);
+}
+
+// N(0,1) from two words: u1 from a and the top byte of b (40 bits), the angle from b's other 24 bits
+__device__ __forceinline__ double normal40(const NoiseTabs &t, uint32_t a, uint32_t b) {
+  const uint64_t n40 = (uint64_t)a | ((uint64_t)(b >> 24) << 32);
+  double c, s;
+  unit2(t, b << 8, c, s);
+  return __dmul_rn(__dsqrt_rn(neg2ln40(t, n40)), c);
+}
+
+// uniform point on the unit sphere from two words
+__device__ __forceinline__ V3 sphere(const NoiseTabs &t, uint32_t a, uint32_t b) {
+  double c, s;
+  unit2(t, a, c, s);
+  const double z = __dsub_rn(1.0, __dmul_rn(__dadd_rn((double)b, 0.5), 4.656612873077393e-10));  // 2^-31
+  const double q = __dsqrt_rn(fmax(__fma_rn(-z, z, 1.0), 0.0));
+  return V3{__dmul_rn(q, c), __dmul_rn(q, s), z};
 }
 
 // element i of the chained sequence "camera centres, then points" (src/baproblem.rs:284-287)
@@ -177,9 +254,13 @@ __global__ void k_nearest_final(const double *__restrict__ pd, const unsigned lo
 }
 
 // ---- add_drift, src/noise.rs:68-116 ------------------------------------------------------------------
-__global__ void k_drift_cams(double *__restrict__ cams, uint64_t C, const double *__restrict__ origin,
-                             V3 dir, double strength, double angle_strength, double std,
-                             uint64_t seed) {
+constexpr int NZ_THREADS = 256;
+
+__global__ void __launch_bounds__(NZ_THREADS)
+    k_drift_cams(double *__restrict__ cams, uint64_t C, const double *__restrict__ origin, V3 dir, double strength,
+                 double angle_strength, double std, uint64_t seed) {
+  __shared__ NoiseTabs tabs;
+  load_noise_tabs(tabs);
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
   double cam[15];
@@ -189,7 +270,12 @@ __global__ void k_drift_cams(double *__restrict__ cams, uint64_t C, const double
   V3 d{dsub(c.x, origin[0]), dsub(c.y, origin[1]), dsub(c.z, origin[2])};
   double distance = mag(d);
   double z0 = 0.0, z1 = 0.0;
-  if (std != 0.0) normal_pair(seed, ST_DRIFT_CAM, i, 0, z0, z1);  // Normal(1, 0) is 1 whatever the draw
+  if (std != 0.0) {  // Normal(1, 0) is 1 whatever the draw
+    uint32_t o[4];
+    noise_block(seed, ST_DRIFT_CAM, i, 0, o);
+    z0 = normal40(tabs, o[0], o[1]);  // the angle's draw first (src/noise.rs:104-107)
+    z1 = normal40(tabs, o[2], o[3]);
+  }
   double v1 = dadd(1.0, dmul(std, z0)), v2 = dadd(1.0, dmul(std, z1));
   double angle = dmul(dmul(angle_strength, v1), pow(distance, 1.2));
   V3 dl{dmul(dmul(dmul(dmul(dir.x, strength), v2), distance), distance),
@@ -202,38 +288,48 @@ __global__ void k_drift_cams(double *__restrict__ cams, uint64_t C, const double
   for (int k = 0; k < 15; ++k) cams[15 * i + k] = out[k];
 }
 
-__global__ void k_drift_pts(double *__restrict__ pts, uint64_t P, const double *__restrict__ origin,
-                            V3 dir, double strength, double std, uint64_t seed) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
-  V3 d{dsub(p.x, origin[0]), dsub(p.y, origin[1]), dsub(p.z, origin[2])};
-  double distance = mag(d);
-  double z0 = 0.0, z1 = 0.0;
-  if (std != 0.0) normal_pair(seed, ST_DRIFT_PT, i, 0, z0, z1);  // Normal(1, 0) is 1 whatever the draw
-  double v = dadd(1.0, dmul(std, z0));
-  pts[3 * i] = dadd(p.x, dmul(dmul(dmul(dmul(dir.x, strength), v), distance), distance));
-  pts[3 * i + 1] = dadd(p.y, dmul(dmul(dmul(dmul(dir.y, strength), v), distance), distance));
-  pts[3 * i + 2] = dadd(p.z, dmul(dmul(dmul(dmul(dir.z, strength), v), distance), distance));
+__global__ void __launch_bounds__(NZ_THREADS)
+    k_drift_pts(double *__restrict__ pts, uint64_t P, const double *__restrict__ origin, V3 dir, double strength,
+                double std, uint64_t seed) {
+  __shared__ NoiseTabs tabs;
+  if (std != 0.0) load_noise_tabs(tabs);
+  const double ox = origin[0], oy = origin[1], oz = origin[2];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+    V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    V3 d{dsub(p.x, ox), dsub(p.y, oy), dsub(p.z, oz)};
+    double distance = mag(d);
+    double z0 = 0.0;
+    if (std != 0.0) {
+      uint32_t o[4];
+      noise_block(seed, ST_DRIFT_PT, i, 0, o);
+      z0 = normal40(tabs, o[0], o[1]);
+    }
+    double v = dadd(1.0, dmul(std, z0));
+    pts[3 * i] = dadd(p.x, dmul(dmul(dmul(dmul(dir.x, strength), v), distance), distance));
+    pts[3 * i + 1] = dadd(p.y, dmul(dmul(dmul(dmul(dir.y, strength), v), distance), distance));
+    pts[3 * i + 2] = dadd(p.z, dmul(dmul(dmul(dmul(dir.z, strength), v), distance), distance));
+  }
 }
 
 // ---- add_noise, src/noise.rs:119-177 --------------------------------------------------------------------
-__global__ void k_noise_cams(double *__restrict__ cams, uint64_t C, double bal_std,
-                             double translation_std, double rotation_std, uint64_t seed) {
+// per camera: axis, angle, translation direction, magnitude (:140-141) = block 0 {sphere, N}, block 1 {sphere, N}
+__global__ void __launch_bounds__(NZ_THREADS)
+    k_noise_cams(double *__restrict__ cams, uint64_t C, double bal_std, double translation_std, double rotation_std,
+                 uint64_t seed) {
+  __shared__ NoiseTabs tabs;
+  load_noise_tabs(tabs);
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
   double cam[15];
 #pragma unroll
   for (int k = 0; k < 15; ++k) cam[k] = cams[15 * i + k];
-  double a0, a1, a2, ang, b0, b1, b2, mg;
-  normal_pair(seed, ST_NOISE_CAM, i, 0, a0, a1);
-  normal_pair(seed, ST_NOISE_CAM, i, 1, a2, ang);
-  normal_pair(seed, ST_NOISE_CAM, i, 2, b0, b1);
-  normal_pair(seed, ST_NOISE_CAM, i, 3, b2, mg);
-  V3 ax = normalize(V3{a0, a1, a2});
-  double angle = dadd(0.0, dmul(rotation_std, ang));
-  V3 tr = normalize(V3{b0, b1, b2});
-  double m = dadd(0.0, dmul(translation_std, mg));
+  uint32_t o0[4], o1[4];
+  noise_block(seed, ST_NOISE_CAM, i, 0, o0);
+  noise_block(seed, ST_NOISE_CAM, i, 1, o1);
+  const V3 ax = sphere(tabs, o0[0], o0[1]);
+  const double angle = dadd(0.0, dmul(rotation_std, normal40(tabs, o0[2], o0[3])));
+  const V3 tr = sphere(tabs, o1[0], o1[1]);
+  const double m = dadd(0.0, dmul(translation_std, normal40(tabs, o1[2], o1[3])));
   double R[9], out[15];
   from_axis_angle(ax, angle, R);
   V3 dl{dmul(dmul(tr.x, bal_std), m), dmul(dmul(tr.y, bal_std), m), dmul(dmul(tr.z, bal_std), m)};
@@ -242,32 +338,39 @@ __global__ void k_noise_cams(double *__restrict__ cams, uint64_t C, double bal_s
   for (int k = 0; k < 15; ++k) cams[15 * i + k] = out[k];
 }
 
-__global__ void k_noise_pts(double *__restrict__ pts, uint64_t P, double point_std, uint64_t seed) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  double a0, a1, a2, mg;
-  normal_pair(seed, ST_NOISE_PT, i, 0, a0, a1);
-  normal_pair(seed, ST_NOISE_PT, i, 1, a2, mg);
-  V3 ax = normalize(V3{a0, a1, a2});
-  double m = dadd(0.0, dmul(point_std, mg));
-  pts[3 * i] = dadd(pts[3 * i], dmul(ax.x, m));
-  pts[3 * i + 1] = dadd(pts[3 * i + 1], dmul(ax.y, m));
-  pts[3 * i + 2] = dadd(pts[3 * i + 2], dmul(ax.z, m));
+// per point: direction, magnitude (:149) = one block {sphere, N}
+__global__ void __launch_bounds__(NZ_THREADS)
+    k_noise_pts(double *__restrict__ pts, uint64_t P, double point_std, uint64_t seed) {
+  __shared__ NoiseTabs tabs;
+  load_noise_tabs(tabs);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t o[4];
+    noise_block(seed, ST_NOISE_PT, i, 0, o);
+    const V3 ax = sphere(tabs, o[0], o[1]);
+    const double m = dadd(0.0, dmul(point_std, normal40(tabs, o[2], o[3])));
+    pts[3 * i] = dadd(pts[3 * i], dmul(ax.x, m));
+    pts[3 * i + 1] = dadd(pts[3 * i + 1], dmul(ax.y, m));
+    pts[3 * i + 2] = dadd(pts[3 * i + 2], dmul(ax.z, m));
+  }
 }
 
-__global__ void k_noise_obs(double2 *__restrict__ uv, uint64_t O, double observations_std,
-                            uint64_t seed) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= O) return;
-  double nx, ny, r0, unused;
-  normal_pair(seed, ST_NOISE_OBS, i, 0, nx, ny);
-  normal_pair(seed, ST_NOISE_OBS, i, 1, r0, unused);
-  double m = dsqrt(dadd(dmul(nx, nx), dmul(ny, ny)));
-  double r = dadd(0.0, dmul(observations_std, r0));
-  double2 q = uv[i];
-  q.x = dadd(q.x, dmul(ddiv(nx, m), r));
-  q.y = dadd(q.y, dmul(ddiv(ny, m), r));
-  uv[i] = q;
+// per observation: direction (nx, ny) / |(nx, ny)|, r (:159-163) = one block {circle, -, N}.  `first` = global
+// index of uv[0] (the host entry streams the array through the GPU in chunks).
+__global__ void __launch_bounds__(NZ_THREADS)
+    k_noise_obs(double2 *__restrict__ uv, uint64_t O, uint64_t first, double observations_std, uint64_t seed) {
+  __shared__ NoiseTabs tabs;
+  load_noise_tabs(tabs);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < O; i += (uint64_t)gridDim.x * blockDim.x) {
+    double2 q = uv[i];
+    uint32_t o[4];
+    noise_block(seed, ST_NOISE_OBS, first + i, 0, o);
+    double nx, ny;
+    unit2(tabs, o[0], nx, ny);
+    const double r = dadd(0.0, dmul(observations_std, normal40(tabs, o[2], o[3])));
+    q.x = dadd(q.x, dmul(nx, r));
+    q.y = dadd(q.y, dmul(ny, r));
+    uv[i] = q;
+  }
 }
 
 // ---- add_sin_noise, src/noise.rs:388-416 --------------------------------------------------------------

@@ -298,6 +298,22 @@ class ResidentProblem:
         check(lib().c2b_download_obs(self.ctx.handle, C.byref(out)))
         return out
 
+    # ---- the noise pass on the resident problem (no PCIe traffic) ----
+    def add_drift(self, strength, angle_strength, std, direction=None, seed=0):
+        """noise::add_drift on the resident cameras / points; direction None = add_drift_normalized"""
+        d = None if direction is None else np.ascontiguousarray(direction, np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        check(lib().c2b_add_drift_resident(self.ctx.handle, float(strength), float(angle_strength), float(std), d, int(seed)))
+
+    def add_noise(self, translation_std, rotation_std, point_std, observations_std, seed=0):
+        check(lib().c2b_add_noise_resident(self.ctx.handle, float(translation_std), float(rotation_std),
+                                           float(point_std), float(observations_std), int(seed)))
+
+    def download_problem(self, num_cameras: int, num_points: int):
+        cams, pts = np.empty((num_cameras, CAM_STRIDE)), np.empty((num_points, 3))
+        pd = C.POINTER(C.c_double)
+        check(lib().c2b_download_problem(self.ctx.handle, cams.ctypes.data_as(pd), pts.ctypes.data_as(pd)))
+        return cams, pts
+
     def reprojection_error(self, norm: float) -> float:
         v = C.c_double(0)
         check(lib().c2b_reprojection_error_resident(self.ctx.handle, float(norm), C.byref(v)))

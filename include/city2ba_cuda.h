@@ -235,7 +235,8 @@ int c2b_reprojection_error_resident(c2b_ctx *ctx, double norm, double *out);
  * In place on host arrays: cams C x 15, pts P x 3, uv O x 2.  Randomness is Philox4x32-10 keyed
  * by `seed` with counter (element index, stream, slot) — the reference uses thread_rng(), which
  * cannot be seeded, so parity is exact against the oracle's identical stream and distributional
- * against the reference. */
+ * against the reference: a direction (the reference's normalised Gaussian pair / triple) is drawn uniformly
+ * on the circle / sphere, a magnitude by Box-Muller (city2ba_b200/csrc/c2b_noise.cuh). */
 /* replaces noise::add_drift (src/noise.rs:68-116) */
 int c2b_add_drift(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, double strength,
                   double angle_strength, double std, const double dir[3], uint64_t seed);
@@ -251,6 +252,18 @@ int c2b_add_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t 
  * BAProblem::dimensions (src/baproblem.rs:307-337; zero extents count as 1e-8).  Deterministic. */
 int c2b_add_sin_noise(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, const double dir[3],
                       const double noise_dir[3], double strength, double frequency);
+/* The same passes on the RESIDENT problem — the cameras and points of the last c2b_upload_* calls and the
+ * (u, v) of the last c2b_visibility_graph_resident — in place in HBM: `generate -> noise` without crossing PCIe.
+ * dir == NULL in c2b_add_drift_resident is add_drift_normalized.  Afterwards c2b_download_problem /
+ * c2b_download_obs fetch the noised problem and c2b_reprojection_error_resident measures it. */
+int c2b_add_drift_resident(c2b_ctx *ctx, double strength, double angle_strength, double std, const double *dir,
+                           uint64_t seed);
+int c2b_add_noise_resident(c2b_ctx *ctx, double translation_std, double rotation_std, double point_std,
+                           double observations_std, uint64_t seed);
+int c2b_add_sin_noise_resident(c2b_ctx *ctx, const double dir[3], const double noise_dir[3], double strength,
+                               double frequency);
+/* cameras (C x 15) and points (P x 3) of the resident problem -> host */
+int c2b_download_problem(c2b_ctx *ctx, double *cams_out, double *pts_out);
 /* device time of the last noise call on this ctx (CUDA events on its stream), milliseconds:
  * ms[0] upload, ms[1] statistics + elementwise kernels, ms[2] download */
 int c2b_noise_timing(c2b_ctx *ctx, float ms[3]);

@@ -858,7 +858,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * 128 intervals of the mantissa and a degree-6 series) with every operation an explicit fma / mul / add in
  * a fixed order.  The CUDA path (c2b_noise.cuh) performs the same operations on the same tables, so points
  * and observations agree with this file bit for bit; the functions themselves are pinned against libm in
- * tests/test_oracle_noise.py (<= 4e-16 absolute) and the distributions by moment / KS tests. */
+ * tests/test_oracle_noise.py (<= 8e-16 absolute) and the distributions by moment / KS tests. */
 static double SC_TAB[256][2]; /* cos, sin of k * 2 pi / 256 */
 static double LN_TAB[128][2]; /* 1 / c_j, ln c_j with c_j = 1 + (2 j + 1) / 256 */
 static int noise_tabs_ready = 0;
@@ -884,8 +884,8 @@ void orc_noise_tables(double *sc, double *ln) {
 /* (cos, sin) of 2 pi w / 2^32 */
 void orc_unit2(uint32_t w, double *c, double *s) {
   if (!noise_tabs_ready) orc_noise_tables(NULL, NULL);
-  const uint32_t k = w >> 24;
-  const double d = (double)(w & 0xffffffu) * 1.4629180792671596e-09; /* 2 pi / 2^32 */
+  const uint32_t k = (w + 0x800000u) >> 24; /* nearest table angle; wraps to 0 at the top */
+  const double d = (double)(int32_t)(w - (k << 24)) * 1.4629180792671596e-09; /* 2 pi / 2^32; |d| <= pi / 256 */
   const double d2 = d * d;
   double ps = fma(d2, 1.0 / 120.0, -1.0 / 6.0);
   ps = fma(d2, ps, 1.0);
@@ -893,7 +893,7 @@ void orc_unit2(uint32_t w, double *c, double *s) {
   double pc = fma(d2, -1.0 / 720.0, 1.0 / 24.0);
   pc = fma(d2, pc, -0.5);
   const double cd = fma(d2, pc, 1.0);
-  const double ca = SC_TAB[k][0], sa = SC_TAB[k][1];
+  const double ca = SC_TAB[k & 255u][0], sa = SC_TAB[k & 255u][1];
   *c = fma(ca, cd, -(sa * sd));
   *s = fma(sa, cd, ca * sd);
 }
@@ -937,6 +937,15 @@ void orc_sphere(uint32_t a, uint32_t b, double *o) {
   o[0] = q * c;
   o[1] = q * s;
   o[2] = z;
+}
+
+/* test helper: the three draws of n blocks of four words */
+void orc_noise_draws(const uint32_t *w, uint64_t n, double *circle, double *sph, double *nrm) {
+  for (uint64_t i = 0; i < n; ++i) {
+    orc_unit2(w[4 * i], &circle[2 * i], &circle[2 * i + 1]);
+    orc_sphere(w[4 * i], w[4 * i + 1], sph + 3 * i);
+    nrm[i] = orc_normal40(w[4 * i + 2], w[4 * i + 3]);
+  }
 }
 
 static void noise_block(uint64_t seed, uint32_t stream, uint64_t index, uint32_t slot, uint32_t *o) {

@@ -133,8 +133,14 @@ void orc_city_mesh(uint64_t n_blocks, double block_length, double block_inset, d
 
 /* ---- noise (src/noise.rs:35-177; src/baproblem.rs:282-304) with a Philox4x32-10 stream ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-/* two N(0,1) draws for (seed, stream, index, slot) */
-void orc_normal_pair(uint64_t seed, uint32_t stream, uint64_t index, uint32_t slot, double *z2);
+/* the draws (c2b_oracle.c "the noise draws"): tables, (cos, sin)(2 pi w / 2^32), -2 ln((n40 + 1) 2^-40),
+ * N(0,1) from two words, a uniform point on the sphere from two words */
+void orc_noise_tables(double *sc /*512 or NULL*/, double *ln /*256 or NULL*/);
+void orc_unit2(uint32_t w, double *c, double *s);
+double orc_neg2ln40(uint64_t n40);
+double orc_normal40(uint32_t a, uint32_t b);
+void orc_sphere(uint32_t a, uint32_t b, double *out3);
+void orc_noise_draws(const uint32_t *words, uint64_t n, double *circle2, double *sphere3, double *normal1);
 void orc_mean(const double *cams, uint64_t C, const double *pts, uint64_t P, double *out3);
 void orc_std(const double *cams, uint64_t C, const double *pts, uint64_t P, double *out3);
 void orc_add_drift(double *cams, uint64_t C, double *pts, uint64_t P, double strength,

@@ -351,10 +351,40 @@ def philox4x32_10(ctr, key):
     return out
 
 
-def normal_pair(seed, stream, index, slot):
-    out = np.empty(2)
-    lib().orc_normal_pair(_u64(seed), C.c_uint32(stream), _u64(index), C.c_uint32(slot), _p(out))
+def unit2(w):
+    """(cos, sin)(2 pi w / 2^32) as the noise draws evaluate it"""
+    c, s = C.c_double(0), C.c_double(0)
+    lib().orc_unit2(C.c_uint32(int(w)), C.byref(c), C.byref(s))
+    return c.value, s.value
+
+
+def neg2ln40(n40):
+    f = lib().orc_neg2ln40
+    f.restype = C.c_double
+    return f(_u64(n40))
+
+
+def normal40(a, b):
+    f = lib().orc_normal40
+    f.restype = C.c_double
+    return f(C.c_uint32(int(a)), C.c_uint32(int(b)))
+
+
+def sphere(a, b):
+    out = np.empty(3)
+    lib().orc_sphere(C.c_uint32(int(a)), C.c_uint32(int(b)), _p(out))
     return out
+
+
+def noise_draws(words):
+    """vectorised helper for the distribution tests: words (n, 4) uint32 -> dict of the draws one Philox
+    block supplies: circle from word 0, sphere from words 0-1, N(0,1) from words 2-3"""
+    w = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1, 4)
+    n = len(w)
+    circle, sph, nrm = np.empty((n, 2)), np.empty((n, 3)), np.empty(n)
+    f = lib().orc_noise_draws
+    f(_p(w, C.c_uint32), _u64(n), _p(circle), _p(sph), _p(nrm))
+    return {"circle": circle, "sphere": sph, "normal": nrm}
 
 
 def mean(cams, pts):
