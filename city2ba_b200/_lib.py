@@ -29,6 +29,8 @@ class VisOptions(C.Structure):
         ("count_traversal", C.c_int),
         ("block_length", C.c_double),
         ("block_inset", C.c_double),
+        ("predicate", C.c_int),
+        ("reserved", C.c_int),
     ]
 
 
@@ -80,6 +82,7 @@ class MultiStats(C.Structure):
 
 CULL_GRID, CULL_EXHAUSTIVE = 0, 1
 OCC_MESH, OCC_NONE, OCC_ANALYTIC = 0, 1, 2
+PRED_WATERTIGHT, PRED_MT = 0, 1
 
 # every symbol include/city2ba_cuda.h declares
 EXPORTS = [

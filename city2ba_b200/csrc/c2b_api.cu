@@ -75,6 +75,11 @@ struct GridCache {
   uint64_t points_version = 0;
   GridDesc desc;
   uint64_t n_cells = 0;
+  // hinted: the cells cover only what the cameras of that call could reach (their centres' box grown by
+  // max_dist), because cells of side max_dist/4 over the bounding box of ALL points would have exceeded the
+  // cell budget (outliers); such a grid serves a later call only if its cameras stay inside the hint
+  bool hinted = false;
+  double hint_lo[3] = {0, 0, 0}, hint_hi[3] = {0, 0, 0};
 };
 
 // Measurement / test hooks (include/city2ba_cuda.h, c2b_tune).  Defaults are the product's behaviour; the
@@ -383,6 +388,8 @@ void c2b_vis_options_default(c2b_vis_options *opt) {
   opt->count_traversal = 0;
   opt->block_length = 20.0;
   opt->block_inset = 1.0;
+  opt->predicate = C2B_PRED_WATERTIGHT;
+  opt->reserved = 0;
 }
 
 // Host -> device copy of a caller's array on ctx->stream.  A pinned (or registered) source goes to the copy
@@ -543,6 +550,36 @@ static int read_counters(c2b_ctx *ctx, unsigned long long *h_cnt) {
   return C2B_OK;
 }
 
+// bounding box of the resident cameras' centres (tiny two-stage reduction; synchronises the stream)
+static int camera_bbox(c2b_ctx *ctx, double lo[3], double hi[3]) {
+  const uint64_t C = ctx->C;
+  const double *cx = ctx->cam_center.as<double>();
+  int nb = (int)std::min<uint64_t>(std::max<uint64_t>(blocks_for(C, 256), 1), (uint64_t)ctx->sm_count);
+  C2B_TRY(ctx->misc.ensure((size_t)nb * 48 + 64));
+  double *partial = ctx->misc.as<double>() + 8;
+  k_pts_bounds_partial<<<nb, 256, 0, ctx->stream>>>(cx, cx + C, cx + 2 * C, C, partial);
+  C2B_KERNEL_CHECK();
+  k_pts_bounds_final<<<1, 32, 0, ctx->stream>>>(partial, nb, ctx->misc.as<double>());
+  C2B_KERNEL_CHECK();
+  double b[6];
+  C2B_CUDA(cudaMemcpyAsync(b, ctx->misc.p, 48, cudaMemcpyDeviceToHost, ctx->stream));
+  C2B_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 3; ++k) {
+    lo[k] = b[k];
+    hi[k] = b[3 + k];
+  }
+  return C2B_OK;
+}
+
+// what the cameras can reach: their centres' box grown by max_dist (and a little)
+static void reach_box(const double clo[3], const double chi[3], double max_dist, double lo[3], double hi[3]) {
+  for (int k = 0; k < 3; ++k) {
+    const double pad = max_dist + 1e-6 * (std::fabs(max_dist) + std::fabs(clo[k]) + std::fabs(chi[k]));
+    lo[k] = clo[k] - pad;
+    hi[k] = chi[k] + pad;
+  }
+}
+
 static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   cudaStream_t st = ctx->stream;
   const uint64_t P = ctx->P;
@@ -559,6 +596,33 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   }
   if (!(h > 0.0) || !std::isfinite(h)) h = 1.0;
   const double max_cells = 4194304.0;  // 2^22
+  auto cells_at = [&](double hh) {
+    double total = 1.0;
+    for (int k = 0; k < 3; ++k) total *= std::min(std::floor(ext[k] / hh) + 1.0, 1e9);
+    return total;
+  };
+  x->grid.hinted = false;
+  if (cells_at(h) > max_cells && ctx->C) {
+    // A few far-away points (outliers of an OBJ scene) would coarsen every cell.  No point farther than
+    // max_dist from every camera can be observed, so the cells only have to resolve the cameras' reach;
+    // grid_coord clamps everything outside into the edge cells, whose rows extend to the data bounds
+    // (camera_row), and the exact predicate still runs on every point read.
+    double clo[3], chi[3], rlo[3], rhi[3];
+    C2B_TRY(camera_bbox(ctx, clo, chi));
+    reach_box(clo, chi, max_dist, rlo, rhi);
+    bool usable = true;
+    for (int k = 0; k < 3; ++k) usable = usable && std::isfinite(rlo[k]) && std::isfinite(rhi[k]) && rlo[k] <= rhi[k];
+    if (usable) {
+      for (int k = 0; k < 3; ++k) {
+        const double a = std::max(g.lo[k], rlo[k]), b = std::min(std::isfinite(g.max_c[k]) ? g.max_c[k] : g.lo[k], rhi[k]);
+        g.lo[k] = a <= b ? a : std::min(std::max(rlo[k], g.lo[k]), g.lo[k] + ext[k]);
+        ext[k] = a <= b ? b - a : 0.0;
+        x->grid.hint_lo[k] = rlo[k];
+        x->grid.hint_hi[k] = rhi[k];
+      }
+      x->grid.hinted = true;
+    }
+  }
   for (;;) {
     double total = 1.0;
     for (int k = 0; k < 3; ++k) {
@@ -633,8 +697,16 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   cudaStream_t st = ctx->stream;
   const uint64_t C = ctx->C, P = ctx->P;
   const int sel = ctx->out_sel;
-  if (C && P && !(x->grid.valid && x->grid.max_dist == max_dist && x->grid.points_version == x->points_version))
-    C2B_TRY(build_grid(ctx, x, max_dist));
+  if (C && P) {
+    bool valid = x->grid.valid && x->grid.max_dist == max_dist && x->grid.points_version == x->points_version;
+    if (valid && x->grid.hinted) {  // built for other cameras' reach: still good if these stay inside it
+      double clo[3], chi[3], rlo[3], rhi[3];
+      C2B_TRY(camera_bbox(ctx, clo, chi));
+      reach_box(clo, chi, max_dist, rlo, rhi);
+      for (int k = 0; k < 3; ++k) valid = valid && rlo[k] >= x->grid.hint_lo[k] && rhi[k] <= x->grid.hint_hi[k];
+    }
+    if (!valid) C2B_TRY(build_grid(ctx, x, max_dist));
+  }
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
 
   C2B_TRY(ctx->counters.ensure(64));
@@ -758,7 +830,10 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3).  Measured at cfg4: 2.68 ms; 3 CTAs/SM 2.69 ms; 5 CTAs/SM at
     // 48 registers 2.74 ms
     const bool occ4 = !x->tun.fu_occ3;
-    if (mesh) {
+    if (mesh && opt.predicate == C2B_PRED_MT) {
+      // candidates only; k_filter_candidates_mt decides occlusion below
+      k_visibility_fused<FU_OCC_NONE, false, 3, false><<<nb, nt, 0, st>>>(fa);
+    } else if (mesh) {
       if (cnt)
         k_visibility_fused<FU_OCC_MESH, true, 3, true><<<nb, nt, 0, st>>>(fa);
       else if (any_overflow)
@@ -773,6 +848,12 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
       k_visibility_fused<FU_OCC_NONE, false, 3, false><<<nb, nt, 0, st>>>(fa);
     }
     C2B_KERNEL_CHECK();
+    if (mesh && opt.predicate == C2B_PRED_MT) {
+      FilterArgs f{fa.nodes, fa.tris, fa.n_nodes, fa.scene_absmax, fa.cen_x, fa.cen_y, fa.cen_z, ctx->pts_aos.as<double>(),
+                   slots, parts_log2, opt.endpoint_guard_rel, fa.ev_count, fa.scratch_idx, fa.vis_count, fa.counters};
+      k_filter_candidates_mt<<<blocks_for(slots, 8), 256, 0, st>>>(f);
+      C2B_KERNEL_CHECK();
+    }
   }
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
 
@@ -869,6 +950,8 @@ static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double
     return set_error(C2B_ERR_INVALID, "unknown cull_mode %d", opt.cull_mode);
   if (opt.occlusion < C2B_OCC_MESH || opt.occlusion > C2B_OCC_ANALYTIC)
     return set_error(C2B_ERR_INVALID, "unknown occlusion %d", opt.occlusion);
+  if (opt.predicate != C2B_PRED_WATERTIGHT && opt.predicate != C2B_PRED_MT)
+    return set_error(C2B_ERR_INVALID, "unknown predicate %d", opt.predicate);
   C2B_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint64_t C = ctx->C, P = ctx->P;
@@ -965,7 +1048,9 @@ static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double
       t.endpoint_guard_rel = opt.endpoint_guard_rel;
       t.vis_words = ctx->vis_words.as<uint32_t>();
       t.counters = ctx->counters.as<unsigned long long>();
-      if (opt.count_traversal)
+      if (opt.predicate == C2B_PRED_MT)
+        k_traverse<false, true><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
+      else if (opt.count_traversal)
         k_traverse<true><<<blocks_for(n_words, 8), 256, 0, st>>>(t);
       else
         k_traverse<false><<<blocks_for(n_words, 8), 256, 0, st>>>(t);

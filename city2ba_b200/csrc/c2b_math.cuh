@@ -296,4 +296,36 @@ C2B_HD bool ray_triangle(const Ray &r, float v0x, float v0y, float v0z, float v1
   return ray_tri_record(r.dx, r.dy, r.dz, r.tfar, t, t_out);
 }
 
+// ---- Moeller-Trumbore test in the form of Embree 3's DEFAULT (non-robust) triangle intersector ----------
+// What the reference's scene actually runs (a default scene, src/bin/city2ba.rs:515-521, src/generate.rs:472).
+// With e1 = v0 - v1, e2 = v2 - v0, Ng = e2 x e1, C = v0 - org, R = C x dir, den = Ng . dir:
+//     hit  <=>  den != 0  and  U >= 0  and  V >= 0  and  U + V <= |den|,  U = (R . e2) ^ sign(den),
+//               V = (R . e1) ^ sign(den),  and  0 < T <= |den| tfar  with  T = (Ng . C) ^ sign(den),
+// cross products unfused, dot products as fused multiply-add chains a0 b0 + (a1 b1 + a2 b2).  Restated from
+// the published algorithm (Embree is not vendored by the reference: unpinned like everything at that
+// boundary); not watertight on shared edges.  Selected with c2b_vis_options::predicate = C2B_PRED_MT.
+C2B_HD float dot3m(float ax, float ay, float az, float bx, float by, float bz) {
+  return ffma(ax, bx, ffma(ay, by, fmul(az, bz)));
+}
+
+C2B_HD bool ray_triangle_mt(const Ray &r, float v0x, float v0y, float v0z, float v1x, float v1y, float v1z,
+                            float v2x, float v2y, float v2z) {
+  const float e1x = fsub(v0x, v1x), e1y = fsub(v0y, v1y), e1z = fsub(v0z, v1z);
+  const float e2x = fsub(v2x, v0x), e2y = fsub(v2y, v0y), e2z = fsub(v2z, v0z);
+  const float cx = fsub(v0x, r.ox), cy = fsub(v0y, r.oy), cz = fsub(v0z, r.oz);
+  const float ngx = fsub(fmul(e2y, e1z), fmul(e2z, e1y));
+  const float ngy = fsub(fmul(e2z, e1x), fmul(e2x, e1z));
+  const float ngz = fsub(fmul(e2x, e1y), fmul(e2y, e1x));
+  const float rx = fsub(fmul(cy, r.dz), fmul(cz, r.dy));
+  const float ry = fsub(fmul(cz, r.dx), fmul(cx, r.dz));
+  const float rz = fsub(fmul(cx, r.dy), fmul(cy, r.dx));
+  const float den = dot3m(ngx, ngy, ngz, r.dx, r.dy, r.dz);
+  const float ad = fabsf(den);
+  const float sg = den < 0.0f ? -1.0f : 1.0f;
+  const float U = fmul(dot3m(rx, ry, rz, e2x, e2y, e2z), sg), V = fmul(dot3m(rx, ry, rz, e1x, e1y, e1z), sg);
+  if (!(den != 0.0f && U >= 0.0f && V >= 0.0f && fadd(U, V) <= ad)) return false;
+  const float T = fmul(dot3m(ngx, ngy, ngz, cx, cy, cz), sg);
+  return fmul(ad, 0.0f) < T && T <= fmul(ad, r.tfar);
+}
+
 }  // namespace c2b

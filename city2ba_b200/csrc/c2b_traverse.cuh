@@ -70,7 +70,8 @@ __device__ __forceinline__ bool box_overlap(const BoxRay &r, float4 lo, float4 h
 
 // warp-cooperative any-hit.  `alive` = this lane has a ray that is not yet occluded.
 // Returns true if this lane's ray is occluded.
-template <bool COUNT>
+// MT = the Moeller-Trumbore predicate (c2b_math.cuh: ray_triangle_mt) instead of the watertight one
+template <bool COUNT, bool MT = false>
 __device__ __forceinline__ bool warp_any_hit(const float4 *__restrict__ nodes,
                                              const float4 *__restrict__ tris, int n_nodes,
                                              const Ray &ray, bool alive, float scene_absmax,
@@ -99,7 +100,8 @@ __device__ __forceinline__ bool warp_any_hit(const float4 *__restrict__ nodes,
       const float4 v1 = __ldg(&tris[3 * leaf + 1]);
       const float4 v2 = __ldg(&tris[3 * leaf + 2]);
       if (COUNT) ++n_tri;
-      if (hit && ray_triangle(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)) {
+      if (hit && (MT ? ray_triangle_mt(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z)
+                     : ray_triangle(ray, v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z))) {
         occluded = true;
         alive = false;
       }
@@ -130,7 +132,7 @@ struct TraverseArgs {
   unsigned long long *counters;
 };
 
-template <bool COUNT>
+template <bool COUNT, bool MT = false>
 __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
   const int lane = threadIdx.x & 31;
   const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -149,9 +151,63 @@ __global__ void __launch_bounds__(256) k_traverse(TraverseArgs a) {
     V3 p{a.p_aos[3 * pt], a.p_aos[3 * pt + 1], a.p_aos[3 * pt + 2]};
     ray = make_ray(c, p, a.endpoint_guard_rel != 0);
   }
-  const bool occ = warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
+  const bool occ = warp_any_hit<COUNT, MT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
   const unsigned vm = __ballot_sync(0xffffffffu, have && !occ);
   if (lane == 0) a.vis_words[w] = vm;
+}
+
+// ---- grid schedule with the Moeller-Trumbore predicate ---------------------------------------------------
+// The fused kernel's packet machinery (origin-relative records, direction-box prefilter) is built around the
+// watertight edge functions.  For the non-default MT predicate the fused pass runs WITHOUT occlusion, which
+// leaves every camera's candidates in its scratch slice, and this kernel — one warp per slot, 32 candidates at
+// a time through the generic walk — keeps the visible ones, compacted in place (the write position never
+// passes the read position, and a chunk is read completely before anything is written).
+struct FilterArgs {
+  const float4 *nodes;
+  const float4 *tris;
+  int n_nodes;
+  float scene_absmax;
+  const double *cen_x, *cen_y, *cen_z;
+  const double *p_aos;
+  uint64_t slots;
+  int parts_log2;
+  int endpoint_guard_rel;
+  const uint32_t *ev_off;  // [slots + 1] scratch slice starts
+  uint32_t *scratch_idx;
+  uint32_t *vis_count;     // [slots] candidates in, visible out
+  unsigned long long *counters;
+};
+
+__global__ void __launch_bounds__(256) k_filter_candidates_mt(FilterArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= a.slots) return;
+  const uint64_t cam = slot >> a.parts_log2;
+  const uint32_t n = a.vis_count[slot];
+  uint32_t *list = a.scratch_idx + a.ev_off[slot];
+  const V3 c{a.cen_x[cam], a.cen_y[cam], a.cen_z[cam]};
+  uint32_t kept = 0;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const bool have = base + lane < n;
+    uint32_t pt = 0;
+    Ray ray;
+    ray.ox = ray.oy = ray.oz = 0.0f;
+    ray.dx = ray.dy = ray.dz = 1.0f;
+    ray.tfar = -1.0f;
+    if (have) {
+      pt = list[base + lane];
+      ray = make_ray(c, V3{a.p_aos[3 * (uint64_t)pt], a.p_aos[3 * (uint64_t)pt + 1], a.p_aos[3 * (uint64_t)pt + 2]},
+                     a.endpoint_guard_rel != 0);
+    }
+    const bool occ = warp_any_hit<false, true>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters);
+    const bool vis = have && !occ;
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    __syncwarp();
+    if (vis) list[kept + __popc(m & ((1u << lane) - 1u))] = pt;
+    kept += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) a.vis_count[slot] = kept;
 }
 
 // ---- per-camera triangle lists ------------------------------------------------------------------------

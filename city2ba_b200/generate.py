@@ -158,7 +158,7 @@ class VisGraph:
         return np.diff(self.offsets.astype(np.int64))
 
 
-def _options(cull_mode, occlusion, endpoint_guard_rel, count_traversal, block_length, block_inset):
+def _options(cull_mode, occlusion, endpoint_guard_rel, count_traversal, block_length, block_inset, predicate="watertight"):
     o = VisOptions()
     lib().c2b_vis_options_default(C.byref(o))
     o.cull_mode = {"grid": _lib.CULL_GRID, "exhaustive": _lib.CULL_EXHAUSTIVE}[cull_mode]
@@ -167,6 +167,7 @@ def _options(cull_mode, occlusion, endpoint_guard_rel, count_traversal, block_le
     o.count_traversal = int(bool(count_traversal))
     o.block_length = float(block_length)
     o.block_inset = float(block_inset)
+    o.predicate = {"watertight": _lib.PRED_WATERTIGHT, "mt": _lib.PRED_MT}[predicate]
     return o
 
 
@@ -176,17 +177,18 @@ def _stats(o: Obs) -> dict:
 
 def visibility_graph(scene, cameras, points, max_dist, verbose=False, *, cull_mode="grid",
                      occlusion="mesh", endpoint_guard_rel=False, count_traversal=False,
-                     block_length=20.0, block_inset=1.0, ctx=None) -> VisGraph:
+                     block_length=20.0, block_inset=1.0, predicate="watertight", ctx=None) -> VisGraph:
     """Compute the camera-point visibility graph (src/generate.rs:424-481).
 
     scene: Scene or None (only with occlusion != "mesh").  cameras: (C,15) records or
     SnavelyCamera list.  points: (P,3).  Returns a VisGraph (camera-major CSR).
     `verbose` is accepted for signature parity; there is no progress bar (the call is one
-    kernel pipeline).
+    kernel pipeline).  predicate = "mt" decides occlusion with the Moeller-Trumbore test of Embree's default
+    intersector (what the reference's scene runs) instead of the watertight default.
     """
     ctx = ctx or (scene.ctx if scene is not None else context())
     cams, pts = _cam_array(cameras), _pts_array(points)
-    opt = _options(cull_mode, occlusion, endpoint_guard_rel, count_traversal, block_length, block_inset)
+    opt = _options(cull_mode, occlusion, endpoint_guard_rel, count_traversal, block_length, block_inset, predicate)
     out = Obs()
     check(lib().c2b_visibility_graph(
         ctx.handle, scene.handle if scene is not None else None, cams.ctypes.data, cams.shape[0],

@@ -119,6 +119,13 @@ typedef enum {
   C2B_OCC_ANALYTIC = 2 /* 2-D wall test of `synthetic` (src/synthetic.rs:52-124) */
 } c2b_occlusion;
 
+typedef enum {
+  C2B_PRED_WATERTIGHT = 0, /* default: watertight edge-function test (what the north star asks for) */
+  C2B_PRED_MT = 1          /* Moeller-Trumbore in the form of Embree 3's default intersector — what the
+                              reference's default scene runs (src/bin/city2ba.rs:515-521, src/generate.rs:472);
+                              restated from the published algorithm, not watertight on shared edges */
+} c2b_predicate;
+
 typedef struct {
   int cull_mode;          /* c2b_cull_mode */
   int occlusion;          /* c2b_occlusion; MESH needs a scene */
@@ -127,6 +134,8 @@ typedef struct {
   int count_traversal;    /* 1 = count BVH nodes visited / triangles tested (slower) */
   double block_length;    /* C2B_OCC_ANALYTIC only */
   double block_inset;     /* C2B_OCC_ANALYTIC only */
+  int predicate;          /* c2b_predicate; C2B_OCC_MESH only */
+  int reserved;           /* 0 */
 } c2b_vis_options;
 void c2b_vis_options_default(c2b_vis_options *opt);
 

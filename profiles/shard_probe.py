@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--shard", default="0/8")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--max-dist", type=float, default=None, help="override the workload's max_dist (startup-cost probe)")
+    ap.add_argument("--noise", type=int, default=0, help="then this many resident add_noise passes (for ncu -k regex:k_noise)")
+    ap.add_argument("--drop-grid", action="store_true", help="rebuild the point grid in every pass")
     a = ap.parse_args()
     md = bench.MAX_DIST if a.max_dist is None else a.max_dist
     r, n = (int(x) for x in a.shard.split("/"))
@@ -40,10 +42,17 @@ def main():
     for s in range(3 + a.steps):
         flush.zero_()
         torch.cuda.synchronize()
+        if a.drop_grid:
+            c2b._lib.check(c2b._lib.lib().c2b_drop_point_grid(ctx.handle))
         st = rp.run(scene, md, cull_mode="grid", count_traversal=False)
         if s >= 3:
             for k in ("ms_total", "ms_cull", "ms_traverse", "ms_compact"):
                 tot[k] = tot.get(k, 0.0) + st[k] / a.steps
+    for k in range(a.noise):
+        flush.zero_()
+        torch.cuda.synchronize()
+        rp.add_noise(0.0, 0.0001, 0.01, 0.001, seed=42 + k)
+        print("add_noise resident: upload / kernels / download ms", c2b.noise.last_timing(ctx))
     print(json.dumps({"shard": a.shard, "max_dist": md, "cameras": c1 - c0, "pairs": int(st["pairs_evaluated"]), "rays": int(st["n_candidates"]), **{k: round(v, 4) for k, v in tot.items()}}))
 
 

@@ -547,3 +547,64 @@ def test_oversized_batches_are_split(c2b, ctx, orc, cfg2, request):
     ctx.tune("max_pairs", 10)                             # not even one camera fits: a clean error
     with pytest.raises(c2b.C2BError, match="shard the cameras"):
         c2b.visibility_graph(scene, cams, pts, 10.0, ctx=ctx)
+
+
+def test_outlier_points_do_not_coarsen_the_grid(c2b, ctx, orc, cfg2):
+    """a handful of far-away vertices (stray geometry of an OBJ scene) used to stretch the point grid's cells
+    until the schedule degenerated into ~C x P; the cells now resolve the cameras' reach only and everything
+    outside is clamped into the edge cells.  Same graph as the oracle, and a PERFORMANCE assertion: the grid
+    schedule evaluates a small fraction of the pairs."""
+    cams, pts, xyz, tri = cfg2
+    far = np.array([[1e7, 3.0, -2e7], [-4e8, 1.0, 5.0], [30.0, 9e6, 40.0], [np.inf, 0.0, 0.0], [12.0, -3e9, 7.0]])
+    pts2 = np.concatenate([pts[:1200], far, pts[1200:]])
+    scene = c2b.Scene(xyz, tri, ctx=ctx)
+    g = c2b.visibility_graph(scene, cams, pts2, 10.0, ctx=ctx)
+    ref = orc.visibility_graph(xyz, tri, cams, pts2, 10.0)
+    assert_same_graph(g, ref, "outliers")
+    assert ref.n_obs > 10000
+    assert g.stats["pairs_evaluated"] < 0.05 * len(cams) * len(pts2), g.stats["pairs_evaluated"]
+    # the cached (hinted) grid must not be reused by cameras outside its reach: shift a few cameras far away
+    moved = cams.copy()
+    for k in range(0, len(moved), 7):
+        pos = orc.center(moved[k]) + np.array([1e7 - 40.0, 0.0, -2e7 + 40.0])
+        moved[k] = orc.from_position_direction(pos, moved[k][:9])
+    g2 = c2b.visibility_graph(scene, moved, pts2, 10.0, ctx=ctx)
+    assert_same_graph(g2, orc.visibility_graph(xyz, tri, moved, pts2, 10.0), "outliers, cameras moved")
+
+
+def mt_reference(orc, xyz, tri, cams, pts, md):
+    """the graph under the oracle's Moeller-Trumbore restatement: candidates of the cull that orc_occluded_mt
+    (brute force over all triangles) does not call occluded"""
+    v = orc.visibility_graph(xyz, tri, cams, pts, md)
+    occ = orc.occluded_mt(xyz, tri, cams, pts, v).astype(bool)
+    cam_of = np.repeat(np.arange(len(cams)), np.diff(v.cand_offsets.astype(np.int64)))
+    keep = ~occ
+    off = np.concatenate([[0], np.cumsum(np.bincount(cam_of[keep], minlength=len(cams)))]).astype(np.uint64)
+    return off, v.cand_point[keep], v.cand_uv[keep], int(occ.sum()), v
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_predicate_mt_matches_oracle_mt(c2b, ctx, orc, cfg2, mode):
+    """c2b_vis_options::predicate = C2B_PRED_MT (Embree's default intersector, what the reference's scene
+    runs): bit for bit the oracle's orc_ray_triangle_mt on the cfg2 lattice, the cfg1-shaped scene, box.obj's
+    golden scene and a random scene; the watertight default is unchanged and differs on some rays"""
+    cases = [("cfg2", cfg2[2], cfg2[3], cfg2[0], cfg2[1], 10.0)]
+    g1 = np.load(os.path.join(GOLDEN, "cfg1_scene.npz"))
+    cases.append(("cfg1 scene", g1["xyz"], g1["tri"], g1["cams"], g1["pts"], 100.0))
+    gb = np.load(os.path.join(GOLDEN, "box_obj.npz"))
+    cases.append(("box.obj", gb["xyz"], gb["tri"], gb["cams"], gb["pts"], float(gb["max_dist"]) if "max_dist" in gb.files else 100.0))
+    rng = np.random.default_rng(77)
+    xyz, tri = procedural_scene(3)
+    cases.append(("random", xyz, tri, random_cameras(rng, 40), points_on_mesh(rng, xyz, tri, 900), 30.0))
+    differs = 0
+    for name, xyz, tri, cams, pts, md in cases:
+        off, idx, uv, n_occ, v = mt_reference(orc, xyz, tri, cams, pts, md)
+        scene = c2b.Scene(xyz, tri, ctx=ctx)
+        g = c2b.visibility_graph(scene, cams, pts, md, cull_mode=mode, predicate="mt", ctx=ctx)
+        assert np.array_equal(g.offsets, off), f"{name}/{mode}: offsets differ under the MT predicate"
+        assert np.array_equal(g.point_idx, idx) and np.array_equal(g.uv, uv), f"{name}/{mode}"
+        assert g.stats["n_candidates"] == v.n_candidates
+        w = c2b.visibility_graph(scene, cams, pts, md, cull_mode=mode, ctx=ctx)
+        assert_same_graph(w, v, f"{name}/{mode} watertight default")
+        differs += int(w.num_observations != g.num_observations)
+    assert differs > 0   # the two predicates do not decide every end-point ray alike (DESIGN.md section 2)
