@@ -96,6 +96,7 @@ struct Tunables {
   double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
   int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
                                    // driver copy from pageable memory itself
+  int epilogue = 1;                // sort + CSR write inside the fused kernel (0: count scan + k_sort_write)
 };
 
 struct CtxExtra {
@@ -132,6 +133,7 @@ static bool tune(Tunables &t, const char *name, double v) {
   else if (n == "fu_occ3") t.fu_occ3 = v != 0;
   else if (n == "grid_cell_factor") t.grid_cell_factor = v > 0 ? v : 0.25;
   else if (n == "stage_threads") t.stage_threads = std::min(std::max(0, (int)v), 16);
+  else if (n == "epilogue") t.epilogue = v != 0;
   else return false;
   return true;
 }
@@ -212,7 +214,7 @@ int c2b_init(int device, c2b_ctx **out) {
         {"C2B_PARTS_LOG2", "parts_log2"}, {"C2B_TRILIST_CAP", "trilist_cap"}, {"C2B_MAX_PAIRS", "max_pairs"},
         {"C2B_HOIST_MAX", "hoist_max"}, {"C2B_PACKET_BVH", "packet_bvh"}, {"C2B_TRILIST_WARP", "trilist_warp"},
         {"C2B_BATCHES", "batches"}, {"C2B_FU_OCC3", "fu_occ3"}, {"C2B_GRID_CELL_FACTOR", "grid_cell_factor"},
-        {"C2B_STAGE_THREADS", "stage_threads"}};
+        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}};
     for (auto &h : hooks)
       if (const char *e = getenv(h.env)) (void)tune(x->tun, h.name, atof(e));
   }
@@ -246,7 +248,8 @@ void c2b_shutdown(c2b_ctx *ctx) {
                     &ctx->out_uv[0], &ctx->out_offsets[1], &ctx->out_idx[1], &ctx->out_uv[1],
                     &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos, &ctx->ev_off,
                     &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx, &ctx->plan_rows, &ctx->plan_row_count,
-                    &ctx->nz_cams, &ctx->nz_centers, &ctx->nz_pts, &ctx->nz_uv, &ctx->nz_scratch};
+                    &ctx->nz_cams, &ctx->nz_centers, &ctx->nz_pts, &ctx->nz_uv, &ctx->nz_scratch,
+                    &ctx->epi_status, &ctx->epi_prefix};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
@@ -540,13 +543,13 @@ int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C) {
 }
 
 // ---- the pipeline ---------------------------------------------------------------------------------------
-// the 64-byte counter block -> host, synchronising the compute stream
+// the 128-byte counter block -> host, synchronising the compute stream
 static int read_counters(c2b_ctx *ctx, unsigned long long *h_cnt) {
   C2B_TRY(ctx->h_small.ensure(256));
-  k_copy_words<<<1, 32, 0, ctx->stream>>>(ctx->counters.as<uint32_t>(), ctx->h_small.as<uint32_t>(), 16);
+  k_copy_words<<<1, 32, 0, ctx->stream>>>(ctx->counters.as<uint32_t>(), ctx->h_small.as<uint32_t>(), 32);
   C2B_KERNEL_CHECK();
   C2B_CUDA(cudaStreamSynchronize(ctx->stream));
-  memcpy(h_cnt, ctx->h_small.p, 64);
+  memcpy(h_cnt, ctx->h_small.p, 128);
   return C2B_OK;
 }
 
@@ -709,9 +712,9 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   }
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
 
-  C2B_TRY(ctx->counters.ensure(64));
+  C2B_TRY(ctx->counters.ensure(128));
   C2B_TRY(ctx->out_offsets[sel].ensure((C + 1) * 8));
-  C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+  C2B_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
   uint64_t n_cand = 0, pairs_eval = 0, total_obs = 0, nodes = 0, tris_t = 0;
   if (!(C && P)) {
     C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[sel].p, 0, (C + 1) * 8, st));
@@ -770,7 +773,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
 
   uint32_t *d_total = ctx->counters.as<uint32_t>() + 12;  // bytes 48..51 of the counter block
   uint32_t *d_max = ctx->counters.as<uint32_t>() + 13;    // bytes 52..55
-  unsigned long long h_cnt[8];
+  unsigned long long h_cnt[16];
 
   // Per-camera leaf lists (cameras + BVH only) and the plan (cameras + point grid only) are independent and
   // each too small to fill the GPU (one thread or warp per camera, latency-bound): the lists run on a
@@ -821,8 +824,27 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_CULL], st));
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
 
-  // fused cull + occlusion
+  // fused cull + occlusion (+ the in-kernel sort / CSR write: see epilogue_sort_write)
   C2B_CUDA(cudaMemsetAsync(ctx->vis_count.p, 0, (slots + 1) * 4, st));
+  const bool mt = mesh && opt.predicate == C2B_PRED_MT;
+  const bool epi = x->tun.epilogue && parts_log2 == 0 && !opt.count_traversal && !mt && !(mesh && x->tun.fu_occ3);
+  if (epi) {
+    // the visible count is at most the planned row points: output arrays of that size can never overflow
+    C2B_TRY(ctx->out_idx[sel].ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
+    C2B_TRY(ctx->out_uv[sel].ensure(std::max<uint64_t>(pairs_eval, 1) * 16));
+    C2B_TRY(ctx->epi_status.ensure(C * 4));
+    C2B_TRY(ctx->epi_prefix.ensure(C * 8));
+    C2B_CUDA(cudaMemsetAsync(ctx->epi_status.p, 0, C * 4, st));
+    C2B_CUDA(cudaMemsetAsync(ctx->epi_prefix.p, 0, C * 8, st));
+    fa.status = ctx->epi_status.as<uint32_t>();
+    fa.prefix = ctx->epi_prefix.as<unsigned long long>();
+    fa.p_aos = ctx->pts_aos.as<double>();
+    fa.out_offsets = ctx->out_offsets[sel].as<uint64_t>();
+    fa.out_idx = ctx->out_idx[sel].as<uint32_t>();
+    fa.out_uv = ctx->out_uv[sel].as<double2>();
+    fa.out_cap = std::min<uint64_t>(ctx->out_idx[sel].cap / 4, ctx->out_uv[sel].cap / 16);
+    fa.key_bits = std::max(pbits, 1);
+  }
   {
     // persistent warps draw cameras from a ticket; more CTAs than can be resident is harmless
     const unsigned nb = (unsigned)std::min<uint64_t>(blocks_for(slots, FU_WARPS), (uint64_t)ctx->sm_count * 8), nt = FU_WARPS * 32;
@@ -830,25 +852,35 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3).  Measured at cfg4: 2.68 ms; 3 CTAs/SM 2.69 ms; 5 CTAs/SM at
     // 48 registers 2.74 ms
     const bool occ4 = !x->tun.fu_occ3;
-    if (mesh && opt.predicate == C2B_PRED_MT) {
+    if (mt) {
       // candidates only; k_filter_candidates_mt decides occlusion below
       k_visibility_fused<FU_OCC_NONE, false, 3, false><<<nb, nt, 0, st>>>(fa);
     } else if (mesh) {
       if (cnt)
         k_visibility_fused<FU_OCC_MESH, true, 3, true><<<nb, nt, 0, st>>>(fa);
+      else if (any_overflow && epi)
+        k_visibility_fused<FU_OCC_MESH, false, 4, true, true><<<nb + 1, nt, 0, st>>>(fa);
       else if (any_overflow)
         k_visibility_fused<FU_OCC_MESH, false, 4, true><<<nb, nt, 0, st>>>(fa);
+      else if (epi)
+        k_visibility_fused<FU_OCC_MESH, false, 4, false, true><<<nb + 1, nt, 0, st>>>(fa);
       else if (occ4)
         k_visibility_fused<FU_OCC_MESH, false, 4, false><<<nb, nt, 0, st>>>(fa);
       else
         k_visibility_fused<FU_OCC_MESH, false, 3, false><<<nb, nt, 0, st>>>(fa);
     } else if (opt.occlusion == C2B_OCC_ANALYTIC) {
-      k_visibility_fused<FU_OCC_ANALYTIC, false, 2, false><<<nb, nt, 0, st>>>(fa);
+      if (epi)
+        k_visibility_fused<FU_OCC_ANALYTIC, false, 2, false, true><<<nb + 1, nt, 0, st>>>(fa);
+      else
+        k_visibility_fused<FU_OCC_ANALYTIC, false, 2, false><<<nb, nt, 0, st>>>(fa);
     } else {
-      k_visibility_fused<FU_OCC_NONE, false, 3, false><<<nb, nt, 0, st>>>(fa);
+      if (epi)
+        k_visibility_fused<FU_OCC_NONE, false, 3, false, true><<<nb + 1, nt, 0, st>>>(fa);
+      else
+        k_visibility_fused<FU_OCC_NONE, false, 3, false><<<nb, nt, 0, st>>>(fa);
     }
     C2B_KERNEL_CHECK();
-    if (mesh && opt.predicate == C2B_PRED_MT) {
+    if (mt) {
       FilterArgs f{fa.nodes, fa.tris, fa.n_nodes, fa.scene_absmax, fa.cen_x, fa.cen_y, fa.cen_z, ctx->pts_aos.as<double>(),
                    slots, parts_log2, opt.endpoint_guard_rel, fa.ev_count, fa.scratch_idx, fa.vis_count, fa.counters};
       k_filter_candidates_mt<<<blocks_for(slots, 8), 256, 0, st>>>(f);
@@ -857,6 +889,20 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   }
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_TRAVERSE], st));
 
+  bool epi_done = false;
+  if (epi) {
+    // the kernel has written the CSR; the counters say whether every camera took part
+    C2B_TRY(read_counters(ctx, h_cnt));
+    if (h_cnt[5]) return set_error(C2B_ERR_CUDA, "internal: a camera's scratch slice overflowed");
+    if (h_cnt[11]) return set_error(C2B_ERR_CUDA, "internal: the fused kernel's epilogue gave up waiting for a camera's count");
+    n_cand = h_cnt[4];
+    if (h_cnt[9] <= SW_WARP_MAX && h_cnt[10] == 0) {
+      total_obs = h_cnt[8];
+      epi_done = true;
+    }
+    // else: a camera sees more points than the warp sort holds — the two-kernel path below redoes the tail
+  }
+  if (!epi_done) {
   // visible counts -> CSR offsets
   C2B_TRY(exclusive_scan_u32(st, fa.vis_count, ctx->seg_off.as<uint32_t>(), slots + 1, d_total, ctx->scan_tmp));
   k_max_cam<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C, parts_log2, d_max);
@@ -911,6 +957,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   } else {
     C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[sel].p, 0, (C + 1) * 8, st));
   }
+  }  // !epi_done
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));
   C2B_CUDA(cudaStreamSynchronize(st));
@@ -966,7 +1013,7 @@ static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double
   if (opt.cull_mode == C2B_CULL_GRID) return visibility_grid_fused(ctx, x, scene, max_dist, opt, pbits, cbits, stats);
 
   // ---- exhaustive schedule: every pair -> pool -> radix sort -> ordered traversal -> stream compaction --
-  C2B_TRY(ctx->counters.ensure(64));
+  C2B_TRY(ctx->counters.ensure(128));
   C2B_TRY(ctx->cam_count.ensure((C + 1) * 4));
   C2B_TRY(ctx->out_offsets[ctx->out_sel].ensure((C + 1) * 8));
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
@@ -1008,7 +1055,7 @@ static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double
       if (grid.y > 65535u) return set_error(C2B_ERR_INVALID, "too many cameras for one exhaustive launch");
       k_cull_exhaustive<<<grid, CB_THREADS, 0, st>>>(a);
       C2B_KERNEL_CHECK();
-      unsigned long long h_cnt[8];
+      unsigned long long h_cnt[16];
       C2B_TRY(read_counters(ctx, h_cnt));
       pool_n = h_cnt[0];
       n_cand = h_cnt[0];
@@ -1067,7 +1114,7 @@ static int visibility_resident_impl(c2b_ctx *ctx, const c2b_scene *scene, double
 
   uint32_t *d_total = ctx->counters.as<uint32_t>() + 12;  // bytes 48..51 of the counter block
   uint64_t total_obs = 0;
-  unsigned long long h_fin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long h_fin[16] = {0};
   {
     C2B_TRY(exclusive_scan_u32(st, ctx->cam_count.as<uint32_t>(), ctx->cam_count.as<uint32_t>(), C + 1,
                                nullptr, ctx->scan_tmp));

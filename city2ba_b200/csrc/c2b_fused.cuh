@@ -66,8 +66,25 @@ struct FusedArgs {
   uint32_t *scratch_idx;      // visible point indices, slot s at [ev_off[s], ev_off[s] + vis_count[s])
   uint32_t *vis_count;        // [slots+1]
   unsigned long long *counters;  // [1] pairs evaluated, [2] list entries / nodes, [3] warp triangle tests,
-                                 // [4] candidates (rays), [5] scratch slice overflow flag, [7] camera ticket
+                                 // [4] candidates (rays), [5] scratch slice overflow flag, [7] camera ticket,
+                                 // EPI: [8] total observations, [9] largest per-camera count, [10] flags
+  // ---- in-kernel epilogue (template EPI, parts_log2 == 0): a camera's visible list is sorted and its CSR
+  // records are written by the warp that produced it, one camera later (see k_visibility_fused) ----
+  uint32_t *status;            // [C] EPI_READY | visible count, published after the camera's fused phase
+  unsigned long long *prefix;  // [C] EPI_FLAG | exclusive prefix of the counts = CSR offset, by the scanner warp
+  const double *p_aos;         // xyz records, original point order
+  uint64_t *out_offsets;       // [C + 1]
+  uint32_t *out_idx;
+  double2 *out_uv;
+  uint64_t out_cap;            // observations the output arrays hold
+  int key_bits;                // bits of the largest point index
 };
+constexpr uint32_t EPI_READY = 0x80000000u;
+constexpr unsigned long long EPI_FLAG = 1ull << 63;
+enum { EPI_OUT_OVERFLOW = 1, EPI_TIMED_OUT = 2 };
+// A wait that does not end within ~2 s (it cannot, short of a bug or a fault on another warp) gives up and
+// raises counters[11]; every other wait sees that and gives up too, so the launch ends and the host reports it.
+constexpr unsigned EPI_SPIN_LIMIT = 8u << 20;
 
 // camera_cell_range / camera_row run in BOTH k_cam_plan (which sizes each camera's scratch slice) and
 // k_visibility_fused (which scans the rows), so they must round identically in both inlined copies:
@@ -308,6 +325,167 @@ __global__ void __launch_bounds__(128, 5) k_cam_plan(FusedArgs a) {
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(&a.counters[1], n);
 }
+
+// ---- warp-private radix sort of a camera's visible point indices (used by k_sort_write and by the
+// fused kernel's in-kernel epilogue) --------------------------------------------------------------------
+struct SortWriteArgs {
+  const uint32_t *ev_off;     // [C+1] scratch slice starts
+  const uint32_t *seg_off;    // [C+1] exclusive scan of vis_count = CSR offsets
+  uint64_t C;
+  const uint32_t *scratch_idx;
+  const double *cams;
+  const double *p_aos;  // xyz records, original point order
+  uint64_t *out_offsets;
+  uint32_t *out_idx;
+  double2 *out_uv;
+  int key_bits;    // bits of the largest point index: the radix passes cover exactly these
+  int parts_log2;  // slots per camera (FusedArgs::parts_log2); ev_off / seg_off are indexed by slot
+};
+
+// a camera's visible list is the concatenation of its slots' scratch slices
+struct CamSlices {
+  uint32_t base, n;         // CSR segment of the camera
+  uint32_t sub[4], eo[4];   // slot q starts at list position sub[q] and at scratch_idx[eo[q]]
+};
+// MULTI = false: one slot per camera (parts_log2 == 0), the common case, compiled without the slot search
+template <bool MULTI>
+__device__ __forceinline__ CamSlices cam_slices(const SortWriteArgs &s, uint64_t cam) {
+  CamSlices cs;
+  if (!MULTI) {
+    cs.base = s.seg_off[cam];
+    cs.n = s.seg_off[cam + 1] - cs.base;
+    cs.sub[0] = 0u;
+    cs.eo[0] = s.ev_off[cam];
+    return cs;
+  }
+  const uint64_t slot0 = cam << s.parts_log2;
+  const int S = 1 << s.parts_log2;
+  cs.base = s.seg_off[slot0];
+  cs.n = s.seg_off[slot0 + S] - cs.base;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cs.sub[q] = q < S ? s.seg_off[slot0 + q] - cs.base : 0xffffffffu;
+    cs.eo[q] = q < S ? s.ev_off[slot0 + q] : 0u;
+  }
+  return cs;
+}
+template <bool MULTI>
+__device__ __forceinline__ uint32_t cam_key(const SortWriteArgs &s, const CamSlices &cs, uint32_t t) {
+  if (!MULTI) return s.scratch_idx[cs.eo[0] + t];
+  uint32_t sub = cs.sub[0], eo = cs.eo[0];
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (t >= cs.sub[q]) {
+      sub = cs.sub[q];
+      eo = cs.eo[q];
+    }
+  return s.scratch_idx[eo + (t - sub)];
+}
+
+constexpr uint32_t SW_WARP_MAX = 1024;   // one warp per camera
+constexpr uint32_t SW_BLOCK_MAX = 4096;  // shared-memory sort, one block per camera
+
+constexpr int SW_WARPS = 4;
+constexpr int SW_RADIX_BITS = 8;
+constexpr int SW_BINS = 1 << SW_RADIX_BITS;
+
+// sorted[] is indexed with one pad word per 32 (i + i/32), so that the lane*E + r stores and the
+// consecutive reads are both free of bank conflicts
+__device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
+
+// Warp-private LSD radix sort of n <= 32*E keys, 8-bit digits.  Keys live in registers in list order
+// (a[r] = key r*32 + lane); one pass = digit histogram in shared memory (ATOMS), exclusive scan of the
+// 256 counters (8 per lane + one warp scan), then a stable scatter chunk by chunk: the rank of a key
+// among the equal digits of its chunk is popc(__match_any_sync & lanes below), the chunk's first lane
+// per digit advances the counter with one shared-memory atomic and hands the old value to its peers
+// by shuffle (no warp barrier inside the chunk loop: they cost a quarter of the kernel's instructions
+// in the first version, profiles/r01j).  A pass whose keys all share the digit is skipped (common for the top
+// digit: a camera's points are usually close in index).  About 0.4k warp instructions per pass at
+// n = 532 against ~3k for the 1024-key bitonic network this replaces (profiles/r01h: k_sort_write spent
+// 878 M warp instructions, 16.5 per observation).  The sorted keys end up in `sorted` (padded layout).
+template <int E, bool MULTI>
+__device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const CamSlices &cs, int lane,
+                                                  uint32_t *sorted, uint32_t *hist) {
+  const uint32_t n = cs.n;
+  const int key_bits = s.key_bits;
+  uint32_t a[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const uint32_t t = r * 32 + lane;
+    a[r] = t < n ? cam_key<MULTI>(s, cs, t) : 0xffffffffu;
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  bool in_smem = false;
+  for (int shift = 0; shift < key_bits; shift += SW_RADIX_BITS) {
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+      if ((uint32_t)(r * 32 + lane) < n) atomicAdd(&hist[(a[r] >> shift) & (SW_BINS - 1)], 1u);
+    __syncwarp();
+    // exclusive scan: lane owns counters [8*lane, 8*lane + 8)
+    uint32_t c[SW_BINS / 32];
+    uint32_t sum = 0;
+    bool one_bin = false;
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      c[k] = hist[lane * (SW_BINS / 32) + k];
+      one_bin |= c[k] == n;
+      sum += c[k];
+    }
+    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
+      __syncwarp();                          // (the counters are cleared again by the next pass)
+      continue;
+    }
+    uint32_t pre = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    pre -= sum;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      hist[lane * (SW_BINS / 32) + k] = pre;
+      pre += c[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      if ((uint32_t)(r * 32) < n) {  // warp-uniform
+        const bool valid = (uint32_t)(r * 32 + lane) < n;
+        const uint32_t d = valid ? (a[r] >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & lt);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
+        const uint32_t base = __shfl_sync(0xffffffffu, old, leader);
+        if (valid) sorted[sw_pad(base + rank)] = a[r];
+      }
+    }
+    __syncwarp();
+    in_smem = true;
+    if (shift + SW_RADIX_BITS < key_bits) {
+#pragma unroll
+      for (int r = 0; r < E; ++r) {
+        const uint32_t t = r * 32 + lane;
+        if (t < n) a[r] = sorted[sw_pad(t)];
+      }
+      __syncwarp();
+    }
+  }
+  if (!in_smem) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const uint32_t t = r * 32 + lane;
+      if (t < n) sorted[sw_pad(t)] = a[r];
+    }
+  }
+}
+
 
 // ---- the fused pass ---------------------------------------------------------------------------------
 constexpr int FU_WARPS = 8;
@@ -627,22 +805,150 @@ __device__ __forceinline__ int packet_bvh_hit(const FusedArgs &a, const Ray &ray
   return occ ? 1 : 0;
 }
 
+// ---- in-kernel epilogue -----------------------------------------------------------------------------
+// Sorting a camera's visible indices and writing its CSR records needs the camera's offset in the CSR = the
+// sum of the visible counts of ALL cameras before it.  Instead of ending the kernel there (count scan on the
+// host's clock, then a second kernel that re-reads the scratch lists: 0.79 ms of the 3.6 ms pass at cfg4,
+// latency-bound at 52 % issue-active) the persistent kernel finishes the job itself:
+//   * a worker warp publishes status[cam] = READY | count when its camera's fused phase ends;
+//   * ONE scanner warp (block 0, warp 0; it takes no tickets) walks the cameras in order, 32 per step, waits
+//     for their counts, and publishes prefix[cam] (and the CSR offsets, the total and the largest count);
+//   * a worker handles the epilogue of a camera only AFTER the fused phase of its NEXT camera (tickets are
+//     handed out in camera order, so by then every earlier camera has long been counted and the wait for
+//     prefix[cam] is over before it starts): sort (the same warp-private radix sort as k_sort_write, in the
+//     warp's shared-memory region), gather the points, recompute (u, v) bit-identically, write coalesced.
+// The epilogue's loads and shared-memory round trips interleave with other warps' fused phases, which is what
+// hides its latency.  Deadlock-free: publishing a count never waits, the scanner only waits for counts, and
+// every ticket holder is resident (block 0 is dispatched first).  Cameras that see more than SW_WARP_MAX points
+// or an output array that is too small are left to the host's fallback (the two-kernel path).
+__device__ __noinline__ void epilogue_sort_write(const FusedArgs &a, uint64_t cam, uint32_t n, uint32_t ev0,
+                                                 const double *c, uint32_t *region, int lane) {
+  n = __reduce_max_sync(0xffffffffu, n);  // uniform register (see k_sort_write)
+  if (n == 0u || n > SW_WARP_MAX) return;
+  unsigned long long w = 0ull;
+  if (lane == 0) {
+    const volatile unsigned long long *p = a.prefix + cam;
+    const volatile unsigned long long *abort_flag = a.counters + 11;
+    unsigned spins = 0;
+    while (!((w = *p) & EPI_FLAG)) {
+      __nanosleep(200);
+      if ((++spins & 1023u) == 0u && (*abort_flag || spins > EPI_SPIN_LIMIT)) {
+        atomicOr(&a.counters[11], 1ull);
+        break;
+      }
+    }
+  }
+  w = __shfl_sync(0xffffffffu, w, 0);
+  if (!(w & EPI_FLAG)) return;  // gave up: the host reports the failure
+  const uint64_t base = w & ~EPI_FLAG;
+  if (base + n > a.out_cap) {
+    if (lane == 0) atomicOr(&a.counters[10], (unsigned long long)EPI_OUT_OVERFLOW);
+    return;
+  }
+  uint32_t *sorted = region, *hist = region + (SW_WARP_MAX + SW_WARP_MAX / 32);
+  SortWriteArgs sw;
+  sw.scratch_idx = a.scratch_idx;
+  sw.key_bits = a.key_bits;
+  CamSlices cs;
+  cs.base = 0u;
+  cs.n = n;
+  cs.eo[0] = ev0;
+  cs.sub[0] = 0u;
+  if (n <= 128)
+    sort_warp_to_smem<4, false>(sw, cs, lane, sorted, hist);
+  else if (n <= 256)
+    sort_warp_to_smem<8, false>(sw, cs, lane, sorted, hist);
+  else if (n <= 512)
+    sort_warp_to_smem<16, false>(sw, cs, lane, sorted, hist);
+  else if (n <= 768)
+    sort_warp_to_smem<24, false>(sw, cs, lane, sorted, hist);
+  else
+    sort_warp_to_smem<32, false>(sw, cs, lane, sorted, hist);
+  __syncwarp();
+#pragma unroll 2
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t pt = sorted[sw_pad(i)];
+    const double *p = a.p_aos + 3 * (uint64_t)pt;
+    a.out_idx[base + i] = pt;
+    a.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ void epilogue_scanner(const FusedArgs &a, int lane) {
+  unsigned long long running = 0ull;
+  uint32_t mx = 0u;
+  for (uint64_t base = 0; base < a.C; base += 32) {
+    const uint64_t cam = base + lane;
+    uint32_t st = EPI_READY;
+    bool gave_up = false;
+    if (cam < a.C) {
+      const volatile uint32_t *p = a.status + cam;
+      const volatile unsigned long long *abort_flag = a.counters + 11;
+      unsigned spins = 0;
+      while (!((st = *p) & EPI_READY)) {
+        __nanosleep(100);
+        if ((++spins & 1023u) == 0u && (*abort_flag || spins > 2 * EPI_SPIN_LIMIT)) {
+          atomicOr(&a.counters[11], 1ull);
+          gave_up = true;
+          break;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, gave_up)) return;
+    const uint32_t n = st & ~EPI_READY;
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned long long excl = running + (unsigned long long)(incl - n);
+    if (cam < a.C) {
+      a.out_offsets[cam] = excl;
+      *(volatile unsigned long long *)(a.prefix + cam) = excl | EPI_FLAG;
+    }
+    running += (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+    mx = max(mx, n);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) {
+    a.out_offsets[a.C] = running;
+    a.counters[8] = running;
+    a.counters[9] = mx;
+  }
+}
+
 // Persistent warps: every warp draws the next camera from a global ticket (counters[7]), so a warp
 // that drew a cheap camera (city edge, few points in range) immediately gets another one and no
 // warp idles waiting for the slowest camera of its block.
 // WALK = the BVH traversals for cameras whose leaf list overflowed are compiled in; the host picks
 // the variant without them when k_cam_trilist reported no overflow (coarse meshes), which keeps
 // their registers out of the list-driven fast path.
-template <int OCC, bool COUNT, int MIN_CTAS, bool WALK>
+// EPI = the in-kernel epilogue above (parts_log2 must be 0): two camera-record slots per warp (the pending
+// camera's record stays put while the next camera is scanned) and a per-warp region large enough for the sort.
+constexpr int FU_REGION_F4 = 4 * FU_HOIST;                                                   // 4 KB
+constexpr int FU_REGION_EPI_F4 = ((SW_WARP_MAX + SW_WARP_MAX / 32 + SW_BINS) * 4 + 15) / 16;  // 5.1 KB
+static_assert(FU_REGION_EPI_F4 >= FU_REGION_F4, "the sort region also holds the triangle records");
+
+template <int OCC, bool COUNT, int MIN_CTAS, bool WALK, bool EPI = false>
 __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
-  __shared__ double s_cam[FU_WARPS][16];
+  __shared__ double s_cam[FU_WARPS][EPI ? 2 : 1][16];
   // survivors of the cull wait here for their packet: a ring of FU_STAGE grid positions per warp.  (Staging
   // the coordinates as well, so that the ray set-up needs no second trip through L1, was measured: 48 KB of
   // shared memory per CTA instead of 36 shrink L1, 3.11 ms against 3.07 ms at cfg4.)
   __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
-  __shared__ float4 s_rec[FU_WARPS][4 * FU_HOIST];  // hoisted: 4 planes x FU_HOIST; chunked: 32 x 3
+  __shared__ float4 s_rec[FU_WARPS][EPI ? FU_REGION_EPI_F4 : FU_REGION_F4];  // hoisted: 4 planes x FU_HOIST; chunked: 32 x 3
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *c = s_cam[warp];
+  if (EPI && blockIdx.x == 0 && warp == 0) {
+    epilogue_scanner(a, lane);
+    return;
+  }
+  int cur = 0;  // EPI: the record slot of the camera being scanned
+  double *c = s_cam[warp][0];
+  bool pending = false;  // EPI: a finished camera waits for its epilogue
+  uint64_t pend_cam = 0;
+  uint32_t pend_n = 0, pend_ev0 = 0;
   uint32_t *stage = s_stage[warp];
   unsigned long long found_total = 0;
   unsigned n_vis_nodes = 0, n_tri = 0;
@@ -672,10 +978,14 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       if ((uint32_t)lane < a.tri_cap) l0 = mylist[lane];
       if ((uint32_t)lane + 32u < a.tri_cap) l1 = mylist[lane + 32];
     }
+    if (EPI) c = s_cam[warp][cur];
     if (lane < 15) c[lane] = creg;
     __syncwarp();
     if (planned_rows == 0u) {  // the plan found nothing to scan (ball outside the data, NaN centre, ...)
-      if (lane == 0) a.vis_count[slot] = 0;
+      if (lane == 0) {
+        a.vis_count[slot] = 0;
+        if (EPI) *(volatile uint32_t *)(a.status + cam) = EPI_READY;
+      }
       continue;
     }
     const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
@@ -799,8 +1109,24 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       resolve(qn);
       found_total += qn;
     }
-    if (lane == 0) a.vis_count[slot] = nvis < out_cap ? nvis : out_cap;
+    nvis = nvis < out_cap ? nvis : out_cap;
+    if (lane == 0) {
+      a.vis_count[slot] = nvis;
+      if (EPI) *(volatile uint32_t *)(a.status + cam) = EPI_READY | nvis;
+    }
+    if (EPI) {
+      __syncwarp();
+      if (pending)
+        epilogue_sort_write(a, pend_cam, pend_n, pend_ev0, s_cam[warp][cur ^ 1], reinterpret_cast<uint32_t *>(s_rec[warp]), lane);
+      pending = true;
+      pend_cam = cam;
+      pend_n = nvis;
+      pend_ev0 = ev0;
+      cur ^= 1;
+    }
   }
+  if (EPI && pending)
+    epilogue_sort_write(a, pend_cam, pend_n, pend_ev0, s_cam[warp][cur ^ 1], reinterpret_cast<uint32_t *>(s_rec[warp]), lane);
   if (lane == 0) {
     if (found_total) atomicAdd(&a.counters[4], found_total);
     if (COUNT) {
@@ -811,230 +1137,6 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
 }
 
 // ---- per-camera sort + final write -------------------------------------------------------------------
-// Bitonic network over E*32 keys in registers, element index i = lane*E + r: partner distance
-// j < E is a register-to-register compare, j >= E one __shfl_xor per register (15 of the 55 stages
-// at E = 32).  Descending blocks are handled by complementing the keys (x -> ~x reverses the order),
-// once per level k, so every compare-exchange is a plain (min, max) without direction selects.  The
-// (k, j) loops are NOT unrolled — only the E registers of a stage are — which keeps the code a few
-// hundred instructions (the fully unrolled network thrashed the instruction cache: 8 of 12 stall
-// cycles were no_instruction, profiles/r01c).
-template <int E, int RJ>
-__device__ __forceinline__ void bitonic_reg_stage(uint32_t (&a)[E]) {
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    const int p = r ^ RJ;
-    if (p > r) {
-      const uint32_t lo = min(a[r], a[p]), hi = max(a[r], a[p]);
-      a[r] = lo;
-      a[p] = hi;
-    }
-  }
-}
-
-template <int E>
-__device__ __forceinline__ void warp_bitonic_sort(uint32_t (&a)[E], int lane) {
-  // flipped[r]: key r currently stored complemented.  Direction of element i at level k is
-  // ascending iff (i & k) == 0 (k == E*32: always ascending).
-  unsigned flipped = 0u;  // bit r
-#pragma unroll 1
-  for (unsigned k = 2; k <= (unsigned)E * 32u; k <<= 1) {
-    // bring every key to the representation its direction at this level needs
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-      const unsigned i = (unsigned)lane * E + r;
-      const bool desc = (i & k) != 0u && k < (unsigned)E * 32u;
-      const bool is = (flipped >> r) & 1u;
-      if (desc != is) a[r] = ~a[r];
-    }
-    {
-      unsigned f = 0u;
-#pragma unroll
-      for (int r = 0; r < E; ++r) {
-        const unsigned i = (unsigned)lane * E + r;
-        if ((i & k) != 0u && k < (unsigned)E * 32u) f |= 1u << r;
-      }
-      flipped = f;
-    }
-#pragma unroll 1
-    for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      if (j >= (unsigned)E) {
-        const int lj = (int)(j / E);
-        const bool lower = (lane & lj) == 0;
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, a[r], lj);
-          a[r] = lower ? min(a[r], other) : max(a[r], other);
-        }
-      } else {
-        if constexpr (E > 1) { if (j == 1u) bitonic_reg_stage<E, 1>(a); }
-        if constexpr (E > 2) { if (j == 2u) bitonic_reg_stage<E, 2>(a); }
-        if constexpr (E > 4) { if (j == 4u) bitonic_reg_stage<E, 4>(a); }
-        if constexpr (E > 8) { if (j == 8u) bitonic_reg_stage<E, 8>(a); }
-        if constexpr (E > 16) { if (j == 16u) bitonic_reg_stage<E, 16>(a); }
-      }
-    }
-  }
-  // the last level is ascending everywhere: nothing is left complemented
-}
-
-struct SortWriteArgs {
-  const uint32_t *ev_off;     // [C+1] scratch slice starts
-  const uint32_t *seg_off;    // [C+1] exclusive scan of vis_count = CSR offsets
-  uint64_t C;
-  const uint32_t *scratch_idx;
-  const double *cams;
-  const double *p_aos;  // xyz records, original point order
-  uint64_t *out_offsets;
-  uint32_t *out_idx;
-  double2 *out_uv;
-  int key_bits;    // bits of the largest point index: the radix passes cover exactly these
-  int parts_log2;  // slots per camera (FusedArgs::parts_log2); ev_off / seg_off are indexed by slot
-};
-
-// a camera's visible list is the concatenation of its slots' scratch slices
-struct CamSlices {
-  uint32_t base, n;         // CSR segment of the camera
-  uint32_t sub[4], eo[4];   // slot q starts at list position sub[q] and at scratch_idx[eo[q]]
-};
-// MULTI = false: one slot per camera (parts_log2 == 0), the common case, compiled without the slot search
-template <bool MULTI>
-__device__ __forceinline__ CamSlices cam_slices(const SortWriteArgs &s, uint64_t cam) {
-  CamSlices cs;
-  if (!MULTI) {
-    cs.base = s.seg_off[cam];
-    cs.n = s.seg_off[cam + 1] - cs.base;
-    cs.sub[0] = 0u;
-    cs.eo[0] = s.ev_off[cam];
-    return cs;
-  }
-  const uint64_t slot0 = cam << s.parts_log2;
-  const int S = 1 << s.parts_log2;
-  cs.base = s.seg_off[slot0];
-  cs.n = s.seg_off[slot0 + S] - cs.base;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    cs.sub[q] = q < S ? s.seg_off[slot0 + q] - cs.base : 0xffffffffu;
-    cs.eo[q] = q < S ? s.ev_off[slot0 + q] : 0u;
-  }
-  return cs;
-}
-template <bool MULTI>
-__device__ __forceinline__ uint32_t cam_key(const SortWriteArgs &s, const CamSlices &cs, uint32_t t) {
-  if (!MULTI) return s.scratch_idx[cs.eo[0] + t];
-  uint32_t sub = cs.sub[0], eo = cs.eo[0];
-#pragma unroll
-  for (int q = 1; q < 4; ++q)
-    if (t >= cs.sub[q]) {
-      sub = cs.sub[q];
-      eo = cs.eo[q];
-    }
-  return s.scratch_idx[eo + (t - sub)];
-}
-
-constexpr uint32_t SW_WARP_MAX = 1024;   // one warp per camera
-constexpr uint32_t SW_BLOCK_MAX = 4096;  // shared-memory sort, one block per camera
-
-constexpr int SW_WARPS = 4;
-constexpr int SW_RADIX_BITS = 8;
-constexpr int SW_BINS = 1 << SW_RADIX_BITS;
-
-// sorted[] is indexed with one pad word per 32 (i + i/32), so that the lane*E + r stores and the
-// consecutive reads are both free of bank conflicts
-__device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
-
-// Warp-private LSD radix sort of n <= 32*E keys, 8-bit digits.  Keys live in registers in list order
-// (a[r] = key r*32 + lane); one pass = digit histogram in shared memory (ATOMS), exclusive scan of the
-// 256 counters (8 per lane + one warp scan), then a stable scatter chunk by chunk: the rank of a key
-// among the equal digits of its chunk is popc(__match_any_sync & lanes below), the chunk's first lane
-// per digit advances the counter with one shared-memory atomic and hands the old value to its peers
-// by shuffle (no warp barrier inside the chunk loop: they cost a quarter of the kernel's instructions
-// in the first version, profiles/r01j).  A pass whose keys all share the digit is skipped (common for the top
-// digit: a camera's points are usually close in index).  About 0.4k warp instructions per pass at
-// n = 532 against ~3k for the 1024-key bitonic network this replaces (profiles/r01h: k_sort_write spent
-// 878 M warp instructions, 16.5 per observation).  The sorted keys end up in `sorted` (padded layout).
-template <int E, bool MULTI>
-__device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const CamSlices &cs, int lane,
-                                                  uint32_t *sorted, uint32_t *hist) {
-  const uint32_t n = cs.n;
-  const int key_bits = s.key_bits;
-  uint32_t a[E];
-#pragma unroll
-  for (int r = 0; r < E; ++r) {
-    const uint32_t t = r * 32 + lane;
-    a[r] = t < n ? cam_key<MULTI>(s, cs, t) : 0xffffffffu;
-  }
-  const unsigned lt = (1u << lane) - 1u;
-  bool in_smem = false;
-  for (int shift = 0; shift < key_bits; shift += SW_RADIX_BITS) {
-#pragma unroll
-    for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < E; ++r)
-      if ((uint32_t)(r * 32 + lane) < n) atomicAdd(&hist[(a[r] >> shift) & (SW_BINS - 1)], 1u);
-    __syncwarp();
-    // exclusive scan: lane owns counters [8*lane, 8*lane + 8)
-    uint32_t c[SW_BINS / 32];
-    uint32_t sum = 0;
-    bool one_bin = false;
-#pragma unroll
-    for (int k = 0; k < SW_BINS / 32; ++k) {
-      c[k] = hist[lane * (SW_BINS / 32) + k];
-      one_bin |= c[k] == n;
-      sum += c[k];
-    }
-    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
-      __syncwarp();                          // (the counters are cleared again by the next pass)
-      continue;
-    }
-    uint32_t pre = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
-      if (lane >= o) pre += v;
-    }
-    pre -= sum;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < SW_BINS / 32; ++k) {
-      hist[lane * (SW_BINS / 32) + k] = pre;
-      pre += c[k];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-      if ((uint32_t)(r * 32) < n) {  // warp-uniform
-        const bool valid = (uint32_t)(r * 32 + lane) < n;
-        const uint32_t d = valid ? (a[r] >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t rank = __popc(peers & lt);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
-        const uint32_t base = __shfl_sync(0xffffffffu, old, leader);
-        if (valid) sorted[sw_pad(base + rank)] = a[r];
-      }
-    }
-    __syncwarp();
-    in_smem = true;
-    if (shift + SW_RADIX_BITS < key_bits) {
-#pragma unroll
-      for (int r = 0; r < E; ++r) {
-        const uint32_t t = r * 32 + lane;
-        if (t < n) a[r] = sorted[sw_pad(t)];
-      }
-      __syncwarp();
-    }
-  }
-  if (!in_smem) {
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-      const uint32_t t = r * 32 + lane;
-      if (t < n) sorted[sw_pad(t)] = a[r];
-    }
-  }
-}
-
 template <int MIN_CTAS, bool MULTI>
 __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWriteArgs s) {
   __shared__ uint32_t s_sorted[SW_WARPS][SW_WARP_MAX + SW_WARP_MAX / 32];
