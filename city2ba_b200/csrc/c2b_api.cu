@@ -99,8 +99,16 @@ struct Tunables {
   int epilogue = 1;                // sort + CSR write inside the fused kernel (0: count scan + k_sort_write)
 };
 
+// what the previous host-buffer call cost per camera: decides whether the next one is bound by the result
+// transfer or by the kernels (camera batch policy of c2b_visibility_graph)
+struct CallHist {
+  bool valid = false;
+  double ms_compute_per_cam = 0, d2h_bytes_per_cam = 0;
+};
+
 struct CtxExtra {
   Tunables tun;
+  CallHist hist;
   GridCache grid;
   uint64_t points_version = 0;
   double pts_bounds[6] = {0, 0, 0, 0, 0, 0};
@@ -605,7 +613,9 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
     return total;
   };
   x->grid.hinted = false;
-  if (cells_at(h) > max_cells && ctx->C) {
+  bool odd_bounds = false;  // an infinite coordinate would collapse its axis to one cell
+  for (int k = 0; k < 3; ++k) odd_bounds = odd_bounds || !std::isfinite(g.min_c[k]) || !std::isfinite(g.max_c[k]);
+  if ((cells_at(h) > max_cells || odd_bounds) && ctx->C) {
     // A few far-away points (outliers of an OBJ scene) would coarsen every cell.  No point farther than
     // max_dist from every camera can be observed, so the cells only have to resolve the cameras' reach;
     // grid_coord clamps everything outside into the edge cells, whose rows extend to the data bounds
@@ -617,8 +627,9 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
     for (int k = 0; k < 3; ++k) usable = usable && std::isfinite(rlo[k]) && std::isfinite(rhi[k]) && rlo[k] <= rhi[k];
     if (usable) {
       for (int k = 0; k < 3; ++k) {
-        const double a = std::max(g.lo[k], rlo[k]), b = std::min(std::isfinite(g.max_c[k]) ? g.max_c[k] : g.lo[k], rhi[k]);
-        g.lo[k] = a <= b ? a : std::min(std::max(rlo[k], g.lo[k]), g.lo[k] + ext[k]);
+        // the reach intersected with the data bounds (which may be infinite); empty: one cell at the reach's edge
+        const double a = std::fmax(g.min_c[k], rlo[k]), b = std::fmin(g.max_c[k], rhi[k]);
+        g.lo[k] = a <= b ? a : rlo[k];
         ext[k] = a <= b ? b - a : 0.0;
         x->grid.hint_lo[k] = rlo[k];
         x->grid.hint_hi[k] = rhi[k];
@@ -832,10 +843,11 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     // the visible count is at most the planned row points: output arrays of that size can never overflow
     C2B_TRY(ctx->out_idx[sel].ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
     C2B_TRY(ctx->out_uv[sel].ensure(std::max<uint64_t>(pairs_eval, 1) * 16));
-    C2B_TRY(ctx->epi_status.ensure(C * 4));
-    C2B_TRY(ctx->epi_prefix.ensure(C * 8));
-    C2B_CUDA(cudaMemsetAsync(ctx->epi_status.p, 0, C * 4, st));
-    C2B_CUDA(cudaMemsetAsync(ctx->epi_prefix.p, 0, C * 8, st));
+    const uint64_t c_pad = (C + 127) & ~127ull;  // the scanner reads and writes whole 128-camera steps
+    C2B_TRY(ctx->epi_status.ensure(c_pad * 4));
+    C2B_TRY(ctx->epi_prefix.ensure(c_pad * 8));
+    C2B_CUDA(cudaMemsetAsync(ctx->epi_status.p, 0, c_pad * 4, st));
+    C2B_CUDA(cudaMemsetAsync(ctx->epi_prefix.p, 0, c_pad * 8, st));
     fa.status = ctx->epi_status.as<uint32_t>();
     fa.prefix = ctx->epi_prefix.as<unsigned long long>();
     fa.p_aos = ctx->pts_aos.as<double>();
@@ -1277,17 +1289,33 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
     return set_error(C2B_ERR_INVALID, "c2b_visibility_graph: pts is null and no %llu resident points were uploaded",
                      (unsigned long long)P);
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
-  // camera batches: the CSR slab of batch b travels to the host while batch b+1 is computed
-  // The result transfer is the longest leg (20 B per observation over PCIe), so it should start as
-  // early as possible: the first batches are small (1/32, 1/32, 1/16, 1/8 of the cameras), the rest 1/8.
+  // Camera batches: the CSR slab of batch b travels to the host while batch b+1 is computed.  A batch should
+  // give every resident warp of the fused kernel more than one camera (a short batch leaves warps idle at its
+  // tail and repeats the per-batch plan / scan / sync), and:
+  //   * when the result transfer is the longest leg (20 B per observation over PCIe: cfg4) it should start
+  //     early — a small first batch, then growing ones;
+  //   * when the kernels are (fine meshes: cfg5) the batches should be few and equal — only the last slab's
+  //     transfer is exposed.
+  // Which case applies is taken from the previous call on this ctx; the first call assumes the transfer.
   std::vector<uint64_t> bounds;  // batch b = cameras [bounds[b], bounds[b+1])
   bounds.push_back(0);
+  const uint64_t W = (uint64_t)ctx->sm_count * 4 * FU_WARPS;  // resident warps of the fused kernel
   if (x->tun.batches > 0) {
     const uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)x->tun.batches));
     for (uint64_t b = 1; b <= nb; ++b) bounds.push_back((b * C) / nb);
-  } else if (C >= 16384) {
-    for (uint64_t f : {1, 2, 4, 8, 12, 16, 20, 24, 28, 32}) bounds.push_back((f * C) / 32);
+  } else if (C < 3 * W) {
+    bounds.push_back(C);
+  } else if (x->hist.valid && x->hist.ms_compute_per_cam > x->hist.d2h_bytes_per_cam / 52e6) {
+    const uint64_t nb = std::min<uint64_t>(std::max<uint64_t>(C / (3 * W), 2), 4);
+    for (uint64_t b = 1; b <= nb; ++b) bounds.push_back((b * C) / nb);
   } else {
+    uint64_t done = 0, size = std::max<uint64_t>(3 * W / 2, C / 32);
+    const uint64_t cap = std::max<uint64_t>(3 * W, C / 6);
+    while (C - done > size + size / 2) {
+      done += size;
+      bounds.push_back(done);
+      size = std::min(2 * size, cap);
+    }
     bounds.push_back(C);
   }
   const uint64_t n_batches = bounds.size() - 1;
@@ -1387,6 +1415,11 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   acc.d2h_bytes = (C + 1) * 8 + obs_base * 20;
   acc.ms_d2h = ms_copy;  // first to last result copy on the copy stream; overlaps the compute of later batches
   acc.ms_total += ms_upload;
+  if (C) {
+    x->hist.valid = true;
+    x->hist.ms_compute_per_cam = (acc.ms_prep + acc.ms_cull + acc.ms_sort + acc.ms_traverse + acc.ms_compact) / (double)C;
+    x->hist.d2h_bytes_per_cam = (double)acc.d2h_bytes / (double)C;
+  }
   *out = acc;
   return C2B_OK;
 }

@@ -12,7 +12,9 @@ fn main() {
                "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o"])
         .arg(&so)
         .arg(root.join("city2ba_b200/csrc/c2b_api.cu"))
+        .arg(root.join("city2ba_b200/csrc/c2b_multi.cu"))
         .arg(root.join("city2ba_b200/csrc/c2b_host.cpp"))
+        .arg("-ldl")  // libnccl.so.2 is loaded with dlopen by c2b_init_multi only
         .status().expect("nvcc not found");
     assert!(status.success());
     println!("cargo:rustc-link-search=native={}", out.display());

@@ -16,10 +16,13 @@ impl GpuScene {
         let (mut xyz, mut tri, mut base) = (Vec::<f32>::new(), Vec::<u32>::new(), 0u32);
         for m in models {
             xyz.extend_from_slice(&m.mesh.positions);
-            tri.extend(m.mesh.indices.iter().map(|i| i + base));
+            // model_to_geometry regroups EACH model's index list into triples on its own
+            // (num_tri = indices.len() / 3, src/generate.rs:78): drop a model's trailing 1-2 indices (an
+            // odd number of `l` pairs) here, or every later model's triangles would shift
+            let n = m.mesh.indices.len() / 3 * 3;
+            tri.extend(m.mesh.indices[..n].iter().map(|i| i + base));
             base += (m.mesh.positions.len() / 3) as u32;
         }
-        tri.truncate(tri.len() / 3 * 3);
         let mut ctx = std::ptr::null_mut();
         let mut raw = std::ptr::null_mut();
         unsafe {

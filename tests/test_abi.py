@@ -52,3 +52,21 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and False, \
                     f"{f} mentions the oracle; the product must not depend on it"
+
+
+def test_rust_ffi_declares_every_export():
+    """rust/src/ffi.rs (the binding a maintainer would add; not compilable here) must declare exactly the
+    header's symbols, so that the uncompiled source cannot drift from the ABI"""
+    import re
+    txt = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (c2b_[a-z0-9_]+)\(", txt)))
+    assert declared == _declared_symbols()
+    hdr = open(os.path.join(ROOT, "include", "city2ba_cuda.h")).read()
+    ver = re.search(r"#define C2B_ABI_VERSION (\d+)", hdr).group(1)
+    assert f"C2B_ABI_VERSION: c_int = {ver};" in txt
+    # struct fields in the header's order (names only)
+    for struct, fields in (("c2b_vis_options", ["cull_mode", "occlusion", "endpoint_guard_rel", "count_traversal",
+                                                "block_length", "block_inset", "predicate", "reserved"]),):
+        body = txt[txt.index(f"pub struct {struct}"):]
+        body = body[:body.index("}")]
+        assert re.findall(r"pub ([a-z_]+):", body) == fields
