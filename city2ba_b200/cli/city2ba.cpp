@@ -211,8 +211,8 @@ int run_generate(int argc, char **argv) {
   const Args a(argc, argv, 2,
                {{"cameras", "100"}, {"intrinsics-start", "1,0,0"}, {"intrinsics-end", "1,0,0"}, {"points", "1000"},
                 {"max-dist", "100"}, {"ground", "0"}, {"height", "1"}, {"path", ""}, {"step-size", "0"}, {"device", "0"},
-                {"seed", "0"}, {"gpus", "1"}},
-               {"no-lcc", "move-to-origin"});
+                {"seed", "0"}, {"gpus", "1"}, {"predicate", "watertight"}},
+               {"no-lcc", "move-to-origin", "compare-predicates"});
   if (a.positional.size() != 2) throw UsageError("The following required arguments were not provided:\n    <FILE> <OUT>");
   if (a.given.count("path") && a.given.count("ground"))
     throw UsageError("The argument '--path <path>' cannot be used with '--ground <ground>'");
@@ -222,6 +222,10 @@ int run_generate(int argc, char **argv) {
                step_size = a.f64("step-size");
   const Vector3 intrinsics_start = a.vec3("intrinsics-start"), intrinsics_end = a.vec3("intrinsics-end");
   const int device = (int)a.usize("device"), gpus = gpus_of(a);
+  const std::string pred_name = a.values.at("predicate");
+  if (pred_name != "watertight" && pred_name != "mt")
+    throw UsageError("Invalid value for '--predicate <predicate>': '" + pred_name + "' (expected watertight or mt)");
+  const int predicate = pred_name == "mt" ? C2B_PRED_MT : C2B_PRED_WATERTIGHT;
   std::vector<tobj::Model> models = tobj::load_obj(a.positional[0]);
 
   std::optional<tobj::Model> model_path;
@@ -263,10 +267,19 @@ int run_generate(int argc, char **argv) {
       generate::generate_world_points_uniform(ctx, models, cameras, num_points, max_dist, seed + 3);
   std::cout << "Generated " << points.size() << " world points\n";
 
-  VisGraph vis_graph = generate::visibility_graph(cscene, cameras, points, max_dist, true);
+  VisGraph vis_graph = generate::visibility_graph(cscene, cameras, points, max_dist, true, predicate);
   size_t edges = 0;
   for (const auto &v : vis_graph) edges += v.size();
   std::cout << "Computed visibility graph with " << edges << " edges\n";
+  if (a.flag("compare-predicates")) {
+    // how many edges the other occlusion predicate keeps (the two differ on rays that end ON the mesh, which
+    // every ray of this generator does: DESIGN.md section 2)
+    const int other = predicate == C2B_PRED_MT ? C2B_PRED_WATERTIGHT : C2B_PRED_MT;
+    size_t other_edges = 0;
+    for (const auto &v : generate::visibility_graph(cscene, cameras, points, max_dist, true, other)) other_edges += v.size();
+    std::cout << "Occlusion predicate " << pred_name << ": " << edges << " edges; "
+              << (other == C2B_PRED_MT ? "mt" : "watertight") << ": " << other_edges << " edges\n";
+  }
   const BAProblem bal = BAProblem::from_visibility(std::move(cameras), std::move(points), std::move(vis_graph));
 
   // Remove cameras that view too few points and points that are viewed by too few cameras.

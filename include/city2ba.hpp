@@ -404,11 +404,12 @@ inline VisGraph unpack(const c2b_obs &o) {
 }
 inline VisGraph run_visibility(const Context &ctx, const Scene *scene, const std::vector<SnavelyCamera> &cameras,
                                const std::vector<Point3> &points, double max_dist, int occlusion,
-                               double block_length, double block_inset) {
+                               double block_length, double block_inset, int predicate = C2B_PRED_WATERTIGHT) {
   const std::vector<double> cams = flatten(cameras);
   c2b_vis_options opt;
   c2b_vis_options_default(&opt);
   opt.occlusion = occlusion;
+  opt.predicate = predicate;
   opt.block_length = block_length;
   opt.block_inset = block_inset;
   c2b_obs out;
@@ -626,9 +627,12 @@ inline std::vector<std::pair<Point3, Point3>> path_segments(const tobj::Model &p
 namespace generate {
 // src/generate.rs:424-481.  Per camera: every point within max_dist, in front, inside the frustum and
 // not occluded by the scene, in ascending point order, with its projection.
+// predicate: C2B_PRED_WATERTIGHT (default) or C2B_PRED_MT, the Moeller-Trumbore test of Embree's default
+// intersector — what the reference's scene runs (not in the reference's signature).
 inline VisGraph visibility_graph(const Scene &scene, const std::vector<SnavelyCamera> &cameras,
-                                 const std::vector<Point3> &points, double max_dist, bool /*verbose*/) {
-  return detail::run_visibility(scene.context(), &scene, cameras, points, max_dist, C2B_OCC_MESH, 20.0, 1.0);
+                                 const std::vector<Point3> &points, double max_dist, bool /*verbose*/,
+                                 int predicate = C2B_PRED_WATERTIGHT) {
+  return detail::run_visibility(scene.context(), &scene, cameras, points, max_dist, C2B_OCC_MESH, 20.0, 1.0, predicate);
 }
 
 // src/generate.rs:356-420 (seeded; the reference draws from thread_rng())

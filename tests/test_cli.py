@@ -173,3 +173,38 @@ def test_baseline_config1_command(tmp_path, box_obj, c2b, ctx):
     assert run("generate", box_obj, out2, "--cameras", "100", "--points", "200", "--ground", "10", "--no-lcc",
                "--seed", "5").returncode == 0
     assert open(out, "rb").read() == open(out2, "rb").read()
+
+
+@pytest.mark.gpu
+def test_gpus_predicate_and_mesh_occlusion_flags(tmp_path, box_obj, c2b):
+    """the flags this build adds to the reference's command line: --gpus N (same output file as one GPU),
+    --predicate mt / --compare-predicates, synthetic --occlusion mesh"""
+    import torch
+    base = ("generate", box_obj, "--cameras", "100", "--points", "200", "--ground", "10", "--no-lcc", "--seed", "5")
+    one = tmp_path / "one.bbal"
+    r = run(base[0], base[1], one, *base[2:], "--compare-predicates")
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("Occlusion predicate watertight: ")]
+    assert len(line) == 1 and "; mt: " in line[0]
+    n_water = int(line[0].split()[3])
+    n_mt = int(line[0].split()[-2])
+    assert f"Computed visibility graph with {n_water} edges" in r.stdout
+    mt = tmp_path / "mt.bbal"
+    r = run(base[0], base[1], mt, *base[2:], "--predicate", "mt")
+    assert r.returncode == 0 and f"Computed visibility graph with {n_mt} edges" in r.stdout
+    assert run(base[0], base[1], mt, *base[2:], "--predicate", "embree").returncode == 2
+    G = min(torch.cuda.device_count(), 4)
+    many = tmp_path / "many.bbal"
+    r = run(base[0], base[1], many, *base[2:], "--gpus", G)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(one, "rb").read() == open(many, "rb").read()
+    assert run(base[0], base[1], many, *base[2:], "--gpus", "0").returncode == 2
+    # synthetic: analytic (reference) and mesh occlusion, one GPU and all of them
+    a1, aG, m1 = tmp_path / "a1.bbal", tmp_path / "aG.bbal", tmp_path / "m1.bbal"
+    assert run("synthetic", a1, "--blocks", "3").returncode == 0
+    assert run("synthetic", aG, "--blocks", "3", "--gpus", G).returncode == 0
+    assert open(a1, "rb").read() == open(aG, "rb").read()
+    r = run("synthetic", m1, "--blocks", "3", "--occlusion", "mesh")
+    assert r.returncode == 0 and "Bundle Adjustment Problem" in r.stdout
+    assert c2b.BAProblem.from_file(str(m1)).num_cameras() > 0
+    assert run("synthetic", m1, "--occlusion", "raytrace").returncode == 2
