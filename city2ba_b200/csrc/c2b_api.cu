@@ -658,17 +658,16 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   C2B_TRY(ctx->grid_z.ensure(P * 8));
   C2B_TRY(ctx->grid_idx.ensure(P * 4));
   C2B_CUDA(cudaMemsetAsync(ctx->cell_start.p, 0, (n_cells + 1) * 4, st));
-  C2B_CUDA(cudaMemsetAsync(ctx->cell_cursor.p, 0, (n_cells + 1) * 4, st));
   const double *px = ctx->pts.as<double>(), *py = px + P, *pz = py + P;
   k_grid_count<<<blocks_for(P, 256), 256, 0, st>>>(px, py, pz, P, g, ctx->cell_of_pt.as<uint32_t>(),
                                                    ctx->cell_start.as<uint32_t>());
   C2B_KERNEL_CHECK();
   C2B_TRY(exclusive_scan_u32(st, ctx->cell_start.as<uint32_t>(), ctx->cell_start.as<uint32_t>(),
                              n_cells + 1, nullptr, ctx->scan_tmp));
+  C2B_CUDA(cudaMemcpyAsync(ctx->cell_cursor.p, ctx->cell_start.p, (n_cells + 1) * 4, cudaMemcpyDeviceToDevice, st));
   k_grid_fill<<<blocks_for(P, 256), 256, 0, st>>>(
-      px, py, pz, P, ctx->cell_of_pt.as<uint32_t>(), ctx->cell_start.as<uint32_t>(),
-      ctx->cell_cursor.as<uint32_t>(), ctx->grid_x.as<double>(), ctx->grid_y.as<double>(),
-      ctx->grid_z.as<double>(), ctx->grid_idx.as<uint32_t>());
+      px, py, pz, P, ctx->cell_of_pt.as<uint32_t>(), ctx->cell_cursor.as<uint32_t>(), ctx->grid_x.as<double>(),
+      ctx->grid_y.as<double>(), ctx->grid_z.as<double>(), ctx->grid_idx.as<uint32_t>());
   C2B_KERNEL_CHECK();
   x->grid.valid = true;
   x->grid.max_dist = max_dist;

@@ -189,31 +189,51 @@ __device__ __forceinline__ int grid_coord(const GridDesc &g, int k, double x) {
   return c;
 }
 
-__global__ void k_grid_count(const double *__restrict__ px, const double *__restrict__ py,
-                             const double *__restrict__ pz, uint64_t P, GridDesc g,
-                             uint32_t *__restrict__ cell_of_pt, uint32_t *__restrict__ cell_count) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  int cx = grid_coord(g, 0, px[i]), cy = grid_coord(g, 1, py[i]), cz = grid_coord(g, 2, pz[i]);
-  uint32_t cell = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
-  cell_of_pt[i] = cell;
-  atomicAdd(&cell_count[cell], 1u);
+// Both grid kernels aggregate their atomics per warp: neighbouring points of the input usually fall into the
+// same cell (lattices, meshes sampled triangle by triangle), so __match_any_sync groups the lanes of a warp by
+// cell and one lane per group issues a single atomic for the whole group.
+__global__ void __launch_bounds__(256) k_grid_count(const double *__restrict__ px, const double *__restrict__ py,
+                                                    const double *__restrict__ pz, uint64_t P, GridDesc g,
+                                                    uint32_t *__restrict__ cell_of_pt, uint32_t *__restrict__ cell_count) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t cell = 0xffffffffu;  // lanes past the end keep to themselves
+  if (i < P) {
+    int cx = grid_coord(g, 0, px[i]), cy = grid_coord(g, 1, py[i]), cz = grid_coord(g, 2, pz[i]);
+    cell = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
+    cell_of_pt[i] = cell;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);
+  if (i < P && lane == __ffs(peers) - 1) atomicAdd(&cell_count[cell], (uint32_t)__popc(peers));
 }
 
-__global__ void k_grid_fill(const double *__restrict__ px, const double *__restrict__ py,
-                            const double *__restrict__ pz, uint64_t P,
-                            const uint32_t *__restrict__ cell_of_pt,
-                            const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ cursor,
-                            double *__restrict__ gx, double *__restrict__ gy, double *__restrict__ gz,
-                            uint32_t *__restrict__ gidx) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  uint32_t cell = cell_of_pt[i];
-  uint32_t pos = cell_start[cell] + atomicAdd(&cursor[cell], 1u);
-  gx[pos] = px[i];
-  gy[pos] = py[i];
-  gz[pos] = pz[i];
-  gidx[pos] = (uint32_t)i;
+// cursor[] starts as a copy of cell_start[], so the atomic returns the absolute position
+__global__ void __launch_bounds__(256) k_grid_fill(const double *__restrict__ px, const double *__restrict__ py,
+                                                   const double *__restrict__ pz, uint64_t P,
+                                                   const uint32_t *__restrict__ cell_of_pt, uint32_t *__restrict__ cursor,
+                                                   double *__restrict__ gx, double *__restrict__ gy,
+                                                   double *__restrict__ gz, uint32_t *__restrict__ gidx) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = i < P;
+  const uint32_t cell = valid ? cell_of_pt[i] : 0xffffffffu;
+  double x = 0.0, y = 0.0, z = 0.0;
+  if (valid) {
+    x = px[i];
+    y = py[i];
+    z = pz[i];
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);
+  const int leader = __ffs(peers) - 1;
+  uint32_t first = 0;
+  if (valid && lane == leader) first = atomicAdd(&cursor[cell], (uint32_t)__popc(peers));
+  const uint32_t pos = __shfl_sync(0xffffffffu, first, leader) + __popc(peers & ((1u << lane) - 1u));
+  if (valid) {
+    gx[pos] = x;
+    gy[pos] = y;
+    gz[pos] = z;
+    gidx[pos] = (uint32_t)i;
+  }
 }
 
 // min / max of point coordinates (two-stage, deterministic): out[0..2] = min, out[3..5] = max

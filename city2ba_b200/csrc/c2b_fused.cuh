@@ -845,29 +845,72 @@ __device__ __noinline__ void epilogue_sort_write(const FusedArgs &a, uint64_t ca
     if (lane == 0) atomicOr(&a.counters[10], (unsigned long long)EPI_OUT_OVERFLOW);
     return;
   }
-  uint32_t *sorted = region, *hist = region + (SW_WARP_MAX + SW_WARP_MAX / 32);
-  SortWriteArgs sw;
-  sw.scratch_idx = a.scratch_idx;
-  sw.key_bits = a.key_bits;
-  CamSlices cs;
-  cs.base = 0u;
-  cs.n = n;
-  cs.eo[0] = ev0;
-  cs.sub[0] = 0u;
-  if (n <= 128)
-    sort_warp_to_smem<4, false>(sw, cs, lane, sorted, hist);
-  else if (n <= 256)
-    sort_warp_to_smem<8, false>(sw, cs, lane, sorted, hist);
-  else if (n <= 512)
-    sort_warp_to_smem<16, false>(sw, cs, lane, sorted, hist);
-  else if (n <= 768)
-    sort_warp_to_smem<24, false>(sw, cs, lane, sorted, hist);
-  else
-    sort_warp_to_smem<32, false>(sw, cs, lane, sorted, hist);
-  __syncwarp();
+  // Warp-private LSD radix sort, 8-bit digits, like sort_warp_to_smem — but written as ROLLED loops over
+  // 32-key chunks that ping-pong between the camera's scratch slice (global, L2-resident) and the warp's
+  // shared-memory region instead of keeping the keys in up to 32 unrolled registers: the register version's
+  // five instantiations tripled this kernel's code (14.0 k SASS lines against 4.7 k) and the instruction
+  // cache thrashed — 8 of 16 stall cycles no_instruction, 6.0 ms against 2.7 + 0.8 (profiles/r02e).
+  uint32_t *buf = region, *hist = region + SW_WARP_MAX;
+  uint32_t *slice = a.scratch_idx + ev0;
+  const uint32_t *src = slice;
+  uint32_t *dst = buf;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int shift = 0; shift < a.key_bits; shift += SW_RADIX_BITS) {
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t t = lane; t < n; t += 32) atomicAdd(&hist[(src[t] >> shift) & (SW_BINS - 1)], 1u);
+    __syncwarp();
+    uint32_t cnt[SW_BINS / 32];
+    uint32_t sum = 0;
+    bool one_bin = false;
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      cnt[k] = hist[lane * (SW_BINS / 32) + k];
+      one_bin |= cnt[k] == n;
+      sum += cnt[k];
+    }
+    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
+      __syncwarp();
+      continue;
+    }
+    uint32_t pre = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    pre -= sum;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      hist[lane * (SW_BINS / 32) + k] = pre;
+      pre += cnt[k];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t first = 0; first < n; first += 32) {
+      const uint32_t t = first + lane;
+      const bool valid = t < n;
+      const uint32_t key = valid ? src[t] : 0u;
+      const uint32_t d = valid ? (key >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
+      const uint32_t pos = __shfl_sync(0xffffffffu, old, leader) + __popc(peers & lt);
+      if (valid) dst[pos] = key;
+    }
+    __syncwarp();
+    const uint32_t *filled = dst;
+    dst = dst == buf ? slice : buf;
+    src = filled;
+  }
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t pt = sorted[sw_pad(i)];
+    const uint32_t pt = src[i];
     const double *p = a.p_aos + 3 * (uint64_t)pt;
     a.out_idx[base + i] = pt;
     a.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
@@ -875,11 +918,6 @@ __device__ __noinline__ void epilogue_sort_write(const FusedArgs &a, uint64_t ca
   __syncwarp();
 }
 
-// The scanner must publish prefixes faster than cameras complete (37 per microsecond at cfg4), and a step is
-// a dependent chain load -> warp scan -> store.  So a step covers 128 cameras (one 16-byte load and 64 bytes of
-// stores per lane) and the NEXT step's load is in flight while this one is scanned; a lane re-polls only while
-// one of its own four counts is missing.  (The first version, 32 cameras per step without the prefetch, took
-// ~2 us per step and held the whole kernel back: 6.6 ms instead of 2.7 + 0.8, profiles/r02c.)
 __device__ __noinline__ void epilogue_scanner(const FusedArgs &a, int lane) {
   const volatile unsigned long long *abort_flag = a.counters + 11;
   unsigned long long running = 0ull;
@@ -962,7 +1000,7 @@ __device__ __noinline__ void epilogue_scanner(const FusedArgs &a, int lane) {
 // EPI = the in-kernel epilogue above (parts_log2 must be 0): two camera-record slots per warp (the pending
 // camera's record stays put while the next camera is scanned) and a per-warp region large enough for the sort.
 constexpr int FU_REGION_F4 = 4 * FU_HOIST;                                                   // 4 KB
-constexpr int FU_REGION_EPI_F4 = ((SW_WARP_MAX + SW_WARP_MAX / 32 + SW_BINS) * 4 + 15) / 16;  // 5.1 KB
+constexpr int FU_REGION_EPI_F4 = ((SW_WARP_MAX + SW_BINS) * 4 + 15) / 16;                     // 5 KB
 static_assert(FU_REGION_EPI_F4 >= FU_REGION_F4, "the sort region also holds the triangle records");
 
 template <int OCC, bool COUNT, int MIN_CTAS, bool WALK, bool EPI = false>
