@@ -96,7 +96,11 @@ struct Tunables {
   double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
   int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
                                    // driver copy from pageable memory itself
-  int epilogue = 1;                // sort + CSR write inside the fused kernel (0: count scan + k_sort_write)
+  int epilogue = 0;                // 1: sort + CSR write inside the fused kernel instead of the count scan +
+                                   // k_sort_write.  Measured slower (cfg4: 4.04 ms against 2.69 + 0.80): at the
+                                   // same 32 warps per SM a warp's epilogue is just appended to its serial
+                                   // chain, and warps parked in its latency-bound loops leave fewer warps to
+                                   // fill the issue slots (64.6 % issue-active against 77 %; profiles/r02f)
 };
 
 // what the previous host-buffer call cost per camera: decides whether the next one is bound by the result

@@ -61,7 +61,8 @@ uint64_t c2b_kernel_launches(void);
  *   batches (0 auto)             camera batches of the host-buffer call
  *   fu_occ3 (0)                  fused kernel at 3 CTAs/SM
  *   grid_cell_factor (0.25)      point-grid cell side / max_dist
- *   epilogue (1)                 sort + CSR write inside the fused kernel (0: count scan + a second kernel)
+ *   epilogue (0)                 1: sort + CSR write inside the fused kernel (scanner warp + deferred per-camera
+ *                                epilogue) instead of the count scan + k_sort_write; measured slower, kept for study
  *   stage_threads (4)            host threads staging a PAGEABLE input array through the pinned ring (0: leave
  *                                the pageable copy to the driver)
  * Unknown names are C2B_ERR_INVALID. */
