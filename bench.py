@@ -58,6 +58,12 @@ BLOCK_LENGTH, BLOCK_INSET, CAM_H, PT_H, BUILDING_H = 20.0, 1.0, 1.0, 1.0, 10.0
 HASHES = os.path.join(ROOT, "tests", "golden", "result_hashes.json")
 
 
+def trace(msg):
+    """progress on stderr when C2B_BENCH_TRACE=1 (debugging multi-rank runs)"""
+    if os.environ.get("C2B_BENCH_TRACE") == "1":
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -431,8 +437,10 @@ def main():
                     t += dt
             return t, out
 
+    trace("building the workload")
     prob = Problem(args.workload)
     C, P = prob.C, prob.P
+    trace(f"workload ready: {C} x {P}")
 
     # ---- device-resident arm ("value") ----------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
@@ -442,6 +450,7 @@ def main():
     launches_per_step = launches // (K + args.warmup)
     t_dev = tot["ms_total"] / 1e3
     tot_cached, _ = prob.resident(args.cull_mode, K, 1, drop_grid=False)
+    trace("resident arms done")
 
     # ---- end-to-end arm: host buffers -> C-ABI call -> ONE host CSR ------------------------------------------
     mctx = mscene = None
@@ -455,8 +464,10 @@ def main():
         if rank == 0:
             # the library's multi-GPU entry: this process drives all `world` GPUs (the other ranks wait at the
             # barrier below with their GPUs idle)
+            trace("creating the multi-GPU context")
             mctx = c2b.MultiContext(world)
             mscene = c2b.MultiScene(prob.xyz, prob.tri, mctx)
+            trace("multi-GPU context and scene ready")
             ms = _lib.MultiStats()
             for s in range(args.warmup + K):
                 flush_l2()
@@ -472,8 +483,10 @@ def main():
             multi_stats["n_obs"] = [int(ms.n_obs[g]) for g in range(world)]
             multi_stats["ms_wall_last_step"] = float(ms.ms_wall)
         # a CPU barrier: an NCCL one would park a spinning kernel on GPUs 1..N-1 while rank 0 is timing them
+        trace("e2e arm done, waiting at the host barrier")
         dist.barrier(group=cpu_group)
     clocks = sampler.stop() if sampler else None
+    trace("past the e2e arm")
 
     csr = None
     res_hash = None
@@ -616,6 +629,7 @@ def main():
         ex_t = rmax(ex[0]["ms_total"] / 1e3 / ex[2])
         ex_cull = rmax(ex[0]["ms_cull"] / ex[2])
 
+    trace("reductions done")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

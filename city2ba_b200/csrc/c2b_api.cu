@@ -617,27 +617,41 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
     return total;
   };
   x->grid.hinted = false;
+  g.drop = 0;
+  for (int k = 0; k < 3; ++k) g.rlo[k] = g.rhi[k] = 0.0;
   bool odd_bounds = false;  // an infinite coordinate would collapse its axis to one cell
   for (int k = 0; k < 3; ++k) odd_bounds = odd_bounds || !std::isfinite(g.min_c[k]) || !std::isfinite(g.max_c[k]);
-  if ((cells_at(h) > max_cells || odd_bounds) && ctx->C) {
-    // A few far-away points (outliers of an OBJ scene) would coarsen every cell.  No point farther than
-    // max_dist from every camera can be observed, so the cells only have to resolve the cameras' reach;
-    // grid_coord clamps everything outside into the edge cells, whose rows extend to the data bounds
-    // (camera_row), and the exact predicate still runs on every point read.
+  if (ctx->C) {
+    // No point farther than max_dist from every camera can be observed, so only the cameras' REACH (their
+    // centres' box grown by max_dist) has to be binned.  When the reach is clearly smaller than the data —
+    // a camera shard of a multi-GPU run, or a few far-away outlier vertices of an OBJ scene that would stretch
+    // every cell — the cells cover the reach only and points outside it are left out of the grid altogether
+    // (k_grid_count); a GPU that owns 1/8 of the cameras then bins about 1/8 of the points.
     double clo[3], chi[3], rlo[3], rhi[3];
     C2B_TRY(camera_bbox(ctx, clo, chi));
     reach_box(clo, chi, max_dist, rlo, rhi);
     bool usable = true;
     for (int k = 0; k < 3; ++k) usable = usable && std::isfinite(rlo[k]) && std::isfinite(rhi[k]) && rlo[k] <= rhi[k];
-    if (usable) {
+    double frac = 1.0;  // share of the data's box the reach covers
+    if (usable)
+      for (int k = 0; k < 3; ++k) {
+        const double a = std::fmax(g.min_c[k], rlo[k]), b = std::fmin(g.max_c[k], rhi[k]);
+        if (ext[k] > 0.0) frac *= a <= b ? std::fmin((b - a) / ext[k], 1.0) : 0.0;
+      }
+    if (usable && (cells_at(h) > max_cells || odd_bounds || frac < 0.7)) {
       for (int k = 0; k < 3; ++k) {
         // the reach intersected with the data bounds (which may be infinite); empty: one cell at the reach's edge
         const double a = std::fmax(g.min_c[k], rlo[k]), b = std::fmin(g.max_c[k], rhi[k]);
         g.lo[k] = a <= b ? a : rlo[k];
         ext[k] = a <= b ? b - a : 0.0;
+        g.min_c[k] = g.lo[k];  // what is IN the grid: rows of edge cells end here (camera_row)
+        g.max_c[k] = a <= b ? b : g.lo[k];
+        g.rlo[k] = rlo[k];
+        g.rhi[k] = rhi[k];
         x->grid.hint_lo[k] = rlo[k];
         x->grid.hint_hi[k] = rhi[k];
       }
+      g.drop = 1;
       x->grid.hinted = true;
     }
   }

@@ -178,8 +178,10 @@ struct GridDesc {
   double lo[3];
   double inv_h;
   int n[3];
-  double max_c[3];  // point bounds (for the ball / grid early-out)
+  int drop;         // 1: points outside [rlo, rhi] (the cameras' reach) are not in the grid at all
+  double max_c[3];  // bounds of the points IN the grid (for the ball / grid early-out, rows of edge cells)
   double min_c[3];
+  double rlo[3], rhi[3];
 };
 
 __device__ __forceinline__ int grid_coord(const GridDesc &g, int k, double x) {
@@ -199,12 +201,17 @@ __global__ void __launch_bounds__(256) k_grid_count(const double *__restrict__ p
   const int lane = threadIdx.x & 31;
   uint32_t cell = 0xffffffffu;  // lanes past the end keep to themselves
   if (i < P) {
-    int cx = grid_coord(g, 0, px[i]), cy = grid_coord(g, 1, py[i]), cz = grid_coord(g, 2, pz[i]);
-    cell = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
+    const double x = px[i], y = py[i], z = pz[i];
+    // outside the cameras' reach: farther than max_dist from every camera, never observed (NaN stays in)
+    const bool out = g.drop && (x < g.rlo[0] || x > g.rhi[0] || y < g.rlo[1] || y > g.rhi[1] || z < g.rlo[2] || z > g.rhi[2]);
+    if (!out) {
+      int cx = grid_coord(g, 0, x), cy = grid_coord(g, 1, y), cz = grid_coord(g, 2, z);
+      cell = ((uint32_t)cz * g.n[1] + cy) * g.n[0] + cx;
+    }
     cell_of_pt[i] = cell;
   }
   const unsigned peers = __match_any_sync(0xffffffffu, cell);
-  if (i < P && lane == __ffs(peers) - 1) atomicAdd(&cell_count[cell], (uint32_t)__popc(peers));
+  if (cell != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&cell_count[cell], (uint32_t)__popc(peers));
 }
 
 // cursor[] starts as a copy of cell_start[], so the atomic returns the absolute position
@@ -215,8 +222,8 @@ __global__ void __launch_bounds__(256) k_grid_fill(const double *__restrict__ px
                                                    double *__restrict__ gz, uint32_t *__restrict__ gidx) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool valid = i < P;
-  const uint32_t cell = valid ? cell_of_pt[i] : 0xffffffffu;
+  const uint32_t cell = i < P ? cell_of_pt[i] : 0xffffffffu;
+  const bool valid = cell != 0xffffffffu;  // past the end, or outside the cameras' reach
   double x = 0.0, y = 0.0, z = 0.0;
   if (valid) {
     x = px[i];
