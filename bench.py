@@ -333,6 +333,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     os.environ["C2B_ORACLE_NATIVE"] = "1"  # the CPU arm below is built -O3 -march=native on this box
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL announces its version on
+    # stdout when a communicator is created) goes to stderr instead; the line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import ctypes as Ct
 
@@ -514,6 +519,7 @@ def main():
             ms_h2d_drv = float(o3.ms_h2d)
         else:
             o2 = _lib.Obs()
+            ms2 = _lib.MultiStats()
             def multi_pageable(n):
                 t = 0.0
                 for s in range(1 + n):
@@ -521,12 +527,15 @@ def main():
                     t0 = time.perf_counter()
                     _lib.check(L.c2b_visibility_graph_multi(mctx.handle, mscene.handle, pg_cams.ctypes.data, C,
                                                             pg_pts.ctypes.data, P, MAX_DIST, Ct.byref(prob.opt),
-                                                            Ct.byref(o2), None))
+                                                            Ct.byref(o2), Ct.byref(ms2)))
                     if s >= 1:
                         t += time.perf_counter() - t0
                 return t
             t_pg = multi_pageable(steps_pg)
             ms_h2d_pg = float(o2.ms_h2d)
+            extras["e2e_pageable_per_gpu_last_step"] = {
+                k: [round(float(getattr(ms2, k)[g]), 4) for g in range(world)]
+                for k in ("ms_points", "ms_compute", "ms_exchange", "ms_d2h")}
             mctx.tune("stage_threads", 0)
             t_drv = multi_pageable(steps_pg)
             mctx.tune("reset", 0)
@@ -775,7 +784,8 @@ def main():
             p2.scene.close()
             del p2
         line["secondary"] = sec
-    print(json.dumps(line), flush=True)
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -96,6 +96,8 @@ struct Tunables {
   double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
   int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
                                    // driver copy from pageable memory itself
+  int optimistic = 1;              // launch a pass's kernels without waiting for the plan's totals when the
+                                   // previous pass on this ctx left sizes to go by (one host sync instead of three)
   int epilogue = 0;                // 1: sort + CSR write inside the fused kernel instead of the count scan +
                                    // k_sort_write.  Measured slower (cfg4: 4.04 ms against 2.69 + 0.80): at the
                                    // same 32 warps per SM a warp's epilogue is just appended to its serial
@@ -110,9 +112,16 @@ struct CallHist {
   double ms_compute_per_cam = 0, d2h_bytes_per_cam = 0;
 };
 
+// what the previous resident pass (grid schedule) found: lets the next one launch its kernels without waiting
+// for the plan's totals (the kernels check every assumption and flag a misfit)
+struct PassMemo {
+  bool valid = false, any_overflow = false, big = false;
+};
+
 struct CtxExtra {
   Tunables tun;
   CallHist hist;
+  PassMemo memo;
   GridCache grid;
   uint64_t points_version = 0;
   double pts_bounds[6] = {0, 0, 0, 0, 0, 0};
@@ -146,6 +155,7 @@ static bool tune(Tunables &t, const char *name, double v) {
   else if (n == "grid_cell_factor") t.grid_cell_factor = v > 0 ? v : 0.25;
   else if (n == "stage_threads") t.stage_threads = std::min(std::max(0, (int)v), 16);
   else if (n == "epilogue") t.epilogue = v != 0;
+  else if (n == "optimistic") t.optimistic = v != 0;
   else return false;
   return true;
 }
@@ -226,7 +236,7 @@ int c2b_init(int device, c2b_ctx **out) {
         {"C2B_PARTS_LOG2", "parts_log2"}, {"C2B_TRILIST_CAP", "trilist_cap"}, {"C2B_MAX_PAIRS", "max_pairs"},
         {"C2B_HOIST_MAX", "hoist_max"}, {"C2B_PACKET_BVH", "packet_bvh"}, {"C2B_TRILIST_WARP", "trilist_warp"},
         {"C2B_BATCHES", "batches"}, {"C2B_FU_OCC3", "fu_occ3"}, {"C2B_GRID_CELL_FACTOR", "grid_cell_factor"},
-        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}};
+        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}};
     for (auto &h : hooks)
       if (const char *e = getenv(h.env)) (void)tune(x->tun, h.name, atof(e));
   }
@@ -841,21 +851,30 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_KERNEL_CHECK();
   C2B_TRY(exclusive_scan_u32(st, fa.ev_count, fa.ev_count, slots + 1, nullptr, ctx->scan_tmp));
   if (mesh) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-  C2B_TRY(read_counters(ctx, h_cnt));
-  pairs_eval = h_cnt[1];
-  const bool any_overflow = h_cnt[0] != 0;  // cameras whose leaf list exceeded the cap
+  // Sizes of the scratch / output arrays and the kernel variant depend on the plan's totals.  The first pass
+  // waits for them; later passes go by what the previous pass left (grow-only buffers, the remembered variant),
+  // launch everything back to back, and check at the one final sync that it all fitted.
   const uint64_t max_pairs = x->tun.max_pairs;  // 32-bit scratch offsets (lower: test hook)
-  if (pairs_eval >= max_pairs)
-    return set_error(ERR_TOO_LARGE, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
-  C2B_TRY(ctx->scratch_idx.ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
+  const bool mt = mesh && opt.predicate == C2B_PRED_MT;
+  const bool epi = x->tun.epilogue && parts_log2 == 0 && !opt.count_traversal && !mt && !(mesh && x->tun.fu_occ3);
+  const bool optimistic = x->tun.optimistic && x->memo.valid && !epi && !opt.count_traversal && ctx->scratch_idx.cap >= 4 &&
+                          ctx->out_idx[sel].cap >= 4 && ctx->out_uv[sel].cap >= 16;
+  bool any_overflow = x->memo.any_overflow;
+  if (!optimistic) {
+    C2B_TRY(read_counters(ctx, h_cnt));
+    pairs_eval = h_cnt[1];
+    any_overflow = h_cnt[0] != 0;  // cameras whose leaf list exceeded the cap
+    if (pairs_eval >= max_pairs)
+      return set_error(ERR_TOO_LARGE, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
+    C2B_TRY(ctx->scratch_idx.ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
+  }
   fa.scratch_idx = ctx->scratch_idx.as<uint32_t>();
+  fa.scratch_cap = ctx->scratch_idx.cap / 4;
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_CULL], st));
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_SORT], st));
 
   // fused cull + occlusion (+ the in-kernel sort / CSR write: see epilogue_sort_write)
   C2B_CUDA(cudaMemsetAsync(ctx->vis_count.p, 0, (slots + 1) * 4, st));
-  const bool mt = mesh && opt.predicate == C2B_PRED_MT;
-  const bool epi = x->tun.epilogue && parts_log2 == 0 && !opt.count_traversal && !mt && !(mesh && x->tun.fu_occ3);
   if (epi) {
     // the visible count is at most the planned row points: output arrays of that size can never overflow
     C2B_TRY(ctx->out_idx[sel].ensure(std::max<uint64_t>(pairs_eval, 1) * 4));
@@ -936,24 +955,61 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   C2B_TRY(exclusive_scan_u32(st, fa.vis_count, ctx->seg_off.as<uint32_t>(), slots + 1, d_total, ctx->scan_tmp));
   k_max_cam<<<(unsigned)std::min<uint64_t>(blocks_for(C, 256), 1024), 256, 0, st>>>(ctx->seg_off.as<uint32_t>(), C, parts_log2, d_max);
   C2B_KERNEL_CHECK();
-  C2B_TRY(read_counters(ctx, h_cnt));
-  if (h_cnt[5]) return set_error(C2B_ERR_CUDA, "internal: a camera's scratch slice overflowed");
-  uint32_t total32, max32;
-  memcpy(&total32, reinterpret_cast<const char *>(h_cnt) + 48, 4);
-  memcpy(&max32, reinterpret_cast<const char *>(h_cnt) + 52, 4);
-  total_obs = total32;
-  n_cand = h_cnt[4];
-  nodes = h_cnt[2];
-  tris_t = h_cnt[3];
+  uint32_t total32 = 0, max32 = 0;
+  auto read_totals = [&]() -> int {
+    C2B_TRY(read_counters(ctx, h_cnt));
+    if (h_cnt[5]) return set_error(C2B_ERR_CUDA, "internal: a camera's scratch slice overflowed");
+    memcpy(&total32, reinterpret_cast<const char *>(h_cnt) + 48, 4);
+    memcpy(&max32, reinterpret_cast<const char *>(h_cnt) + 52, 4);
+    total_obs = total32;
+    n_cand = h_cnt[4];
+    nodes = h_cnt[2];
+    tris_t = h_cnt[3];
+    return C2B_OK;
+  };
+  auto sort_write_args = [&]() {
+    return SortWriteArgs{fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, fa.cams, ctx->pts_aos.as<double>(),
+                         ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>(),
+                         std::max(pbits, 1), parts_log2,
+                         std::min<uint64_t>(ctx->out_idx[sel].cap / 4, ctx->out_uv[sel].cap / 16), fa.counters + 12};
+  };
+  const unsigned swb = (unsigned)blocks_for(C, SW_WARPS), swt = SW_WARPS * 32;
+  if (optimistic) {
+    // sort + write straight away into the arrays as they are; the one sync of the pass comes after it
+    const SortWriteArgs sw = sort_write_args();
+    if (parts_log2 > 0)
+      k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
+    else
+      k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
+    C2B_KERNEL_CHECK();
+    if (x->memo.big) {
+      k_sort_write_block<<<(unsigned)C, 256, 0, st>>>(sw);
+      C2B_KERNEL_CHECK();
+    }
+    C2B_TRY(read_totals());
+    pairs_eval = h_cnt[1];
+    const bool fits = h_cnt[12] == 0 && pairs_eval <= fa.scratch_cap && pairs_eval < max_pairs &&
+                      (max32 <= SW_WARP_MAX || (x->memo.big && max32 <= SW_BLOCK_MAX));
+    if (!fits) {
+      // this pass is larger than what the previous one left behind: size everything exactly and repeat it
+      x->memo.valid = false;
+      if (pairs_eval >= max_pairs)
+        return set_error(ERR_TOO_LARGE, "more than 2^32 camera-point pairs inside max_dist in one call; shard the cameras");
+      return visibility_grid_fused(ctx, x, scene, max_dist, opt, pbits, cbits, stats);
+    }
+    x->memo.any_overflow = h_cnt[0] != 0;
+    x->memo.big = max32 > SW_WARP_MAX;
+  } else {
+  C2B_TRY(read_totals());
+  x->memo.valid = true;
+  x->memo.any_overflow = any_overflow;
+  x->memo.big = max32 > SW_WARP_MAX;
   if (total_obs) {
     C2B_TRY(ctx->out_idx[sel].ensure(total_obs * 4));
     C2B_TRY(ctx->out_uv[sel].ensure(total_obs * 16));
-    SortWriteArgs sw{fa.ev_count, ctx->seg_off.as<uint32_t>(), C, fa.scratch_idx, fa.cams, ctx->pts_aos.as<double>(),
-                     ctx->out_offsets[sel].as<uint64_t>(), ctx->out_idx[sel].as<uint32_t>(), ctx->out_uv[sel].as<double2>(),
-                     std::max(pbits, 1), parts_log2};
+    const SortWriteArgs sw = sort_write_args();
     if (max32 <= SW_BLOCK_MAX) {
       // registers capped for 8 CTAs/SM (measured at cfg4: 0.81 ms; 6 CTAs/SM 0.91 ms, 4 CTAs/SM 1.12 ms)
-      const unsigned swb = (unsigned)blocks_for(C, SW_WARPS), swt = SW_WARPS * 32;
       if (parts_log2 > 0)
         k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
       else
@@ -986,6 +1042,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   } else {
     C2B_CUDA(cudaMemsetAsync(ctx->out_offsets[sel].p, 0, (C + 1) * 8, st));
   }
+  }  // !optimistic
   }  // !epi_done
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_COMPACT], st));
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_D2H], st));

@@ -64,10 +64,13 @@ struct FusedArgs {
   uint32_t *row_count;  // [C] number of rows; 0 = nothing to scan; FU_ROWS_MANY = more than FU_ROWS (recompute)
   uint32_t *ev_count;         // [slots+1] points on the slot's rows (k_cam_plan), then its exclusive scan
   uint32_t *scratch_idx;      // visible point indices, slot s at [ev_off[s], ev_off[s] + vis_count[s])
+  uint64_t scratch_cap;       // entries scratch_idx holds (a slice beyond it raises counters[12] bit 0)
   uint32_t *vis_count;        // [slots+1]
   unsigned long long *counters;  // [1] pairs evaluated, [2] list entries / nodes, [3] warp triangle tests,
                                  // [4] candidates (rays), [5] scratch slice overflow flag, [7] camera ticket,
-                                 // EPI: [8] total observations, [9] largest per-camera count, [10] flags
+                                 // EPI: [8] total observations, [9] largest per-camera count, [10] flags;
+                                 // [12] optimistic-launch flags (FU_FLAG_*): the host sized a buffer or chose a
+                                 // kernel variant from the previous pass and this pass does not fit
   // ---- in-kernel epilogue (template EPI, parts_log2 == 0): a camera's visible list is sorted and its CSR
   // records are written by the warp that produced it, one camera later (see k_visibility_fused) ----
   uint32_t *status;            // [C] EPI_READY | visible count, published after the camera's fused phase
@@ -79,6 +82,7 @@ struct FusedArgs {
   uint64_t out_cap;            // observations the output arrays hold
   int key_bits;                // bits of the largest point index
 };
+enum { FU_FLAG_SCRATCH = 1, FU_FLAG_NEED_WALK = 2, FU_FLAG_OUT = 4 };
 constexpr uint32_t EPI_READY = 0x80000000u;
 constexpr unsigned long long EPI_FLAG = 1ull << 63;
 enum { EPI_OUT_OVERFLOW = 1, EPI_TIMED_OUT = 2 };
@@ -340,6 +344,8 @@ struct SortWriteArgs {
   double2 *out_uv;
   int key_bits;    // bits of the largest point index: the radix passes cover exactly these
   int parts_log2;  // slots per camera (FusedArgs::parts_log2); ev_off / seg_off are indexed by slot
+  uint64_t out_cap;            // observations out_idx / out_uv hold
+  unsigned long long *flags;   // counters[12]: FU_FLAG_OUT when a camera's records do not fit
 };
 
 // a camera's visible list is the concatenation of its slots' scratch slices
@@ -1053,7 +1059,13 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     if (EPI) c = s_cam[warp][cur];
     if (lane < 15) c[lane] = creg;
     __syncwarp();
-    if (planned_rows == 0u) {  // the plan found nothing to scan (ball outside the data, NaN centre, ...)
+    // launched without waiting for the plan's totals (sizes and variant from the previous pass): a camera
+    // whose slice lies beyond the scratch array, or that needs the BVH walk this variant was compiled without,
+    // is skipped and flagged — the host then repeats the pass with exact sizes
+    const bool misfit = (uint64_t)ev1 > a.scratch_cap || (OCC == FU_OCC_MESH && !WALK && n_list == TRILIST_OVERFLOW);
+    if (misfit && lane == 0)
+      atomicOr(&a.counters[12], (unsigned long long)((uint64_t)ev1 > a.scratch_cap ? FU_FLAG_SCRATCH : FU_FLAG_NEED_WALK));
+    if (planned_rows == 0u || misfit) {  // nothing to scan (ball outside the data, NaN centre, ...)
       if (lane == 0) {
         a.vis_count[slot] = 0;
         if (EPI) *(volatile uint32_t *)(a.status + cam) = EPI_READY;
@@ -1228,6 +1240,10 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
     if (cam == s.C - 1) s.out_offsets[s.C] = s.seg_off[s.C << s.parts_log2];
   }
   if (n == 0 || n > SW_WARP_MAX) return;
+  if ((uint64_t)base + n > s.out_cap) {
+    if (lane == 0) atomicOr(s.flags, (unsigned long long)FU_FLAG_OUT);
+    return;
+  }
   uint32_t *sorted = s_sorted[warp];
   if (n <= 128)
     sort_warp_to_smem<4, MULTI>(s, cs, lane, sorted, s_hist[warp]);
@@ -1260,6 +1276,10 @@ __global__ void __launch_bounds__(256) k_sort_write_block(SortWriteArgs s) {
   const CamSlices cs = cam_slices<true>(s, cam);
   const uint32_t base = cs.base, n = cs.n;
   if (n <= SW_WARP_MAX || n > SW_BLOCK_MAX) return;
+  if ((uint64_t)base + n > s.out_cap) {
+    if (threadIdx.x == 0) atomicOr(s.flags, (unsigned long long)FU_FLAG_OUT);
+    return;
+  }
   uint32_t n2 = 2;
   while (n2 < n) n2 <<= 1;
   for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) s_sort[t] = t < n ? cam_key<true>(s, cs, t) : 0xffffffffu;
