@@ -122,6 +122,7 @@ struct CtxExtra {
   Tunables tun;
   CallHist hist;
   PassMemo memo;
+  bool grid_locked = false;  // inside c2b_visibility_graph: the grid was built for all of the call's cameras
   GridCache grid;
   uint64_t points_version = 0;
   double pts_bounds[6] = {0, 0, 0, 0, 0, 0};
@@ -705,6 +706,22 @@ static int build_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
   return C2B_OK;
 }
 
+// the point grid for the resident cameras: the cached one if it still serves them, else a new one
+static int ensure_grid(c2b_ctx *ctx, CtxExtra *x, double max_dist) {
+  if (!(ctx->C && ctx->P)) return C2B_OK;
+  bool valid = x->grid.valid && x->grid.max_dist == max_dist && x->grid.points_version == x->points_version;
+  // built for some cameras' reach: still good if the current ones stay inside it (a host-buffer call builds it
+  // once for ALL its cameras and locks it for the call's batches)
+  if (valid && x->grid.hinted && !x->grid_locked) {
+    double clo[3], chi[3], rlo[3], rhi[3];
+    C2B_TRY(camera_bbox(ctx, clo, chi));
+    reach_box(clo, chi, max_dist, rlo, rhi);
+    for (int k = 0; k < 3; ++k) valid = valid && rlo[k] >= x->grid.hint_lo[k] && rhi[k] <= x->grid.hint_hi[k];
+  }
+  if (!valid) C2B_TRY(build_grid(ctx, x, max_dist));
+  return C2B_OK;
+}
+
 namespace {
 
 void fill_stats(c2b_ctx *ctx, c2b_obs *stats, uint64_t C, uint64_t n_cand, uint64_t pairs_eval,
@@ -738,16 +755,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   cudaStream_t st = ctx->stream;
   const uint64_t C = ctx->C, P = ctx->P;
   const int sel = ctx->out_sel;
-  if (C && P) {
-    bool valid = x->grid.valid && x->grid.max_dist == max_dist && x->grid.points_version == x->points_version;
-    if (valid && x->grid.hinted) {  // built for other cameras' reach: still good if these stay inside it
-      double clo[3], chi[3], rlo[3], rhi[3];
-      C2B_TRY(camera_bbox(ctx, clo, chi));
-      reach_box(clo, chi, max_dist, rlo, rhi);
-      for (int k = 0; k < 3; ++k) valid = valid && rlo[k] >= x->grid.hint_lo[k] && rhi[k] <= x->grid.hint_hi[k];
-    }
-    if (!valid) C2B_TRY(build_grid(ctx, x, max_dist));
-  }
+  C2B_TRY(ensure_grid(ctx, x, max_dist));
   C2B_CUDA(cudaEventRecord(ctx->ev[EV_PREP], st));
 
   C2B_TRY(ctx->counters.ensure(128));
@@ -1408,6 +1416,13 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
     C2B_CUDA(cudaEventRecord(u0, st));
     if (!resident_pts) C2B_TRY(c2b_upload_points(ctx, pts, P));
     C2B_CUDA(cudaEventRecord(u1, st));
+    // the point grid once, for the reach of ALL of this call's cameras (each batch's reach lies inside it)
+    const bool grid_mode = !opt || opt->cull_mode == C2B_CULL_GRID;
+    if (grid_mode && n_batches > 1 && C && P) {
+      C2B_TRY(c2b_upload_cameras(ctx, cams, C));
+      C2B_TRY(ensure_grid(ctx, x, max_dist));
+      x->grid_locked = true;
+    }
     C2B_TRY(ctx->h_offsets.ensure((C + 1) * 8));
     // camera ranges still to do, in order; a range that turns out too large for 32-bit offsets is halved
     std::vector<std::pair<uint64_t, uint64_t>> todo;
@@ -1469,6 +1484,7 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
     return C2B_OK;
   };
   rc = run();
+  x->grid_locked = false;
   cudaEventDestroy(u0);
   cudaEventDestroy(u1);
   cudaEventDestroy(d0);
