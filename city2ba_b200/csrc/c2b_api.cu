@@ -1350,7 +1350,7 @@ int grow_pinned(c2b_ctx *ctx, PinBuf &b, size_t need, size_t used) {
   C2B_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   PinBuf nb;
   nb.node = b.node;
-  C2B_TRY(nb.ensure(need + need / 2));
+  C2B_TRY(nb.ensure(need + need / 16));
   if (used) memcpy(nb.p, b.p, used);
   b.release();
   b = nb;

@@ -126,6 +126,7 @@ struct PinBuf {
   void *p = nullptr;
   size_t cap = 0;
   int node = -1;  // NUMA node of the GPU these buffers feed (-1: unknown / off)
+  bool portable = false;  // every device of the process may DMA into it (the one host CSR of c2b_visibility_graph_multi)
   int ensure(size_t bytes) {
     if (bytes <= cap) return C2B_OK;
     if (p) {
@@ -133,10 +134,11 @@ struct PinBuf {
       p = nullptr;
       cap = 0;
     }
-    size_t want = bytes + bytes / 4 + 256;
+    // pinning costs ~0.5 s per GB on this pool's hosts (profiles/r02b_alloc_probe.txt): large buffers get
+    // little slack, small ones a quarter
+    size_t want = bytes + (bytes > (64u << 20) ? bytes / 32 : bytes / 4) + 256;
     NumaPreferred local(node);
-    // portable: every device of the process may DMA into it (the one host CSR of c2b_visibility_graph_multi)
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+    cudaError_t e = cudaHostAlloc(&p, want, portable ? cudaHostAllocPortable : cudaHostAllocDefault);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       p = nullptr;

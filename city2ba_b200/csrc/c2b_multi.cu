@@ -194,6 +194,7 @@ int c2b_init_multi(int n_gpus, const int *devices, c2b_multi **out) {
   c2b_multi *m = new (std::nothrow) c2b_multi();
   if (!m) return set_error(C2B_ERR_OOM, "out of host memory");
   m->n = n_gpus;
+  m->h_offsets.portable = m->h_idx.portable = m->h_uv.portable = true;
   for (int g = 0; g < n_gpus; ++g) {
     m->dev[g] = devices ? devices[g] : g;
     for (int q = 0; q < g; ++q)

@@ -24,6 +24,15 @@ int main() {
     double t2 = now();
     printf("cudaMalloc %5.2f GB: %8.3f ms   cudaFree %8.3f ms\n", sz / 1e9, t1 - t0, t2 - t1);
   }
+  for (unsigned flags : {cudaHostAllocDefault, cudaHostAllocPortable})
+    for (size_t sz : {(size_t)4096, (size_t)1 << 20, (size_t)64 << 20}) {
+      void *h = nullptr;
+      double t0 = now();
+      cudaHostAlloc(&h, sz, flags);
+      double t1 = now();
+      cudaFreeHost(h);
+      printf("cudaHostAlloc %9zu B flags %u: %8.3f ms   cudaFreeHost %8.3f ms\n", sz, flags, t1 - t0, now() - t1);
+    }
   for (int rep = 0; rep < 2; ++rep) {
     void *h = nullptr;
     double t0 = now();
