@@ -272,7 +272,7 @@ void c2b_shutdown(c2b_ctx *ctx) {
                     &ctx->misc, &ctx->tri_list, &ctx->tri_count, &ctx->pts_aos, &ctx->ev_off,
                     &ctx->vis_count, &ctx->seg_off, &ctx->scratch_idx, &ctx->plan_rows, &ctx->plan_row_count,
                     &ctx->nz_cams, &ctx->nz_centers, &ctx->nz_pts, &ctx->nz_uv, &ctx->nz_scratch,
-                    &ctx->epi_status, &ctx->epi_prefix};
+                    &ctx->epi_status, &ctx->epi_prefix, &ctx->cams_all};
   for (auto *b : bufs) b->release();
   PinBuf *pins[] = {&ctx->pin_in, &ctx->h_offsets, &ctx->h_idx, &ctx->h_uv, &ctx->h_small};
   for (auto *p : pins) p->release();
@@ -429,7 +429,7 @@ int copy_in(c2b_ctx *ctx, void *d, const void *h, size_t bytes, cudaMemcpyKind k
   const int T = extra_of(ctx)->tun.stage_threads;
   constexpr size_t CH = 4u << 20;
   bool pageable = false;
-  if (kind == cudaMemcpyHostToDevice && T > 0 && bytes >= 4 * CH) {
+  if (kind == cudaMemcpyHostToDevice && T > 0 && bytes >= (64u << 10)) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, h) == cudaSuccess)
       pageable = at.type == cudaMemoryTypeUnregistered;
@@ -440,11 +440,21 @@ int copy_in(c2b_ctx *ctx, void *d, const void *h, size_t bytes, cudaMemcpyKind k
     C2B_CUDA(cudaMemcpyAsync(d, h, bytes, kind, st));
     return C2B_OK;
   }
+  if (bytes < 4 * CH) {
+    // a small pageable array (a camera range): one hop through the ring on this thread.  Left to the driver,
+    // pageable copies issued for several GPUs at once queue behind one another — 12 ms for 1.5 MB per GPU at
+    // N = 8 (profiles/r02k_bench_cfg4_8gpu.json: e2e_pageable)
+    C2B_CUDA(cudaStreamSynchronize(st));  // the ring may still feed an earlier copy
+    C2B_TRY(ctx->pin_in.ensure(std::max<size_t>(bytes, 8 * CH)));
+    memcpy(ctx->pin_in.p, h, bytes);
+    C2B_CUDA(cudaMemcpyAsync(d, ctx->pin_in.p, bytes, cudaMemcpyHostToDevice, st));
+    return C2B_OK;
+  }
   const size_t n_chunks = (bytes + CH - 1) / CH;
   const int nt = (int)std::min<size_t>((size_t)T, n_chunks);
-  C2B_TRY(ctx->pin_in.ensure((size_t)nt * 2 * CH));
   // the ring may still feed the previous call's DMA
   C2B_CUDA(cudaStreamSynchronize(st));
+  C2B_TRY(ctx->pin_in.ensure(std::max<size_t>((size_t)nt * 2 * CH, 8 * CH)));
   std::vector<cudaError_t> err((size_t)nt, cudaSuccess);
   std::vector<std::thread> workers;
   const int device = ctx->device;
@@ -558,9 +568,27 @@ int c2b_upload_cameras(c2b_ctx *ctx, const double *cams, uint64_t C) {
   if (C == 0) return C2B_OK;
   C2B_TRY(ctx->cams.ensure(C * 120));
   C2B_TRY(ctx->cam_center.ensure(C * 24));
-  C2B_CUDA(cudaMemcpyAsync(ctx->cams.p, cams, C * 120, cudaMemcpyHostToDevice, ctx->stream));
+  C2B_TRY(copy_in(ctx, ctx->cams.p, cams, C * 120, cudaMemcpyHostToDevice));
   double *cx = ctx->cam_center.as<double>();
   k_cam_prep<<<blocks_for(C, 128), 128, 0, ctx->stream>>>(ctx->cams.as<double>(), C, cx, cx + C, cx + 2 * C);
+  C2B_KERNEL_CHECK();
+  return C2B_OK;
+}
+
+// cameras [first, first + count) of the call's device copy (ctx->cams_all) become the resident cameras:
+// what c2b_upload_cameras does for a batch, without touching host memory again
+static int select_cameras(c2b_ctx *ctx, uint64_t first, uint64_t count) {
+  CtxExtra *x = extra_of(ctx);
+  ctx->C = count;
+  x->have_cameras = true;
+  x->have_result = false;
+  if (count == 0) return C2B_OK;
+  C2B_TRY(ctx->cams.ensure(count * 120));
+  C2B_TRY(ctx->cam_center.ensure(count * 24));
+  C2B_CUDA(cudaMemcpyAsync(ctx->cams.p, ctx->cams_all.as<double>() + 15 * first, count * 120, cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  double *cx = ctx->cam_center.as<double>();
+  k_cam_prep<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(ctx->cams.as<double>(), count, cx, cx + count, cx + 2 * count);
   C2B_KERNEL_CHECK();
   return C2B_OK;
 }
@@ -1418,8 +1446,13 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
     C2B_CUDA(cudaEventRecord(u1, st));
     // the point grid once, for the reach of ALL of this call's cameras (each batch's reach lies inside it)
     const bool grid_mode = !opt || opt->cull_mode == C2B_CULL_GRID;
+    // all cameras cross PCIe once; the batches are device-side slices of that copy
+    if (C) {
+      C2B_TRY(ctx->cams_all.ensure(C * 120));
+      C2B_TRY(copy_in(ctx, ctx->cams_all.p, cams, C * 120, cudaMemcpyHostToDevice));
+    }
     if (grid_mode && n_batches > 1 && C && P) {
-      C2B_TRY(c2b_upload_cameras(ctx, cams, C));
+      C2B_TRY(select_cameras(ctx, 0, C));
       C2B_TRY(ensure_grid(ctx, x, max_dist));
       x->grid_locked = true;
     }
@@ -1433,7 +1466,7 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
       const int sel = (int)(b & 1);
       ctx->out_sel = sel;
       if (b >= 2) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[sel], 0));  // set `sel` is free again
-      C2B_TRY(c2b_upload_cameras(ctx, cams ? cams + 15 * c0 : nullptr, nc));
+      C2B_TRY(select_cameras(ctx, c0, nc));
       c2b_obs s1;
       const int rcb = visibility_resident_impl(ctx, scene, max_dist, opt, &s1);
       if (rcb == ERR_TOO_LARGE && nc > 1) {

@@ -190,6 +190,7 @@ struct c2b_ctx {
 
   // resident problem
   uint64_t C = 0, P = 0;
+  c2b::DevBuf cams_all;      // host-buffer call: all of the call's cameras (its batches are slices of it)
   c2b::DevBuf cams;          // double[15*C] as given
   c2b::DevBuf cam_center;    // double[3*C]  SoA: x[C], y[C], z[C]
   c2b::DevBuf pts;           // double[3*P]  SoA: x[P], y[P], z[P] (streamed by the cull kernels)
