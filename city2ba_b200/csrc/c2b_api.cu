@@ -2,13 +2,20 @@
 // host-side orchestration of the kernels: upload -> (grid build) -> cull -> radix sort ->
 // warp-cooperative BVH traversal -> compaction -> download.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
+
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include "c2b_bvh.cuh"
 #include "c2b_common.cuh"
@@ -96,6 +103,8 @@ struct Tunables {
   double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
   int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
                                    // driver copy from pageable memory itself
+  int cold_staged = 1;             // first host-buffer call on a ctx returns its CSR in unpinned memory filled
+                                   // through a pinned ring (0: pin the result arrays at once, as later calls do)
   int optimistic = 1;              // launch a pass's kernels without waiting for the plan's totals when the
                                    // previous pass on this ctx left sizes to go by (one host sync instead of three)
   int epilogue = 0;                // 1: sort + CSR write inside the fused kernel instead of the count scan +
@@ -103,6 +112,148 @@ struct Tunables {
                                    // same 32 warps per SM a warp's epilogue is just appended to its serial
                                    // chain, and warps parked in its latency-bound loops leave fewer warps to
                                    // fill the issue slots (64.6 % issue-active against 77 %; profiles/r02f)
+};
+
+// Pageable host memory backed by transparent huge pages (mmap + MADV_HUGEPAGE): what the FIRST host-buffer call
+// on a ctx returns its CSR in.  Pinning 1.1 GB takes 0.55-1.3 s on this pool's hosts
+// (profiles/r02b_alloc_probe.txt, r02l_cold_probe.json) — far longer than computing and transferring the result —
+// so a one-shot caller gets an unpinned array filled through a small pinned ring by host threads (Drainer);
+// a second call on the same ctx is no one-shot any more and switches to pinned arrays.
+struct PageBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure_fresh(size_t bytes) {  // contents are not kept
+    if (bytes <= cap) return C2B_OK;
+    release();
+    const size_t want = (bytes + bytes / 16 + (2u << 20)) & ~(size_t)((2u << 20) - 1);
+#if defined(__linux__)
+    void *q = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (q == MAP_FAILED) return set_error(C2B_ERR_OOM, "mmap(%zu bytes) failed", want);
+    (void)madvise(q, want, MADV_HUGEPAGE);
+#else
+    void *q = malloc(want);
+    if (!q) return set_error(C2B_ERR_OOM, "malloc(%zu bytes) failed", want);
+#endif
+    p = q;
+    cap = want;
+    return C2B_OK;
+  }
+  void release() {
+#if defined(__linux__)
+    if (p) munmap(p, cap);
+#else
+    free(p);
+#endif
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+// Device -> pageable host memory through a pinned ring: `threads` host threads, each with its own stream and two
+// 2 MB ring slots, take 2 MB chunks off a queue: DMA into a slot, then memcpy the slot to its destination (the
+// first touch of the destination's pages happens there, in parallel).  submit() never blocks the caller.
+class Drainer {
+ public:
+  static constexpr size_t CH = 2u << 20;  // pinning the ring itself costs ~1 ms per MB: keep it small
+  int start(int device, int threads, char *ring) {
+    n_ = threads;
+    for (int t = 0; t < n_; ++t)
+      workers_.emplace_back([this, device, t, ring]() { loop(device, ring + (size_t)t * 2 * CH); });
+    return C2B_OK;
+  }
+  // bytes from dev_src (valid once `ready` has fired on its stream) to host_dst; `batch` tags the chunks
+  void submit(const void *dev_src, void *host_dst, size_t bytes, cudaEvent_t ready, int batch) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if ((size_t)batch >= dma_left_.size()) dma_left_.resize((size_t)batch + 1, 0);
+    for (size_t off = 0; off < bytes; off += CH) {
+      q_.push_back(Chunk{static_cast<const char *>(dev_src) + off, static_cast<char *>(host_dst) + off,
+                         std::min(CH, bytes - off), ready, batch});
+      ++dma_left_[(size_t)batch];
+      ++left_;
+    }
+    cv_.notify_all();
+  }
+  // every chunk of `batch` has left the device (its device buffers may be overwritten)
+  void wait_dma(int batch) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return (size_t)batch >= dma_left_.size() || dma_left_[(size_t)batch] == 0 || err_ != cudaSuccess; });
+  }
+  // everything submitted so far has landed in host memory
+  void wait_all() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return left_ == 0 || err_ != cudaSuccess; });
+  }
+  // everything submitted has landed in host memory; joins the threads
+  cudaError_t finish() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_done_.wait(lk, [&] { return left_ == 0 || err_ != cudaSuccess; });
+      quit_ = true;
+    }
+    cv_.notify_all();
+    for (auto &w : workers_) w.join();
+    workers_.clear();
+    return err_;
+  }
+  ~Drainer() {
+    if (!workers_.empty()) (void)finish();
+  }
+
+ private:
+  struct Chunk {
+    const char *src;
+    char *dst;
+    size_t n;
+    cudaEvent_t ready;
+    int batch;
+  };
+  void loop(int device, char *slots) {
+    cudaError_t e = cudaSetDevice(device);
+    cudaStream_t st = nullptr;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (int turn = 0;; ++turn) {
+      Chunk c;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !q_.empty() || quit_ || err_ != cudaSuccess; });
+        if (q_.empty() || err_ != cudaSuccess) break;
+        c = q_.front();
+        q_.pop_front();
+      }
+      char *slot = slots + (size_t)(turn & 1) * CH;
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c.ready, 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(slot, c.src, c.n, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (e != cudaSuccess) err_ = e;
+        --dma_left_[(size_t)c.batch];
+      }
+      cv_done_.notify_all();
+      if (e == cudaSuccess) memcpy(c.dst, slot, c.n);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        --left_;
+      }
+      cv_done_.notify_all();
+      if (e != cudaSuccess) break;
+    }
+    if (st) cudaStreamDestroy(st);
+    cv_done_.notify_all();
+  }
+  int n_ = 0;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, cv_done_;
+  std::deque<Chunk> q_;
+  std::vector<size_t> dma_left_;
+  size_t left_ = 0;
+  bool quit_ = false;
+  cudaError_t err_ = cudaSuccess;
 };
 
 // what the previous host-buffer call cost per camera: decides whether the next one is bound by the result
@@ -123,6 +274,13 @@ struct CtxExtra {
   CallHist hist;
   PassMemo memo;
   bool grid_locked = false;  // inside c2b_visibility_graph: the grid was built for all of the call's cameras
+  PageBuf pg_idx, pg_uv;     // first host-buffer call: unpinned result arrays (see PageBuf)
+  PinBuf pin_out;            // and the ring they are filled through
+  ~CtxExtra() {
+    pg_idx.release();
+    pg_uv.release();
+    pin_out.release();
+  }
   GridCache grid;
   uint64_t points_version = 0;
   double pts_bounds[6] = {0, 0, 0, 0, 0, 0};
@@ -157,6 +315,7 @@ static bool tune(Tunables &t, const char *name, double v) {
   else if (n == "stage_threads") t.stage_threads = std::min(std::max(0, (int)v), 16);
   else if (n == "epilogue") t.epilogue = v != 0;
   else if (n == "optimistic") t.optimistic = v != 0;
+  else if (n == "cold_staged") t.cold_staged = v != 0;
   else return false;
   return true;
 }
@@ -237,7 +396,7 @@ int c2b_init(int device, c2b_ctx **out) {
         {"C2B_PARTS_LOG2", "parts_log2"}, {"C2B_TRILIST_CAP", "trilist_cap"}, {"C2B_MAX_PAIRS", "max_pairs"},
         {"C2B_HOIST_MAX", "hoist_max"}, {"C2B_PACKET_BVH", "packet_bvh"}, {"C2B_TRILIST_WARP", "trilist_warp"},
         {"C2B_BATCHES", "batches"}, {"C2B_FU_OCC3", "fu_occ3"}, {"C2B_GRID_CELL_FACTOR", "grid_cell_factor"},
-        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}};
+        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}, {"C2B_COLD_STAGED", "cold_staged"}};
     for (auto &h : hooks)
       if (const char *e = getenv(h.env)) (void)tune(x->tun, h.name, atof(e));
   }
@@ -421,13 +580,13 @@ void c2b_vis_options_default(c2b_vis_options *opt) {
 // Host -> device copy of a caller's array on ctx->stream.  A pinned (or registered) source goes to the copy
 // engine as it is.  A PAGEABLE one — what `points.as_ptr()` of a Rust Vec or a numpy array is — would be
 // staged by the driver through its own bounce buffer on one thread; instead `stage_threads` host threads
-// copy 4 MB chunks into the ctx's pinned ring (two slots per thread) and queue each chunk's DMA as soon as
+// copy 2 MB chunks into the ctx's pinned ring (two slots per thread) and queue each chunk's DMA as soon as
 // it is staged, so the host-side memcpy runs at several cores' bandwidth and overlaps the PCIe transfer.
 int copy_in(c2b_ctx *ctx, void *d, const void *h, size_t bytes, cudaMemcpyKind kind) {
   cudaStream_t st = ctx->stream;
   if (bytes == 0) return C2B_OK;
   const int T = extra_of(ctx)->tun.stage_threads;
-  constexpr size_t CH = 4u << 20;
+  constexpr size_t CH = 2u << 20;  // pinning the ring itself costs ~1 ms per MB: keep it small
   bool pageable = false;
   if (kind == cudaMemcpyHostToDevice && T > 0 && bytes >= (64u << 10)) {
     cudaPointerAttributes at;
@@ -1440,7 +1599,22 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   int rc = C2B_OK;
   uint64_t obs_base = 0;
   float ms_upload = 0, ms_copy = 0;
+  // First host-buffer call on this ctx: the CSR goes to unpinned memory through the Drainer (see PageBuf).
+  const bool staged = x->tun.cold_staged && x->tun.stage_threads > 0 && !x->hist.valid && ctx->h_uv.cap < (64u << 20);
+  Drainer drain;
+  std::chrono::steady_clock::time_point t_first_copy;
+  bool copy_started = false;
+  if (!staged) {
+    x->pg_idx.release();
+    x->pg_uv.release();
+  }
   auto run = [&]() -> int {
+    if (staged) {
+      const int nthreads = std::max(2, x->tun.stage_threads);
+      x->pin_out.node = ctx->numa_node;
+      C2B_TRY(x->pin_out.ensure((size_t)nthreads * 2 * Drainer::CH));
+      C2B_TRY(drain.start(ctx->device, nthreads, x->pin_out.as<char>()));
+    }
     C2B_CUDA(cudaEventRecord(u0, st));
     if (!resident_pts) C2B_TRY(c2b_upload_points(ctx, pts, P));
     C2B_CUDA(cudaEventRecord(u1, st));
@@ -1465,7 +1639,12 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
       todo.pop_back();
       const int sel = (int)(b & 1);
       ctx->out_sel = sel;
-      if (b >= 2) C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[sel], 0));  // set `sel` is free again
+      if (b >= 2) {  // set `sel` is free again once batch b - 2 has left the device
+        if (staged)
+          drain.wait_dma((int)b - 2);
+        else
+          C2B_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[sel], 0));
+      }
       C2B_TRY(select_cameras(ctx, c0, nc));
       c2b_obs s1;
       const int rcb = visibility_resident_impl(ctx, scene, max_dist, opt, &s1);
@@ -1481,22 +1660,46 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
         k_add_u64<<<blocks_for(nc + 1, 256), 256, 0, st>>>(ctx->out_offsets[sel].as<uint64_t>(), nc + 1, obs_base);
       ++launch_counter();
       C2B_CUDA(cudaEventRecord(ctx->ev_ready[sel], st));
-      // pinned result arrays: sized from the first batch's density, grown if the guess was short
+      // result arrays: sized from the first batch's density, grown if the guess was short
       size_t need = obs_base + O;
       if (!todo.empty()) need = std::max<size_t>(need, (size_t)((double)(obs_base + O) * (double)C / (double)c1 * 1.05) + 1024);
-      C2B_TRY(grow_pinned(ctx, ctx->h_idx, std::max<size_t>(need, 1) * 4, obs_base * 4));
-      C2B_TRY(grow_pinned(ctx, ctx->h_uv, std::max<size_t>(need, 1) * 16, obs_base * 16));
       C2B_CUDA(cudaStreamWaitEvent(cs, ctx->ev_ready[sel], 0));
       if (b == 0) C2B_CUDA(cudaEventRecord(d0, cs));
       C2B_CUDA(cudaMemcpyAsync(ctx->h_offsets.as<uint64_t>() + c0, ctx->out_offsets[sel].p, (nc + 1) * 8,
                                cudaMemcpyDeviceToHost, cs));
-      if (O) {
-        C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.as<uint32_t>() + obs_base, ctx->out_idx[sel].p, O * 4,
-                                 cudaMemcpyDeviceToHost, cs));
-        C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.as<double>() + 2 * obs_base, ctx->out_uv[sel].p, O * 16,
-                                 cudaMemcpyDeviceToHost, cs));
+      if (staged) {
+        // untouched virtual memory costs nothing: reserve twice the estimate; a second reservation (after
+        // draining, with the landed part carried over) only if even that was short
+        for (PageBuf *pb : {&x->pg_idx, &x->pg_uv}) {
+          const size_t unit = pb == &x->pg_idx ? 4 : 16;
+          if (std::max<size_t>(need, 1) * unit > pb->cap) {
+            drain.wait_all();
+            PageBuf bigger;
+            C2B_TRY(bigger.ensure_fresh(2 * std::max<size_t>(need, 1) * unit));
+            if (obs_base) memcpy(bigger.p, pb->p, obs_base * unit);
+            pb->release();
+            *pb = bigger;
+          }
+        }
+        if (!copy_started) {
+          copy_started = true;
+          t_first_copy = std::chrono::steady_clock::now();
+        }
+        if (O) {
+          drain.submit(ctx->out_idx[sel].p, x->pg_idx.as<uint32_t>() + obs_base, O * 4, ctx->ev_ready[sel], (int)b);
+          drain.submit(ctx->out_uv[sel].p, x->pg_uv.as<double>() + 2 * obs_base, O * 16, ctx->ev_ready[sel], (int)b);
+        }
+      } else {
+        C2B_TRY(grow_pinned(ctx, ctx->h_idx, std::max<size_t>(need, 1) * 4, obs_base * 4));
+        C2B_TRY(grow_pinned(ctx, ctx->h_uv, std::max<size_t>(need, 1) * 16, obs_base * 16));
+        if (O) {
+          C2B_CUDA(cudaMemcpyAsync(ctx->h_idx.as<uint32_t>() + obs_base, ctx->out_idx[sel].p, O * 4,
+                                   cudaMemcpyDeviceToHost, cs));
+          C2B_CUDA(cudaMemcpyAsync(ctx->h_uv.as<double>() + 2 * obs_base, ctx->out_uv[sel].p, O * 16,
+                                   cudaMemcpyDeviceToHost, cs));
+        }
+        C2B_CUDA(cudaEventRecord(ctx->ev_copied[sel], cs));
       }
-      C2B_CUDA(cudaEventRecord(ctx->ev_copied[sel], cs));
       obs_base += O;
       acc.n_candidates += s1.n_candidates;
       acc.pairs_evaluated += s1.pairs_evaluated;
@@ -1514,6 +1717,12 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
     C2B_CUDA(cudaStreamSynchronize(st));
     C2B_CUDA(cudaEventElapsedTime(&ms_upload, u0, u1));
     C2B_CUDA(cudaEventElapsedTime(&ms_copy, d0, d1));
+    if (staged) {
+      const cudaError_t e = drain.finish();
+      if (e != cudaSuccess) return set_error(C2B_ERR_CUDA, "staged device-to-host copy failed: %s", cudaGetErrorString(e));
+      if (copy_started)
+        ms_copy = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_first_copy).count();
+    }
     return C2B_OK;
   };
   rc = run();
@@ -1531,8 +1740,8 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   acc.n_cameras = C;
   acc.n_obs = obs_base;
   acc.offsets = ctx->h_offsets.as<uint64_t>();
-  acc.point_idx = ctx->h_idx.as<uint32_t>();
-  acc.uv = ctx->h_uv.as<double>();
+  acc.point_idx = staged ? x->pg_idx.as<uint32_t>() : ctx->h_idx.as<uint32_t>();
+  acc.uv = staged ? x->pg_uv.as<double>() : ctx->h_uv.as<double>();
   acc.ms_h2d = ms_upload;
   acc.h2d_bytes = (resident_pts ? 0 : P * 24) + C * 120;
   acc.d2h_bytes = (C + 1) * 8 + obs_base * 20;

@@ -61,6 +61,9 @@ uint64_t c2b_kernel_launches(void);
  *   batches (0 auto)             camera batches of the host-buffer call
  *   fu_occ3 (0)                  fused kernel at 3 CTAs/SM
  *   grid_cell_factor (0.25)      point-grid cell side / max_dist
+ *   optimistic (1)               later passes on a ctx launch their kernels without waiting for the plan's totals
+ *                                (sizes and kernel variant from the previous pass, checked by the kernels)
+ *   cold_staged (1)              first host-buffer call on a ctx: CSR in unpinned memory through a pinned ring
  *   epilogue (0)                 1: sort + CSR write inside the fused kernel (scanner warp + deferred per-camera
  *                                epilogue) instead of the count scan + k_sort_write; measured slower, kept for study
  *   stage_threads (4)            host threads staging a PAGEABLE input array through the pinned ring (0: leave
@@ -143,8 +146,10 @@ void c2b_vis_options_default(c2b_vis_options *opt);
 
 typedef struct {
   /* CSR of visible observations, camera-major, ascending point index inside each camera
-   * (the order src/generate.rs:446,473-478 produces).  Pinned host memory owned by the ctx:
-   * valid until the next c2b_visibility_graph* call on the same ctx or c2b_obs_free. */
+   * (the order src/generate.rs:446,473-478 produces).  Host memory owned by the ctx (pinned; the first
+   * host-buffer call on a ctx uses unpinned memory filled through a pinned ring, because pinning a large result
+   * takes longer than producing it — hook cold_staged): valid until the next c2b_visibility_graph* call on the
+   * same ctx or c2b_shutdown. */
   uint64_t n_cameras;
   uint64_t n_obs;
   uint64_t *offsets;   /* [n_cameras+1] */

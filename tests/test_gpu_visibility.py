@@ -638,3 +638,36 @@ def test_in_kernel_epilogue_gives_the_same_graph(c2b, ctx, orc, cfg2, occlusion,
         assert want_dense.counts().max() > 1024     # the large-camera fallback ran
     if occlusion == "mesh":
         assert_same_graph(got, orc.visibility_graph(xyz, tri, cams, pts, 10.0), "epilogue")
+
+
+def test_first_call_on_a_fresh_ctx_returns_the_same_graph(c2b, orc, cfg2):
+    """the first host-buffer call on a ctx returns its CSR in unpinned memory filled through a pinned ring by host
+    threads (pinning a large result costs more than computing it); later calls, and a ctx with the hook
+    cold_staged = 0, use pinned arrays — all of them the same graph, with pageable and with large inputs"""
+    from city2ba_b200 import _lib
+    cams, pts, xyz, tri = cfg2
+    ref = orc.visibility_graph(xyz, tri, cams, pts, 10.0)
+    for hook in (1, 0):
+        fresh = _lib.Context(0)
+        try:
+            fresh.tune("cold_staged", hook)
+            scene = c2b.Scene(xyz, tri, ctx=fresh)
+            for call in range(3):
+                assert_same_graph(c2b.visibility_graph(scene, cams, pts, 10.0, ctx=fresh), ref, f"cold_staged={hook} call {call}")
+            scene.close()
+        finally:
+            fresh.close()
+    # a result large enough for many ring chunks and several camera batches: cfg3 on a fresh ctx, twice
+    import bench
+    cams3, pts3, xyz3, tri3 = bench.build_workload("cfg3")
+    fresh = _lib.Context(0)
+    try:
+        fresh.tune("batches", 5)
+        scene = c2b.Scene(xyz3, tri3, ctx=fresh)
+        first = c2b.visibility_graph(scene, cams3, pts3, bench.MAX_DIST, ctx=fresh)
+        second = c2b.visibility_graph(scene, cams3, pts3, bench.MAX_DIST, ctx=fresh)
+        assert bench.result_hash(first.offsets, first.point_idx, first.uv) == bench.expected_hash("cfg3")
+        assert np.array_equal(first.point_idx, second.point_idx) and np.array_equal(first.uv, second.uv)
+        scene.close()
+    finally:
+        fresh.close()
