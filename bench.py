@@ -559,8 +559,10 @@ def main():
             t_cold = time.perf_counter() - t0
             extras["e2e_cold"] = {
                 "value": C * P / t_cold, "unit": "tests/s", "ms": 1e3 * t_cold, "scene_build_ms": 1e3 * t_scene,
-                "note": "first call on a fresh c2b_ctx with pageable inputs: every device buffer and the pinned "
-                        "result arrays are allocated inside the call (the CUDA primary context already exists)"}
+                "note": "first call on a fresh c2b_ctx with pageable inputs: every device buffer is allocated inside the "
+                        "call and the CSR comes back in unpinned huge-page memory through a pinned ring (pinning 1.1 GB "
+                        "would cost 0.55-1.3 s on this host; the second call on a ctx does pin); the CUDA primary "
+                        "context already exists"}
             cold_scene.close()
             cold.close()
     if mctx is not None:

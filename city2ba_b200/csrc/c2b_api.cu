@@ -103,6 +103,7 @@ struct Tunables {
   double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
   int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
                                    // driver copy from pageable memory itself
+  int sort_rolled = 0;             // k_sort_write_rolled (rolled ping-pong sort, 11 CTAs/SM) instead of k_sort_write
   int cold_staged = 1;             // first host-buffer call on a ctx returns its CSR in unpinned memory filled
                                    // through a pinned ring (0: pin the result arrays at once, as later calls do)
   int optimistic = 1;              // launch a pass's kernels without waiting for the plan's totals when the
@@ -316,6 +317,7 @@ static bool tune(Tunables &t, const char *name, double v) {
   else if (n == "epilogue") t.epilogue = v != 0;
   else if (n == "optimistic") t.optimistic = v != 0;
   else if (n == "cold_staged") t.cold_staged = v != 0;
+  else if (n == "sort_rolled") t.sort_rolled = v != 0;
   else return false;
   return true;
 }
@@ -396,7 +398,7 @@ int c2b_init(int device, c2b_ctx **out) {
         {"C2B_PARTS_LOG2", "parts_log2"}, {"C2B_TRILIST_CAP", "trilist_cap"}, {"C2B_MAX_PAIRS", "max_pairs"},
         {"C2B_HOIST_MAX", "hoist_max"}, {"C2B_PACKET_BVH", "packet_bvh"}, {"C2B_TRILIST_WARP", "trilist_warp"},
         {"C2B_BATCHES", "batches"}, {"C2B_FU_OCC3", "fu_occ3"}, {"C2B_GRID_CELL_FACTOR", "grid_cell_factor"},
-        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}, {"C2B_COLD_STAGED", "cold_staged"}};
+        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}, {"C2B_COLD_STAGED", "cold_staged"}, {"C2B_SORT_ROLLED", "sort_rolled"}};
     for (auto &h : hooks)
       if (const char *e = getenv(h.env)) (void)tune(x->tun, h.name, atof(e));
   }
@@ -1174,6 +1176,8 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     const SortWriteArgs sw = sort_write_args();
     if (parts_log2 > 0)
       k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
+    else if (x->tun.sort_rolled)
+      k_sort_write_rolled<<<swb, swt, 0, st>>>(sw, fa.scratch_idx);
     else
       k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
     C2B_KERNEL_CHECK();
@@ -1207,6 +1211,8 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
       // registers capped for 8 CTAs/SM (measured at cfg4: 0.81 ms; 6 CTAs/SM 0.91 ms, 4 CTAs/SM 1.12 ms)
       if (parts_log2 > 0)
         k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
+      else if (x->tun.sort_rolled)
+        k_sort_write_rolled<<<swb, swt, 0, st>>>(sw, fa.scratch_idx);
       else
         k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
       C2B_KERNEL_CHECK();

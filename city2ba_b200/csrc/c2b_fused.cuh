@@ -493,6 +493,72 @@ __device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const 
 }
 
 
+// Warp-private LSD radix sort of a camera's n <= SW_WARP_MAX visible indices, 8-bit digits, as ROLLED loops over
+// 32-key chunks that ping-pong between the camera's scratch slice (global, L2-resident) and a shared-memory
+// buffer.  Returns where the sorted keys ended up (the slice or `buf`).  About 30 registers and ~1.4 k SASS
+// lines; sort_warp_to_smem keeps the keys in up to 32 unrolled registers instead (fewer instructions executed,
+// 64 registers, five instantiations).
+__device__ __forceinline__ const uint32_t *rolled_warp_sort(uint32_t *slice, uint32_t n, int key_bits, uint32_t *buf,
+                                                            uint32_t *hist, int lane) {
+  const uint32_t *src = slice;
+  uint32_t *dst = buf;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int shift = 0; shift < key_bits; shift += SW_RADIX_BITS) {
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t t = lane; t < n; t += 32) atomicAdd(&hist[(src[t] >> shift) & (SW_BINS - 1)], 1u);
+    __syncwarp();
+    uint32_t cnt[SW_BINS / 32];
+    uint32_t sum = 0;
+    bool one_bin = false;
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      cnt[k] = hist[lane * (SW_BINS / 32) + k];
+      one_bin |= cnt[k] == n;
+      sum += cnt[k];
+    }
+    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
+      __syncwarp();
+      continue;
+    }
+    uint32_t pre = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    pre -= sum;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SW_BINS / 32; ++k) {
+      hist[lane * (SW_BINS / 32) + k] = pre;
+      pre += cnt[k];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t first = 0; first < n; first += 32) {
+      const uint32_t t = first + lane;
+      const bool valid = t < n;
+      const uint32_t key = valid ? src[t] : 0u;
+      const uint32_t d = valid ? (key >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
+      const uint32_t pos = __shfl_sync(0xffffffffu, old, leader) + __popc(peers & lt);
+      if (valid) dst[pos] = key;
+    }
+    __syncwarp();
+    const uint32_t *filled = dst;
+    dst = dst == buf ? slice : buf;
+    src = filled;
+  }
+  return src;
+}
+
 // ---- the fused pass ---------------------------------------------------------------------------------
 constexpr int FU_WARPS = 8;
 constexpr int FU_STAGE = 64;
@@ -851,69 +917,10 @@ __device__ __noinline__ void epilogue_sort_write(const FusedArgs &a, uint64_t ca
     if (lane == 0) atomicOr(&a.counters[10], (unsigned long long)EPI_OUT_OVERFLOW);
     return;
   }
-  // Warp-private LSD radix sort, 8-bit digits, like sort_warp_to_smem — but written as ROLLED loops over
-  // 32-key chunks that ping-pong between the camera's scratch slice (global, L2-resident) and the warp's
-  // shared-memory region instead of keeping the keys in up to 32 unrolled registers: the register version's
-  // five instantiations tripled this kernel's code (14.0 k SASS lines against 4.7 k) and the instruction
-  // cache thrashed — 8 of 16 stall cycles no_instruction, 6.0 ms against 2.7 + 0.8 (profiles/r02e).
-  uint32_t *buf = region, *hist = region + SW_WARP_MAX;
-  uint32_t *slice = a.scratch_idx + ev0;
-  const uint32_t *src = slice;
-  uint32_t *dst = buf;
-  const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 1
-  for (int shift = 0; shift < a.key_bits; shift += SW_RADIX_BITS) {
-#pragma unroll
-    for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
-    __syncwarp();
-#pragma unroll 1
-    for (uint32_t t = lane; t < n; t += 32) atomicAdd(&hist[(src[t] >> shift) & (SW_BINS - 1)], 1u);
-    __syncwarp();
-    uint32_t cnt[SW_BINS / 32];
-    uint32_t sum = 0;
-    bool one_bin = false;
-#pragma unroll
-    for (int k = 0; k < SW_BINS / 32; ++k) {
-      cnt[k] = hist[lane * (SW_BINS / 32) + k];
-      one_bin |= cnt[k] == n;
-      sum += cnt[k];
-    }
-    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
-      __syncwarp();
-      continue;
-    }
-    uint32_t pre = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
-      if (lane >= o) pre += v;
-    }
-    pre -= sum;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < SW_BINS / 32; ++k) {
-      hist[lane * (SW_BINS / 32) + k] = pre;
-      pre += cnt[k];
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (uint32_t first = 0; first < n; first += 32) {
-      const uint32_t t = first + lane;
-      const bool valid = t < n;
-      const uint32_t key = valid ? src[t] : 0u;
-      const uint32_t d = valid ? (key >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
-      const int leader = __ffs(peers) - 1;
-      uint32_t old = 0;
-      if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
-      const uint32_t pos = __shfl_sync(0xffffffffu, old, leader) + __popc(peers & lt);
-      if (valid) dst[pos] = key;
-    }
-    __syncwarp();
-    const uint32_t *filled = dst;
-    dst = dst == buf ? slice : buf;
-    src = filled;
-  }
+  // the rolled sort: the register version's five instantiations tripled this kernel's code (14.0 k SASS lines
+  // against 4.7 k) and the instruction cache thrashed — 8 of 16 stall cycles no_instruction, 6.0 ms against
+  // 2.7 + 0.8 (profiles/r02e)
+  const uint32_t *src = rolled_warp_sort(a.scratch_idx + ev0, n, a.key_bits, region, region + SW_WARP_MAX, lane);
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t pt = src[i];
@@ -1263,6 +1270,39 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t pt = sorted[sw_pad(i)];
+    const double *p = s.p_aos + 3 * (uint64_t)pt;
+    s.out_idx[base + i] = pt;
+    s.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
+  }
+}
+
+// The same pass with the rolled sort (hook sort_rolled): ~30 registers instead of 64 and 5 KB of shared memory per
+// warp let 11 CTAs of 4 warps share an SM instead of 8 — more warps to hide this kernel's latencies.  One slot
+// per camera only (parts_log2 == 0); the scratch slice is overwritten (it is dead after this kernel).
+__global__ void __launch_bounds__(SW_WARPS * 32, 11) k_sort_write_rolled(SortWriteArgs s, uint32_t *scratch_rw) {
+  __shared__ uint32_t s_buf[SW_WARPS][SW_WARP_MAX];
+  __shared__ uint32_t s_hist[SW_WARPS][SW_BINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
+  if (cam >= s.C) return;
+  const uint32_t base = s.seg_off[cam];
+  const uint32_t n = __reduce_max_sync(0xffffffffu, s.seg_off[cam + 1] - base);
+  if (lane == 0) {
+    s.out_offsets[cam] = base;
+    if (cam == s.C - 1) s.out_offsets[s.C] = s.seg_off[s.C];
+  }
+  if (n == 0 || n > SW_WARP_MAX) return;
+  if ((uint64_t)base + n > s.out_cap) {
+    if (lane == 0) atomicOr(s.flags, (unsigned long long)FU_FLAG_OUT);
+    return;
+  }
+  const uint32_t *src = rolled_warp_sort(scratch_rw + s.ev_off[cam], n, s.key_bits, s_buf[warp], s_hist[warp], lane);
+  double c[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
+#pragma unroll 2
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t pt = src[i];
     const double *p = s.p_aos + 3 * (uint64_t)pt;
     s.out_idx[base + i] = pt;
     s.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
