@@ -103,7 +103,6 @@ struct Tunables {
   double grid_cell_factor = 0.25;  // point-grid cell side / max_dist
   int stage_threads = 4;           // host threads staging a pageable input through the pinned ring; 0 = let the
                                    // driver copy from pageable memory itself
-  int sort_rolled = 0;             // k_sort_write_rolled (rolled ping-pong sort, 11 CTAs/SM) instead of k_sort_write
   int cold_staged = 1;             // first host-buffer call on a ctx returns its CSR in unpinned memory filled
                                    // through a pinned ring (0: pin the result arrays at once, as later calls do)
   int optimistic = 1;              // launch a pass's kernels without waiting for the plan's totals when the
@@ -317,7 +316,6 @@ static bool tune(Tunables &t, const char *name, double v) {
   else if (n == "epilogue") t.epilogue = v != 0;
   else if (n == "optimistic") t.optimistic = v != 0;
   else if (n == "cold_staged") t.cold_staged = v != 0;
-  else if (n == "sort_rolled") t.sort_rolled = v != 0;
   else return false;
   return true;
 }
@@ -398,7 +396,7 @@ int c2b_init(int device, c2b_ctx **out) {
         {"C2B_PARTS_LOG2", "parts_log2"}, {"C2B_TRILIST_CAP", "trilist_cap"}, {"C2B_MAX_PAIRS", "max_pairs"},
         {"C2B_HOIST_MAX", "hoist_max"}, {"C2B_PACKET_BVH", "packet_bvh"}, {"C2B_TRILIST_WARP", "trilist_warp"},
         {"C2B_BATCHES", "batches"}, {"C2B_FU_OCC3", "fu_occ3"}, {"C2B_GRID_CELL_FACTOR", "grid_cell_factor"},
-        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}, {"C2B_COLD_STAGED", "cold_staged"}, {"C2B_SORT_ROLLED", "sort_rolled"}};
+        {"C2B_STAGE_THREADS", "stage_threads"}, {"C2B_EPILOGUE", "epilogue"}, {"C2B_OPTIMISTIC", "optimistic"}, {"C2B_COLD_STAGED", "cold_staged"}};
     for (auto &h : hooks)
       if (const char *e = getenv(h.env)) (void)tune(x->tun, h.name, atof(e));
   }
@@ -1176,8 +1174,6 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     const SortWriteArgs sw = sort_write_args();
     if (parts_log2 > 0)
       k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
-    else if (x->tun.sort_rolled)
-      k_sort_write_rolled<<<swb, swt, 0, st>>>(sw, fa.scratch_idx);
     else
       k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
     C2B_KERNEL_CHECK();
@@ -1211,8 +1207,6 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
       // registers capped for 8 CTAs/SM (measured at cfg4: 0.81 ms; 6 CTAs/SM 0.91 ms, 4 CTAs/SM 1.12 ms)
       if (parts_log2 > 0)
         k_sort_write<6, true><<<swb, swt, 0, st>>>(sw);
-      else if (x->tun.sort_rolled)
-        k_sort_write_rolled<<<swb, swt, 0, st>>>(sw, fa.scratch_idx);
       else
         k_sort_write<8, false><<<swb, swt, 0, st>>>(sw);
       C2B_KERNEL_CHECK();
@@ -1835,7 +1829,7 @@ inline unsigned nz_grid(c2b_ctx *ctx, uint64_t n) {
 
 // mean / std / nearest-origin of the chained sequence on the device.  scratch layout (doubles):
 // [0..2] mean, [3..5] sumsq, [6..8] origin, then partials.
-int device_stats(c2b_ctx *ctx, const NoiseView &v, double mean[3], double sd[3], bool want_origin) {
+int device_stats(c2b_ctx *ctx, const NoiseView &v, double mean[3], double sd[3], bool want_origin, bool to_host = true) {
   cudaStream_t st = ctx->stream;
   const uint64_t C = v.C, P = v.P, n = C + P;
   const double num = (double)n;
@@ -1845,21 +1839,17 @@ int device_stats(c2b_ctx *ctx, const NoiseView &v, double mean[3], double sd[3],
   double *partial = s + 16;
   const double *cx = v.centers;
   const double *pts = v.pts;
-  k_stats_partial<0><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num, V3{0, 0, 0}, partial);
+  // the chain stays on the device: the second pass reads the mean the first one left in s[0..2]
+  k_stats_partial<0><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num, s, partial);
   C2B_KERNEL_CHECK();
   k_stats_final<<<1, 32, 0, st>>>(partial, blocks, s);
   C2B_KERNEL_CHECK();
-  C2B_CUDA(cudaMemcpyAsync(mean, s, 24, cudaMemcpyDeviceToHost, st));
-  C2B_CUDA(cudaStreamSynchronize(st));
-  k_stats_partial<1><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num,
-                                                   V3{mean[0], mean[1], mean[2]}, partial);
+  k_stats_partial<1><<<blocks, ST_THREADS, 0, st>>>(cx, cx + C, cx + 2 * C, C, pts, P, num, s, partial);
   C2B_KERNEL_CHECK();
   k_stats_final<<<1, 32, 0, st>>>(partial, blocks, s + 3);
   C2B_KERNEL_CHECK();
-  double ss[3];
-  C2B_CUDA(cudaMemcpyAsync(ss, s + 3, 24, cudaMemcpyDeviceToHost, st));
-  C2B_CUDA(cudaStreamSynchronize(st));
-  for (int k = 0; k < 3; ++k) sd[k] = std::sqrt(ss[k] / num);
+  k_bal_std<<<1, 32, 0, st>>>(s, num);
+  C2B_KERNEL_CHECK();
   if (want_origin) {
     double *pd = partial;
     unsigned long long *pi = reinterpret_cast<unsigned long long *>(partial + blocks);
@@ -1867,6 +1857,15 @@ int device_stats(c2b_ctx *ctx, const NoiseView &v, double mean[3], double sd[3],
     C2B_KERNEL_CHECK();
     k_nearest_final<<<1, 32, 0, st>>>(pd, pi, blocks, cx, cx + C, cx + 2 * C, C, pts, s + 6);
     C2B_KERNEL_CHECK();
+  }
+  if (to_host) {
+    double h[6];
+    C2B_CUDA(cudaMemcpyAsync(h, s, 48, cudaMemcpyDeviceToHost, st));
+    C2B_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) {
+      mean[k] = h[k];
+      sd[k] = std::sqrt(h[3 + k] / num);
+    }
   }
   return C2B_OK;
 }
@@ -1975,11 +1974,11 @@ int drift_impl(c2b_ctx *ctx, double *cams, uint64_t C, double *pts, uint64_t P, 
 int noise_kernels(c2b_ctx *ctx, const NoiseView &v, double translation_std, double rotation_std, double point_std,
                   uint64_t seed) {
   cudaStream_t st = ctx->stream;
-  double mean[3], sd[3];
-  C2B_TRY(device_stats(ctx, v, mean, sd, false));
-  double bal_std = std::sqrt((sd[0] * sd[0] + sd[1] * sd[1]) + sd[2] * sd[2]);
+  // |std()| scales the camera translations (src/noise.rs:127,141); it stays on the device (scratch[9])
+  C2B_TRY(device_stats(ctx, v, nullptr, nullptr, false, false));
   if (v.C) {
-    k_noise_cams<<<blocks_for(v.C, NZ_THREADS), NZ_THREADS, 0, st>>>(v.cams, v.C, bal_std, translation_std, rotation_std, seed);
+    k_noise_cams<<<blocks_for(v.C, NZ_THREADS), NZ_THREADS, 0, st>>>(v.cams, v.C, ctx->nz_scratch.as<double>() + 9,
+                                                                    translation_std, rotation_std, seed);
     C2B_KERNEL_CHECK();
   }
   // a zero standard deviation adds unit_random() * 0 (src/noise.rs:149,159-168): the array is unchanged, so its

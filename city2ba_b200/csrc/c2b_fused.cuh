@@ -496,8 +496,10 @@ __device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const 
 // Warp-private LSD radix sort of a camera's n <= SW_WARP_MAX visible indices, 8-bit digits, as ROLLED loops over
 // 32-key chunks that ping-pong between the camera's scratch slice (global, L2-resident) and a shared-memory
 // buffer.  Returns where the sorted keys ended up (the slice or `buf`).  About 30 registers and ~1.4 k SASS
-// lines; sort_warp_to_smem keeps the keys in up to 32 unrolled registers instead (fewer instructions executed,
-// 64 registers, five instantiations).
+// lines; sort_warp_to_smem keeps the keys in up to 32 unrolled registers instead (64 registers, five
+// instantiations) and is the faster of the two as a kernel of its own: k_sort_write with this sort at 11 CTAs
+// per SM measured 1.35 ms against 0.82 ms at cfg4 (the ping-pong's global round trips cost more than the extra
+// warps hide; r02n) — so it serves the in-kernel epilogue only, where code size decides.
 __device__ __forceinline__ const uint32_t *rolled_warp_sort(uint32_t *slice, uint32_t n, int key_bits, uint32_t *buf,
                                                             uint32_t *hist, int lane) {
   const uint32_t *src = slice;
@@ -1270,39 +1272,6 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t pt = sorted[sw_pad(i)];
-    const double *p = s.p_aos + 3 * (uint64_t)pt;
-    s.out_idx[base + i] = pt;
-    s.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
-  }
-}
-
-// The same pass with the rolled sort (hook sort_rolled): ~30 registers instead of 64 and 5 KB of shared memory per
-// warp let 11 CTAs of 4 warps share an SM instead of 8 — more warps to hide this kernel's latencies.  One slot
-// per camera only (parts_log2 == 0); the scratch slice is overwritten (it is dead after this kernel).
-__global__ void __launch_bounds__(SW_WARPS * 32, 11) k_sort_write_rolled(SortWriteArgs s, uint32_t *scratch_rw) {
-  __shared__ uint32_t s_buf[SW_WARPS][SW_WARP_MAX];
-  __shared__ uint32_t s_hist[SW_WARPS][SW_BINS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
-  if (cam >= s.C) return;
-  const uint32_t base = s.seg_off[cam];
-  const uint32_t n = __reduce_max_sync(0xffffffffu, s.seg_off[cam + 1] - base);
-  if (lane == 0) {
-    s.out_offsets[cam] = base;
-    if (cam == s.C - 1) s.out_offsets[s.C] = s.seg_off[s.C];
-  }
-  if (n == 0 || n > SW_WARP_MAX) return;
-  if ((uint64_t)base + n > s.out_cap) {
-    if (lane == 0) atomicOr(s.flags, (unsigned long long)FU_FLAG_OUT);
-    return;
-  }
-  const uint32_t *src = rolled_warp_sort(scratch_rw + s.ev_off[cam], n, s.key_bits, s_buf[warp], s_hist[warp], lane);
-  double c[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
-#pragma unroll 2
-  for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t pt = src[i];
     const double *p = s.p_aos + 3 * (uint64_t)pt;
     s.out_idx[base + i] = pt;
     s.out_uv[base + i] = observe(c, p[0], p[1], p[2]);

@@ -143,7 +143,9 @@ template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS)
     k_stats_partial(const double *__restrict__ cx, const double *__restrict__ cy,
                     const double *__restrict__ cz, uint64_t C, const double *__restrict__ pts,
-                    uint64_t P, double num, V3 mean, double *__restrict__ partial) {
+                    uint64_t P, double num, const double *__restrict__ mean_dev, double *__restrict__ partial) {
+  // MODE 1 reads the mean the MODE 0 pass left on the device: no host round trip between the two
+  const V3 mean = MODE == 1 ? V3{mean_dev[0], mean_dev[1], mean_dev[2]} : V3{0.0, 0.0, 0.0};
   double s[3] = {0, 0, 0};
   uint64_t n = C + P;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -180,6 +182,15 @@ __global__ void k_stats_final(const double *__restrict__ partial, int nb, double
     double r = 0;
     for (int b = 0; b < nb; ++b) r += partial[3 * b + threadIdx.x];
     out3[threadIdx.x] = r;
+  }
+}
+
+// s[3..5] = sum of squared deviations, num = element count  ->  s[9] = |std()| (BAProblem::std, src/baproblem.rs:292-304,
+// then its magnitude, src/noise.rs:127): the scale of add_noise's camera translations, left on the device
+__global__ void k_bal_std(double *__restrict__ s, double num) {
+  if (threadIdx.x == 0) {
+    const double a = dsqrt(ddiv(s[3], num)), b = dsqrt(ddiv(s[4], num)), c = dsqrt(ddiv(s[5], num));
+    s[9] = dsqrt(dadd(dadd(dmul(a, a), dmul(b, b)), dmul(c, c)));
   }
 }
 
@@ -314,10 +325,11 @@ __global__ void __launch_bounds__(NZ_THREADS)
 // ---- add_noise, src/noise.rs:119-177 --------------------------------------------------------------------
 // per camera: axis, angle, translation direction, magnitude (:140-141) = block 0 {sphere, N}, block 1 {sphere, N}
 __global__ void __launch_bounds__(NZ_THREADS)
-    k_noise_cams(double *__restrict__ cams, uint64_t C, double bal_std, double translation_std, double rotation_std,
-                 uint64_t seed) {
+    k_noise_cams(double *__restrict__ cams, uint64_t C, const double *__restrict__ bal_std_dev, double translation_std,
+                 double rotation_std, uint64_t seed) {
   __shared__ NoiseTabs tabs;
   load_noise_tabs(tabs);
+  const double bal_std = *bal_std_dev;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
   double cam[15];
