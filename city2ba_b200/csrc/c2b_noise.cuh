@@ -177,12 +177,22 @@ __global__ void __launch_bounds__(ST_THREADS)
   }
 }
 
+// one warp: lane = block partial (strided, ascending), then a shuffle tree — a fixed order, so the sums are
+// reproducible run to run (a single thread folding 592 partials took ~50 us of dependent loads: three such
+// folds were a third of the drift pass)
 __global__ void k_stats_final(const double *__restrict__ partial, int nb, double *__restrict__ out3) {
-  if (threadIdx.x < 3) {
-    double r = 0;
-    for (int b = 0; b < nb; ++b) r += partial[3 * b + threadIdx.x];
-    out3[threadIdx.x] = r;
+  const int lane = threadIdx.x & 31;
+  double r[3] = {0.0, 0.0, 0.0};
+  for (int b = lane; b < nb; b += 32) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[k] += partial[3 * b + k];
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+  }
+  if (lane < 3) out3[lane] = lane == 0 ? r[0] : (lane == 1 ? r[1] : r[2]);
 }
 
 // s[3..5] = sum of squared deviations, num = element count  ->  s[9] = |std()| (BAProblem::std, src/baproblem.rs:292-304,
@@ -247,16 +257,28 @@ __global__ void k_nearest_final(const double *__restrict__ pd, const unsigned lo
                                 int nb, const double *__restrict__ cx, const double *__restrict__ cy,
                                 const double *__restrict__ cz, uint64_t C,
                                 const double *__restrict__ pts, double *__restrict__ origin3) {
-  if (threadIdx.x == 0) {
-    double bd = INFINITY;
-    unsigned long long bi = ~0ull;
-    for (int b = 0; b < nb; ++b) {
-      if (pi[b] == ~0ull) continue;
-      if (bi == ~0ull || nearer(pd[b], pi[b], bd, bi)) {
-        bd = pd[b];
-        bi = pi[b];
-      }
+  // one warp: lane = block partial (strided), then a shuffle tree; the order (distance asc, index desc) is total,
+  // so the result does not depend on how the partials are combined
+  const int lane = threadIdx.x & 31;
+  double bd = INFINITY;
+  unsigned long long bi = ~0ull;
+  for (int b = lane; b < nb; b += 32) {
+    if (pi[b] == ~0ull) continue;
+    if (bi == ~0ull || nearer(pd[b], pi[b], bd, bi)) {
+      bd = pd[b];
+      bi = pi[b];
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+    const unsigned long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != ~0ull && (bi == ~0ull || nearer(od, oi, bd, bi))) {
+      bd = od;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
     V3 e = bi == ~0ull ? V3{0, 0, 0} : chain_element(cx, cy, cz, C, pts, bi);
     origin3[0] = e.x;
     origin3[1] = e.y;
@@ -423,11 +445,29 @@ __global__ void __launch_bounds__(ST_THREADS)
 }
 // out6 = min xyz, max xyz
 __global__ void k_extent_final(const double *__restrict__ partial, int nb, double *__restrict__ out6) {
-  if (threadIdx.x < 6) {
-    double r = partial[threadIdx.x];
-    for (int b = 1; b < nb; ++b)
-      r = threadIdx.x < 3 ? fmin(r, partial[6 * b + threadIdx.x]) : fmax(r, partial[6 * b + threadIdx.x]);
-    out6[threadIdx.x] = r;
+  const int lane = threadIdx.x & 31;  // one warp: lane = block partial (strided), then a shuffle tree
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int b = lane; b < nb; b += 32) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fmin(lo[k], partial[6 * b + k]);
+      hi[k] = fmax(hi[k], partial[6 * b + 3 + k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      out6[k] = lo[k];
+      out6[3 + k] = hi[k];
+    }
   }
 }
 

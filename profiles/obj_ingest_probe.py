@@ -3,6 +3,7 @@ tessellated city of bench.py's cfg5 as a Wavefront OBJ (one object per city bloc
 
   * tobj-rule OBJ ingest alone (tests/cpp/test_host.cpp `obj` mode = include/city2ba.hpp tobj::load_obj), and
   * the whole command line:  city2ba generate city.obj out.bbal --cameras 50000 --points 5000000 --max-dist 10
+    [--gpus N], then  city2ba noise out.bbal noised.bbal --drift-strength 0.001 --rotation-std 0.0001 ...
 
     python profiles/obj_ingest_probe.py [--blocks 64] [--out /tmp/c2b_city]
 """
@@ -39,6 +40,7 @@ def main():
     ap.add_argument("--out", default="/tmp/c2b_city")
     ap.add_argument("--cameras", type=int, default=50000)
     ap.add_argument("--points", type=int, default=5000000)
+    ap.add_argument("--gpus", type=int, default=1)
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     obj = os.path.join(a.out, "city.obj")
@@ -61,14 +63,24 @@ def main():
     out = os.path.join(a.out, "city.bbal")
     t0 = time.perf_counter()
     r = subprocess.run([cli, "generate", obj, out, "--cameras", str(a.cameras), "--points", str(a.points),
-                        "--max-dist", "10", "--ground", "1000", "--height", "1", "--seed", "7"],
+                        "--max-dist", "10", "--ground", "1000", "--height", "1", "--seed", "7", "--gpus", str(a.gpus)],
                        capture_output=True, text=True, timeout=1500)
+    res["gpus"] = a.gpus
     res["generate_s"] = round(time.perf_counter() - t0, 2)
     res["generate_rc"] = r.returncode
     res["generate_stdout"] = r.stdout.strip().splitlines()
     res["generate_stderr_tail"] = r.stderr.strip()[-400:]
     if os.path.exists(out):
         res["bbal_bytes"] = os.path.getsize(out)
+        # BASELINE config 5 ends with "plus full noise pass": drift + Gaussian camera / point / observation noise
+        noised = os.path.join(a.out, "city_noised.bbal")
+        t0 = time.perf_counter()
+        r = subprocess.run([cli, "noise", out, noised, "--drift-strength", "0.001", "--rotation-std", "0.0001",
+                            "--point-std", "0.01", "--observation-std", "0.001", "--seed", "7"],
+                           capture_output=True, text=True, timeout=600)
+        res["noise_s"] = round(time.perf_counter() - t0, 2)
+        res["noise_rc"] = r.returncode
+        res["noise_stdout"] = r.stdout.strip().splitlines()
     print(json.dumps(res))
 
 
