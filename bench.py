@@ -568,6 +568,10 @@ def main():
     if mctx is not None:
         mscene.close()
         mctx.close()
+    if world > 1:
+        # the other ranks keep their GPUs idle until rank 0 is done driving them (their next arms would time-slice
+        # with rank 0's e2e_pageable calls: that cost 11-12 ms per GPU in r02k / r02p)
+        dist.barrier(group=cpu_group)
 
     # ---- noise pass on the generated problem (config 2 / 5: drift + Gaussian noise), N = 1 only ------
     noise = None

@@ -339,14 +339,23 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     C2B_NCCL(nccl().GroupEnd());
   }
   // ---- phase 2: the resident pass on each GPU's camera range ----
+  static const bool trace = getenv("C2B_TRACE") != nullptr;
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  if (trace) fprintf(stderr, "[c2b_multi] phase 2 starts at %.3f ms\n", since());
   C2B_TRY(run_all(m, [&](int g) -> int {
     c2b_ctx *ctx = m->ctx[g];
     C2B_CUDA(cudaSetDevice(m->dev[g]));
+    const double ta = since();
     C2B_TRY(c2b_points_commit(ctx, P));
     C2B_CUDA(cudaEventRecord(m->ev[g][1], ctx->stream));
     const uint64_t c0 = ((uint64_t)g * C) / (uint64_t)G, c1 = (((uint64_t)g + 1) * C) / (uint64_t)G;
+    const double tb = since();
     C2B_TRY(c2b_upload_cameras(ctx, cams ? cams + 15 * c0 : nullptr, c1 - c0));
+    const double tc = since();
     C2B_TRY(c2b_visibility_graph_resident(ctx, scene ? scene->scene[g] : nullptr, max_dist, &opt, &part[(size_t)g]));
+    if (trace)
+      fprintf(stderr, "[c2b_multi] gpu %d phase 2: start %.3f commit %.3f cameras %.3f resident pass %.3f ms (host clock)\n", g, ta,
+              tb - ta, tc - tb, since() - tc);
     C2B_CUDA(cudaEventRecord(m->ev[g][2], ctx->stream));
     k_set_u64<<<1, 1, 0, ctx->stream>>>(m->d_counts[g].as<uint64_t>() + g, part[(size_t)g].n_obs);
     C2B_KERNEL_CHECK();

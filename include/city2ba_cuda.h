@@ -6,9 +6,9 @@
  * tkonolige/city2ba source tree).  Plain pointers and sizes only; no exceptions cross this
  * boundary; every function returns C2B_OK (0) or a negative c2b_status and leaves a message
  * retrievable with c2b_last_error() (thread local).  Calls are blocking.  One c2b_ctx drives
- * one GPU; issue calls from one host thread at a time per ctx (one process per GPU under
- * torchrun / MPI is the intended multi-GPU layout: each rank passes its own contiguous camera
- * range, see c2b_visibility_graph).
+ * one GPU; issue calls from one host thread at a time per ctx.  Several GPUs of one box: c2b_init_multi /
+ * c2b_visibility_graph_multi (one process, one ctx and worker thread per GPU, NCCL for the two exchanges), or one
+ * process per GPU with each rank passing its own contiguous camera range to c2b_visibility_graph.
  *
  * There is NO CPU fallback: c2b_init fails with C2B_ERR_NO_DEVICE when no sm_100 GPU is
  * visible, and nothing else works without a ctx.
