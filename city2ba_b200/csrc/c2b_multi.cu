@@ -154,6 +154,12 @@ struct c2b_multi {
   cudaEvent_t ev[C2B_MAX_GPUS][4] = {};
   PinBuf h_offsets, h_idx, h_uv;  // the ONE host CSR
   std::mutex mu;
+  // share of the cameras each GPU gets: equal at first, then proportional to the rate at which each GPU's slab
+  // reached host memory in the previous call.  The result transfer is the longest leg of a call and the GPUs of a
+  // box do not all reach host memory equally fast (8-GPU box, all copying at once: 6.5-7.5 ms for GPUs 4-7,
+  // 11 ms for GPUs 0-3, profiles/r02k_bench_cfg4_8gpu.json), so equal ranges wait for the slowest link.
+  double share[C2B_MAX_GPUS] = {};
+  bool adaptive = true;
 };
 
 struct c2b_multi_scene {
@@ -195,6 +201,8 @@ int c2b_init_multi(int n_gpus, const int *devices, c2b_multi **out) {
   if (!m) return set_error(C2B_ERR_OOM, "out of host memory");
   m->n = n_gpus;
   m->h_offsets.portable = m->h_idx.portable = m->h_uv.portable = true;
+  for (int g = 0; g < n_gpus; ++g) m->share[g] = 1.0 / n_gpus;
+  if (const char *e = getenv("C2B_MULTI_ADAPTIVE")) m->adaptive = atoi(e) != 0;
   for (int g = 0; g < n_gpus; ++g) {
     m->dev[g] = devices ? devices[g] : g;
     for (int q = 0; q < g; ++q)
@@ -311,6 +319,15 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
   const int G = m->n;
   const auto t0 = std::chrono::steady_clock::now();
   const uint64_t per = (P + (uint64_t)G - 1) / (uint64_t)G;  // points per shard (the last one may be short)
+  // contiguous camera ranges, sized by the GPUs' shares
+  std::vector<uint64_t> cam_lo((size_t)G + 1, 0);
+  {
+    double cum = 0.0;
+    for (int g = 0; g < G; ++g) {
+      cum += m->share[g];
+      cam_lo[(size_t)g + 1] = g == G - 1 ? C : std::min<uint64_t>(C, std::max<uint64_t>(cam_lo[(size_t)g], (uint64_t)(cum * (double)C + 0.5)));
+    }
+  }
   std::vector<double *> d_pts((size_t)G, nullptr);
   std::vector<c2b_obs> part((size_t)G);
 
@@ -348,7 +365,7 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     const double ta = since();
     C2B_TRY(c2b_points_commit(ctx, P));
     C2B_CUDA(cudaEventRecord(m->ev[g][1], ctx->stream));
-    const uint64_t c0 = ((uint64_t)g * C) / (uint64_t)G, c1 = (((uint64_t)g + 1) * C) / (uint64_t)G;
+    const uint64_t c0 = cam_lo[(size_t)g], c1 = cam_lo[(size_t)g + 1];
     const double tb = since();
     C2B_TRY(c2b_upload_cameras(ctx, cams ? cams + 15 * c0 : nullptr, c1 - c0));
     const double tc = since();
@@ -400,7 +417,7 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
       C2B_TRY(m->h_idx.ensure(std::max<uint64_t>(t, 1) * 4));
       C2B_TRY(m->h_uv.ensure(std::max<uint64_t>(t, 1) * 16));
     }
-    const uint64_t c0 = ((uint64_t)g * C) / (uint64_t)G;
+    const uint64_t c0 = cam_lo[(size_t)g];
     return c2b_download_obs_into(ctx, b, m->h_offsets.as<uint64_t>() + c0, m->h_idx.as<uint32_t>() + b,
                                  m->h_uv.as<double>() + 2 * b, g == G - 1, &ms_d2h[(size_t)g]);
   }));
@@ -433,8 +450,8 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     if (cudaEventElapsedTime(&a, m->ev[g][0], m->ev[g][1]) != cudaSuccess) (void)cudaGetLastError();
     if (cudaEventElapsedTime(&b, m->ev[g][1], m->ev[g][2]) != cudaSuccess) (void)cudaGetLastError();
     if (cudaEventElapsedTime(&c, m->ev[g][2], m->ev[g][3]) != cudaSuccess) (void)cudaGetLastError();
-    st.cam_begin[g] = ((uint64_t)g * C) / (uint64_t)G;
-    st.cam_end[g] = (((uint64_t)g + 1) * C) / (uint64_t)G;
+    st.cam_begin[g] = cam_lo[(size_t)g];
+    st.cam_end[g] = cam_lo[(size_t)g + 1];
     st.n_obs[g] = p.n_obs;
     st.obs_base[g] = base[(size_t)g];
     st.ms_points[g] = a;
@@ -444,6 +461,27 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     acc.ms_h2d = std::max(acc.ms_h2d, a);
     acc.ms_d2h = std::max(acc.ms_d2h, ms_d2h[(size_t)g]);
     acc.ms_total = std::max(acc.ms_total, a + b + c + ms_d2h[(size_t)g]);
+  }
+  // next call's shares: proportional to each GPU's measured slab rate (only when the slabs were large enough for
+  // the measurement to mean something), half-way from the current ones, each within [1/2, 2] of an equal share
+  if (m->adaptive && G > 1 && acc.n_obs * 20 >= (64ull << 20)) {
+    double rate[C2B_MAX_GPUS], total_rate = 0.0;
+    bool ok = true;
+    for (int g = 0; g < G; ++g) {
+      rate[g] = ms_d2h[(size_t)g] > 0.0f && part[(size_t)g].n_obs ? (double)part[(size_t)g].n_obs / (double)ms_d2h[(size_t)g] : 0.0;
+      ok = ok && rate[g] > 0.0;
+      total_rate += rate[g];
+    }
+    if (ok) {
+      double sum = 0.0;
+      for (int g = 0; g < G; ++g) {
+        double sh = 0.5 * m->share[g] + 0.5 * rate[g] / total_rate;
+        sh = std::min(std::max(sh, 0.5 / G), 2.0 / G);
+        m->share[g] = sh;
+        sum += sh;
+      }
+      for (int g = 0; g < G; ++g) m->share[g] /= sum;
+    }
   }
   st.ms_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (stats) *stats = st;

@@ -204,8 +204,9 @@ int c2b_download_obs_into(c2b_ctx *ctx, uint64_t obs_base, uint64_t *offsets_dst
  * replaces the rayon par_iter over cameras (src/generate.rs:434-441) and its order-preserving collect
  * (:479-481).  ONE process drives n_gpus devices: one c2b_ctx + stream set + host thread per device and one
  * NCCL communicator (ncclCommInitAll; libnccl.so.2 is loaded with dlopen the first time, so single-GPU users
- * need no NCCL).  Mesh / BVH and points are replicated, GPU g owns the contiguous camera range
- * [floor(g C / G), floor((g+1) C / G)).  Data exchanged over NVLink: (1) every GPU uploads 1/G of the point
+ * need no NCCL).  Mesh / BVH and points are replicated, every GPU owns a contiguous camera range — equal ranges at
+ * first, then sized in proportion to the rate at which each GPU's slab reached host memory in the previous call
+ * (the GPUs of a box do not all reach host memory equally fast; C2B_MULTI_ADAPTIVE=0 keeps them equal).  Data exchanged over NVLink: (1) every GPU uploads 1/G of the point
  * array over its own PCIe link and the shards are all-gathered (ncclAllGather) into each GPU's point array;
  * (2) ONE ncclAllGather of the per-GPU observation counts, from which every GPU rebases its CSR offsets on
  * the device and learns where its slab starts; every GPU then copies its slab into the SAME pinned host CSR
