@@ -229,7 +229,17 @@ int c2b_init_multi(int n_gpus, const int *devices, c2b_multi **out) {
   if (n_gpus > 1) {
     const int rc = load_nccl();
     if (rc != C2B_OK) return fail(rc);
+    // NCCL announces its version on stdout when the first communicator is created; a command line whose stdout
+    // lines are the reference's (and bench.py's one JSON line) keeps it on stderr
+    fflush(stdout);
+    const int saved_stdout = dup(1);
+    if (saved_stdout >= 0) dup2(2, 1);
     const ncclResult_t r = nccl().CommInitAll(m->comm, n_gpus, m->dev);
+    if (saved_stdout >= 0) {
+      fflush(stdout);
+      dup2(saved_stdout, 1);
+      close(saved_stdout);
+    }
     if (r != ncclSuccess)
       return fail(set_error(C2B_ERR_NCCL, "ncclCommInitAll(%d devices) -> %s", n_gpus, nccl().GetErrorString(r)));
     m->have_comm = true;
@@ -462,23 +472,25 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     acc.ms_d2h = std::max(acc.ms_d2h, ms_d2h[(size_t)g]);
     acc.ms_total = std::max(acc.ms_total, a + b + c + ms_d2h[(size_t)g]);
   }
-  // next call's shares: proportional to each GPU's measured slab rate (only when the slabs were large enough for
-  // the measurement to mean something), half-way from the current ones, each within [1/2, 2] of an equal share
+  // next call's shares: when the slowest slab took clearly longer than the fastest (> 15 %), proportional to each
+  // GPU's measured slab rate, each within [1/2, 2] of an equal share; otherwise unchanged, so that the ranges —
+  // and with them every per-GPU buffer size — settle after one or two calls
   if (m->adaptive && G > 1 && acc.n_obs * 20 >= (64ull << 20)) {
     double rate[C2B_MAX_GPUS], total_rate = 0.0;
+    float tmin = 1e30f, tmax = 0.0f;
     bool ok = true;
     for (int g = 0; g < G; ++g) {
       rate[g] = ms_d2h[(size_t)g] > 0.0f && part[(size_t)g].n_obs ? (double)part[(size_t)g].n_obs / (double)ms_d2h[(size_t)g] : 0.0;
       ok = ok && rate[g] > 0.0;
       total_rate += rate[g];
+      tmin = std::min(tmin, ms_d2h[(size_t)g]);
+      tmax = std::max(tmax, ms_d2h[(size_t)g]);
     }
-    if (ok) {
+    if (ok && tmax > 1.15f * tmin) {
       double sum = 0.0;
       for (int g = 0; g < G; ++g) {
-        double sh = 0.5 * m->share[g] + 0.5 * rate[g] / total_rate;
-        sh = std::min(std::max(sh, 0.5 / G), 2.0 / G);
-        m->share[g] = sh;
-        sum += sh;
+        m->share[g] = std::min(std::max(rate[g] / total_rate, 0.5 / G), 2.0 / G);
+        sum += m->share[g];
       }
       for (int g = 0; g < G; ++g) m->share[g] /= sum;
     }
