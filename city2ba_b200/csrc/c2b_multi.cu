@@ -154,10 +154,10 @@ struct c2b_multi {
   cudaEvent_t ev[C2B_MAX_GPUS][4] = {};
   PinBuf h_offsets, h_idx, h_uv;  // the ONE host CSR
   std::mutex mu;
-  // share of the cameras each GPU gets: equal at first, then proportional to the rate at which each GPU's slab
-  // reached host memory in the previous call.  The result transfer is the longest leg of a call and the GPUs of a
-  // box do not all reach host memory equally fast (8-GPU box, all copying at once: 6.5-7.5 ms for GPUs 4-7,
-  // 11 ms for GPUs 0-3, profiles/r02k_bench_cfg4_8gpu.json), so equal ranges wait for the slowest link.
+  // share of the cameras each GPU gets: equal at first, then following each GPU's measured speed (pass + slab
+  // transfer per camera) in the previous call.  The result transfer is usually the longest leg of a call and the
+  // GPUs of a box do not all reach host memory equally fast (8-GPU box, all copying at once: 6.5-7.5 ms for GPUs
+  // 4-7, 11 ms for GPUs 0-3, profiles/r02k_bench_cfg4_8gpu.json), so equal ranges wait for the slowest link.
   double share[C2B_MAX_GPUS] = {};
   bool adaptive = true;
 };
@@ -472,24 +472,27 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     acc.ms_d2h = std::max(acc.ms_d2h, ms_d2h[(size_t)g]);
     acc.ms_total = std::max(acc.ms_total, a + b + c + ms_d2h[(size_t)g]);
   }
-  // next call's shares: when the slowest slab took clearly longer than the fastest (> 15 %), proportional to each
-  // GPU's measured slab rate, each within [1/2, 2] of an equal share; otherwise unchanged, so that the ranges —
-  // and with them every per-GPU buffer size — settle after one or two calls
+  // next call's shares: what a GPU spends per camera AFTER the point exchange — its pass plus its slab's way to
+  // host memory — is measured; when the slowest GPU took clearly longer than the fastest (> 15 %), the shares
+  // become proportional to the GPUs' measured speeds (1 / ms per camera), each within [1/2, 2] of an equal share;
+  // otherwise they stay, so that the ranges — and with them every per-GPU buffer size — settle after a call or two
   if (m->adaptive && G > 1 && acc.n_obs * 20 >= (64ull << 20)) {
-    double rate[C2B_MAX_GPUS], total_rate = 0.0;
+    double speed[C2B_MAX_GPUS], total_speed = 0.0;
     float tmin = 1e30f, tmax = 0.0f;
     bool ok = true;
     for (int g = 0; g < G; ++g) {
-      rate[g] = ms_d2h[(size_t)g] > 0.0f && part[(size_t)g].n_obs ? (double)part[(size_t)g].n_obs / (double)ms_d2h[(size_t)g] : 0.0;
-      ok = ok && rate[g] > 0.0;
-      total_rate += rate[g];
-      tmin = std::min(tmin, ms_d2h[(size_t)g]);
-      tmax = std::max(tmax, ms_d2h[(size_t)g]);
+      const float t = st.ms_compute[g] + st.ms_d2h[g];
+      const uint64_t nc = cam_lo[(size_t)g + 1] - cam_lo[(size_t)g];
+      speed[g] = t > 0.0f && nc ? (double)nc / (double)t : 0.0;
+      ok = ok && speed[g] > 0.0;
+      total_speed += speed[g];
+      tmin = std::min(tmin, t);
+      tmax = std::max(tmax, t);
     }
     if (ok && tmax > 1.15f * tmin) {
       double sum = 0.0;
       for (int g = 0; g < G; ++g) {
-        m->share[g] = std::min(std::max(rate[g] / total_rate, 0.5 / G), 2.0 / G);
+        m->share[g] = std::min(std::max(speed[g] / total_speed, 0.5 / G), 2.0 / G);
         sum += m->share[g];
       }
       for (int g = 0; g < G; ++g) m->share[g] /= sum;
