@@ -160,6 +160,7 @@ struct c2b_multi {
   // 4-7, 11 ms for GPUs 0-3, profiles/r02k_bench_cfg4_8gpu.json), so equal ranges wait for the slowest link.
   double share[C2B_MAX_GPUS] = {};
   bool adaptive = true;
+  int adjustments = 0;
 };
 
 struct c2b_multi_scene {
@@ -473,29 +474,37 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
     acc.ms_total = std::max(acc.ms_total, a + b + c + ms_d2h[(size_t)g]);
   }
   // next call's shares: what a GPU spends per camera AFTER the point exchange — its pass plus its slab's way to
-  // host memory — is measured; when the slowest GPU took clearly longer than the fastest (> 15 %), the shares
-  // become proportional to the GPUs' measured speeds (1 / ms per camera), each within [1/2, 2] of an equal share;
-  // otherwise they stay, so that the ranges — and with them every per-GPU buffer size — settle after a call or two
+  // host memory — is estimated from this call: the pass as cameras x the SMALLEST per-camera pass time any GPU
+  // showed (the GPUs are alike; a call in which a GPU had to grow its buffers or repeat an optimistic pass would
+  // otherwise pollute the estimate), the transfer as measured (CUDA events around the copies).  When the slowest
+  // GPU took clearly longer than the fastest (> 15 %; > 30 % after three adjustments), the shares become
+  // proportional to the GPUs' speeds, each within [1/2, 2] of an equal share; otherwise they stay, so that the
+  // ranges — and with them every per-GPU buffer size — settle after a call or two
   if (m->adaptive && G > 1 && acc.n_obs * 20 >= (64ull << 20)) {
-    double speed[C2B_MAX_GPUS], total_speed = 0.0;
-    float tmin = 1e30f, tmax = 0.0f;
-    bool ok = true;
+    double c_bar = 1e300;
     for (int g = 0; g < G; ++g) {
-      const float t = st.ms_compute[g] + st.ms_d2h[g];
       const uint64_t nc = cam_lo[(size_t)g + 1] - cam_lo[(size_t)g];
-      speed[g] = t > 0.0f && nc ? (double)nc / (double)t : 0.0;
-      ok = ok && speed[g] > 0.0;
+      if (nc && st.ms_compute[g] > 0.0f) c_bar = std::min(c_bar, (double)st.ms_compute[g] / (double)nc);
+    }
+    double speed[C2B_MAX_GPUS], total_speed = 0.0, tmin = 1e300, tmax = 0.0;
+    bool ok = c_bar < 1e300;
+    for (int g = 0; g < G && ok; ++g) {
+      const uint64_t nc = cam_lo[(size_t)g + 1] - cam_lo[(size_t)g];
+      const double t = (double)nc * c_bar + (double)st.ms_d2h[g];
+      speed[g] = t > 0.0 && nc ? (double)nc / t : 0.0;
+      ok = speed[g] > 0.0;
       total_speed += speed[g];
       tmin = std::min(tmin, t);
       tmax = std::max(tmax, t);
     }
-    if (ok && tmax > 1.15f * tmin) {
+    if (ok && tmax > (m->adjustments < 3 ? 1.15 : 1.30) * tmin) {
       double sum = 0.0;
       for (int g = 0; g < G; ++g) {
         m->share[g] = std::min(std::max(speed[g] / total_speed, 0.5 / G), 2.0 / G);
         sum += m->share[g];
       }
       for (int g = 0; g < G; ++g) m->share[g] /= sum;
+      ++m->adjustments;
     }
   }
   st.ms_wall = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
