@@ -477,7 +477,7 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
   // host memory — is estimated from this call: the pass as cameras x the SMALLEST per-camera pass time any GPU
   // showed (the GPUs are alike; a call in which a GPU had to grow its buffers or repeat an optimistic pass would
   // otherwise pollute the estimate), the transfer as measured (CUDA events around the copies).  When the slowest
-  // GPU took clearly longer than the fastest (> 15 %; > 30 % after three adjustments), the shares become
+  // GPU took clearly longer than the fastest (> 15 %; > 50 % after two adjustments), the shares become
   // proportional to the GPUs' speeds, each within [1/2, 2] of an equal share; otherwise they stay, so that the
   // ranges — and with them every per-GPU buffer size — settle after a call or two
   if (m->adaptive && G > 1 && acc.n_obs * 20 >= (64ull << 20)) {
@@ -497,7 +497,7 @@ int c2b_visibility_graph_multi(c2b_multi *m, const c2b_multi_scene *scene, const
       tmin = std::min(tmin, t);
       tmax = std::max(tmax, t);
     }
-    if (ok && tmax > (m->adjustments < 3 ? 1.15 : 1.30) * tmin) {
+    if (ok && tmax > (m->adjustments < 2 ? 1.15 : 1.50) * tmin) {
       double sum = 0.0;
       for (int g = 0; g < G; ++g) {
         m->share[g] = std::min(std::max(speed[g] / total_speed, 0.5 / G), 2.0 / G);

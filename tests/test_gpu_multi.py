@@ -66,9 +66,16 @@ def test_multi_full_size_hash_equals_single(c2b, ctx):
     single = c2b.visibility_graph(c2b.Scene(xyz, tri, ctx=ctx), cams, pts, bench.MAX_DIST, ctx=ctx)
     m = c2b.MultiContext(G)
     try:
-        g = c2b.visibility_graph_multi(m, c2b.MultiScene(xyz, tri, m), cams, pts, bench.MAX_DIST)
-        assert bench.result_hash(g.offsets, g.point_idx, g.uv) == bench.result_hash(single.offsets, single.point_idx, single.uv)
+        scene = c2b.MultiScene(xyz, tri, m)
+        want = bench.result_hash(single.offsets, single.point_idx, single.uv)
+        assert want == bench.expected_hash("cfg3")
+        ranges = set()
+        for call in range(4):   # later calls may move the range boundaries (measured shares): the CSR must not change
+            g = c2b.visibility_graph_multi(m, scene, cams, pts, bench.MAX_DIST)
+            assert bench.result_hash(g.offsets, g.point_idx, g.uv) == want, f"call {call}"
+            ranges.add(tuple(g.stats["multi"]["cam_end"]))
         assert np.array_equal(g.point_idx, single.point_idx) and np.array_equal(g.uv, single.uv)
+        print(f"\n  camera range ends over 4 calls on {G} GPU(s): {sorted(ranges)}")
     finally:
         m.close()
     assert torch.cuda.device_count() >= G
