@@ -567,13 +567,20 @@ constexpr int FU_STAGE = 64;
 
 enum { FU_OCC_MESH = 0, FU_OCC_NONE = 1, FU_OCC_ANALYTIC = 2 };
 
-// float <-> unsigned with the same ordering (no NaNs), for REDUX min / max
-__device__ __forceinline__ unsigned f2ord(float f) {
-  const int b = __float_as_int(f);
-  return (unsigned)b ^ ((unsigned)(b >> 31) | 0x80000000u);  // negative: ~b, else b ^ sign
+// warp-wide float min / max in ONE instruction: sm_100a's redux.sync.{min,max}.f32 (CREDUX.MIN.F32 / .MAX.F32,
+// result in a uniform register).  Until r02w the floats went through order-preserving integer images for the
+// integer REDUX (shift, xor before; compare, select, xor after: ~10 instructions per reduction, 125 per packet
+// for the twelve bounds = 12 % of the kernel's warp instructions at cfg4, profiles/r02w_sass_dynamic.txt).
+// NaN inputs are ignored unless every lane holds one; -0 < +0.  The bounds are identical either way.
+__device__ __forceinline__ float warp_min_f32(float v) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
-__device__ __forceinline__ float ord2f(unsigned u) {
-  return __uint_as_float(u ^ ((unsigned)((int)~u >> 31) | 0x80000000u));
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 __device__ __forceinline__ TriRec load_rec(const float4 *rec, int k) {
@@ -651,7 +658,7 @@ __device__ __forceinline__ bool direction_box_may_hit(const TriRec &t, float dlx
 }
 
 // bounding box of a packet's ray segments (origin + end points, conservatively padded) and of its
-// directions, reduced over the warp with REDUX on order-preserving integer images of the floats
+// directions, reduced over the warp with one CREDUX.F32 each
 struct PacketBounds {
   float blx, bly, blz, bhx, bhy, bhz;  // segments
   float dlx, dly, dlz, dhx, dhy, dhz;  // directions
@@ -676,18 +683,18 @@ __device__ __forceinline__ PacketBounds packet_bounds(const Ray &ray, bool alive
     dlz = dhz = ray.dz;
   }
   PacketBounds b;
-  b.blx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lx)));
-  b.bly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(ly)));
-  b.blz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(lz)));
-  b.bhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hx)));
-  b.bhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hy)));
-  b.bhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(hz)));
-  b.dlx = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlx)));
-  b.dly = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dly)));
-  b.dlz = ord2f(__reduce_min_sync(0xffffffffu, f2ord(dlz)));
-  b.dhx = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhx)));
-  b.dhy = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhy)));
-  b.dhz = ord2f(__reduce_max_sync(0xffffffffu, f2ord(dhz)));
+  b.blx = warp_min_f32(lx);
+  b.bly = warp_min_f32(ly);
+  b.blz = warp_min_f32(lz);
+  b.bhx = warp_max_f32(hx);
+  b.bhy = warp_max_f32(hy);
+  b.bhz = warp_max_f32(hz);
+  b.dlx = warp_min_f32(dlx);
+  b.dly = warp_min_f32(dly);
+  b.dlz = warp_min_f32(dlz);
+  b.dhx = warp_max_f32(dhx);
+  b.dhy = warp_max_f32(dhy);
+  b.dhz = warp_max_f32(dhz);
   return b;
 }
 
@@ -698,10 +705,12 @@ __device__ __forceinline__ bool box_meets_packet(const PacketBounds &b, float4 l
 
 // lane = triangle: lanes with `want` load triangle `slot`, build its record for the origin, drop it
 // if the direction box cannot hit it, and park the survivors' records in rec[0..3*cnt);
-// then lane = ray: every record is tested.  Returns false when no ray of the packet is left alive.
+// then lane = ray: every record is tested.  `am` = the rays of the packet that are still unoccluded, as a
+// warp-uniform lane mask (one VOTE + one logic op per pair of tests; per-lane alive / occluded flags cost a dozen
+// select / pack instructions per pair).  Returns false when no ray of the packet is left alive.
 template <bool COUNT>
 __device__ __forceinline__ bool test_leaf_chunk(const FusedArgs &a, const PacketBounds &pb, int slot, bool want,
-                                                const Ray &ray, bool &alive, bool &occ, float ox, float oy,
+                                                const Ray &ray, unsigned &am, float ox, float oy,
                                                 float oz, float4 *rec, int lane, unsigned &n_tri) {
   TriRec t;
   if (want) {
@@ -722,26 +731,20 @@ __device__ __forceinline__ bool test_leaf_chunk(const FusedArgs &a, const Packet
   __syncwarp();
   const int cnt = __popc(m);
   if (COUNT) n_tri += cnt;
-  bool any_alive = true;
   int k = 0;
   for (; k + 1 < cnt; k += 2) {
     const TriRec t0 = load_rec(rec, k), t1 = load_rec(rec, k + 1);
     const bool h0 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
     const bool h1 = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t1);
-    occ |= alive & (h0 | h1);
-    alive &= !(h0 | h1);
-    any_alive = __ballot_sync(0xffffffffu, alive) != 0u;
-    if (!any_alive) break;
+    am &= ~__ballot_sync(0xffffffffu, h0 | h1);
+    if (am == 0u) break;
   }
-  if (any_alive && (cnt & 1)) {
+  if (am != 0u && (cnt & 1)) {
     const TriRec t0 = load_rec(rec, cnt - 1);
-    const bool h = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0);
-    occ |= alive & h;
-    alive &= !h;
-    any_alive = __ballot_sync(0xffffffffu, alive) != 0u;
+    am &= ~__ballot_sync(0xffffffffu, ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, t0));
   }
   __syncwarp();
-  return any_alive;
+  return am != 0u;
 }
 
 // list-driven any-hit for a packet of rays that share the origin (ox, oy, oz).  Returns true when
@@ -757,9 +760,9 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
                                                uint32_t n_list, const Ray &ray, bool have, float ox,
                                                float oy, float oz, float4 *rec, bool hoisted, int lane,
                                                unsigned &n_vis, unsigned &n_tri) {
-  bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
-  bool occ = false;
-  if (__ballot_sync(0xffffffffu, alive) == 0u) return false;
+  const bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
+  unsigned am = __ballot_sync(0xffffffffu, alive);  // rays not yet known to be occluded (warp-uniform)
+  if (am == 0u) return false;
   const PacketBounds pb = packet_bounds(ray, alive, ox, oy, oz, a.scene_absmax);
   if (hoisted) {
     for (uint32_t base = 0; base < n_list; base += 32) {
@@ -777,21 +780,26 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
         n_vis += min(32u, n_list - base);
         n_tri += __popc(m);
       }
+      // the records' shared-memory address as ONE opaque 32-bit register: left to itself the compiler
+      // re-derives it from %tid and the shared window (ten instructions) for every second triangle
+      uint32_t rk_s = (uint32_t)__cvta_generic_to_shared(rec + base);
+      asm volatile("" : "+r"(rk_s));
+      const float4 *rk = reinterpret_cast<const float4 *>(__cvta_shared_to_generic((size_t)rk_s));
       while (m) {
-        const int k0 = (int)base + __ffs(m) - 1;
+        const int k0 = __ffs(m) - 1;
         m &= m - 1;
-        bool h = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rec[k0], rec[FU_HOIST + k0], rec[2 * FU_HOIST + k0]));
+        bool h = ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rk[k0], rk[FU_HOIST + k0], rk[2 * FU_HOIST + k0]));
         if (m) {
-          const int k1 = (int)base + __ffs(m) - 1;
+          const int k1 = __ffs(m) - 1;
           m &= m - 1;
-          h |= ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rec[k1], rec[FU_HOIST + k1], rec[2 * FU_HOIST + k1]));
+          h |= ray_tri_record(ray.dx, ray.dy, ray.dz, ray.tfar, unpack_rec(rk[k1], rk[FU_HOIST + k1], rk[2 * FU_HOIST + k1]));
         }
-        occ |= alive & h;
-        alive &= !h;
-        if (__ballot_sync(0xffffffffu, alive) == 0u) return occ;
+        // (a lane that was never alive may report a "hit" of its placeholder ray: its bit is clear already)
+        am &= ~__ballot_sync(0xffffffffu, h);
+        if (am == 0u) return alive;  // every live ray of the packet is occluded
       }
     }
-    return occ;
+    return alive && !((am >> lane) & 1u);
   }
   for (uint32_t base = 0; base < n_list; base += 32) {
     const uint32_t j = base + lane;
@@ -805,9 +813,9 @@ __device__ __forceinline__ bool packet_any_hit(const FusedArgs &a, const uint32_
       slot = __float_as_int(hi.w);
     }
     if (COUNT) n_vis += min(32u, n_list - base);
-    if (!test_leaf_chunk<COUNT>(a, pb, slot, overlap, ray, alive, occ, ox, oy, oz, rec, lane, n_tri)) break;
+    if (!test_leaf_chunk<COUNT>(a, pb, slot, overlap, ray, am, ox, oy, oz, rec, lane, n_tri)) break;
   }
-  return occ;
+  return alive && !((am >> lane) & 1u);
 }
 
 // ---- packet traversal of the BVH, lane = node --------------------------------------------------------
@@ -825,9 +833,9 @@ template <bool COUNT>
 __device__ __forceinline__ int packet_bvh_hit(const FusedArgs &a, const Ray &ray, bool have, float ox, float oy,
                                               float oz, float4 *region, int lane, unsigned &n_vis,
                                               unsigned &n_tri) {
-  bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
-  bool occ = false;
-  if (__ballot_sync(0xffffffffu, alive) == 0u) return 0;
+  const bool alive = have && (ray.tfar >= 0.0f) && (ray.dx == ray.dx) && (ray.dy == ray.dy) && (ray.dz == ray.dz);
+  unsigned am = __ballot_sync(0xffffffffu, alive);  // rays not yet known to be occluded (warp-uniform)
+  if (am == 0u) return 0;
   const PacketBounds pb = packet_bounds(ray, alive, ox, oy, oz, a.scene_absmax);
   float4 *rec = region;
   uint32_t *pending = reinterpret_cast<uint32_t *>(region + 96);
@@ -873,10 +881,10 @@ __device__ __forceinline__ int packet_bvh_hit(const FusedArgs &a, const Ray &ray
       const bool want = lane < cnt;
       const int slot = want ? (int)pending[np - cnt + lane] : 0;
       np -= cnt;
-      if (!test_leaf_chunk<COUNT>(a, pb, slot, want, ray, alive, occ, ox, oy, oz, rec, lane, n_tri)) break;
+      if (!test_leaf_chunk<COUNT>(a, pb, slot, want, ray, am, ox, oy, oz, rec, lane, n_tri)) break;
     }
   }
-  return occ ? 1 : 0;
+  return alive && !((am >> lane) & 1u) ? 1 : 0;
 }
 
 // ---- in-kernel epilogue -----------------------------------------------------------------------------

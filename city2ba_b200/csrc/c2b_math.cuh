@@ -98,9 +98,23 @@ C2B_HD V3 project_world(const double *cam, V3 p) {
   return V3{dadd(r.x, cam[9]), dadd(r.y, cam[10]), dadd(r.z, cam[11])};
 }
 
+// a / b of the perspective division, bit for bit IEEE 754 like ddiv.  The device's division routine sends a
+// ZERO NUMERATOR through its slow path (a call of ~55 dependent instructions), and the reference's synthetic
+// cities produce exactly that for every observation: cameras and points share one height and the camera axes
+// are lattice-aligned, so pc.y == 0 exactly.  At cfg4 that call was 24 % of k_sort_write's warp instructions
+// (profiles/r02w_sass_dynamic.txt).  (+-0) / b = +-0 with sign(a) ^ sign(b) for every b that is neither zero
+// nor NaN (infinite b included); everything else takes the general division.
+C2B_HD double ddiv_persp(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  if (a == 0.0 && b == b && b != 0.0)
+    return __hiloint2double((__double2hiint(a) ^ __double2hiint(b)) & (int)0x80000000, 0);
+#endif
+  return ddiv(a, b);
+}
+
 // SnavelyCamera::project, src/baproblem.rs:145-151; |p_|^4 as m2*m2
 C2B_HD void project(double f, double k1, double k2, V3 pc, double &u, double &v) {
-  double px = ddiv(-pc.x, pc.z), py = ddiv(-pc.y, pc.z);
+  double px = ddiv_persp(-pc.x, pc.z), py = ddiv_persp(-pc.y, pc.z);
   double m2 = dadd(dmul(px, px), dmul(py, py));
   double r = dadd(dadd(1.0, dmul(k1, m2)), dmul(k2, dmul(m2, m2)));
   double fr = dmul(f, r);
