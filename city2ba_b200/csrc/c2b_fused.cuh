@@ -570,7 +570,7 @@ enum { FU_OCC_MESH = 0, FU_OCC_NONE = 1, FU_OCC_ANALYTIC = 2 };
 // warp-wide float min / max in ONE instruction: sm_100a's redux.sync.{min,max}.f32 (CREDUX.MIN.F32 / .MAX.F32,
 // result in a uniform register).  Until r02w the floats went through order-preserving integer images for the
 // integer REDUX (shift, xor before; compare, select, xor after: ~10 instructions per reduction, 125 per packet
-// for the twelve bounds = 12 % of the kernel's warp instructions at cfg4, profiles/r02w_sass_dynamic.txt).
+// for the twelve bounds = 12 % of the kernel's warp instructions at cfg4, profiles/r02j_sass_dynamic_fused.txt).
 // NaN inputs are ignored unless every lane holds one; -0 < +0.  The bounds are identical either way.
 __device__ __forceinline__ float warp_min_f32(float v) {
   float r;

@@ -102,7 +102,7 @@ C2B_HD V3 project_world(const double *cam, V3 p) {
 // ZERO NUMERATOR through its slow path (a call of ~55 dependent instructions), and the reference's synthetic
 // cities produce exactly that for every observation: cameras and points share one height and the camera axes
 // are lattice-aligned, so pc.y == 0 exactly.  At cfg4 that call was 24 % of k_sort_write's warp instructions
-// (profiles/r02w_sass_dynamic.txt).  (+-0) / b = +-0 with sign(a) ^ sign(b) for every b that is neither zero
+// (profiles/r02j_sass_dynamic_sort_write.txt).  (+-0) / b = +-0 with sign(a) ^ sign(b) for every b that is neither zero
 // nor NaN (infinite b included); everything else takes the general division.
 C2B_HD double ddiv_persp(double a, double b) {
 #if defined(__CUDA_ARCH__)
