@@ -1026,25 +1026,38 @@ constexpr int FU_REGION_F4 = 4 * FU_HOIST;                                      
 constexpr int FU_REGION_EPI_F4 = ((SW_WARP_MAX + SW_BINS) * 4 + 15) / 16;                     // 5 KB
 static_assert(FU_REGION_EPI_F4 >= FU_REGION_F4, "the sort region also holds the triangle records");
 
+// a warp's shared memory: triangle records (hoisted: 4 planes x FU_HOIST; chunked: 32 x 3; EPI: also the sort's
+// keys and counters), the camera record(s), and the ring of FU_STAGE grid positions in which the survivors of the
+// cull wait for their packet.  (Staging the coordinates as well, so that the ray set-up needs no second trip
+// through L1, was measured: 48 KB of shared memory per CTA instead of 36 shrink L1, 3.11 ms against 3.07 ms at cfg4.)
+template <bool EPI, bool MESH>
+struct alignas(16) FuWarpSmem {
+  float4 rec[EPI ? FU_REGION_EPI_F4 : MESH ? FU_REGION_F4 : 1];
+  double cam[EPI ? 2 : 1][16];
+  uint32_t stage[FU_STAGE];
+};
+
 template <int OCC, bool COUNT, int MIN_CTAS, bool WALK, bool EPI = false>
 __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
-  __shared__ double s_cam[FU_WARPS][EPI ? 2 : 1][16];
-  // survivors of the cull wait here for their packet: a ring of FU_STAGE grid positions per warp.  (Staging
-  // the coordinates as well, so that the ray set-up needs no second trip through L1, was measured: 48 KB of
-  // shared memory per CTA instead of 36 shrink L1, 3.11 ms against 3.07 ms at cfg4.)
-  __shared__ uint32_t s_stage[FU_WARPS][FU_STAGE];
-  __shared__ float4 s_rec[FU_WARPS][EPI ? FU_REGION_EPI_F4 : FU_REGION_F4];  // hoisted: 4 planes x FU_HOIST; chunked: 32 x 3
+  // One block of shared memory per warp (FuWarpSmem), addressed through ONE opaque 32-bit register: with three
+  // separate arrays indexed by the warp number the compiler re-derived every address from %tid and the shared
+  // window at each use (5-10 instructions, eight times per chunk / packet: profiles/r02w_sass_dynamic_fused.txt).
+  typedef FuWarpSmem<EPI, OCC == FU_OCC_MESH> WarpSmem;
+  __shared__ WarpSmem s_w[FU_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (EPI && blockIdx.x == 0 && warp == 0) {
     epilogue_scanner(a, lane);
     return;
   }
+  uint32_t w_s = (uint32_t)__cvta_generic_to_shared(&s_w[warp]);
+  asm volatile("" : "+r"(w_s));
+  WarpSmem *const w = reinterpret_cast<WarpSmem *>(__cvta_shared_to_generic((size_t)w_s));
   int cur = 0;  // EPI: the record slot of the camera being scanned
-  double *c = s_cam[warp][0];
+  double *c = w->cam[0];
   bool pending = false;  // EPI: a finished camera waits for its epilogue
   uint64_t pend_cam = 0;
   uint32_t pend_n = 0, pend_ev0 = 0;
-  uint32_t *stage = s_stage[warp];
+  uint32_t *stage = w->stage;
   unsigned long long found_total = 0;
   unsigned n_vis_nodes = 0, n_tri = 0;
   const double cell_h = ddiv(1.0, a.g.inv_h);
@@ -1073,7 +1086,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       if ((uint32_t)lane < a.tri_cap) l0 = mylist[lane];
       if ((uint32_t)lane + 32u < a.tri_cap) l1 = mylist[lane + 32];
     }
-    if (EPI) c = s_cam[warp][cur];
+    if (EPI) c = w->cam[cur];
     if (lane < 15) c[lane] = creg;
     __syncwarp();
     // launched without waiting for the plan's totals (sizes and variant from the previous pass): a camera
@@ -1091,7 +1104,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     }
     const float ox = d2f(cen.x), oy = d2f(cen.y), oz = d2f(cen.z);
     const bool hoisted = OCC == FU_OCC_MESH && n_list <= a.hoist_max;  // (OVERFLOW is 2^32 - 1)
-    if (hoisted) hoist_records(a, l0, l1, n_list, ox, oy, oz, s_rec[warp], lane);
+    if (hoisted) hoist_records(a, l0, l1, n_list, ox, oy, oz, w->rec, lane);
     uint32_t *out = a.scratch_idx + ev0;
     const uint32_t out_cap = ev1 - ev0;
     uint32_t nvis = 0;
@@ -1115,11 +1128,11 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
       bool occ = false;
       if (OCC == FU_OCC_MESH) {
         if (WALK && n_list == TRILIST_OVERFLOW) {
-          const int r = a.packet_bvh ? packet_bvh_hit<COUNT>(a, ray, have, ox, oy, oz, s_rec[warp], lane, n_vis_nodes, n_tri) : 2;
+          const int r = a.packet_bvh ? packet_bvh_hit<COUNT>(a, ray, have, ox, oy, oz, w->rec, lane, n_vis_nodes, n_tri) : 2;
           occ = r == 2 ? warp_any_hit<COUNT>(a.nodes, a.tris, a.n_nodes, ray, have, a.scene_absmax, a.counters)
                        : r == 1;
         } else
-          occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, s_rec[warp], hoisted, lane, n_vis_nodes, n_tri);
+          occ = packet_any_hit<COUNT>(a, mylist, n_list, ray, have, ox, oy, oz, w->rec, hoisted, lane, n_vis_nodes, n_tri);
       } else if (OCC == FU_OCC_ANALYTIC) {
         occ = have && hits_building(cen, p, a.block_length, a.block_inset);
       }
@@ -1218,7 +1231,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     if (EPI) {
       __syncwarp();
       if (pending)
-        epilogue_sort_write(a, pend_cam, pend_n, pend_ev0, s_cam[warp][cur ^ 1], reinterpret_cast<uint32_t *>(s_rec[warp]), lane);
+        epilogue_sort_write(a, pend_cam, pend_n, pend_ev0, w->cam[cur ^ 1], reinterpret_cast<uint32_t *>(w->rec), lane);
       pending = true;
       pend_cam = cam;
       pend_n = nvis;
@@ -1227,7 +1240,7 @@ __global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(Fu
     }
   }
   if (EPI && pending)
-    epilogue_sort_write(a, pend_cam, pend_n, pend_ev0, s_cam[warp][cur ^ 1], reinterpret_cast<uint32_t *>(s_rec[warp]), lane);
+    epilogue_sort_write(a, pend_cam, pend_n, pend_ev0, w->cam[cur ^ 1], reinterpret_cast<uint32_t *>(w->rec), lane);
   if (lane == 0) {
     if (found_total) atomicAdd(&a.counters[4], found_total);
     if (COUNT) {
