@@ -404,25 +404,40 @@ __device__ __forceinline__ uint32_t sw_pad(uint32_t i) { return i + (i >> 5); }
 // 256 counters (8 per lane + one warp scan), then a stable scatter chunk by chunk: the rank of a key
 // among the equal digits of its chunk is popc(__match_any_sync & lanes below), the chunk's first lane
 // per digit advances the counter with one shared-memory atomic and hands the old value to its peers
-// by shuffle (no warp barrier inside the chunk loop: they cost a quarter of the kernel's instructions
-// in the first version, profiles/r01j).  A pass whose keys all share the digit is skipped (common for the top
-// digit: a camera's points are usually close in index).  About 0.4k warp instructions per pass at
-// n = 532 against ~3k for the 1024-key bitonic network this replaces (profiles/r01h: k_sort_write spent
-// 878 M warp instructions, 16.5 per observation).  The sorted keys end up in `sorted` (padded layout).
+// by shuffle.  About 0.4k warp instructions per pass at n = 532 against ~3k for the 1024-key bitonic network
+// this replaces (profiles/r01h: k_sort_write spent 878 M warp instructions, 16.5 per observation).  The sorted
+// keys end up in `sorted` (padded layout).
+//   * A digit on which all keys agree needs no pass (common for the top digit: a camera's points are usually
+//     close in index).  One OR and one AND reduction over the keys tell which digits vary, so a skipped pass
+//     costs nothing (until r02x its histogram was built first and then found to have a single bin).
+//   * The scatter handles FOUR chunks at a time: four MATCHes, then the four leaders' atomics, then four
+//     shuffles + stores.  Chunk by chunk the chain MATCH -> ATOMS -> SHFL -> STS exposed its ~120 cycles of
+//     latency 17 times per pass: 45 % of the kernel's stall samples sat on the instruction after a MATCH or an
+//     ATOMS (profiles/r02w_sass_dynamic_sort_write.txt, short_scoreboard 7.6 warps per issue).
 template <int E, bool MULTI>
 __device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const CamSlices &cs, int lane,
                                                   uint32_t *sorted, uint32_t *hist) {
+  static_assert(E % 4 == 0, "the scatter takes four chunks at a time");
   const uint32_t n = cs.n;
   const int key_bits = s.key_bits;
   uint32_t a[E];
+  uint32_t v_or = 0u, v_and = 0xffffffffu;
 #pragma unroll
   for (int r = 0; r < E; ++r) {
     const uint32_t t = r * 32 + lane;
-    a[r] = t < n ? cam_key<MULTI>(s, cs, t) : 0xffffffffu;
+    a[r] = 0xffffffffu;
+    if (t < n) {
+      a[r] = cam_key<MULTI>(s, cs, t);
+      v_or |= a[r];
+      v_and &= a[r];
+    }
   }
+  // bits in which the camera's keys differ (warp-uniform; lanes without keys contribute the neutral elements)
+  const uint32_t varying = __reduce_or_sync(0xffffffffu, v_or) ^ __reduce_and_sync(0xffffffffu, v_and);
   const unsigned lt = (1u << lane) - 1u;
   bool in_smem = false;
   for (int shift = 0; shift < key_bits; shift += SW_RADIX_BITS) {
+    if (((varying >> shift) & (SW_BINS - 1)) == 0u) continue;  // every key has the same digit: order unchanged
 #pragma unroll
     for (int k = 0; k < SW_BINS / 32; ++k) hist[k * 32 + lane] = 0u;
     __syncwarp();
@@ -433,16 +448,10 @@ __device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const 
     // exclusive scan: lane owns counters [8*lane, 8*lane + 8)
     uint32_t c[SW_BINS / 32];
     uint32_t sum = 0;
-    bool one_bin = false;
 #pragma unroll
     for (int k = 0; k < SW_BINS / 32; ++k) {
       c[k] = hist[lane * (SW_BINS / 32) + k];
-      one_bin |= c[k] == n;
       sum += c[k];
-    }
-    if (__any_sync(0xffffffffu, one_bin)) {  // every key has the same digit: order unchanged
-      __syncwarp();                          // (the counters are cleared again by the next pass)
-      continue;
     }
     uint32_t pre = sum;
 #pragma unroll
@@ -459,22 +468,33 @@ __device__ __forceinline__ void sort_warp_to_smem(const SortWriteArgs &s, const 
     }
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < E; ++r) {
-      if ((uint32_t)(r * 32) < n) {  // warp-uniform
-        const bool valid = (uint32_t)(r * 32 + lane) < n;
-        const uint32_t d = valid ? (a[r] >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t rank = __popc(peers & lt);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) old = atomicAdd(&hist[d], (uint32_t)__popc(peers));  // warp-aggregated
-        const uint32_t base = __shfl_sync(0xffffffffu, old, leader);
-        if (valid) sorted[sw_pad(base + rank)] = a[r];
+    for (int r0 = 0; r0 < E; r0 += 4) {
+      if ((uint32_t)(r0 * 32) < n) {  // warp-uniform
+        uint32_t d[4], old[4];
+        unsigned peers[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const bool valid = (uint32_t)((r0 + g) * 32 + lane) < n;
+          d[g] = valid ? (a[r0 + g] >> shift) & (SW_BINS - 1) : (uint32_t)SW_BINS;  // padding keeps to itself
+          peers[g] = __match_any_sync(0xffffffffu, d[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          old[g] = 0u;
+          if (d[g] != (uint32_t)SW_BINS && lane == __ffs(peers[g]) - 1)
+            old[g] = atomicAdd(&hist[d[g]], (uint32_t)__popc(peers[g]));  // warp-aggregated
+          __syncwarp();  // a later chunk's leaders advance the counters after this chunk's (stable order)
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t base = __shfl_sync(0xffffffffu, old[g], __ffs(peers[g]) - 1);
+          if (d[g] != (uint32_t)SW_BINS) sorted[sw_pad(base + __popc(peers[g] & lt))] = a[r0 + g];
+        }
       }
     }
     __syncwarp();
     in_smem = true;
-    if (shift + SW_RADIX_BITS < key_bits) {
+    if (shift + SW_RADIX_BITS < key_bits && (varying >> (shift + SW_RADIX_BITS)) != 0u) {  // another pass follows
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         const uint32_t t = r * 32 + lane;
@@ -1290,12 +1310,15 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
 #pragma unroll
   for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
   // (an explicit software pipeline of the point gathers measured 0.85 ms against 0.83 ms for this form)
+  // (the points are read-only for the kernel: through the non-coherent path the gathers of the second unrolled
+  // iteration may move above the first one's stores)
 #pragma unroll 2
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t pt = sorted[sw_pad(i)];
     const double *p = s.p_aos + 3 * (uint64_t)pt;
+    const double x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
     s.out_idx[base + i] = pt;
-    s.out_uv[base + i] = observe(c, p[0], p[1], p[2]);
+    s.out_uv[base + i] = observe(c, x, y, z);
   }
 }
 
