@@ -1275,6 +1275,7 @@ template <int MIN_CTAS, bool MULTI>
 __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWriteArgs s) {
   __shared__ uint32_t s_sorted[SW_WARPS][SW_WARP_MAX + SW_WARP_MAX / 32];
   __shared__ uint32_t s_hist[SW_WARPS][SW_BINS];
+  __shared__ double s_cam[SW_WARPS][16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t cam = (uint64_t)blockIdx.x * SW_WARPS + warp;
   if (cam >= s.C) return;
@@ -1306,19 +1307,45 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
   else
     sort_warp_to_smem<32, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   __syncwarp();
-  double c[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) c[k] = __ldg(&s.cams[15 * cam + k]);
-  // (an explicit software pipeline of the point gathers measured 0.85 ms against 0.83 ms for this form)
-  // (the points are read-only for the kernel: through the non-coherent path the gathers of the second unrolled
-  // iteration may move above the first one's stores)
-#pragma unroll 2
-  for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t pt = sorted[sw_pad(i)];
+  // Final write, one point ahead: the gather of iteration i + 1 (24 B per lane from anywhere in the point array,
+  // an L2 or HBM round trip) is in flight while iteration i is projected and stored.  The camera record waits in
+  // shared memory (broadcast LDS.128) instead of 30 registers, which is what makes room for the second point at
+  // 64 registers; its address goes through an opaque register inside the loop, or the compiler hoists the
+  // fifteen loads back into registers.  (r01: the same pipeline WITH the record in registers measured 0.85 ms
+  // against 0.83 ms — it spilled.)
+  double *crec = s_cam[warp];
+  if (lane < 15) crec[lane] = __ldg(&s.cams[15 * cam + lane]);
+  __syncwarp();
+  uint32_t c_s = (uint32_t)__cvta_generic_to_shared(crec);
+  uint32_t i = lane, pt = 0u;
+  double x = 0.0, y = 0.0, z = 0.0;
+  if (i < n) {
+    pt = sorted[sw_pad(i)];
     const double *p = s.p_aos + 3 * (uint64_t)pt;
-    const double x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    x = __ldg(p);
+    y = __ldg(p + 1);
+    z = __ldg(p + 2);
+  }
+  while (i < n) {
+    const uint32_t ni = i + 32;
+    uint32_t npt = 0u;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    if (ni < n) {
+      npt = sorted[sw_pad(ni)];
+      const double *p = s.p_aos + 3 * (uint64_t)npt;
+      nx = __ldg(p);
+      ny = __ldg(p + 1);
+      nz = __ldg(p + 2);
+    }
+    asm volatile("" : "+r"(c_s));
+    const double *c = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)c_s));
     s.out_idx[base + i] = pt;
     s.out_uv[base + i] = observe(c, x, y, z);
+    i = ni;
+    pt = npt;
+    x = nx;
+    y = ny;
+    z = nz;
   }
 }
 
