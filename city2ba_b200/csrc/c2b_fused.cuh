@@ -1307,9 +1307,9 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
   else
     sort_warp_to_smem<32, MULTI>(s, cs, lane, sorted, s_hist[warp]);
   __syncwarp();
-  // Final write, one point ahead: the gather of iteration i + 1 (24 B per lane from anywhere in the point array,
-  // an L2 or HBM round trip) is in flight while iteration i is projected and stored.  The camera record waits in
-  // shared memory (broadcast LDS.128) instead of 30 registers, which is what makes room for the second point at
+  // Final write, two points ahead: the gathers of iterations i + 1 and i + 2 (24 B per lane from anywhere in the point array,
+  // an L2 or HBM round trip) are in flight while iteration i is projected and stored.  The camera record waits in
+  // shared memory (broadcast LDS.128) instead of 30 registers, which is what makes room for the extra points at
   // 64 registers; its address goes through an opaque register inside the loop, or the compiler hoists the
   // fifteen loads back into registers.  (r01: the same pipeline WITH the record in registers measured 0.85 ms
   // against 0.83 ms — it spilled.)
@@ -1317,35 +1317,34 @@ __global__ void __launch_bounds__(SW_WARPS * 32, MIN_CTAS) k_sort_write(SortWrit
   if (lane < 15) crec[lane] = __ldg(&s.cams[15 * cam + lane]);
   __syncwarp();
   uint32_t c_s = (uint32_t)__cvta_generic_to_shared(crec);
-  uint32_t i = lane, pt = 0u;
-  double x = 0.0, y = 0.0, z = 0.0;
-  if (i < n) {
-    pt = sorted[sw_pad(i)];
-    const double *p = s.p_aos + 3 * (uint64_t)pt;
-    x = __ldg(p);
-    y = __ldg(p + 1);
-    z = __ldg(p + 2);
-  }
-  while (i < n) {
-    const uint32_t ni = i + 32;
-    uint32_t npt = 0u;
-    double nx = 0.0, ny = 0.0, nz = 0.0;
-    if (ni < n) {
-      npt = sorted[sw_pad(ni)];
-      const double *p = s.p_aos + 3 * (uint64_t)npt;
-      nx = __ldg(p);
-      ny = __ldg(p + 1);
-      nz = __ldg(p + 2);
+  // two gathers in flight per lane: (pt0, p0) is the point being written, (pt1, p1) the next one, and the loop
+  // body starts the one after that
+  struct Pt {
+    uint32_t idx;
+    double x, y, z;
+  };
+  auto gather = [&](uint32_t k) {
+    Pt q{0u, 0.0, 0.0, 0.0};
+    if (k < n) {
+      q.idx = sorted[sw_pad(k)];
+      const double *p = s.p_aos + 3 * (uint64_t)q.idx;
+      q.x = __ldg(p);
+      q.y = __ldg(p + 1);
+      q.z = __ldg(p + 2);
     }
+    return q;
+  };
+  uint32_t i = lane;
+  Pt p0 = gather(i), p1 = gather(i + 32);
+  while (i < n) {
+    const Pt p2 = gather(i + 64);
     asm volatile("" : "+r"(c_s));
     const double *c = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)c_s));
-    s.out_idx[base + i] = pt;
-    s.out_uv[base + i] = observe(c, x, y, z);
-    i = ni;
-    pt = npt;
-    x = nx;
-    y = ny;
-    z = nz;
+    s.out_idx[base + i] = p0.idx;
+    s.out_uv[base + i] = observe(c, p0.x, p0.y, p0.z);
+    i += 32;
+    p0 = p1;
+    p1 = p2;
   }
 }
 
