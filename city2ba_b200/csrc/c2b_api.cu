@@ -965,7 +965,7 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
   // tickets (a ticket repeats the per-camera set-up, so it only pays on warps that would otherwise idle).
   int parts_log2 = 0;
   {
-    const uint64_t warps = (uint64_t)ctx->sm_count * 4 * FU_WARPS;
+    const uint64_t warps = (uint64_t)ctx->sm_count * FU_RESIDENT_WARPS;
     if (2 * C <= warps) parts_log2 = 1;
     if (4 * C <= warps) parts_log2 = 2;
     if (x->tun.parts_log2 >= 0) parts_log2 = x->tun.parts_log2;  // test hook
@@ -1092,8 +1092,9 @@ int visibility_grid_fused(c2b_ctx *ctx, CtxExtra *x, const c2b_scene *scene, dou
     // persistent warps draw cameras from a ticket; more CTAs than can be resident is harmless
     const unsigned nb = (unsigned)std::min<uint64_t>(blocks_for(slots, FU_WARPS), (uint64_t)ctx->sm_count * 8), nt = FU_WARPS * 32;
     const bool cnt = opt.count_traversal != 0;
-    // 64 registers, 4 CTAs/SM (C2B_FU_OCC3: 80 / 3).  Measured at cfg4: 2.68 ms; 3 CTAs/SM 2.69 ms; 5 CTAs/SM at
-    // 48 registers 2.74 ms
+    // The template's third argument counts CTAs of EIGHT warps per SM (fu_min_ctas translates for four-warp CTAs).
+    // Eight-warp CTAs, r01m kernels at cfg4: 4 CTAs/SM at 64 registers 2.68 ms; 3 at 80 (C2B_FU_OCC3) 2.69 ms; 5 at 48
+    // 2.74 ms.  Four-warp CTAs, r02y kernels: 7 CTAs/SM at 72 registers 2.31 ms against 2.38 ms for 4 x 8 warps at 64.
     const bool occ4 = !x->tun.fu_occ3;
     if (mt) {
       // candidates only; k_filter_candidates_mt decides occlusion below
@@ -1568,7 +1569,7 @@ int c2b_visibility_graph(c2b_ctx *ctx, const c2b_scene *scene, const double *cam
   // Which case applies is taken from the previous call on this ctx; the first call assumes the transfer.
   std::vector<uint64_t> bounds;  // batch b = cameras [bounds[b], bounds[b+1])
   bounds.push_back(0);
-  const uint64_t W = (uint64_t)ctx->sm_count * 4 * FU_WARPS;  // resident warps of the fused kernel
+  const uint64_t W = (uint64_t)ctx->sm_count * FU_RESIDENT_WARPS;  // resident warps of the fused kernel
   if (x->tun.batches > 0) {
     const uint64_t nb = std::max<uint64_t>(1, std::min<uint64_t>(C ? C : 1, (uint64_t)x->tun.batches));
     for (uint64_t b = 1; b <= nb; ++b) bounds.push_back((b * C) / nb);

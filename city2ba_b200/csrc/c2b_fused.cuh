@@ -582,7 +582,18 @@ __device__ __forceinline__ const uint32_t *rolled_warp_sort(uint32_t *slice, uin
 }
 
 // ---- the fused pass ---------------------------------------------------------------------------------
-constexpr int FU_WARPS = 8;
+// Warps per CTA.  Four-warp CTAs, 7 per SM, give the kernel 72 registers at 28 warps per SM; eight-warp CTAs (until
+// r02y) 64 registers at 32.  At 64 the prefetched coordinates of the next chunk and the camera centre lived in local
+// memory — the spill store right behind the prefetch loads waited for them to arrive (6 % of the kernel's stall
+// samples, profiles/r02x_sass_dynamic_fused.txt) — at 72 they stay in registers: 2.38 -> 2.31 ms at cfg4 on the
+// same box (profiles/r02y_ab_same_box.txt).  -DC2B_FU_WARPS=8 restores the old shape.
+#ifndef C2B_FU_WARPS
+#define C2B_FU_WARPS 4
+#endif
+constexpr int FU_WARPS = C2B_FU_WARPS;
+// CTAs per SM for a variant declared with m CTAs of EIGHT warps (the template argument MIN_CTAS)
+constexpr int fu_min_ctas(int m) { return FU_WARPS == 8 ? m : (m == 4 ? 7 : 2 * m); }
+constexpr int FU_RESIDENT_WARPS = FU_WARPS == 8 ? 32 : 28;  // per SM, of the default (mesh) variant
 constexpr int FU_STAGE = 64;
 
 enum { FU_OCC_MESH = 0, FU_OCC_NONE = 1, FU_OCC_ANALYTIC = 2 };
@@ -1058,7 +1069,7 @@ struct alignas(16) FuWarpSmem {
 };
 
 template <int OCC, bool COUNT, int MIN_CTAS, bool WALK, bool EPI = false>
-__global__ void __launch_bounds__(FU_WARPS * 32, MIN_CTAS) k_visibility_fused(FusedArgs a) {
+__global__ void __launch_bounds__(FU_WARPS * 32, fu_min_ctas(MIN_CTAS)) k_visibility_fused(FusedArgs a) {
   // One block of shared memory per warp (FuWarpSmem), addressed through ONE opaque 32-bit register: with three
   // separate arrays indexed by the warp number the compiler re-derived every address from %tid and the shared
   // window at each use (5-10 instructions, eight times per chunk / packet: profiles/r02w_sass_dynamic_fused.txt).
