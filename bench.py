@@ -246,7 +246,10 @@ def parity_against(sample_idx, vis, offsets, idx, uv):
     for k in np.nonzero(~bad)[0]:
         a, b = off[sample_idx[k]], off[sample_idx[k] + 1]
         ra, rb = int(vis.offsets[k]), int(vis.offsets[k + 1])
-        if not (np.array_equal(np.asarray(idx[a:b], np.uint64), vis.point_idx[ra:rb]) and np.array_equal(uv2[a:b], vis.uv[ra:rb])):
+        # (u, v) compared as raw 64-bit words: the sign of a zero counts (v = +-0 all over the synthetic cities)
+        same_uv = np.array_equal(np.ascontiguousarray(uv2[a:b], np.float64).view(np.uint64),
+                                 np.ascontiguousarray(vis.uv[ra:rb], np.float64).view(np.uint64))
+        if not (np.array_equal(np.asarray(idx[a:b], np.uint64), vis.point_idx[ra:rb]) and same_uv):
             bad[k] = True
     return {"cameras_checked": int(len(sample_idx)), "observations_checked": int(rn.sum()),
             "mismatches": int(bad.sum()), "against": "oracle CPU arm (orc_ref_visibility_graph), bit for bit: "

@@ -92,7 +92,16 @@ def points_on_mesh(rng, xyz, tri, n):
     return a[pick] + r1[:, None] * (b[pick] - a[pick]) + r2[:, None] * (c[pick] - a[pick])
 
 
+def bits_equal(a, b):
+    """f64 arrays equal BIT FOR BIT (np.array_equal calls +0.0 and -0.0 equal and a NaN unequal to itself; the
+    synthetic cities produce v = +-0 for every observation, so the sign of zero is part of the result)"""
+    a = np.ascontiguousarray(a, np.float64).reshape(-1)
+    b = np.ascontiguousarray(b, np.float64).reshape(-1)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
 def assert_same_graph(g, ref, what=""):
     assert np.array_equal(np.asarray(g.offsets, np.uint64), ref.offsets), f"{what}: CSR offsets differ"
     assert np.array_equal(np.asarray(g.point_idx, np.uint64), ref.point_idx), f"{what}: indices differ"
     assert np.array_equal(np.asarray(g.uv), ref.uv), f"{what}: projections differ (bit-exact expected)"
+    assert bits_equal(g.uv, ref.uv), f"{what}: projections differ in the sign of a zero"

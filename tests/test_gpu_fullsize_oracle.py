@@ -8,6 +8,8 @@ camera sample, and those rows must agree bit for bit: offsets, ascending point i
 import numpy as np
 import pytest
 
+from conftest import bits_equal
+
 pytestmark = pytest.mark.gpu
 
 
@@ -26,6 +28,7 @@ def compare_sample(g, ref, cam_idx, what):
                           f"(first: camera {cam_idx[bad[0]]}: {n[bad[0]]} vs oracle {rn[bad[0]]})"
     assert np.array_equal(idx, ref.point_idx), f"{what}: point indices differ"
     assert np.array_equal(uv, ref.uv), f"{what}: projections differ (bit-exact expected)"
+    assert bits_equal(uv, ref.uv), f"{what}: projections differ in the sign of a zero"
     return int(rn.sum())
 
 
