@@ -46,6 +46,17 @@ def test_parity_against_counts_differing_cameras(orc):
     row = int(v.offsets[sample[7]])
     uv[row, 1] += 1e-12
     assert bench.parity_against(sample, ref, v.offsets, v.point_idx, uv)["mismatches"] == 1
+    # the sign of a zero counts: the synthetic city has v = +0 for the observations at camera height
+    uv = v.uv.copy()
+    off = v.offsets.astype(np.int64)
+    rows = np.concatenate([np.arange(off[c], off[c + 1]) for c in sample])
+    zero = rows[uv[rows, 1] == 0.0]
+    assert len(zero) > 0
+    uv[zero[0], 1] = -0.0
+    assert np.array_equal(uv, v.uv)  # invisible to a value comparison
+    assert bench.parity_against(sample, ref, v.offsets, v.point_idx, uv)["mismatches"] == 1
+    # what the bench hands over: the flat (2 * O,) view of the library's uv array
+    assert bench.parity_against(sample, ref, v.offsets, v.point_idx, v.uv.reshape(-1))["mismatches"] == 0
 
 
 def test_workload_generators_agree():
@@ -54,3 +65,13 @@ def test_workload_generators_agree():
     b = bench.build_workload("cfg2", gen="oracle")
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_bits_equal_sees_what_array_equal_does_not():
+    from conftest import bits_equal
+    a = np.array([[0.0, 1.5], [np.nan, -2.0]])
+    assert bits_equal(a, a.copy()) and not np.array_equal(a, a.copy())  # a NaN equals itself bit for bit
+    b = a.copy()
+    b[0, 0] = -0.0
+    assert np.array_equal(a[0], b[0]) and not bits_equal(a, b)
+    assert not bits_equal(a, a[:1])
